@@ -1,0 +1,72 @@
+"""oracle/refport.py must compute what the reference's own functions compute.  Needs
+/root/reference (build container only) -- elsewhere these are skipped and the frozen golden
+fixtures (test_oracle_golden.py) carry the pin."""
+import importlib.util
+import os
+import sys
+
+import cv2
+import numpy as np
+import pytest
+
+from conftest import REFERENCE_DIR
+from oracle import refport as rp
+from helpers import synth, uniform_img
+
+pytestmark = pytest.mark.reference
+
+
+def _load(fname, modname):
+    sys.dont_write_bytecode = True
+    if REFERENCE_DIR not in sys.path:
+        sys.path.append(REFERENCE_DIR)          # for `from config import ...`
+    spec = importlib.util.spec_from_file_location(modname, os.path.join(REFERENCE_DIR, fname))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    return m
+
+
+def test_kmeans_lab_and_assign():
+    ce = _load("02_color_extract.py", "ref_ce")
+    img = synth(300, 400, 5)
+    for K in (4, 8):
+        cv2.setRNGSeed(0)
+        c_ref, l_ref = ce._kmeans_lab(img, K)
+        c = rp.kmeans_lab_centers(img, K)
+        assert np.array_equal(c, c_ref)
+        assert np.array_equal(rp.assign_lab(img, c), l_ref)
+        assert np.array_equal(rp.assign_lab_chunked(img, c, rows=37), l_ref)
+    assert [ce._darkness_rank(n) for n in ("layer_dark", "x_MID", "skin", "Light", "foo")] == \
+           [rp.darkness_rank(n) for n in ("layer_dark", "x_MID", "skin", "Light", "foo")]
+
+
+def test_assign_labels_rgb():
+    pc = _load("process_colors.py", "ref_pc")
+    img = uniform_img(90, 110, 3)
+    for K in (2, 5, 16):
+        pal = np.random.default_rng(K).integers(0, 256, (K, 3), dtype=np.uint8)
+        assert np.array_equal(rp.assign_labels_rgb(img, pal), pc.assign_labels(img, pal))
+
+
+def test_edge_layer_and_resize(tmp_path):
+    ed = _load("03_edge_detect.py", "ref_ed")
+    rz = _load("01_resize.py", "ref_rz")
+    cfgm = sys.modules["config"]
+    img = synth(260, 380, 9)
+    p = str(tmp_path / "in.png")
+    cv2.imwrite(p, img)
+    for md in (2000, 190, 100):
+        assert np.array_equal(rz.resize_if_needed(p, cfgm.Config(max_dimension=md)), rp.resize_if_needed(img, md))
+    K = 4
+    _, _, masks = rp.color_extract(img, K)
+    names = ["layer_dark", "layer_mid", "layer_skin", "layer_light"]
+    for ks, lo, hi in [(3, 50, 150), (6, 22, 70)]:
+        cfg = cfgm.Config(output_dir=str(tmp_path), color_names=names, edge_kernel_size=ks,
+                          edge_low_threshold=lo, edge_high_threshold=hi)
+        cfg.ensure_output_dirs()
+        for n, m in zip(names, masks):
+            cv2.imwrite(str(tmp_path / n / "mask.png"), m)
+            ed.process_color(n, cfg)
+            e = cv2.imread(str(tmp_path / n / "edges.png"), cv2.IMREAD_GRAYSCALE)
+            assert np.array_equal(e, rp.edge_layer(m, lo, hi, ks))
+        assert ed._ensure_odd(ks) == rp.ensure_odd(ks)
