@@ -1,0 +1,152 @@
+/*
+ * omni_b200.h -- C ABI of libomni_b200.so: stages 01_resize / 02_color_extract / 03_edge_detect of
+ * omnirevolve-image-processor as hand-written sm_100a CUDA kernels.
+ *
+ * The reference has NO FFI or operator interface on this path: its stages are Python scripts that
+ * call OpenCV/NumPy and hand results to each other as PNG files.  Each entry point
+ * below therefore replaces a *library call site* inside a reference stage function, cited as
+ * file:line relative to /root/reference/image_processor/.  The Python side that binds these
+ * (ctypes) and keeps the reference's function signatures is omni_b200/stages.py; the binding a
+ * reference maintainer would add is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *   - every function returns 0 (OMNI_OK) or a negative error code; omni_last_error_string() gives
+ *     the detail for the calling thread.  There is no CPU fallback: without a CUDA device every
+ *     compute entry point fails with OMNI_ERR_CUDA.
+ *   - images are 8-bit, row-major, explicit pitches in BYTES.  "d_" pointers are device memory
+ *     owned by the caller (e.g. torch.Tensor.data_ptr()); "h_" pointers are host memory.
+ *     Small parameter blocks (centres, palettes, look-up tables) are always HOST pointers and are
+ *     consumed before the call returns.
+ *   - `stream` is a cudaStream_t passed as void*.  Device-pointer entry points only enqueue work,
+ *     except omni_edges and omni_color_edge, which may synchronise the stream internally when a
+ *     hysteresis chain crosses tile borders more often than the enqueued passes cover (rare; see
+ *     DESIGN.md "hysteresis").  Host-pointer entry points (omni_host_*) copy in, compute, copy out
+ *     and return after the results are in the host buffers.
+ *   - an omni_ctx owns per-device scratch (work planes, resize tables, flags).  One ctx per host
+ *     thread and device; calls on one ctx must not overlap.
+ */
+#ifndef OMNI_B200_H
+#define OMNI_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OMNI_ABI_VERSION 1
+#define OMNI_MAX_K 32            /* colour layers per image (labels are u8; reference configs use 4..16) */
+#define OMNI_MAX_BLUR_K 31       /* largest edge_kernel_size with a built-in 8.8 weight table */
+#define OMNI_MAX_MORPH_K 7       /* largest edge_morph_kernel */
+
+#define OMNI_OK 0
+#define OMNI_ERR_ARG (-1)
+#define OMNI_ERR_CUDA (-2)
+#define OMNI_ERR_UNSUPPORTED (-3)
+#define OMNI_ERR_NOMEM (-4)
+
+typedef struct omni_ctx omni_ctx;
+
+/* 03_edge_detect.py:23-34 knobs, as read from config.json (config.py:31-36). */
+typedef struct omni_edge_params {
+    int32_t morph_k;      /* edge_morph_kernel: ELLIPSE structuring element size, >= 1            */
+    int32_t open_iters;   /* edge_morph_open_iters  (<= 0: skip)                                  */
+    int32_t close_iters;  /* edge_morph_close_iters (<= 0: skip)                                  */
+    int32_t ksize;        /* edge_kernel_size after _ensure_odd (03:9-11): odd, >= 3              */
+    double low, high;     /* edge_low_threshold / edge_high_threshold exactly as given to Canny   */
+} omni_edge_params;
+
+/* ---- library / context ------------------------------------------------------------------- */
+int omni_version(void);
+const char *omni_last_error_string(void);
+int omni_device_count(void);
+/* Which implementation serves the calls: 0 = generic kernels only, 1 = fast bit-plane kernels where
+ * the parameters allow (default).  For tests and A/B measurements. */
+int omni_set_fast_path(omni_ctx *ctx, int enable);
+int omni_ctx_create(int device, omni_ctx **out);
+int omni_ctx_destroy(omni_ctx *ctx);
+/* Pinned host memory for the omni_host_* entry points (pageable memory works, but is slower). */
+int omni_host_alloc(size_t bytes, void **out);
+int omni_host_free(void *p);
+
+/* ---- stage 01: 01_resize.py:20  cv2.resize(img, (dw, dh), interpolation=cv2.INTER_AREA) ------ */
+/* 3-channel u8, shrink only (dh <= sh, dw <= sw).  (dw, dh) come from the host expressions of
+ * 01_resize.py:16-18 -- never recomputed here.  Exact for integer ratios; fractional ratios follow
+ * OpenCV's float32 evaluation order (contract: +-1 LSB). */
+int omni_resize_area_u8c3(omni_ctx *ctx, const uint8_t *d_src, int sh, int sw, size_t spitch,
+                          uint8_t *d_dst, int dh, int dw, size_t dpitch, void *stream);
+int omni_host_resize_area_u8c3(omni_ctx *ctx, const uint8_t *h_src, int sh, int sw, size_t spitch,
+                               uint8_t *h_dst, int dh, int dw, size_t dpitch);
+
+/* ---- stage 02: per-pixel colour assignment ------------------------------------------------- */
+/* 02_color_extract.py:35-36,53-55 + relabel :121-127.
+ * BGR u8 -> 8-bit Lab (cv2.cvtColor COLOR_BGR2LAB) -> argmin_k of the float32 squared distance to
+ * h_centers[K][3] (evaluation order (d0^2+d1^2)+d2^2, every op rounded, first minimum) ->
+ * label = h_lut ? h_lut[k] : k.  d_labels: u8 [h][lpitch]. */
+int omni_assign_lab_f32(omni_ctx *ctx, const uint8_t *d_bgr, int h, int w, size_t pitch,
+                        const float *h_centers, int K, const uint8_t *h_lut,
+                        uint8_t *d_labels, size_t lpitch, void *stream);
+/* process_colors.py:69-77 assign_labels: RGB u8 vs h_palette[K][3] u8, the int16 WRAP of diff*diff
+ * reproduced (d2 = sum_c (int16)(diff_c*diff_c)), first minimum. */
+int omni_assign_rgb_i16wrap(omni_ctx *ctx, const uint8_t *d_rgb, int h, int w, size_t pitch,
+                            const uint8_t *h_palette, int K, uint8_t *d_labels, size_t lpitch, void *stream);
+int omni_host_assign_rgb_i16wrap(omni_ctx *ctx, const uint8_t *h_rgb, int h, int w, size_t pitch,
+                                 const uint8_t *h_palette, int K, uint8_t *h_labels, size_t lpitch);
+
+/* 02_color_extract.py:136-154: for plane p in [0,K): (labels == p) * 255, then MORPH_OPEN x open_iters
+ * and MORPH_CLOSE x close_iters with the 3x3 RECT element.  d_masks: K planes, plane p at
+ * d_masks + p*plane_stride, rows mpitch bytes apart.  open/close_iters <= 0 skip that step
+ * (process_colors.py:171-173 layers are the 0/0 case). */
+int omni_layer_masks(omni_ctx *ctx, const uint8_t *d_labels, int h, int w, size_t lpitch, int K,
+                     int open_iters, int close_iters,
+                     uint8_t *d_masks, size_t plane_stride, size_t mpitch, void *stream);
+
+/* ---- stage 03: 03_edge_detect.py:23-34 per layer ------------------------------------------- */
+/* K independent planes: ELLIPSE(morph_k) open/close -> GaussianBlur(ksize, sigma 0) -> Canny(low,
+ * high) (aperture 3, L1, 8-connected hysteresis).  Output {0,255}.  In and out may not alias.
+ * Masks may hold any u8 values (the reference reads arbitrary mask.png files). */
+int omni_edges(omni_ctx *ctx, const uint8_t *d_masks, int K, int h, int w, size_t m_plane_stride, size_t mpitch,
+               const omni_edge_params *prm,
+               uint8_t *d_edges, size_t e_plane_stride, size_t epitch, void *stream);
+int omni_host_edges(omni_ctx *ctx, const uint8_t *h_masks, int K, int h, int w, size_t m_plane_stride, size_t mpitch,
+                    const omni_edge_params *prm,
+                    uint8_t *h_edges, size_t e_plane_stride, size_t epitch);
+
+/* ---- fused hot path: image -> K layer masks + K edge masks ---------------------------------- */
+/* Equivalent to omni_assign_lab_f32 -> omni_layer_masks(1,1) -> omni_edges, i.e. everything
+ * 02_color_extract.py:53-154 and 03_edge_detect.py:23-34 compute between the k-means centres and
+ * the PNG writes.  d_labels may be NULL. */
+int omni_color_edge(omni_ctx *ctx, const uint8_t *d_bgr, int h, int w, size_t pitch,
+                    const float *h_centers, int K, const uint8_t *h_lut, const omni_edge_params *prm,
+                    uint8_t *d_labels, size_t lpitch,
+                    uint8_t *d_masks, size_t m_plane_stride, size_t mpitch,
+                    uint8_t *d_edges, size_t e_plane_stride, size_t epitch, void *stream);
+/* Host-buffer form: H2D of the image, kernels, D2H of labels (optional), masks and edges.
+ * h_counts (optional, 3*K int64): per plane [pixels labelled p, mask non-zeros, edge non-zeros] --
+ * the numbers 02:168 and 03:38 print and palette_by_name.json records. */
+int omni_host_color_edge(omni_ctx *ctx, const uint8_t *h_bgr, int h, int w, size_t pitch,
+                         const float *h_centers, int K, const uint8_t *h_lut, const omni_edge_params *prm,
+                         uint8_t *h_labels, size_t lpitch,
+                         uint8_t *h_masks, size_t m_plane_stride, size_t mpitch,
+                         uint8_t *h_edges, size_t e_plane_stride, size_t epitch,
+                         int64_t *h_counts);
+
+/* Non-zero count of each of K planes (02:157, 03:38 `np.count_nonzero`); h_counts: K int64.
+ * Synchronises the stream. */
+int omni_count_nonzero(omni_ctx *ctx, const uint8_t *d_planes, int K, int h, int w, size_t plane_stride, size_t pitch,
+                       int64_t *h_counts, void *stream);
+
+/* 03_edge_detect.py:93-106 paint: white BGR canvas, for plane p in order paint h_colors_bgr[p] where
+ * edges > 0 (later planes overwrite earlier ones). */
+int omni_edges_composite(omni_ctx *ctx, const uint8_t *d_edges, int K, int h, int w, size_t e_plane_stride, size_t epitch,
+                         const uint8_t *h_colors_bgr, uint8_t *d_canvas, size_t cpitch, void *stream);
+
+/* Diagnostics of the last omni_edges / omni_color_edge call on this ctx: number of global
+ * hysteresis passes that were needed (>= 1). */
+int omni_last_hysteresis_passes(omni_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OMNI_B200_H */

@@ -1,0 +1,547 @@
+// capi.cu -- extern "C" entry points of libomni_b200.so (declared in include/omni_b200.h).
+#include "omni_internal.cuh"
+#include "fast_kernels.cuh"
+
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+static thread_local char g_err[512] = "";
+
+void omni_set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+extern "C" const char *omni_last_error_string(void) { return g_err; }
+extern "C" int omni_version(void) { return OMNI_ABI_VERSION; }
+
+extern "C" int omni_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+// ---- context -----------------------------------------------------------------------------------
+extern "C" int omni_ctx_create(int device, omni_ctx **out)
+{
+    OMNI_REQUIRE(out != nullptr, "omni_ctx_create: out is NULL");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        omni_set_error("no CUDA device available (%s); libomni_b200 has no CPU fallback",
+                       e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+        cudaGetLastError();
+        return OMNI_ERR_CUDA;
+    }
+    OMNI_REQUIRE(device >= 0 && device < n, "omni_ctx_create: device %d out of range [0,%d)", device, n);
+    OMNI_CUDA(cudaSetDevice(device));
+    omni_ctx *c = new omni_ctx();
+    c->device = device;
+    OMNI_CUDA(cudaMalloc(&c->d_flags, 64 * sizeof(int)));
+    OMNI_CUDA(cudaMemset(c->d_flags, 0, 64 * sizeof(int)));
+    OMNI_CUDA(cudaMalloc(&c->d_counts, 4 * OMNI_MAX_K * sizeof(unsigned long long)));
+    OMNI_CUDA(cudaHostAlloc(&c->h_flags, 64 * sizeof(int), cudaHostAllocDefault));
+    OMNI_CUDA(cudaHostAlloc(&c->h_counts, 4 * OMNI_MAX_K * sizeof(unsigned long long), cudaHostAllocDefault));
+    OMNI_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    *out = c;
+    return OMNI_OK;
+}
+
+extern "C" int omni_ctx_destroy(omni_ctx *c)
+{
+    if (!c) return OMNI_OK;
+    cudaSetDevice(c->device);
+    for (int i = 0; i < 4; i++) if (c->ws[i]) cudaFree(c->ws[i]);
+    for (auto &kv : c->resize_tabs) if (kv.second.d_blob) cudaFree(kv.second.d_blob);
+    if (c->d_flags) cudaFree(c->d_flags);
+    if (c->d_counts) cudaFree(c->d_counts);
+    if (c->h_flags) cudaFreeHost(c->h_flags);
+    if (c->h_counts) cudaFreeHost(c->h_counts);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    fast_ctx_release(c);
+    delete c;
+    return OMNI_OK;
+}
+
+extern "C" int omni_set_fast_path(omni_ctx *ctx, int enable)
+{
+    OMNI_REQUIRE(ctx != nullptr, "omni_set_fast_path: ctx is NULL");
+    ctx->fast = enable ? 1 : 0;
+    return OMNI_OK;
+}
+
+extern "C" int omni_host_alloc(size_t bytes, void **out)
+{
+    OMNI_REQUIRE(out != nullptr, "omni_host_alloc: out is NULL");
+    OMNI_CUDA(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault));
+    return OMNI_OK;
+}
+
+extern "C" int omni_host_free(void *p)
+{
+    if (p) OMNI_CUDA(cudaFreeHost(p));
+    return OMNI_OK;
+}
+
+extern "C" int omni_last_hysteresis_passes(omni_ctx *ctx) { return ctx ? ctx->last_hyst_passes : 0; }
+
+int omni_ws_reserve(omni_ctx *ctx, int slot, size_t bytes)
+{
+    if (ctx->ws_bytes[slot] >= bytes) return OMNI_OK;
+    if (ctx->ws[slot]) { OMNI_CUDA(cudaFree(ctx->ws[slot])); ctx->ws[slot] = nullptr; ctx->ws_bytes[slot] = 0; }
+    size_t want = bytes + bytes / 8;
+    cudaError_t e = cudaMalloc(&ctx->ws[slot], want);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        omni_set_error("workspace slot %d: cudaMalloc(%zu) failed: %s", slot, want, cudaGetErrorString(e));
+        return OMNI_ERR_NOMEM;
+    }
+    ctx->ws_bytes[slot] = want;
+    return OMNI_OK;
+}
+
+// ---- host-side parameter preparation --------------------------------------------------------------
+// cv2.getStructuringElement(MORPH_RECT | MORPH_ELLIPSE, (k,k)) as an offset list.
+void omni_build_se(int shape_ellipse, int k, MorphSE *se)
+{
+    int r = k / 2, c = k / 2, a = k / 2;
+    double inv_r2 = r ? 1.0 / ((double)r * r) : 0.0;
+    se->n = 0;
+    se->k = k;
+    for (int i = 0; i < k; i++) {
+        int j1 = 0, j2 = 0;
+        if (!shape_ellipse) j2 = k;
+        else {
+            int dy = i - r;
+            if (abs(dy) <= r) {
+                int dx = (int)lrint(c * sqrt((r * r - dy * dy) * inv_r2));
+                j1 = c - dx > 0 ? c - dx : 0;
+                j2 = c + dx + 1 < k ? c + dx + 1 : k;
+            }
+        }
+        for (int j = j1; j < j2; j++) { se->dy[se->n] = (int8_t)(i - a); se->dx[se->n] = (int8_t)(j - a); se->n++; }
+    }
+}
+
+// OpenCV's computeResizeAreaTab (double arithmetic on the host, float weights) -- SURVEY A.1(iii).
+static void area_tab(int ssize, int dsize, double scale, std::vector<int> &ofs, std::vector<int> &si, std::vector<float> &al)
+{
+    ofs.assign(1, 0);
+    for (int dx = 0; dx < dsize; dx++) {
+        double fsx1 = dx * scale, fsx2 = fsx1 + scale;
+        double cw = scale < ssize - fsx1 ? scale : ssize - fsx1;
+        int sx1 = (int)ceil(fsx1), sx2 = (int)floor(fsx2);
+        if (sx2 > ssize - 1) sx2 = ssize - 1;
+        if (sx1 > sx2) sx1 = sx2;
+        if (sx1 - fsx1 > 1e-3) { si.push_back(sx1 - 1); al.push_back((float)((sx1 - fsx1) / cw)); }
+        for (int sx = sx1; sx < sx2; sx++) { si.push_back(sx); al.push_back((float)(1.0 / cw)); }
+        if (fsx2 - sx2 > 1e-3) {
+            double a = fsx2 - sx2; if (a > 1.0) a = 1.0; if (a > cw) a = cw;
+            si.push_back(sx2); al.push_back((float)(a / cw));
+        }
+        ofs.push_back((int)si.size());
+    }
+}
+
+const ResizeTab *omni_get_resize_tab(omni_ctx *ctx, int sh, int sw, int dh, int dw, cudaStream_t st)
+{
+    auto key = std::make_tuple(sh, sw, dh, dw);
+    auto it = ctx->resize_tabs.find(key);
+    if (it != ctx->resize_tabs.end()) return &it->second;
+    std::vector<int> xo, xs, yo, ys;
+    std::vector<float> xa, ya;
+    area_tab(sw, dw, (double)sw / dw, xo, xs, xa);
+    area_tab(sh, dh, (double)sh / dh, yo, ys, ya);
+    size_t n_int = xo.size() + xs.size() + yo.size() + ys.size(), n_f = xa.size() + ya.size();
+    std::vector<int> blob(n_int + n_f);
+    size_t o = 0, o_xo = o; memcpy(&blob[o], xo.data(), xo.size() * 4); o += xo.size();
+    size_t o_xs = o; memcpy(&blob[o], xs.data(), xs.size() * 4); o += xs.size();
+    size_t o_yo = o; memcpy(&blob[o], yo.data(), yo.size() * 4); o += yo.size();
+    size_t o_ys = o; memcpy(&blob[o], ys.data(), ys.size() * 4); o += ys.size();
+    size_t o_xa = o; memcpy(&blob[o], xa.data(), xa.size() * 4); o += xa.size();
+    size_t o_ya = o; memcpy(&blob[o], ya.data(), ya.size() * 4); o += ya.size();
+    ResizeTab t;
+    if (cudaMalloc(&t.d_blob, blob.size() * 4) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    // synchronous copy from pageable memory: tables are built once per geometry and cached
+    if (cudaMemcpy(t.d_blob, blob.data(), blob.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess) {
+        cudaGetLastError(); cudaFree(t.d_blob); return nullptr;
+    }
+    (void)st;
+    const int *b = (const int *)t.d_blob;
+    t.dev.xofs = b + o_xo; t.dev.xsi = b + o_xs; t.dev.yofs = b + o_yo; t.dev.ysi = b + o_ys;
+    t.dev.xal = (const float *)(b + o_xa); t.dev.yal = (const float *)(b + o_ya);
+    auto ins = ctx->resize_tabs.emplace(key, t);
+    return &ins.first->second;
+}
+
+static int set_device(omni_ctx *ctx)
+{
+    OMNI_REQUIRE(ctx != nullptr, "ctx is NULL");
+    OMNI_CUDA(cudaSetDevice(ctx->device));
+    return OMNI_OK;
+}
+#define OMNI_TRY(expr) do { int rc__ = (expr); if (rc__ != OMNI_OK) return rc__; } while (0)
+
+// ---- stage 01 ----------------------------------------------------------------------------------------
+extern "C" int omni_resize_area_u8c3(omni_ctx *ctx, const uint8_t *d_src, int sh, int sw, size_t spitch,
+                                     uint8_t *d_dst, int dh, int dw, size_t dpitch, void *stream)
+{
+    OMNI_TRY(set_device(ctx));
+    OMNI_REQUIRE(d_src && d_dst, "omni_resize_area_u8c3: NULL image pointer");
+    OMNI_REQUIRE(sh > 0 && sw > 0 && dh > 0 && dw > 0 && dh <= sh && dw <= sw,
+                 "omni_resize_area_u8c3: INTER_AREA shrink only, got %dx%d -> %dx%d", sw, sh, dw, dh);
+    OMNI_REQUIRE(spitch >= (size_t)sw * 3 && dpitch >= (size_t)dw * 3, "omni_resize_area_u8c3: pitch smaller than a row");
+    cudaStream_t st = (cudaStream_t)stream;
+    double scx = (double)sw / dw, scy = (double)sh / dh;
+    long isx = lrint(scx), isy = lrint(scy);
+    bool fast = fabs(scx - isx) < 2.220446049250313e-16 && fabs(scy - isy) < 2.220446049250313e-16;
+    if (fast) {
+        if (ctx->fast && isx == 2 && isy == 2 && fast_resize_2x_ok(d_src, sw, spitch, d_dst, dw, dpitch))
+            OMNI_CUDA(fast_resize_2x(d_src, spitch, d_dst, dh, dw, dpitch, st));
+        else
+            OMNI_CUDA(g_resize_area(d_src, sh, sw, spitch, d_dst, dh, dw, dpitch, nullptr, st));
+    } else {
+        const ResizeTab *t = omni_get_resize_tab(ctx, sh, sw, dh, dw, st);
+        if (!t) { omni_set_error("omni_resize_area_u8c3: cannot build resize tables"); return OMNI_ERR_NOMEM; }
+        OMNI_CUDA(g_resize_area(d_src, sh, sw, spitch, d_dst, dh, dw, dpitch, &t->dev, st));
+    }
+    return OMNI_OK;
+}
+
+// ---- stage 02 ----------------------------------------------------------------------------------------
+static int fill_assign(AssignParams *P, const float *h_centers, const uint8_t *h_pal, int K, const uint8_t *h_lut)
+{
+    OMNI_REQUIRE(K >= 1 && K <= OMNI_MAX_K, "K=%d outside [1,%d]", K, OMNI_MAX_K);
+    memset(P, 0, sizeof(*P));
+    P->K = K;
+    for (int i = 0; i < 3 * K; i++) {
+        if (h_centers) P->c[i] = h_centers[i];
+        if (h_pal) P->pal[i] = h_pal[i];
+    }
+    for (int k = 0; k < K; k++) {
+        P->lut[k] = h_lut ? h_lut[k] : (u8)k;
+        OMNI_REQUIRE(P->lut[k] < OMNI_MAX_K, "lut[%d]=%d out of range", k, P->lut[k]);
+    }
+    return OMNI_OK;
+}
+
+extern "C" int omni_assign_lab_f32(omni_ctx *ctx, const uint8_t *d_bgr, int h, int w, size_t pitch,
+                                   const float *h_centers, int K, const uint8_t *h_lut,
+                                   uint8_t *d_labels, size_t lpitch, void *stream)
+{
+    OMNI_TRY(set_device(ctx));
+    OMNI_REQUIRE(d_bgr && d_labels && h_centers, "omni_assign_lab_f32: NULL pointer");
+    OMNI_REQUIRE(h > 0 && w > 0 && pitch >= (size_t)w * 3 && lpitch >= (size_t)w, "omni_assign_lab_f32: bad geometry");
+    AssignParams P;
+    OMNI_TRY(fill_assign(&P, h_centers, nullptr, K, h_lut));
+    if (ctx->fast) OMNI_CUDA(fast_assign(ctx, d_bgr, h, w, pitch, P, 1, d_labels, lpitch, (cudaStream_t)stream));
+    else OMNI_CUDA(g_assign(d_bgr, h, w, pitch, P, 1, d_labels, lpitch, (cudaStream_t)stream));
+    return OMNI_OK;
+}
+
+extern "C" int omni_assign_rgb_i16wrap(omni_ctx *ctx, const uint8_t *d_rgb, int h, int w, size_t pitch,
+                                       const uint8_t *h_palette, int K, uint8_t *d_labels, size_t lpitch, void *stream)
+{
+    OMNI_TRY(set_device(ctx));
+    OMNI_REQUIRE(d_rgb && d_labels && h_palette, "omni_assign_rgb_i16wrap: NULL pointer");
+    OMNI_REQUIRE(h > 0 && w > 0 && pitch >= (size_t)w * 3 && lpitch >= (size_t)w, "omni_assign_rgb_i16wrap: bad geometry");
+    AssignParams P;
+    OMNI_TRY(fill_assign(&P, nullptr, h_palette, K, nullptr));
+    if (ctx->fast) OMNI_CUDA(fast_assign(ctx, d_rgb, h, w, pitch, P, 0, d_labels, lpitch, (cudaStream_t)stream));
+    else OMNI_CUDA(g_assign(d_rgb, h, w, pitch, P, 0, d_labels, lpitch, (cudaStream_t)stream));
+    return OMNI_OK;
+}
+
+// generic: one-hot planes, then erode/dilate passes ping-ponging between the output and scratch
+static int generic_layer_masks(omni_ctx *ctx, const uint8_t *d_labels, int h, int w, size_t lpitch, int K,
+                               int open_iters, int close_iters, uint8_t *d_masks, size_t plane_stride, size_t mpitch,
+                               cudaStream_t st)
+{
+    size_t wp = ((size_t)w + 15) & ~(size_t)15, wplane = wp * h;
+    OMNI_TRY(omni_ws_reserve(ctx, 0, wplane * K));
+    u8 *tmp = (u8 *)ctx->ws[0];
+    OMNI_CUDA(g_onehot(d_labels, h, w, lpitch, K, d_masks, plane_stride, mpitch, st));
+    MorphSE se;
+    omni_build_se(0, 3, &se);
+    int oi = open_iters > 0 ? open_iters : 0, ci = close_iters > 0 ? close_iters : 0;
+    // OPEN = erode^oi dilate^oi ; CLOSE = dilate^ci erode^ci
+    int seq_n = 0, seq[4 * 64];
+    OMNI_REQUIRE(oi <= 32 && ci <= 32, "morphology iterations too large");
+    for (int i = 0; i < oi; i++) seq[seq_n++] = 0;
+    for (int i = 0; i < oi; i++) seq[seq_n++] = 1;
+    for (int i = 0; i < ci; i++) seq[seq_n++] = 1;
+    for (int i = 0; i < ci; i++) seq[seq_n++] = 0;
+    bool in_out = true;   // current data lives in d_masks
+    for (int i = 0; i < seq_n; i++) {
+        if (in_out) OMNI_CUDA(g_morph(d_masks, plane_stride, mpitch, tmp, wplane, wp, K, h, w, se, seq[i], st));
+        else OMNI_CUDA(g_morph(tmp, wplane, wp, d_masks, plane_stride, mpitch, K, h, w, se, seq[i], st));
+        in_out = !in_out;
+    }
+    if (!in_out) OMNI_CUDA(g_copy2d_planes(tmp, wplane, wp, d_masks, plane_stride, mpitch, K, h, w, st));
+    return OMNI_OK;
+}
+
+extern "C" int omni_layer_masks(omni_ctx *ctx, const uint8_t *d_labels, int h, int w, size_t lpitch, int K,
+                                int open_iters, int close_iters,
+                                uint8_t *d_masks, size_t plane_stride, size_t mpitch, void *stream)
+{
+    OMNI_TRY(set_device(ctx));
+    OMNI_REQUIRE(d_labels && d_masks, "omni_layer_masks: NULL pointer");
+    OMNI_REQUIRE(K >= 1 && K <= OMNI_MAX_K, "omni_layer_masks: K=%d outside [1,%d]", K, OMNI_MAX_K);
+    OMNI_REQUIRE(h > 0 && w > 0 && lpitch >= (size_t)w && mpitch >= (size_t)w && plane_stride >= mpitch * (size_t)(h - 1) + w,
+                 "omni_layer_masks: bad geometry");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (ctx->fast && fast_masks_supported(open_iters, close_iters))
+        return fast_layer_masks(ctx, d_labels, h, w, lpitch, K, open_iters, close_iters, d_masks, plane_stride, mpitch, st);
+    return generic_layer_masks(ctx, d_labels, h, w, lpitch, K, open_iters, close_iters, d_masks, plane_stride, mpitch, st);
+}
+
+// ---- stage 03 ----------------------------------------------------------------------------------------
+static int check_edge_params(const omni_edge_params *p, BlurParams *bp, int *low, int *high)
+{
+    OMNI_REQUIRE(p != nullptr, "edge params NULL");
+    OMNI_REQUIRE(p->morph_k >= 1 && p->morph_k <= OMNI_MAX_MORPH_K, "edge_morph_kernel=%d outside [1,%d]", p->morph_k, OMNI_MAX_MORPH_K);
+    OMNI_REQUIRE(p->open_iters <= 32 && p->close_iters <= 32, "edge morph iterations too large");
+    if (omni_gauss_weights(p->ksize, bp)) {
+        omni_set_error("edge_kernel_size=%d: need an odd size in [3,%d] (apply _ensure_odd first)", p->ksize, OMNI_MAX_BLUR_K);
+        return OMNI_ERR_UNSUPPORTED;
+    }
+    // cv2.Canny: swap if low > high, then floor both for the integer L1 magnitude
+    double lo = p->low < p->high ? p->low : p->high, hi = p->low < p->high ? p->high : p->low;
+    OMNI_REQUIRE(lo == lo && hi == hi, "Canny thresholds are NaN");
+    lo = floor(lo); hi = floor(hi);
+    *low = lo > 1e9 ? 1000000000 : lo < -1e9 ? -1000000000 : (int)lo;
+    *high = hi > 1e9 ? 1000000000 : hi < -1e9 ? -1000000000 : (int)hi;
+    return OMNI_OK;
+}
+
+// run hysteresis passes until one changes nothing (flag read back through pinned memory)
+static int generic_hysteresis(omni_ctx *ctx, u8 *state, size_t plane, size_t pitch, int K, int h, int w, cudaStream_t st)
+{
+    int passes = 0;
+    for (;;) {
+        OMNI_CUDA(cudaMemsetAsync(ctx->d_flags, 0, sizeof(int), st));
+        OMNI_CUDA(g_hyst_pass(state, plane, pitch, K, h, w, ctx->d_flags, st));
+        OMNI_CUDA(cudaMemcpyAsync(ctx->h_flags, ctx->d_flags, sizeof(int), cudaMemcpyDeviceToHost, st));
+        OMNI_CUDA(cudaStreamSynchronize(st));
+        passes++;
+        if (!ctx->h_flags[0]) break;
+        OMNI_REQUIRE(passes < 100000, "hysteresis did not converge");
+    }
+    ctx->last_hyst_passes = passes;
+    OMNI_CUDA(g_hyst_final(state, plane, pitch, K, h, w, st));
+    return OMNI_OK;
+}
+
+static int generic_edges(omni_ctx *ctx, const uint8_t *d_masks, int K, int h, int w, size_t m_plane, size_t mpitch,
+                         const omni_edge_params *prm, const BlurParams &bp, int low, int high,
+                         uint8_t *d_edges, size_t e_plane, size_t epitch, cudaStream_t st)
+{
+    size_t wp = ((size_t)w + 15) & ~(size_t)15, wplane = wp * h;
+    OMNI_TRY(omni_ws_reserve(ctx, 0, wplane * K));
+    OMNI_TRY(omni_ws_reserve(ctx, 1, wplane * K));
+    u8 *A = (u8 *)ctx->ws[0], *B = (u8 *)ctx->ws[1];
+    MorphSE se;
+    omni_build_se(1, prm->morph_k, &se);
+    int oi = prm->open_iters > 0 ? prm->open_iters : 0, ci = prm->close_iters > 0 ? prm->close_iters : 0;
+    int seq_n = 0, seq[4 * 64];
+    for (int i = 0; i < oi; i++) seq[seq_n++] = 0;
+    for (int i = 0; i < oi; i++) seq[seq_n++] = 1;
+    for (int i = 0; i < ci; i++) seq[seq_n++] = 1;
+    for (int i = 0; i < ci; i++) seq[seq_n++] = 0;
+    const u8 *cur = d_masks; size_t cplane = m_plane, cpitch = mpitch;
+    for (int i = 0; i < seq_n; i++) {
+        u8 *dst = (cur == A) ? B : A;
+        OMNI_CUDA(g_morph(cur, cplane, cpitch, dst, wplane, wp, K, h, w, se, seq[i], st));
+        cur = dst; cplane = wplane; cpitch = wp;
+    }
+    u8 *bl = (cur == A) ? B : A;
+    OMNI_CUDA(g_blur(cur, cplane, cpitch, bl, wplane, wp, K, h, w, bp, st));
+    OMNI_CUDA(g_canny_nms(bl, wplane, wp, d_edges, e_plane, epitch, K, h, w, low, high, st));
+    return generic_hysteresis(ctx, d_edges, e_plane, epitch, K, h, w, st);
+}
+
+extern "C" int omni_edges(omni_ctx *ctx, const uint8_t *d_masks, int K, int h, int w, size_t m_plane_stride, size_t mpitch,
+                          const omni_edge_params *prm,
+                          uint8_t *d_edges, size_t e_plane_stride, size_t epitch, void *stream)
+{
+    OMNI_TRY(set_device(ctx));
+    OMNI_REQUIRE(d_masks && d_edges && d_masks != d_edges, "omni_edges: NULL or aliased planes");
+    OMNI_REQUIRE(K >= 1 && K <= OMNI_MAX_K, "omni_edges: K=%d outside [1,%d]", K, OMNI_MAX_K);
+    OMNI_REQUIRE(h > 0 && w > 0 && mpitch >= (size_t)w && epitch >= (size_t)w, "omni_edges: bad geometry");
+    BlurParams bp; int low, high;
+    OMNI_TRY(check_edge_params(prm, &bp, &low, &high));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (ctx->fast && fast_edges_supported(prm)) {
+        int rc = fast_edges(ctx, d_masks, K, h, w, m_plane_stride, mpitch, prm, bp, low, high, d_edges, e_plane_stride, epitch, st);
+        if (rc != OMNI_ERR_UNSUPPORTED) return rc;       // non-binary masks fall through to the generic kernels
+    }
+    return generic_edges(ctx, d_masks, K, h, w, m_plane_stride, mpitch, prm, bp, low, high, d_edges, e_plane_stride, epitch, st);
+}
+
+// ---- fused hot path -------------------------------------------------------------------------------------
+extern "C" int omni_color_edge(omni_ctx *ctx, const uint8_t *d_bgr, int h, int w, size_t pitch,
+                               const float *h_centers, int K, const uint8_t *h_lut, const omni_edge_params *prm,
+                               uint8_t *d_labels, size_t lpitch,
+                               uint8_t *d_masks, size_t m_plane_stride, size_t mpitch,
+                               uint8_t *d_edges, size_t e_plane_stride, size_t epitch, void *stream)
+{
+    OMNI_TRY(set_device(ctx));
+    OMNI_REQUIRE(d_bgr && d_masks && d_edges && h_centers, "omni_color_edge: NULL pointer");
+    OMNI_REQUIRE(h > 0 && w > 0 && pitch >= (size_t)w * 3 && mpitch >= (size_t)w && epitch >= (size_t)w &&
+                 (!d_labels || lpitch >= (size_t)w), "omni_color_edge: bad geometry");
+    BlurParams bp; int low, high;
+    OMNI_TRY(check_edge_params(prm, &bp, &low, &high));
+    AssignParams P;
+    OMNI_TRY(fill_assign(&P, h_centers, nullptr, K, h_lut));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (ctx->fast && fast_edges_supported(prm))
+        return fast_color_edge(ctx, d_bgr, h, w, pitch, P, prm, bp, low, high, d_labels, lpitch,
+                               d_masks, m_plane_stride, mpitch, d_edges, e_plane_stride, epitch, st);
+    // generic composition
+    u8 *labels = d_labels; size_t lp = lpitch;
+    if (!labels) {
+        lp = ((size_t)w + 15) & ~(size_t)15;
+        OMNI_TRY(omni_ws_reserve(ctx, 2, lp * h));
+        labels = (u8 *)ctx->ws[2];
+    }
+    OMNI_CUDA(g_assign(d_bgr, h, w, pitch, P, 1, labels, lp, st));
+    OMNI_TRY(generic_layer_masks(ctx, labels, h, w, lp, K, 1, 1, d_masks, m_plane_stride, mpitch, st));
+    return generic_edges(ctx, d_masks, K, h, w, m_plane_stride, mpitch, prm, bp, low, high, d_edges, e_plane_stride, epitch, st);
+}
+
+// ---- counts / composite -----------------------------------------------------------------------------------
+extern "C" int omni_count_nonzero(omni_ctx *ctx, const uint8_t *d_planes, int K, int h, int w, size_t plane_stride, size_t pitch,
+                                  int64_t *h_counts, void *stream)
+{
+    OMNI_TRY(set_device(ctx));
+    OMNI_REQUIRE(d_planes && h_counts && K >= 1 && K <= OMNI_MAX_K && h > 0 && w > 0, "omni_count_nonzero: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    OMNI_CUDA(cudaMemsetAsync(ctx->d_counts, 0, K * sizeof(unsigned long long), st));
+    OMNI_CUDA(g_count_nonzero(d_planes, plane_stride, pitch, K, h, w, ctx->d_counts, st));
+    OMNI_CUDA(cudaMemcpyAsync(ctx->h_counts, ctx->d_counts, K * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    OMNI_CUDA(cudaStreamSynchronize(st));
+    for (int k = 0; k < K; k++) h_counts[k] = (int64_t)ctx->h_counts[k];
+    return OMNI_OK;
+}
+
+extern "C" int omni_edges_composite(omni_ctx *ctx, const uint8_t *d_edges, int K, int h, int w, size_t e_plane_stride, size_t epitch,
+                                    const uint8_t *h_colors_bgr, uint8_t *d_canvas, size_t cpitch, void *stream)
+{
+    OMNI_TRY(set_device(ctx));
+    OMNI_REQUIRE(d_edges && d_canvas && h_colors_bgr && K >= 1 && K <= OMNI_MAX_K && h > 0 && w > 0 && cpitch >= (size_t)w * 3,
+                 "omni_edges_composite: bad arguments");
+    OMNI_CUDA(g_composite(d_edges, e_plane_stride, epitch, K, h, w, h_colors_bgr, d_canvas, cpitch, (cudaStream_t)stream));
+    return OMNI_OK;
+}
+
+// ---- host-buffer entry points -------------------------------------------------------------------------------
+// Staging layout in workspace slot 3: [image | labels | masks | edges], rows padded to 16 bytes.
+static inline size_t pad16(size_t v) { return (v + 15) & ~(size_t)15; }
+
+extern "C" int omni_host_resize_area_u8c3(omni_ctx *ctx, const uint8_t *h_src, int sh, int sw, size_t spitch,
+                                          uint8_t *h_dst, int dh, int dw, size_t dpitch)
+{
+    OMNI_TRY(set_device(ctx));
+    OMNI_REQUIRE(h_src && h_dst && sh > 0 && sw > 0 && dh > 0 && dw > 0, "omni_host_resize_area_u8c3: bad arguments");
+    size_t sp = pad16((size_t)sw * 3), dp = pad16((size_t)dw * 3);
+    OMNI_TRY(omni_ws_reserve(ctx, 3, sp * sh + dp * dh));
+    u8 *ds = (u8 *)ctx->ws[3], *dd = ds + sp * sh;
+    OMNI_CUDA(cudaMemcpy2DAsync(ds, sp, h_src, spitch, (size_t)sw * 3, sh, cudaMemcpyHostToDevice, ctx->stream));
+    OMNI_TRY(omni_resize_area_u8c3(ctx, ds, sh, sw, sp, dd, dh, dw, dp, ctx->stream));
+    OMNI_CUDA(cudaMemcpy2DAsync(h_dst, dpitch, dd, dp, (size_t)dw * 3, dh, cudaMemcpyDeviceToHost, ctx->stream));
+    OMNI_CUDA(cudaStreamSynchronize(ctx->stream));
+    return OMNI_OK;
+}
+
+extern "C" int omni_host_assign_rgb_i16wrap(omni_ctx *ctx, const uint8_t *h_rgb, int h, int w, size_t pitch,
+                                            const uint8_t *h_palette, int K, uint8_t *h_labels, size_t lpitch)
+{
+    OMNI_TRY(set_device(ctx));
+    OMNI_REQUIRE(h_rgb && h_labels && h > 0 && w > 0, "omni_host_assign_rgb_i16wrap: bad arguments");
+    size_t ip = pad16((size_t)w * 3), lp = pad16((size_t)w);
+    OMNI_TRY(omni_ws_reserve(ctx, 3, ip * h + lp * h));
+    u8 *di = (u8 *)ctx->ws[3], *dl = di + ip * h;
+    OMNI_CUDA(cudaMemcpy2DAsync(di, ip, h_rgb, pitch, (size_t)w * 3, h, cudaMemcpyHostToDevice, ctx->stream));
+    OMNI_TRY(omni_assign_rgb_i16wrap(ctx, di, h, w, ip, h_palette, K, dl, lp, ctx->stream));
+    OMNI_CUDA(cudaMemcpy2DAsync(h_labels, lpitch, dl, lp, (size_t)w, h, cudaMemcpyDeviceToHost, ctx->stream));
+    OMNI_CUDA(cudaStreamSynchronize(ctx->stream));
+    return OMNI_OK;
+}
+
+static int copy_planes_d2h(u8 *h_dst, size_t h_plane, size_t hpitch, const u8 *d_src, size_t d_plane, size_t dpitch,
+                           int K, int h, int w, cudaStream_t st)
+{
+    if (hpitch == dpitch && h_plane == d_plane) {       // one contiguous copy
+        OMNI_CUDA(cudaMemcpyAsync(h_dst, d_src, d_plane * (size_t)(K - 1) + dpitch * (size_t)(h - 1) + w, cudaMemcpyDeviceToHost, st));
+        return OMNI_OK;
+    }
+    for (int k = 0; k < K; k++)
+        OMNI_CUDA(cudaMemcpy2DAsync(h_dst + k * h_plane, hpitch, d_src + k * d_plane, dpitch, (size_t)w, h, cudaMemcpyDeviceToHost, st));
+    return OMNI_OK;
+}
+
+extern "C" int omni_host_edges(omni_ctx *ctx, const uint8_t *h_masks, int K, int h, int w, size_t m_plane_stride, size_t mpitch,
+                               const omni_edge_params *prm,
+                               uint8_t *h_edges, size_t e_plane_stride, size_t epitch)
+{
+    OMNI_TRY(set_device(ctx));
+    OMNI_REQUIRE(h_masks && h_edges && K >= 1 && K <= OMNI_MAX_K && h > 0 && w > 0, "omni_host_edges: bad arguments");
+    // device planes use the caller's pitch when it is 16-byte friendly so the copies are single DMA transfers
+    size_t dp = (mpitch % 16 == 0) ? mpitch : pad16((size_t)w), dplane = (dp == mpitch) ? m_plane_stride : dp * h;
+    size_t ep = (epitch % 16 == 0) ? epitch : pad16((size_t)w), eplane = (ep == epitch) ? e_plane_stride : ep * h;
+    size_t m_bytes = pad16(dplane * K), e_bytes = pad16(eplane * K);
+    OMNI_TRY(omni_ws_reserve(ctx, 3, m_bytes + e_bytes));
+    u8 *dm = (u8 *)ctx->ws[3], *de = dm + m_bytes;
+    if (dp == mpitch) OMNI_CUDA(cudaMemcpyAsync(dm, h_masks, m_plane_stride * (size_t)(K - 1) + mpitch * (size_t)(h - 1) + w, cudaMemcpyHostToDevice, ctx->stream));
+    else for (int k = 0; k < K; k++)
+        OMNI_CUDA(cudaMemcpy2DAsync(dm + k * dplane, dp, h_masks + k * m_plane_stride, mpitch, (size_t)w, h, cudaMemcpyHostToDevice, ctx->stream));
+    OMNI_TRY(omni_edges(ctx, dm, K, h, w, dplane, dp, prm, de, eplane, ep, ctx->stream));
+    OMNI_TRY(copy_planes_d2h(h_edges, e_plane_stride, epitch, de, eplane, ep, K, h, w, ctx->stream));
+    OMNI_CUDA(cudaStreamSynchronize(ctx->stream));
+    return OMNI_OK;
+}
+
+extern "C" int omni_host_color_edge(omni_ctx *ctx, const uint8_t *h_bgr, int h, int w, size_t pitch,
+                                    const float *h_centers, int K, const uint8_t *h_lut, const omni_edge_params *prm,
+                                    uint8_t *h_labels, size_t lpitch,
+                                    uint8_t *h_masks, size_t m_plane_stride, size_t mpitch,
+                                    uint8_t *h_edges, size_t e_plane_stride, size_t epitch,
+                                    int64_t *h_counts)
+{
+    OMNI_TRY(set_device(ctx));
+    OMNI_REQUIRE(h_bgr && h_masks && h_edges && K >= 1 && K <= OMNI_MAX_K && h > 0 && w > 0, "omni_host_color_edge: bad arguments");
+    size_t ip = pad16((size_t)w * 3), lp = pad16((size_t)w);
+    size_t mp = (mpitch % 16 == 0) ? mpitch : pad16((size_t)w), mplane = (mp == mpitch) ? m_plane_stride : mp * h;
+    size_t ep = (epitch % 16 == 0) ? epitch : pad16((size_t)w), eplane = (ep == epitch) ? e_plane_stride : ep * h;
+    size_t i_bytes = pad16(ip * h), l_bytes = pad16(lp * h), m_bytes = pad16(mplane * K), e_bytes = pad16(eplane * K);
+    OMNI_TRY(omni_ws_reserve(ctx, 3, i_bytes + l_bytes + m_bytes + e_bytes));
+    u8 *di = (u8 *)ctx->ws[3], *dl = di + i_bytes, *dm = dl + l_bytes, *de = dm + m_bytes;
+    cudaStream_t st = ctx->stream;
+    OMNI_CUDA(cudaMemcpy2DAsync(di, ip, h_bgr, pitch, (size_t)w * 3, h, cudaMemcpyHostToDevice, st));
+    OMNI_TRY(omni_color_edge(ctx, di, h, w, ip, h_centers, K, h_lut, prm, dl, lp, dm, mplane, mp, de, eplane, ep, st));
+    if (h_labels) OMNI_CUDA(cudaMemcpy2DAsync(h_labels, lpitch, dl, lp, (size_t)w, h, cudaMemcpyDeviceToHost, st));
+    OMNI_TRY(copy_planes_d2h(h_masks, m_plane_stride, mpitch, dm, mplane, mp, K, h, w, st));
+    OMNI_TRY(copy_planes_d2h(h_edges, e_plane_stride, epitch, de, eplane, ep, K, h, w, st));
+    if (h_counts) {
+        OMNI_CUDA(cudaMemsetAsync(ctx->d_counts, 0, 3 * OMNI_MAX_K * sizeof(unsigned long long), st));
+        OMNI_CUDA(g_count_labels(dl, lp, h, w, K, ctx->d_counts, st));
+        OMNI_CUDA(g_count_nonzero(dm, mplane, mp, K, h, w, ctx->d_counts + OMNI_MAX_K, st));
+        OMNI_CUDA(g_count_nonzero(de, eplane, ep, K, h, w, ctx->d_counts + 2 * OMNI_MAX_K, st));
+        OMNI_CUDA(cudaMemcpyAsync(ctx->h_counts, ctx->d_counts, 3 * OMNI_MAX_K * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    }
+    OMNI_CUDA(cudaStreamSynchronize(st));
+    if (h_counts)
+        for (int k = 0; k < K; k++) {
+            h_counts[3 * k] = (int64_t)ctx->h_counts[k];
+            h_counts[3 * k + 1] = (int64_t)ctx->h_counts[OMNI_MAX_K + k];
+            h_counts[3 * k + 2] = (int64_t)ctx->h_counts[2 * OMNI_MAX_K + k];
+        }
+    return OMNI_OK;
+}

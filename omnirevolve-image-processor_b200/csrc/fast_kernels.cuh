@@ -1,0 +1,25 @@
+// fast_kernels.cuh -- the bit-plane fast path (fast_kernels.cu); see DESIGN.md "fast path".
+#pragma once
+#include "omni_internal.cuh"
+
+void fast_ctx_release(omni_ctx *ctx);
+
+bool fast_resize_2x_ok(const u8 *src, int sw, size_t spitch, const u8 *dst, int dw, size_t dpitch);
+cudaError_t fast_resize_2x(const u8 *src, size_t spitch, u8 *dst, int dh, int dw, size_t dpitch, cudaStream_t st);
+
+cudaError_t fast_assign(omni_ctx *ctx, const u8 *px, int h, int w, size_t pitch, const AssignParams &P, int mode_lab,
+                        u8 *labels, size_t lpitch, cudaStream_t st);
+
+bool fast_masks_supported(int open_iters, int close_iters);
+int fast_layer_masks(omni_ctx *ctx, const u8 *d_labels, int h, int w, size_t lpitch, int K, int open_iters, int close_iters,
+                     u8 *d_masks, size_t plane_stride, size_t mpitch, cudaStream_t st);
+
+bool fast_edges_supported(const omni_edge_params *prm);
+// returns OMNI_ERR_UNSUPPORTED when the masks are not strictly {0,255} (caller falls back to the generic kernels)
+int fast_edges(omni_ctx *ctx, const u8 *d_masks, int K, int h, int w, size_t m_plane, size_t mpitch,
+               const omni_edge_params *prm, const BlurParams &bp, int low, int high,
+               u8 *d_edges, size_t e_plane, size_t epitch, cudaStream_t st);
+int fast_color_edge(omni_ctx *ctx, const u8 *d_bgr, int h, int w, size_t pitch, const AssignParams &P,
+                    const omni_edge_params *prm, const BlurParams &bp, int low, int high,
+                    u8 *d_labels, size_t lpitch, u8 *d_masks, size_t m_plane, size_t mpitch,
+                    u8 *d_edges, size_t e_plane, size_t epitch, cudaStream_t st);

@@ -1,0 +1,102 @@
+// omni_internal.cuh -- shared declarations of libomni_b200 (not part of the public ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+#include <map>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "../../include/omni_b200.h"
+
+typedef uint8_t u8;
+typedef uint16_t u16;
+typedef uint32_t u32;
+typedef uint64_t u64;
+
+// ---- error plumbing --------------------------------------------------------------------------
+void omni_set_error(const char *fmt, ...);
+#define OMNI_CUDA(call)                                                                         \
+    do {                                                                                        \
+        cudaError_t e__ = (call);                                                               \
+        if (e__ != cudaSuccess) {                                                               \
+            omni_set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+            return OMNI_ERR_CUDA;                                                               \
+        }                                                                                       \
+    } while (0)
+#define OMNI_REQUIRE(cond, ...)                                                                 \
+    do {                                                                                        \
+        if (!(cond)) { omni_set_error(__VA_ARGS__); return OMNI_ERR_ARG; }                      \
+    } while (0)
+
+// ---- small by-value parameter blocks (live in the kernel parameter bank) -----------------------
+struct AssignParams {
+    float c[OMNI_MAX_K * 3];   // centres (Lab, f32)
+    u8 pal[OMNI_MAX_K * 3];    // palette (RGB u8) for the i16wrap variant
+    u8 lut[OMNI_MAX_K];        // cluster id -> output label
+    int K;
+};
+struct BlurParams {
+    u16 w[OMNI_MAX_BLUR_K];
+    int k;
+};
+struct MorphSE {               // structuring element as offsets, anchor k/2 (un-reflected)
+    int8_t dy[OMNI_MAX_MORPH_K * OMNI_MAX_MORPH_K];
+    int8_t dx[OMNI_MAX_MORPH_K * OMNI_MAX_MORPH_K];
+    int n;
+    int k;
+};
+struct ResizeTabDev {          // fractional INTER_AREA tables on the device (per axis: ofs[D+1], si[], alpha[])
+    const int *xofs; const int *xsi; const float *xal;
+    const int *yofs; const int *ysi; const float *yal;
+};
+
+struct ResizeTab {
+    void *d_blob = nullptr;
+    ResizeTabDev dev{};
+};
+
+struct omni_ctx {
+    int device = 0;
+    int fast = 1;
+    // grow-only device scratch
+    void *ws[4] = {nullptr, nullptr, nullptr, nullptr};
+    size_t ws_bytes[4] = {0, 0, 0, 0};
+    int *d_flags = nullptr;          // 64 ints of device flags / counters
+    unsigned long long *d_counts = nullptr;   // 4*OMNI_MAX_K counters
+    int *h_flags = nullptr;          // pinned mirror
+    unsigned long long *h_counts = nullptr;
+    cudaStream_t stream = nullptr;   // own stream for the omni_host_* entry points
+    std::map<std::tuple<int, int, int, int>, ResizeTab> resize_tabs;
+    int last_hyst_passes = 0;
+};
+
+int omni_ws_reserve(omni_ctx *ctx, int slot, size_t bytes);
+const ResizeTab *omni_get_resize_tab(omni_ctx *ctx, int sh, int sw, int dh, int dw, cudaStream_t st);
+void omni_build_se(int shape_ellipse, int k, MorphSE *se);
+int omni_gauss_weights(int k, BlurParams *bp);
+
+// ---- generic kernels (generic_kernels.cu): any u8 data, any supported parameter --------------
+cudaError_t g_resize_area(const u8 *src, int sh, int sw, size_t spitch, u8 *dst, int dh, int dw, size_t dpitch,
+                          const ResizeTabDev *tab, cudaStream_t st);
+cudaError_t g_assign(const u8 *px, int h, int w, size_t pitch, const AssignParams &P, int mode_lab,
+                     u8 *labels, size_t lpitch, cudaStream_t st);
+cudaError_t g_onehot(const u8 *labels, int h, int w, size_t lpitch, int K, u8 *planes, size_t plane_stride,
+                     size_t pitch, cudaStream_t st);
+cudaError_t g_morph(const u8 *src, size_t s_plane, size_t spitch, u8 *dst, size_t d_plane, size_t dpitch,
+                    int K, int h, int w, const MorphSE &se, int is_dilate, cudaStream_t st);
+cudaError_t g_blur(const u8 *src, size_t s_plane, size_t spitch, u8 *dst, size_t d_plane, size_t dpitch,
+                   int K, int h, int w, const BlurParams &bp, cudaStream_t st);
+cudaError_t g_canny_nms(const u8 *src, size_t s_plane, size_t spitch, u8 *state, size_t d_plane, size_t dpitch,
+                        int K, int h, int w, int low, int high, cudaStream_t st);
+cudaError_t g_hyst_pass(u8 *state, size_t plane, size_t pitch, int K, int h, int w, int *d_changed, cudaStream_t st);
+cudaError_t g_hyst_final(u8 *state, size_t plane, size_t pitch, int K, int h, int w, cudaStream_t st);
+cudaError_t g_count_nonzero(const u8 *planes, size_t plane, size_t pitch, int K, int h, int w,
+                            unsigned long long *d_counts, cudaStream_t st);
+cudaError_t g_count_labels(const u8 *labels, size_t pitch, int h, int w, int K, unsigned long long *d_counts,
+                           cudaStream_t st);
+cudaError_t g_composite(const u8 *edges, size_t plane, size_t pitch, int K, int h, int w, const u8 *colors_bgr,
+                        u8 *canvas, size_t cpitch, cudaStream_t st);
+cudaError_t g_copy2d_planes(const u8 *src, size_t s_plane, size_t spitch, u8 *dst, size_t d_plane, size_t dpitch,
+                            int K, int h, int w, cudaStream_t st);

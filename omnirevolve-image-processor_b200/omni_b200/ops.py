@@ -1,0 +1,283 @@
+"""Device- and host-level operators over libomni_b200.so.
+
+PyTorch is used only as the owner of device memory and streams; every computation below is a
+call through the C ABI (omni_b200.capi) into the hand-written CUDA kernels.  Each operator cites
+the reference call site it replaces (paths relative to /root/reference/image_processor/).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import threading
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from . import capi
+
+
+@dataclass
+class EdgeConfig:
+    """The stage-03 knobs of config.json (config.py:31-36), defaults as in the reference."""
+    low: float = 50
+    high: float = 150
+    ksize: int = 3
+    morph_k: int = 3
+    open_iters: int = 1
+    close_iters: int = 1
+
+    @staticmethod
+    def ensure_odd(n) -> int:
+        """03_edge_detect.py:9-11."""
+        n = max(3, int(n))
+        return n if n % 2 == 1 else n + 1
+
+    @classmethod
+    def from_cfg(cls, cfg) -> "EdgeConfig":
+        """Reads the keys exactly as process_color does (03:23-34)."""
+        return cls(low=cfg.edge_low_threshold, high=cfg.edge_high_threshold, ksize=cfg.edge_kernel_size,
+                   morph_k=max(1, int(getattr(cfg, "edge_morph_kernel", 3))),
+                   open_iters=int(getattr(cfg, "edge_morph_open_iters", 1)),
+                   close_iters=int(getattr(cfg, "edge_morph_close_iters", 1)))
+
+    def to_c(self) -> capi.EdgeParams:
+        return capi.EdgeParams(int(self.morph_k), int(self.open_iters), int(self.close_iters),
+                               self.ensure_odd(self.ksize), float(self.low), float(self.high))
+
+
+def _f32p(a):
+    return a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+def _u8p(a):
+    return a.ctypes.data_as(C.POINTER(C.c_uint8)) if a is not None else None
+
+
+def _check_img(t: torch.Tensor, ch: int | None):
+    if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.uint8):
+        raise TypeError("expected a CUDA uint8 tensor")
+    if ch is not None and (t.dim() != 3 or t.shape[2] != ch or t.stride(2) != 1 or t.stride(1) != ch):
+        raise ValueError(f"expected an HxWx{ch} tensor with packed pixels")
+    if ch is None and (t.dim() != 2 or t.stride(1) != 1):
+        raise ValueError("expected an HxW tensor with unit column stride")
+
+
+def _check_planes(t: torch.Tensor):
+    if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.uint8 and t.dim() == 3 and t.stride(2) == 1):
+        raise TypeError("expected a CUDA uint8 [K,H,W] tensor with unit column stride")
+
+
+class Engine:
+    """One omni_ctx on one device.  Not thread-safe; use one per host thread (get_engine does)."""
+
+    def __init__(self, device: int | None = None):
+        L = capi.lib()
+        if not torch.cuda.is_available():
+            raise capi.OmniError(-2, "no CUDA device visible; libomni_b200 has no CPU fallback")
+        self.device = torch.cuda.current_device() if device is None else int(device)
+        h = C.c_void_p()
+        capi.check(L.omni_ctx_create(self.device, C.byref(h)))
+        self._h, self._L = h, L
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.omni_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_fast_path(self, enable: bool):
+        capi.check(self._L.omni_set_fast_path(self._h, 1 if enable else 0))
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    # ---- stage 01 ------------------------------------------------------------------------------
+    def resize_area(self, src: torch.Tensor, new_w: int, new_h: int, out: torch.Tensor | None = None) -> torch.Tensor:
+        """01_resize.py:20 cv2.resize(img, (new_w,new_h), INTER_AREA); HxWx3 u8, shrink only."""
+        _check_img(src, 3)
+        if out is None:
+            out = torch.empty((new_h, new_w, 3), dtype=torch.uint8, device=src.device)
+        _check_img(out, 3)
+        capi.check(self._L.omni_resize_area_u8c3(self._h, src.data_ptr(), src.shape[0], src.shape[1], src.stride(0),
+                                                 out.data_ptr(), new_h, new_w, out.stride(0), self._stream()))
+        return out
+
+    # ---- stage 02 ------------------------------------------------------------------------------
+    def assign_lab(self, bgr: torch.Tensor, centers, lut=None, out: torch.Tensor | None = None) -> torch.Tensor:
+        """02_color_extract.py:35-36,53-55 (+ relabel lut of :121-127): u8 labels [H,W]."""
+        _check_img(bgr, 3)
+        ctr = np.ascontiguousarray(centers, dtype=np.float32).reshape(-1, 3)
+        lut_a = None if lut is None else np.ascontiguousarray(lut, dtype=np.uint8)
+        if out is None:
+            out = torch.empty(bgr.shape[:2], dtype=torch.uint8, device=bgr.device)
+        _check_img(out, None)
+        capi.check(self._L.omni_assign_lab_f32(self._h, bgr.data_ptr(), bgr.shape[0], bgr.shape[1], bgr.stride(0),
+                                               _f32p(ctr), ctr.shape[0], _u8p(lut_a), out.data_ptr(), out.stride(0),
+                                               self._stream()))
+        return out
+
+    def assign_rgb_i16wrap(self, rgb: torch.Tensor, palette, out: torch.Tensor | None = None) -> torch.Tensor:
+        """process_colors.py:69-77 assign_labels (int16 wrap reproduced): u8 labels [H,W]."""
+        _check_img(rgb, 3)
+        pal = np.ascontiguousarray(palette, dtype=np.uint8).reshape(-1, 3)
+        if out is None:
+            out = torch.empty(rgb.shape[:2], dtype=torch.uint8, device=rgb.device)
+        capi.check(self._L.omni_assign_rgb_i16wrap(self._h, rgb.data_ptr(), rgb.shape[0], rgb.shape[1], rgb.stride(0),
+                                                   _u8p(pal), pal.shape[0], out.data_ptr(), out.stride(0), self._stream()))
+        return out
+
+    def layer_masks(self, labels: torch.Tensor, K: int, open_iters: int = 1, close_iters: int = 1,
+                    out: torch.Tensor | None = None) -> torch.Tensor:
+        """02_color_extract.py:136-154: K planes (labels==p)*255 -> RECT-3 open -> close.  [K,H,W] u8."""
+        _check_img(labels, None)
+        h, w = labels.shape
+        if out is None:
+            out = torch.empty((K, h, w), dtype=torch.uint8, device=labels.device)
+        _check_planes(out)
+        capi.check(self._L.omni_layer_masks(self._h, labels.data_ptr(), h, w, labels.stride(0), K, open_iters, close_iters,
+                                            out.data_ptr(), out.stride(0), out.stride(1), self._stream()))
+        return out
+
+    # ---- stage 03 ------------------------------------------------------------------------------
+    def edges(self, masks: torch.Tensor, ec: EdgeConfig, out: torch.Tensor | None = None) -> torch.Tensor:
+        """03_edge_detect.py:23-34 on K mask planes at once.  [K,H,W] u8 {0,255}."""
+        _check_planes(masks)
+        K, h, w = masks.shape
+        if out is None:
+            out = torch.empty((K, h, w), dtype=torch.uint8, device=masks.device)
+        _check_planes(out)
+        p = ec.to_c()
+        capi.check(self._L.omni_edges(self._h, masks.data_ptr(), K, h, w, masks.stride(0), masks.stride(1), C.byref(p),
+                                      out.data_ptr(), out.stride(0), out.stride(1), self._stream()))
+        return out
+
+    # ---- fused hot path ---------------------------------------------------------------------------
+    def color_edge(self, bgr: torch.Tensor, centers, lut, ec: EdgeConfig, want_labels: bool = False,
+                   masks: torch.Tensor | None = None, edges: torch.Tensor | None = None,
+                   labels: torch.Tensor | None = None):
+        """image -> (labels|None, masks[K,H,W], edges[K,H,W]); 02:53-154 + 03:23-34 in one call."""
+        _check_img(bgr, 3)
+        ctr = np.ascontiguousarray(centers, dtype=np.float32).reshape(-1, 3)
+        K = ctr.shape[0]
+        lut_a = None if lut is None else np.ascontiguousarray(lut, dtype=np.uint8)
+        h, w = bgr.shape[:2]
+        if masks is None:
+            masks = torch.empty((K, h, w), dtype=torch.uint8, device=bgr.device)
+        if edges is None:
+            edges = torch.empty((K, h, w), dtype=torch.uint8, device=bgr.device)
+        if labels is None and want_labels:
+            labels = torch.empty((h, w), dtype=torch.uint8, device=bgr.device)
+        p = ec.to_c()
+        capi.check(self._L.omni_color_edge(
+            self._h, bgr.data_ptr(), h, w, bgr.stride(0), _f32p(ctr), K, _u8p(lut_a), C.byref(p),
+            labels.data_ptr() if labels is not None else None, labels.stride(0) if labels is not None else 0,
+            masks.data_ptr(), masks.stride(0), masks.stride(1), edges.data_ptr(), edges.stride(0), edges.stride(1),
+            self._stream()))
+        return labels, masks, edges
+
+    def count_nonzero(self, planes: torch.Tensor) -> np.ndarray:
+        """np.count_nonzero per plane (02:157, 03:38)."""
+        _check_planes(planes)
+        K, h, w = planes.shape
+        out = np.zeros(K, np.int64)
+        capi.check(self._L.omni_count_nonzero(self._h, planes.data_ptr(), K, h, w, planes.stride(0), planes.stride(1),
+                                              out.ctypes.data_as(C.POINTER(C.c_int64)), self._stream()))
+        return out
+
+    def edges_composite(self, edges: torch.Tensor, colors_bgr) -> torch.Tensor:
+        """03_edge_detect.py:93-106 paint on a white canvas.  HxWx3 u8."""
+        _check_planes(edges)
+        K, h, w = edges.shape
+        col = np.ascontiguousarray(colors_bgr, dtype=np.uint8).reshape(-1, 3)[:K]
+        if col.shape[0] < K:
+            raise IndexError("list index out of range")        # what cfg.colors[i] raises in 03:90
+        out = torch.empty((h, w, 3), dtype=torch.uint8, device=edges.device)
+        capi.check(self._L.omni_edges_composite(self._h, edges.data_ptr(), K, h, w, edges.stride(0), edges.stride(1),
+                                                _u8p(col), out.data_ptr(), out.stride(0), self._stream()))
+        return out
+
+    def last_hysteresis_passes(self) -> int:
+        return int(self._L.omni_last_hysteresis_passes(self._h))
+
+    # ---- host-buffer entry points (H2D + kernels + D2H inside the call) ---------------------------------
+    def host_resize_area(self, img: np.ndarray, new_w: int, new_h: int) -> np.ndarray:
+        img = _as_u8(img, 3)
+        out = np.empty((new_h, new_w, 3), np.uint8)
+        capi.check(self._L.omni_host_resize_area_u8c3(self._h, img.ctypes.data, img.shape[0], img.shape[1], img.strides[0],
+                                                      out.ctypes.data, new_h, new_w, out.strides[0]))
+        return out
+
+    def host_assign_rgb_i16wrap(self, img_rgb: np.ndarray, palette) -> np.ndarray:
+        img = _as_u8(img_rgb, 3)
+        pal = np.ascontiguousarray(palette, dtype=np.uint8).reshape(-1, 3)
+        out = np.empty(img.shape[:2], np.uint8)
+        capi.check(self._L.omni_host_assign_rgb_i16wrap(self._h, img.ctypes.data, img.shape[0], img.shape[1], img.strides[0],
+                                                        _u8p(pal), pal.shape[0], out.ctypes.data, out.strides[0]))
+        return out
+
+    def host_edges(self, masks: np.ndarray, ec: EdgeConfig, out: np.ndarray | None = None) -> np.ndarray:
+        masks = np.ascontiguousarray(masks, dtype=np.uint8)
+        K, h, w = masks.shape
+        if out is None:
+            out = np.empty((K, h, w), np.uint8)
+        p = ec.to_c()
+        capi.check(self._L.omni_host_edges(self._h, masks.ctypes.data, K, h, w, masks.strides[0], masks.strides[1],
+                                           C.byref(p), out.ctypes.data, out.strides[0], out.strides[1]))
+        return out
+
+    def host_color_edge(self, img_bgr: np.ndarray, centers, lut, ec: EdgeConfig, want_labels: bool = True,
+                        masks: np.ndarray | None = None, edges: np.ndarray | None = None, want_counts: bool = True):
+        """Host image -> dict(labels, masks, edges, counts) as host arrays (pass pinned arrays from
+        pinned_empty() as `masks`/`edges` for full-speed copies)."""
+        img = _as_u8(img_bgr, 3)
+        ctr = np.ascontiguousarray(centers, dtype=np.float32).reshape(-1, 3)
+        K = ctr.shape[0]
+        lut_a = None if lut is None else np.ascontiguousarray(lut, dtype=np.uint8)
+        h, w = img.shape[:2]
+        if masks is None:
+            masks = np.empty((K, h, w), np.uint8)
+        if edges is None:
+            edges = np.empty((K, h, w), np.uint8)
+        labels = np.empty((h, w), np.uint8) if want_labels else None
+        counts = np.zeros((K, 3), np.int64) if want_counts else None
+        p = ec.to_c()
+        capi.check(self._L.omni_host_color_edge(
+            self._h, img.ctypes.data, h, w, img.strides[0], _f32p(ctr), K, _u8p(lut_a), C.byref(p),
+            labels.ctypes.data if labels is not None else None, labels.strides[0] if labels is not None else 0,
+            masks.ctypes.data, masks.strides[0], masks.strides[1], edges.ctypes.data, edges.strides[0], edges.strides[1],
+            counts.ctypes.data_as(C.POINTER(C.c_int64)) if counts is not None else None))
+        return {"labels": labels, "masks": masks, "edges": edges, "counts": counts}
+
+
+def _as_u8(a: np.ndarray, ch: int) -> np.ndarray:
+    a = np.asarray(a)
+    if a.dtype != np.uint8 or a.ndim != 3 or a.shape[2] != ch:
+        raise ValueError(f"expected an HxWx{ch} uint8 array")
+    if a.strides[2] != 1 or a.strides[1] != ch:
+        a = np.ascontiguousarray(a)
+    return a
+
+
+def pinned_empty(shape, dtype=np.uint8) -> np.ndarray:
+    """Host array in page-locked memory (torch owns it; the numpy view keeps it alive)."""
+    t = torch.empty(tuple(shape), dtype=getattr(torch, np.dtype(dtype).name), pin_memory=True)
+    return t.numpy()
+
+
+_engines = threading.local()
+
+
+def get_engine(device: int | None = None) -> Engine:
+    """Per-thread, per-device Engine cache."""
+    dev = torch.cuda.current_device() if (device is None and torch.cuda.is_available()) else (device or 0)
+    cache = getattr(_engines, "cache", None)
+    if cache is None:
+        cache = _engines.cache = {}
+    if dev not in cache:
+        cache[dev] = Engine(dev)
+    return cache[dev]
