@@ -146,6 +146,16 @@ int omni_edges_composite(omni_ctx *ctx, const uint8_t *d_edges, int K, int h, in
  * hysteresis passes that were needed (>= 1). */
 int omni_last_hysteresis_passes(omni_ctx *ctx);
 
+/* ---- launch accounting and per-kernel timing (the reference has only ad-hoc perf_counter prints) -- */
+/* Number of CUDA kernels this ctx has launched since it was created. */
+long long omni_launch_count(omni_ctx *ctx);
+/* on != 0: record a CUDA event pair around every kernel this ctx launches (on the launching stream).
+ * Synchronises the device and clears earlier records. */
+int omni_profile_enable(omni_ctx *ctx, int on);
+/* Synchronises, then writes one line per kernel name, "name\tlaunches\ttotal_ms\n", in first-launch
+ * order, NUL-terminated into buf; clears the records. */
+int omni_profile_summary(omni_ctx *ctx, char *buf, size_t buflen);
+
 #ifdef __cplusplus
 }
 #endif

@@ -64,6 +64,8 @@ extern "C" int omni_ctx_destroy(omni_ctx *c)
     if (c->h_flags) cudaFreeHost(c->h_flags);
     if (c->h_counts) cudaFreeHost(c->h_counts);
     if (c->stream) cudaStreamDestroy(c->stream);
+    for (auto &r : c->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    for (auto e : c->ev_pool) cudaEventDestroy(e);
     fast_ctx_release(c);
     delete c;
     return OMNI_OK;
@@ -90,6 +92,65 @@ extern "C" int omni_host_free(void *p)
 }
 
 extern "C" int omni_last_hysteresis_passes(omni_ctx *ctx) { return ctx ? ctx->last_hyst_passes : 0; }
+
+// ---- launch accounting / per-kernel timing ----------------------------------------------------------
+KScope::KScope(omni_ctx *ctx, const char *name, cudaStream_t s) : c(ctx), st(s)
+{
+    c->launches++;
+    if (!c->prof_on) return;
+    cudaEvent_t a = nullptr;
+    for (cudaEvent_t *e : {&a, &b}) {
+        if (!c->ev_pool.empty()) { *e = c->ev_pool.back(); c->ev_pool.pop_back(); }
+        else if (cudaEventCreate(e) != cudaSuccess) { cudaGetLastError(); *e = nullptr; }
+    }
+    if (!a || !b) { b = nullptr; return; }
+    cudaEventRecord(a, st);
+    c->prof.push_back({name, a, b});
+}
+KScope::~KScope() { if (b) cudaEventRecord(b, st); }
+
+extern "C" long long omni_launch_count(omni_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+static void prof_recycle(omni_ctx *ctx)
+{
+    for (auto &r : ctx->prof) { ctx->ev_pool.push_back(r.a); ctx->ev_pool.push_back(r.b); }
+    ctx->prof.clear();
+}
+
+extern "C" int omni_profile_enable(omni_ctx *ctx, int on)
+{
+    OMNI_REQUIRE(ctx != nullptr, "omni_profile_enable: ctx is NULL");
+    OMNI_CUDA(cudaSetDevice(ctx->device));
+    OMNI_CUDA(cudaDeviceSynchronize());
+    prof_recycle(ctx);
+    ctx->prof_on = on ? 1 : 0;
+    return OMNI_OK;
+}
+
+// Text table "name\tlaunches\ttotal_ms\n" per kernel name, in first-launch order; clears the records.
+extern "C" int omni_profile_summary(omni_ctx *ctx, char *buf, size_t buflen)
+{
+    OMNI_REQUIRE(ctx != nullptr && buf != nullptr && buflen > 0, "omni_profile_summary: bad arguments");
+    OMNI_CUDA(cudaSetDevice(ctx->device));
+    OMNI_CUDA(cudaDeviceSynchronize());
+    std::vector<std::tuple<const char *, long, double>> agg;
+    for (auto &r : ctx->prof) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, r.a, r.b) != cudaSuccess) { cudaGetLastError(); ms = 0.f; }
+        size_t i = 0;
+        for (; i < agg.size(); i++) if (!strcmp(std::get<0>(agg[i]), r.name)) break;
+        if (i == agg.size()) agg.emplace_back(r.name, 0L, 0.0);
+        std::get<1>(agg[i])++; std::get<2>(agg[i]) += ms;
+    }
+    prof_recycle(ctx);
+    size_t o = 0; buf[0] = 0;
+    for (auto &a : agg) {
+        int n = snprintf(buf + o, buflen - o, "%s\t%ld\t%.6f\n", std::get<0>(a), std::get<1>(a), std::get<2>(a));
+        if (n < 0 || (size_t)n >= buflen - o) break;
+        o += (size_t)n;
+    }
+    return OMNI_OK;
+}
 
 int omni_ws_reserve(omni_ctx *ctx, int slot, size_t bytes)
 {
@@ -203,13 +264,13 @@ extern "C" int omni_resize_area_u8c3(omni_ctx *ctx, const uint8_t *d_src, int sh
     bool fast = fabs(scx - isx) < 2.220446049250313e-16 && fabs(scy - isy) < 2.220446049250313e-16;
     if (fast) {
         if (ctx->fast && isx == 2 && isy == 2 && fast_resize_2x_ok(d_src, sw, spitch, d_dst, dw, dpitch))
-            OMNI_CUDA(fast_resize_2x(d_src, spitch, d_dst, dh, dw, dpitch, st));
+            OMNI_LAUNCH(ctx, st, "resize_2x_v", fast_resize_2x(d_src, spitch, d_dst, dh, dw, dpitch, st));
         else
-            OMNI_CUDA(g_resize_area(d_src, sh, sw, spitch, d_dst, dh, dw, dpitch, nullptr, st));
+            OMNI_LAUNCH(ctx, st, "resize_area", g_resize_area(d_src, sh, sw, spitch, d_dst, dh, dw, dpitch, nullptr, st));
     } else {
         const ResizeTab *t = omni_get_resize_tab(ctx, sh, sw, dh, dw, st);
         if (!t) { omni_set_error("omni_resize_area_u8c3: cannot build resize tables"); return OMNI_ERR_NOMEM; }
-        OMNI_CUDA(g_resize_area(d_src, sh, sw, spitch, d_dst, dh, dw, dpitch, &t->dev, st));
+        OMNI_LAUNCH(ctx, st, "resize_area", g_resize_area(d_src, sh, sw, spitch, d_dst, dh, dw, dpitch, &t->dev, st));
     }
     return OMNI_OK;
 }
@@ -240,8 +301,8 @@ extern "C" int omni_assign_lab_f32(omni_ctx *ctx, const uint8_t *d_bgr, int h, i
     OMNI_REQUIRE(h > 0 && w > 0 && pitch >= (size_t)w * 3 && lpitch >= (size_t)w, "omni_assign_lab_f32: bad geometry");
     AssignParams P;
     OMNI_TRY(fill_assign(&P, h_centers, nullptr, K, h_lut));
-    if (ctx->fast) OMNI_CUDA(fast_assign(ctx, d_bgr, h, w, pitch, P, 1, d_labels, lpitch, (cudaStream_t)stream));
-    else OMNI_CUDA(g_assign(d_bgr, h, w, pitch, P, 1, d_labels, lpitch, (cudaStream_t)stream));
+    if (ctx->fast) OMNI_LAUNCH(ctx, (cudaStream_t)stream, "assign", fast_assign(ctx, d_bgr, h, w, pitch, P, 1, d_labels, lpitch, (cudaStream_t)stream));
+    else OMNI_LAUNCH(ctx, (cudaStream_t)stream, "assign", g_assign(d_bgr, h, w, pitch, P, 1, d_labels, lpitch, (cudaStream_t)stream));
     return OMNI_OK;
 }
 
@@ -253,8 +314,8 @@ extern "C" int omni_assign_rgb_i16wrap(omni_ctx *ctx, const uint8_t *d_rgb, int 
     OMNI_REQUIRE(h > 0 && w > 0 && pitch >= (size_t)w * 3 && lpitch >= (size_t)w, "omni_assign_rgb_i16wrap: bad geometry");
     AssignParams P;
     OMNI_TRY(fill_assign(&P, nullptr, h_palette, K, nullptr));
-    if (ctx->fast) OMNI_CUDA(fast_assign(ctx, d_rgb, h, w, pitch, P, 0, d_labels, lpitch, (cudaStream_t)stream));
-    else OMNI_CUDA(g_assign(d_rgb, h, w, pitch, P, 0, d_labels, lpitch, (cudaStream_t)stream));
+    if (ctx->fast) OMNI_LAUNCH(ctx, (cudaStream_t)stream, "assign", fast_assign(ctx, d_rgb, h, w, pitch, P, 0, d_labels, lpitch, (cudaStream_t)stream));
+    else OMNI_LAUNCH(ctx, (cudaStream_t)stream, "assign", g_assign(d_rgb, h, w, pitch, P, 0, d_labels, lpitch, (cudaStream_t)stream));
     return OMNI_OK;
 }
 
@@ -266,7 +327,7 @@ static int generic_layer_masks(omni_ctx *ctx, const uint8_t *d_labels, int h, in
     size_t wp = ((size_t)w + 15) & ~(size_t)15, wplane = wp * h;
     OMNI_TRY(omni_ws_reserve(ctx, 0, wplane * K));
     u8 *tmp = (u8 *)ctx->ws[0];
-    OMNI_CUDA(g_onehot(d_labels, h, w, lpitch, K, d_masks, plane_stride, mpitch, st));
+    OMNI_LAUNCH(ctx, st, "onehot", g_onehot(d_labels, h, w, lpitch, K, d_masks, plane_stride, mpitch, st));
     MorphSE se;
     omni_build_se(0, 3, &se);
     int oi = open_iters > 0 ? open_iters : 0, ci = close_iters > 0 ? close_iters : 0;
@@ -279,8 +340,8 @@ static int generic_layer_masks(omni_ctx *ctx, const uint8_t *d_labels, int h, in
     for (int i = 0; i < ci; i++) seq[seq_n++] = 0;
     bool in_out = true;   // current data lives in d_masks
     for (int i = 0; i < seq_n; i++) {
-        if (in_out) OMNI_CUDA(g_morph(d_masks, plane_stride, mpitch, tmp, wplane, wp, K, h, w, se, seq[i], st));
-        else OMNI_CUDA(g_morph(tmp, wplane, wp, d_masks, plane_stride, mpitch, K, h, w, se, seq[i], st));
+        if (in_out) OMNI_LAUNCH(ctx, st, "morph", g_morph(d_masks, plane_stride, mpitch, tmp, wplane, wp, K, h, w, se, seq[i], st));
+        else OMNI_LAUNCH(ctx, st, "morph", g_morph(tmp, wplane, wp, d_masks, plane_stride, mpitch, K, h, w, se, seq[i], st));
         in_out = !in_out;
     }
     if (!in_out) OMNI_CUDA(g_copy2d_planes(tmp, wplane, wp, d_masks, plane_stride, mpitch, K, h, w, st));
@@ -327,7 +388,7 @@ static int generic_hysteresis(omni_ctx *ctx, u8 *state, size_t plane, size_t pit
     int passes = 0;
     for (;;) {
         OMNI_CUDA(cudaMemsetAsync(ctx->d_flags, 0, sizeof(int), st));
-        OMNI_CUDA(g_hyst_pass(state, plane, pitch, K, h, w, ctx->d_flags, st));
+        OMNI_LAUNCH(ctx, st, "hyst_pass", g_hyst_pass(state, plane, pitch, K, h, w, ctx->d_flags, st));
         OMNI_CUDA(cudaMemcpyAsync(ctx->h_flags, ctx->d_flags, sizeof(int), cudaMemcpyDeviceToHost, st));
         OMNI_CUDA(cudaStreamSynchronize(st));
         passes++;
@@ -335,7 +396,7 @@ static int generic_hysteresis(omni_ctx *ctx, u8 *state, size_t plane, size_t pit
         OMNI_REQUIRE(passes < 100000, "hysteresis did not converge");
     }
     ctx->last_hyst_passes = passes;
-    OMNI_CUDA(g_hyst_final(state, plane, pitch, K, h, w, st));
+    OMNI_LAUNCH(ctx, st, "hyst_final", g_hyst_final(state, plane, pitch, K, h, w, st));
     return OMNI_OK;
 }
 
@@ -358,12 +419,12 @@ static int generic_edges(omni_ctx *ctx, const uint8_t *d_masks, int K, int h, in
     const u8 *cur = d_masks; size_t cplane = m_plane, cpitch = mpitch;
     for (int i = 0; i < seq_n; i++) {
         u8 *dst = (cur == A) ? B : A;
-        OMNI_CUDA(g_morph(cur, cplane, cpitch, dst, wplane, wp, K, h, w, se, seq[i], st));
+        OMNI_LAUNCH(ctx, st, "morph", g_morph(cur, cplane, cpitch, dst, wplane, wp, K, h, w, se, seq[i], st));
         cur = dst; cplane = wplane; cpitch = wp;
     }
     u8 *bl = (cur == A) ? B : A;
-    OMNI_CUDA(g_blur(cur, cplane, cpitch, bl, wplane, wp, K, h, w, bp, st));
-    OMNI_CUDA(g_canny_nms(bl, wplane, wp, d_edges, e_plane, epitch, K, h, w, low, high, st));
+    OMNI_LAUNCH(ctx, st, "blur", g_blur(cur, cplane, cpitch, bl, wplane, wp, K, h, w, bp, st));
+    OMNI_LAUNCH(ctx, st, "canny_nms", g_canny_nms(bl, wplane, wp, d_edges, e_plane, epitch, K, h, w, low, high, st));
     return generic_hysteresis(ctx, d_edges, e_plane, epitch, K, h, w, st);
 }
 
@@ -411,7 +472,7 @@ extern "C" int omni_color_edge(omni_ctx *ctx, const uint8_t *d_bgr, int h, int w
         OMNI_TRY(omni_ws_reserve(ctx, 2, lp * h));
         labels = (u8 *)ctx->ws[2];
     }
-    OMNI_CUDA(g_assign(d_bgr, h, w, pitch, P, 1, labels, lp, st));
+    OMNI_LAUNCH(ctx, st, "assign", g_assign(d_bgr, h, w, pitch, P, 1, labels, lp, st));
     OMNI_TRY(generic_layer_masks(ctx, labels, h, w, lp, K, 1, 1, d_masks, m_plane_stride, mpitch, st));
     return generic_edges(ctx, d_masks, K, h, w, m_plane_stride, mpitch, prm, bp, low, high, d_edges, e_plane_stride, epitch, st);
 }
@@ -424,7 +485,7 @@ extern "C" int omni_count_nonzero(omni_ctx *ctx, const uint8_t *d_planes, int K,
     OMNI_REQUIRE(d_planes && h_counts && K >= 1 && K <= OMNI_MAX_K && h > 0 && w > 0, "omni_count_nonzero: bad arguments");
     cudaStream_t st = (cudaStream_t)stream;
     OMNI_CUDA(cudaMemsetAsync(ctx->d_counts, 0, K * sizeof(unsigned long long), st));
-    OMNI_CUDA(g_count_nonzero(d_planes, plane_stride, pitch, K, h, w, ctx->d_counts, st));
+    OMNI_LAUNCH(ctx, st, "count_nonzero", g_count_nonzero(d_planes, plane_stride, pitch, K, h, w, ctx->d_counts, st));
     OMNI_CUDA(cudaMemcpyAsync(ctx->h_counts, ctx->d_counts, K * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
     OMNI_CUDA(cudaStreamSynchronize(st));
     for (int k = 0; k < K; k++) h_counts[k] = (int64_t)ctx->h_counts[k];
@@ -437,7 +498,7 @@ extern "C" int omni_edges_composite(omni_ctx *ctx, const uint8_t *d_edges, int K
     OMNI_TRY(set_device(ctx));
     OMNI_REQUIRE(d_edges && d_canvas && h_colors_bgr && K >= 1 && K <= OMNI_MAX_K && h > 0 && w > 0 && cpitch >= (size_t)w * 3,
                  "omni_edges_composite: bad arguments");
-    OMNI_CUDA(g_composite(d_edges, e_plane_stride, epitch, K, h, w, h_colors_bgr, d_canvas, cpitch, (cudaStream_t)stream));
+    OMNI_LAUNCH(ctx, (cudaStream_t)stream, "composite", g_composite(d_edges, e_plane_stride, epitch, K, h, w, h_colors_bgr, d_canvas, cpitch, (cudaStream_t)stream));
     return OMNI_OK;
 }
 
@@ -531,9 +592,9 @@ extern "C" int omni_host_color_edge(omni_ctx *ctx, const uint8_t *h_bgr, int h, 
     OMNI_TRY(copy_planes_d2h(h_edges, e_plane_stride, epitch, de, eplane, ep, K, h, w, st));
     if (h_counts) {
         OMNI_CUDA(cudaMemsetAsync(ctx->d_counts, 0, 3 * OMNI_MAX_K * sizeof(unsigned long long), st));
-        OMNI_CUDA(g_count_labels(dl, lp, h, w, K, ctx->d_counts, st));
-        OMNI_CUDA(g_count_nonzero(dm, mplane, mp, K, h, w, ctx->d_counts + OMNI_MAX_K, st));
-        OMNI_CUDA(g_count_nonzero(de, eplane, ep, K, h, w, ctx->d_counts + 2 * OMNI_MAX_K, st));
+        OMNI_LAUNCH(ctx, st, "count_labels", g_count_labels(dl, lp, h, w, K, ctx->d_counts, st));
+        OMNI_LAUNCH(ctx, st, "count_nonzero", g_count_nonzero(dm, mplane, mp, K, h, w, ctx->d_counts + OMNI_MAX_K, st));
+        OMNI_LAUNCH(ctx, st, "count_nonzero", g_count_nonzero(de, eplane, ep, K, h, w, ctx->d_counts + 2 * OMNI_MAX_K, st));
         OMNI_CUDA(cudaMemcpyAsync(ctx->h_counts, ctx->d_counts, 3 * OMNI_MAX_K * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
     }
     OMNI_CUDA(cudaStreamSynchronize(st));

@@ -70,7 +70,22 @@ struct omni_ctx {
     cudaStream_t stream = nullptr;   // own stream for the omni_host_* entry points
     std::map<std::tuple<int, int, int, int>, ResizeTab> resize_tabs;
     int last_hyst_passes = 0;
+    // launch accounting / per-kernel CUDA-event timing (omni_profile_*)
+    long long launches = 0;
+    int prof_on = 0;
+    struct ProfRec { const char *name; cudaEvent_t a, b; };
+    std::vector<ProfRec> prof;
+    std::vector<cudaEvent_t> ev_pool;
 };
+
+// Brackets one kernel launch: counts it and, when profiling is on, records a CUDA event pair on the
+// launching stream (read back by omni_profile_summary).
+struct KScope {
+    omni_ctx *c; cudaStream_t st; cudaEvent_t b = nullptr;
+    KScope(omni_ctx *ctx, const char *name, cudaStream_t s);
+    ~KScope();
+};
+#define OMNI_LAUNCH(ctx, st, name, expr) do { KScope ks__(ctx, name, st); OMNI_CUDA(expr); } while (0)
 
 int omni_ws_reserve(omni_ctx *ctx, int slot, size_t bytes);
 const ResizeTab *omni_get_resize_tab(omni_ctx *ctx, int sh, int sw, int dh, int dw, cudaStream_t st);

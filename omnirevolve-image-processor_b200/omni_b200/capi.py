@@ -19,7 +19,8 @@ EXPORTS = [
     "omni_ctx_destroy", "omni_host_alloc", "omni_host_free", "omni_resize_area_u8c3", "omni_host_resize_area_u8c3",
     "omni_assign_lab_f32", "omni_assign_rgb_i16wrap", "omni_host_assign_rgb_i16wrap", "omni_layer_masks",
     "omni_edges", "omni_host_edges", "omni_color_edge", "omni_host_color_edge", "omni_count_nonzero",
-    "omni_edges_composite", "omni_last_hysteresis_passes",
+    "omni_edges_composite", "omni_last_hysteresis_passes", "omni_launch_count", "omni_profile_enable",
+    "omni_profile_summary",
 ]
 
 
@@ -71,6 +72,9 @@ def lib():
         "omni_count_nonzero": ([vp, u8p, i, i, i, sz, sz, i64p, vp], i),
         "omni_edges_composite": ([vp, u8p, i, i, i, sz, sz, hu8, u8p, sz, vp], i),
         "omni_last_hysteresis_passes": ([vp], i),
+        "omni_launch_count": ([vp], C.c_longlong),
+        "omni_profile_enable": ([vp, i], i),
+        "omni_profile_summary": ([vp, C.c_char_p, sz], i),
     }
     for name, (args, res) in sig.items():
         fn = getattr(L, name)

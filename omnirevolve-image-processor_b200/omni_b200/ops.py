@@ -204,6 +204,24 @@ class Engine:
     def last_hysteresis_passes(self) -> int:
         return int(self._L.omni_last_hysteresis_passes(self._h))
 
+    # ---- launch accounting / per-kernel CUDA-event timing -----------------------------------------
+    def launch_count(self) -> int:
+        """Kernels launched by this engine so far."""
+        return int(self._L.omni_launch_count(self._h))
+
+    def profile(self, on: bool):
+        capi.check(self._L.omni_profile_enable(self._h, 1 if on else 0))
+
+    def profile_summary(self) -> dict:
+        """{kernel name: (launches, total_ms)} since profile(True) / the last summary."""
+        buf = C.create_string_buffer(1 << 14)
+        capi.check(self._L.omni_profile_summary(self._h, buf, len(buf)))
+        out = {}
+        for line in buf.value.decode().splitlines():
+            name, n, ms = line.split("\t")
+            out[name] = (int(n), float(ms))
+        return out
+
     # ---- host-buffer entry points (H2D + kernels + D2H inside the call) ---------------------------------
     def host_resize_area(self, img: np.ndarray, new_w: int, new_h: int) -> np.ndarray:
         img = _as_u8(img, 3)

@@ -1,0 +1,268 @@
+"""Host-side mirror of the reference's stage functions for stages 01-03 (same names, arguments, files
+and error behaviour), with the per-pixel arithmetic done by libomni_b200's CUDA kernels.
+
+    reference                                   here
+    01_resize.resize_if_needed(path, cfg)       resize_if_needed(path, cfg)
+    02_color_extract._kmeans_lab(img, k, ..)    _kmeans_lab(img, k, ..)      (k-means itself stays on the host)
+    02_color_extract.main()                     color_extract_main()
+    03_edge_detect.process_color(name, cfg)     process_color(name, cfg)
+    03_edge_detect.detect_all_edges(cfg)        detect_all_edges(cfg)
+    03_edge_detect.save_edges_composite(cfg)    save_edges_composite(cfg)
+    process_colors.assign_labels(img, pal)      assign_labels(img, pal)
+
+Image decode/encode (cv2.imread / cv2.imwrite) and cv2.kmeans stay host-side library calls exactly as in
+the reference: PNG files and k-means centres are the stage boundary / inputs, not the data-parallel path.
+There is no CPU fallback for the pixel work: without a GPU every function here raises.
+"""
+from __future__ import annotations
+
+import json
+import os
+
+import cv2
+import numpy as np
+
+from .ops import EdgeConfig, get_engine
+
+
+# ---- 01_resize.py --------------------------------------------------------------------------------------
+def resize_dims(h: int, w: int, max_dimension):
+    """(new_w, new_h) or None -- the identical Python float expressions of 01_resize.py:15-18."""
+    max_dim = max(h, w)
+    if max_dim > max_dimension:
+        scale = max_dimension / max_dim
+        return int(w * scale), int(h * scale)
+    return None
+
+
+def resize_if_needed(image_path: str, cfg) -> np.ndarray:
+    """01_resize.py:7-23."""
+    img = cv2.imread(image_path)
+    if img is None:
+        raise ValueError(f"Failed to load image: {image_path}")
+    h, w = img.shape[:2]
+    dims = resize_dims(h, w, cfg.max_dimension)
+    if dims is None:
+        print(f"No resize required: {w}x{h}")
+        return img
+    new_w, new_h = dims
+    print(f"Resizing: {w}x{h} -> {new_w}x{new_h}")
+    return get_engine().host_resize_area(img, new_w, new_h)
+
+
+def resize_main(cfg) -> str:
+    """01_resize.py:25-31."""
+    cfg.ensure_output_dirs()
+    out = resize_if_needed(cfg.input_image, cfg)
+    path = os.path.join(cfg.output_dir, "resized.png")
+    cv2.imwrite(path, out)
+    print(f"Saved: {path}")
+    return path
+
+
+# ---- 02_color_extract.py -------------------------------------------------------------------------------
+def _darkness_rank(name: str) -> int:
+    """02_color_extract.py:17-23."""
+    s = name.lower()
+    if "dark" in s:
+        return 0
+    if "mid" in s:
+        return 1
+    if "skin" in s:
+        return 2
+    if "light" in s:
+        return 3
+    return 2
+
+
+def _ensure_bgr(img):
+    if img.ndim == 2:
+        return cv2.cvtColor(img, cv2.COLOR_GRAY2BGR)
+    if img.shape[2] == 4:
+        return cv2.cvtColor(img, cv2.COLOR_BGRA2BGR)
+    return img
+
+
+def kmeans_lab_centers(img_bgr: np.ndarray, k: int, sample_limit: int = 200_000, attempts: int = 3) -> np.ndarray:
+    """02_color_extract.py:35-50: centres from cv2.kmeans on the seeded <=200k-pixel Lab subsample.
+    Only the sampled pixels are converted (cvtColor is per-pixel, so the values are the reference's)."""
+    h, w = img_bgr.shape[:2]
+    n = h * w
+    flat = img_bgr.reshape(-1, 3)
+    if n > sample_limit:
+        pick = np.random.default_rng(42).choice(n, size=sample_limit, replace=False)
+        flat = flat[pick]
+    lab = cv2.cvtColor(np.ascontiguousarray(flat).reshape(-1, 1, 3), cv2.COLOR_BGR2LAB)
+    sample = lab.reshape(-1, 3).astype(np.float32)
+    criteria = (cv2.TERM_CRITERIA_EPS + cv2.TERM_CRITERIA_MAX_ITER, 40, 0.5)
+    _compact, _labels, centers = cv2.kmeans(sample, k, None, criteria, attempts, cv2.KMEANS_PP_CENTERS)
+    return centers.astype(np.float32)
+
+
+def _kmeans_lab(img_bgr: np.ndarray, k: int, sample_limit: int = 200_000, attempts: int = 3):
+    """02_color_extract.py:32-56 -> (centers f32[k,3], labels int32[H,W])."""
+    centers = kmeans_lab_centers(img_bgr, k, sample_limit, attempts)
+    import torch
+    eng = get_engine()
+    labels = eng.assign_lab(torch.from_numpy(np.ascontiguousarray(img_bgr)).cuda(), centers)
+    return centers, labels.cpu().numpy().astype(np.int32)
+
+
+def darkness_lut(centers: np.ndarray):
+    """02_color_extract.py:121-127: the identical NumPy expressions (argsort is not re-implemented)."""
+    order = np.argsort(centers[:, 0])
+    lut = np.zeros_like(order)
+    lut[order] = np.arange(len(order))
+    return order, lut
+
+
+def _lab_to_bgr(lab3) -> tuple:
+    """02_color_extract.py:58-61."""
+    px = np.uint8([[list(lab3)]])
+    bgr = cv2.cvtColor(px, cv2.COLOR_Lab2BGR)[0, 0]
+    return int(bgr[0]), int(bgr[1]), int(bgr[2])
+
+
+_CACHE: dict = {}          # (output_dir) -> fused results, so stage 03 in the same process skips recomputation
+
+
+def color_extract_main(cfg) -> dict:
+    """02_color_extract.py:66-175 (k-means mode, the only mode reachable through config.json).  The fused
+    GPU call also produces the stage-03 edge planes; they are cached for detect_all_edges() when both
+    stages run in one process, and recomputed from mask.png when stage 03 runs on its own."""
+    os.makedirs(cfg.output_dir, exist_ok=True)
+    path = os.path.join(cfg.output_dir, "resized.png")
+    img = cv2.imread(path, cv2.IMREAD_COLOR)
+    if img is None:
+        raise RuntimeError(f"Cannot read resized image: {path}")
+    img = _ensure_bgr(img)
+    names = list(cfg.color_names)
+    K = max(2, len(names))
+    centers = kmeans_lab_centers(img, K)
+    order, lut = darkness_lut(centers)
+    centers_sorted = centers[order]
+    ec = EdgeConfig.from_cfg(cfg)
+    r = get_engine().host_color_edge(img, centers, lut.astype(np.uint8), ec, want_labels=False)
+    names_sorted = sorted(names, key=_darkness_rank)
+    mapping = list(zip(names_sorted, range(len(names_sorted))))
+    palette = {}
+    for name, k in mapping:
+        os.makedirs(os.path.join(cfg.output_dir, name), exist_ok=True)
+        cv2.imwrite(os.path.join(cfg.output_dir, name, "mask.png"), r["masks"][k])
+        lab = centers_sorted[k]
+        palette[name] = {
+            "mode": "kmeans", "cluster_index": int(k), "cluster_lab": [int(lab[0]), int(lab[1]), int(lab[2])],
+            "approx_bgr": list(_lab_to_bgr(np.uint8(lab))), "pixels": int(r["counts"][k, 0]),
+            "mask_nonzero": int(r["counts"][k, 1]),
+        }
+        print(f"Extracted (kmeans): {name} | cluster={k} | L*={lab[0]:.1f} | "
+              f"pixels={palette[name]['pixels']} | nz={palette[name]['mask_nonzero']}")
+    pal_path = os.path.join(cfg.output_dir, "palette_by_name.json")
+    with open(pal_path, "w", encoding="utf-8") as fh:
+        json.dump(palette, fh, ensure_ascii=False, indent=2)
+    print(f"Palette saved: {pal_path}")
+    print("Color extraction: done.")
+    _CACHE[os.path.abspath(cfg.output_dir)] = {"names": dict(mapping), "edges": r["edges"], "masks": r["masks"],
+                                               "ec": ec}
+    return palette
+
+
+# ---- 03_edge_detect.py ---------------------------------------------------------------------------------
+def _ensure_odd(n: int) -> int:
+    """03_edge_detect.py:9-11."""
+    n = max(3, int(n))
+    return n if n % 2 == 1 else n + 1
+
+
+def _read_mask(color_name: str, cfg) -> np.ndarray:
+    mask_path = os.path.join(cfg.output_dir, color_name, "mask.png")
+    if not os.path.exists(mask_path):
+        raise FileNotFoundError(f"Mask not found: {mask_path}")
+    mask = cv2.imread(mask_path, cv2.IMREAD_GRAYSCALE)
+    if mask is None:
+        raise ValueError(f"Failed to load mask image: {mask_path}")
+    return mask
+
+
+def process_color(color_name: str, cfg):
+    """03_edge_detect.py:13-40 for one layer, from <out>/<name>/mask.png."""
+    mask = _read_mask(color_name, cfg)
+    edges = get_engine().host_edges(mask[None], EdgeConfig.from_cfg(cfg))[0]
+    out_path = os.path.join(cfg.output_dir, color_name, "edges.png")
+    cv2.imwrite(out_path, edges)
+    print(f"Edges extracted: {color_name} | nz={int(np.count_nonzero(edges))}")
+    return color_name, out_path
+
+
+def detect_all_edges(cfg) -> list:
+    """03_edge_detect.py:42-48.  The reference fans layers out over a process pool; here all layers of
+    equal size go through ONE batched GPU call (layers are the plane dimension of omni_edges)."""
+    names = list(cfg.color_names)
+    masks = [_read_mask(n, cfg) for n in names]
+    results = []
+    shapes = {m.shape for m in masks}
+    if len(shapes) == 1 and masks:
+        edges = get_engine().host_edges(np.stack(masks), EdgeConfig.from_cfg(cfg))
+    else:                                   # hand-edited masks of different sizes: one call per layer
+        edges = [get_engine().host_edges(m[None], EdgeConfig.from_cfg(cfg))[0] for m in masks]
+    for n, e in zip(names, edges):
+        out_path = os.path.join(cfg.output_dir, n, "edges.png")
+        cv2.imwrite(out_path, e)
+        print(f"Edges extracted: {n} | nz={int(np.count_nonzero(e))}")
+        results.append((n, out_path))
+    return results
+
+
+def save_edges_composite(cfg) -> str:
+    """03_edge_detect.py:60-111.  Colours: palette_by_name.json[name]["bgr"] when present (stage 02 writes
+    "approx_bgr", so in practice never), else cfg.colors[i] taken as (b, g, r) exactly as the reference
+    does -- IndexError when len(colors) < len(color_names)."""
+    import torch
+    names = list(cfg.color_names)
+    resized = cv2.imread(os.path.join(cfg.output_dir, "resized.png"))
+    planes = {}
+    for name in names:
+        p = os.path.join(cfg.output_dir, name, "edges.png")
+        if os.path.exists(p):
+            e = cv2.imread(p, cv2.IMREAD_GRAYSCALE)
+            if e is not None:
+                planes[name] = e
+    if resized is not None:
+        h, w = resized.shape[:2]
+    elif planes:
+        h, w = next(iter(planes.values())).shape[:2]
+    else:
+        raise FileNotFoundError("No edges found to build edges_composite.png")
+    palette = {}
+    pj = os.path.join(cfg.output_dir, "palette_by_name.json")
+    if os.path.exists(pj):
+        try:
+            with open(pj, "r", encoding="utf-8") as fh:
+                palette = json.load(fh) or {}
+        except Exception:
+            palette = {}
+    name_to_bgr = {}
+    for i, name in enumerate(names):
+        if name in palette and "bgr" in palette[name]:
+            b, g, r = palette[name]["bgr"]
+        else:
+            b, g, r = cfg.colors[i]
+        name_to_bgr[name] = (b, g, r)
+    order = [n for n in names if n in planes]
+    out_path = os.path.join(cfg.output_dir, "edges_composite.png")
+    if order:
+        stack = np.stack([planes[n] for n in order])      # a size mismatch raises, as the reference's indexing does
+        if stack.shape[1:] != (h, w):
+            raise IndexError(f"edges.png size {stack.shape[1:]} does not match the canvas {(h, w)}")
+        canvas = get_engine().edges_composite(torch.from_numpy(stack).cuda(), [name_to_bgr[n] for n in order]).cpu().numpy()
+    else:
+        canvas = np.full((h, w, 3), 255, np.uint8)
+    cv2.imwrite(out_path, canvas)
+    print(f"Edges composite saved: {out_path}")
+    return out_path
+
+
+# ---- process_colors.py ---------------------------------------------------------------------------------
+def assign_labels(img_rgb: np.ndarray, palette_rgb: np.ndarray) -> np.ndarray:
+    """process_colors.py:69-77 (the int16 wrap of diff*diff is reference behaviour and is reproduced)."""
+    return get_engine().host_assign_rgb_i16wrap(img_rgb, palette_rgb)

@@ -1,0 +1,324 @@
+"""Parity of the CUDA path (through the C ABI, omni_b200.Engine -> libomni_b200.so) against the CPU
+oracle (oracle.cmodel = plain-C restatement, oracle.refport = cv2/NumPy replay of the reference's call
+sites) and against the golden vectors frozen from the unmodified reference.  Bit-exact for labels, masks
+and edges; +-1 LSB for fractional resize (exact for integer ratios).  Needs a B200: `-m gpu`."""
+import numpy as np
+import pytest
+
+from helpers import PIPE_CASES, load_pipe_case, plane_of_name, GOLDEN, synth, uniform_img, smooth_u8, blob_mask
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+
+@pytest.fixture(scope="module")
+def eng():
+    import omni_b200
+    e = omni_b200.Engine(0)         # raises (no CPU fallback) when the .so or the GPU is missing
+    yield e
+    e.close()
+
+
+@pytest.fixture(scope="module", params=[1, 0], ids=["fast", "generic"])
+def eng_mode(request, eng):
+    eng.set_fast_path(bool(request.param))
+    yield eng
+    eng.set_fast_path(True)
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def host(t):
+    return t.cpu().numpy()
+
+
+def _cm():
+    from oracle import cmodel
+    return cmodel
+
+
+def _rp():
+    from oracle import refport
+    return refport
+
+
+# ---- stage 01 --------------------------------------------------------------------------------------
+@pytest.mark.parametrize("hs,ws,md", [(96, 128, 64), (512, 512, 256), (768, 384, 256), (96, 144, 48), (300, 200, 133),
+                                      (409, 409, 200), (1000, 1500, 700), (1080, 1920, 1000), (33, 1000, 77),
+                                      (2048, 2048, 1024), (2050, 1026, 1025), (1200, 1600, 400)])
+def test_resize_area(eng_mode, hs, ws, md):
+    cm, rp = _cm(), _rp()
+    src = synth(hs, ws, hs + ws, cell=16)
+    nw, nh = rp.resize_dims(hs, ws, md)
+    want = cm.resize_area(src, nw, nh)
+    got = host(eng_mode.resize_area(dev(src), nw, nh))
+    integer_ratio = hs % nh == 0 and ws % nw == 0
+    if integer_ratio:
+        assert np.array_equal(got, want)
+    else:
+        d = np.abs(got.astype(np.int16) - want.astype(np.int16))
+        assert d.max() <= 1                       # contract: +-1 LSB (north_star); in practice identical
+        assert (d != 0).mean() < 1e-3
+
+
+def test_resize_golden(eng_mode):
+    rp = _rp()
+    z = np.load(f"{GOLDEN}/functions.npz")
+    for tag in ("rz_2to1", "rz_3to1", "rz_frac", "rz_frac2"):
+        src, md, dst = z[tag + "_src"], int(z[tag + "_md"]), z[tag + "_dst"]
+        nw, nh = rp.resize_dims(src.shape[0], src.shape[1], md)
+        got = host(eng_mode.resize_area(dev(src), nw, nh))
+        assert np.abs(got.astype(np.int16) - dst.astype(np.int16)).max() <= (0 if "to1" in tag else 1), tag
+
+
+def test_resize_strided_views(eng):
+    """pitch != 3*w on both sides (a crop of a larger tensor)."""
+    cm = _cm()
+    src = synth(300, 420, 1)
+    big = dev(src)
+    crop = big[10:266, 20:404]                       # 256 x 384, pitch 1260
+    out_big = torch.zeros((200, 300, 3), dtype=torch.uint8, device="cuda")
+    eng.resize_area(crop, 192, 128, out=out_big[5:133, 7:199])
+    assert np.array_equal(host(out_big[5:133, 7:199]), cm.resize_area(src[10:266, 20:404], 192, 128))
+
+
+# ---- stage 02 --------------------------------------------------------------------------------------
+@pytest.mark.parametrize("K", [2, 3, 4, 8, 16, 32])
+def test_assign_lab(eng_mode, K):
+    cm, rp = _cm(), _rp()
+    rng = np.random.default_rng(K)
+    for img in (synth(250, 333, K), uniform_img(127, 510, K + 1)):
+        lab = cm.bgr2lab(img)
+        ctr = rp.kmeans_lab_centers(img, K)
+        assert np.array_equal(host(eng_mode.assign_lab(dev(img), ctr)), cm.assign_f32(lab, ctr))
+        # near-ties: half-integer centres, a duplicated centre (first minimum must win), relabel LUT
+        ctr2 = (rng.integers(0, 255, (K, 3)) + 0.5).astype(np.float32)
+        ctr2[K - 1] = ctr2[0]
+        lut = rng.permutation(K).astype(np.uint8)
+        assert np.array_equal(host(eng_mode.assign_lab(dev(img), ctr2, lut)), lut[cm.assign_f32(lab, ctr2)])
+
+
+def test_assign_lab_all_colours(eng):
+    """Every one of the 2^24 BGR colours: the Lab tables + f32 argmin agree with the oracle."""
+    cm = _cm()
+    v = np.arange(1 << 24, dtype=np.uint32)
+    img = np.stack([(v >> 16) & 255, (v >> 8) & 255, v & 255], axis=-1).astype(np.uint8).reshape(4096, 4096, 3)
+    ctr = (np.random.default_rng(3).random((8, 3)) * np.array([255, 120, 120]) + np.array([0, 60, 60])).astype(np.float32)
+    want = cm.assign_f32(cm.bgr2lab(img), ctr)
+    assert np.array_equal(host(eng.assign_lab(dev(img), ctr)), want)
+
+
+@pytest.mark.parametrize("K", [2, 4, 8, 16])
+def test_assign_rgb_i16wrap(eng_mode, K):
+    cm = _cm()
+    z = np.load(f"{GOLDEN}/functions.npz")
+    got = host(eng_mode.assign_rgb_i16wrap(dev(z["al_img"]), z[f"al_pal{K}"]))
+    assert np.array_equal(got, z[f"al_lab{K}"])               # golden from process_colors.assign_labels
+    img = uniform_img(211, 307, K)
+    pal = np.random.default_rng(K).integers(0, 256, (K, 3), dtype=np.uint8)
+    assert np.array_equal(host(eng_mode.assign_rgb_i16wrap(dev(img), pal)), cm.assign_i16wrap(img, pal))
+    assert np.array_equal(eng_mode.host_assign_rgb_i16wrap(img, pal), cm.assign_i16wrap(img, pal))
+
+
+@pytest.mark.parametrize("hw", [(67, 93), (1, 50), (50, 1), (2, 2), (3, 3), (128, 200), (257, 1031), (64, 33)])
+def test_layer_masks(eng_mode, hw):
+    cm = _cm()
+    rng = np.random.default_rng(hw[0] * 7 + hw[1])
+    for K in (2, 5, 8, 16):
+        coarse = rng.integers(0, K, ((hw[0] + 7) // 8, (hw[1] + 7) // 8), dtype=np.uint8)
+        labels = np.kron(coarse, np.ones((8, 8), np.uint8))[:hw[0], :hw[1]]
+        noise = rng.random(hw) < 0.15
+        labels = np.where(noise, rng.integers(0, K, hw, dtype=np.uint8), labels).astype(np.uint8)
+        for oi, ci in ((1, 1), (0, 0), (2, 1), (0, 3)):
+            want = cm.layer_masks(labels, K, None, oi, ci)
+            got = host(eng_mode.layer_masks(dev(labels), K, oi, ci))
+            assert np.array_equal(got, want), (K, oi, ci)
+
+
+# ---- stage 03 --------------------------------------------------------------------------------------
+def _edge_want(masks, **kw):
+    cm = _cm()
+    return np.stack([cm.edge_chain(m, kw.get("morph_k", 3), kw.get("open_iters", 1), kw.get("close_iters", 1),
+                                   kw.get("ksize", 3), kw.get("low", 50), kw.get("high", 150)) for m in masks])
+
+
+@pytest.mark.parametrize("hw", [(67, 93), (128, 200), (1, 200), (200, 1), (2, 2), (3, 300), (300, 3), (513, 1027)])
+def test_edges_binary_masks(eng_mode, hw):
+    import omni_b200
+    masks = np.stack([blob_mask(hw[0], hw[1], s, p) for s, p in ((1, 0.5), (2, 0.2), (3, 0.8))])
+    for ks, lo, hi in [(3, 50, 150), (7, 22, 70), (5, 100, 200), (3, 50, 50), (3, 200, 50), (9, 30.7, 90.2)]:
+        ec = omni_b200.EdgeConfig(low=lo, high=hi, ksize=ks)
+        got = host(eng_mode.edges(dev(masks), ec))
+        assert np.array_equal(got, _edge_want(masks, ksize=ks, low=lo, high=hi)), (ks, lo, hi)
+
+
+@pytest.mark.parametrize("mk,oi,ci", [(1, 1, 1), (5, 1, 1), (3, 2, 0), (3, 0, 2), (2, 1, 1), (3, 0, 0), (7, 1, 2)])
+def test_edges_morph_params(eng_mode, mk, oi, ci):
+    import omni_b200
+    masks = np.stack([blob_mask(150, 210, s, 0.5, k=5) for s in (4, 5)])
+    ec = omni_b200.EdgeConfig(morph_k=mk, open_iters=oi, close_iters=ci)
+    got = host(eng_mode.edges(dev(masks), ec))
+    assert np.array_equal(got, _edge_want(masks, morph_k=mk, open_iters=oi, close_iters=ci))
+
+
+def test_edges_nonbinary_long_chains(eng_mode):
+    """Arbitrary u8 'masks' (the reference reads any mask.png): long weak chains crossing many tiles."""
+    import omni_b200
+    rp = _rp()
+    masks = np.stack([smooth_u8(700, 900, 3), smooth_u8(700, 900, 4, k=11)])
+    for lo, hi in [(10, 60), (5, 200), (50, 150)]:
+        ec = omni_b200.EdgeConfig(low=lo, high=hi, ksize=3, open_iters=0, close_iters=0)
+        got = host(eng_mode.edges(dev(masks), ec))
+        want = np.stack([rp.edge_layer(m, lo, hi, 3, 3, 0, 0) for m in masks])
+        assert np.array_equal(got, want), (lo, hi)
+    assert eng_mode.last_hysteresis_passes() >= 1
+
+
+def test_edges_spiral_worst_case(eng_mode):
+    """A one-pixel weak spiral fed from a single strong seed: hysteresis must walk the whole chain."""
+    import omni_b200
+    cm = _cm()
+    n = 384
+    img = np.zeros((n, n), np.uint8)
+    # concentric square spiral, 6 px pitch, value 60 (weak after blur); one bright seed at the start
+    y = x = 4
+    dy, dx, run = 0, 1, n - 9
+    while run > 12:
+        for _ in range(run):
+            img[y, x] = 90
+            y, x = y + dy, x + dx
+        dy, dx = dx, -dy
+        run -= 6
+    img[4, 4:10] = 255
+    ec = omni_b200.EdgeConfig(low=20, high=250, ksize=3, open_iters=0, close_iters=0)
+    got = host(eng_mode.edges(dev(img[None]), ec))[0]
+    want = cm.edge_chain(img, 3, 0, 0, 3, 20, 250)
+    assert np.array_equal(got, want)
+    assert want.any()
+
+
+def test_edges_strided_planes(eng):
+    import omni_b200
+    masks = np.stack([blob_mask(200, 300, s) for s in (7, 8, 9)])
+    big = torch.zeros((3, 220, 352), dtype=torch.uint8, device="cuda")
+    big[:, 10:210, 16:316] = dev(masks)
+    out = torch.zeros((3, 230, 320), dtype=torch.uint8, device="cuda")
+    eng.edges(big[:, 10:210, 16:316], omni_b200.EdgeConfig(), out=out[:, 3:203, 5:305])
+    assert np.array_equal(host(out[:, 3:203, 5:305]), _edge_want(masks))
+    assert int(out[:, :3].sum()) == 0 and int(out[:, :, :5].sum()) == 0     # nothing written outside the view
+
+
+# ---- fused path + golden pipeline cases ------------------------------------------------------------------
+@pytest.mark.parametrize("case", PIPE_CASES)
+def test_golden_pipeline_case(eng_mode, case):
+    """Frozen outputs of `pipeline.py --start-step 1 --end-step 3` of the unmodified reference."""
+    import omni_b200
+    rp = _rp()
+    z, meta = load_pipe_case(case)
+    cfg, names = meta["config"], meta["names"]
+    K = len(names)
+    src = z["input"]
+    dims = rp.resize_dims(src.shape[0], src.shape[1], cfg["max_dimension"])
+    resized = src if dims is None else host(eng_mode.resize_area(dev(src), dims[0], dims[1]))
+    assert np.abs(resized.astype(np.int16) - z["resized"].astype(np.int16)).max() <= 1
+    ctr = z["centers"]
+    _order, lut = rp.darkness_order(ctr)
+    ec = omni_b200.EdgeConfig(low=cfg["edge_low_threshold"], high=cfg["edge_high_threshold"], ksize=cfg["edge_kernel_size"],
+                              morph_k=cfg["edge_morph_kernel"], open_iters=cfg["edge_morph_open_iters"],
+                              close_iters=cfg["edge_morph_close_iters"])
+    labels, masks, edges = eng_mode.color_edge(dev(z["resized"]), ctr, lut.astype(np.uint8), ec, want_labels=True)
+    assert np.array_equal(host(labels), lut.astype(np.uint8)[z["labels"]])
+    p_of = plane_of_name(names)
+    for i, n in enumerate(names):
+        assert np.array_equal(host(masks[p_of[n]]), z["masks"][i]), n
+        assert np.array_equal(host(edges[p_of[n]]), z["edges"][i]), n
+    order_planes = [p_of[n] for n in names]
+    comp = host(eng_mode.edges_composite(edges[order_planes], cfg["colors"]))
+    assert np.array_equal(comp, z["composite"])
+    # host-buffer entry point: same result + the counts the reference logs / stores in palette_by_name.json
+    r = eng_mode.host_color_edge(z["resized"], ctr, lut.astype(np.uint8), ec)
+    for i, n in enumerate(names):
+        p = p_of[n]
+        assert np.array_equal(r["masks"][p], z["masks"][i]) and np.array_equal(r["edges"][p], z["edges"][i])
+        assert r["counts"][p, 1] == meta["palette_by_name"][n]["mask_nonzero"]
+        assert r["counts"][p, 0] == meta["palette_by_name"][n]["pixels"]
+        assert r["counts"][p, 2] == int(np.count_nonzero(z["edges"][i]))
+
+
+@pytest.mark.parametrize("hw,K", [((1, 1), 2), ((1, 37), 3), ((41, 1), 2), ((5, 7), 4), ((64, 64), 4), ((65, 129), 8),
+                                  ((333, 517), 16), ((1080, 1920), 8)])
+def test_fused_equals_oracle(eng_mode, hw, K):
+    import omni_b200
+    cm, rp = _cm(), _rp()
+    img = synth(hw[0], hw[1], K + hw[1], cell=16) if min(hw) >= 16 else uniform_img(hw[0], hw[1], K)
+    ctr = rp.kmeans_lab_centers(img, K) if hw[0] * hw[1] >= K else \
+        np.random.default_rng(1).random((K, 3)).astype(np.float32) * 255
+    _o, lut = rp.darkness_order(ctr)
+    lut = lut.astype(np.uint8)
+    for ks, lo, hi in [(3, 50, 150), (7, 22, 70)]:
+        ec = omni_b200.EdgeConfig(low=lo, high=hi, ksize=ks)
+        labels, masks, edges = eng_mode.color_edge(dev(img), ctr, lut, ec, want_labels=True)
+        raw = cm.assign_f32(cm.bgr2lab(img), ctr)
+        assert np.array_equal(host(labels), lut[raw])
+        wm = cm.layer_masks(raw, K, lut)
+        assert np.array_equal(host(masks), wm)
+        assert np.array_equal(host(edges), _edge_want(wm, ksize=ks, low=lo, high=hi))
+        assert np.array_equal(eng_mode.count_nonzero(masks), [(m != 0).sum() for m in wm])
+
+
+def test_param_sweep_config5_scaled(eng):
+    """BASELINE config 5 (blur 3/5/7 x thresholds 50..200, K=16) at 1024^2 against the cv2 chain."""
+    import omni_b200
+    rp = _rp()
+    img = synth(1024, 1024, 0)
+    K = 16
+    ctr = rp.kmeans_lab_centers(img, K)
+    _o, lut = rp.darkness_order(ctr)
+    _l, masks_d, _e = eng.color_edge(dev(img), ctr, lut.astype(np.uint8), omni_b200.EdgeConfig())
+    masks = host(masks_d)
+    _c, _ls, want_masks = rp.color_extract(img, K, ctr)
+    assert np.array_equal(masks, want_masks)
+    for ks in (3, 5, 7):
+        for lo in (50, 100, 150):
+            for hi in (100, 150, 200):
+                got = host(eng.edges(masks_d, omni_b200.EdgeConfig(low=lo, high=hi, ksize=ks)))
+                want = rp.edges_all(masks, low=lo, high=hi, ksize=ks)
+                assert np.array_equal(got, want), (ks, lo, hi)
+
+
+def test_full_size_config2(eng):
+    """BASELINE config 2 at full size (4096^2, K=8, 50/150, blur 3): masks and edges bit-exact vs the
+    oracle (C assign + cv2 chain), plus size-independent invariants."""
+    import omni_b200
+    cm, rp = _cm(), _rp()
+    img = synth(4096, 4096, 0)
+    K = 8
+    ctr = rp.kmeans_lab_centers(img, K)
+    _o, lut = rp.darkness_order(ctr)
+    lut = lut.astype(np.uint8)
+    labels, masks, edges = eng.color_edge(dev(img), ctr, lut, omni_b200.EdgeConfig(), want_labels=True)
+    want_labels = lut[cm.assign_f32(cm.bgr2lab(img), ctr)]
+    assert np.array_equal(host(labels), want_labels)
+    want_masks = rp.layer_masks(want_labels, K)
+    assert np.array_equal(host(masks), want_masks)
+    assert np.array_equal(host(edges), rp.edges_all(want_masks))
+    # invariants: label histogram sums to N; edges only where the blurred mask has a gradient, i.e. never
+    # deeper than 3 px inside a uniform region of the mask
+    assert int(torch.bincount(labels.flatten().int(), minlength=K).sum()) == 4096 * 4096
+    # unfused composition == fused call, on the device
+    m2 = eng.layer_masks(eng.assign_lab(dev(img), ctr, lut), K)
+    assert torch.equal(m2, masks)
+    assert torch.equal(eng.edges(m2, omni_b200.EdgeConfig()), edges)
+
+
+def test_no_cpu_fallback_error_paths(eng):
+    import omni_b200
+    with pytest.raises(omni_b200.OmniError):
+        eng.resize_area(dev(synth(64, 64, 0)), 128, 128)          # INTER_AREA path is shrink-only
+    with pytest.raises(omni_b200.OmniError):
+        eng.edges(dev(blob_mask(64, 64, 0)[None]), omni_b200.EdgeConfig(ksize=33))
+    with pytest.raises(omni_b200.OmniError):
+        eng.assign_lab(dev(synth(64, 64, 0)), np.zeros((40, 3), np.float32))
