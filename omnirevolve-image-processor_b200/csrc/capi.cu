@@ -49,6 +49,7 @@ extern "C" int omni_ctx_create(int device, omni_ctx **out)
     OMNI_CUDA(cudaHostAlloc(&c->h_flags, 64 * sizeof(int), cudaHostAllocDefault));
     OMNI_CUDA(cudaHostAlloc(&c->h_counts, 4 * OMNI_MAX_K * sizeof(unsigned long long), cudaHostAllocDefault));
     OMNI_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    OMNI_CUDA(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
     *out = c;
     return OMNI_OK;
 }
@@ -57,7 +58,7 @@ extern "C" int omni_ctx_destroy(omni_ctx *c)
 {
     if (!c) return OMNI_OK;
     cudaSetDevice(c->device);
-    for (int i = 0; i < 4; i++) if (c->ws[i]) cudaFree(c->ws[i]);
+    for (int i = 0; i < OMNI_WS_SLOTS; i++) if (c->ws[i]) cudaFree(c->ws[i]);
     for (auto &kv : c->resize_tabs) if (kv.second.d_blob) cudaFree(kv.second.d_blob);
     if (c->d_flags) cudaFree(c->d_flags);
     if (c->d_counts) cudaFree(c->d_counts);
@@ -91,7 +92,19 @@ extern "C" int omni_host_free(void *p)
     return OMNI_OK;
 }
 
-extern "C" int omni_last_hysteresis_passes(omni_ctx *ctx) { return ctx ? ctx->last_hyst_passes : 0; }
+extern "C" int omni_last_hysteresis_passes(omni_ctx *ctx)
+{
+    if (!ctx) return 0;
+    if (ctx->last_hyst_passes < 0) {              // the bit-plane kernel leaves its round count in d_flags[0]
+        int v = 0;
+        if (cudaSetDevice(ctx->device) != cudaSuccess || cudaMemcpy(&v, ctx->d_flags, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) {
+            cudaGetLastError();
+            return 0;
+        }
+        ctx->last_hyst_passes = v;
+    }
+    return ctx->last_hyst_passes;
+}
 
 // ---- launch accounting / per-kernel timing ----------------------------------------------------------
 KScope::KScope(omni_ctx *ctx, const char *name, cudaStream_t s) : c(ctx), st(s)
@@ -462,18 +475,29 @@ extern "C" int omni_color_edge(omni_ctx *ctx, const uint8_t *d_bgr, int h, int w
     AssignParams P;
     OMNI_TRY(fill_assign(&P, h_centers, nullptr, K, h_lut));
     cudaStream_t st = (cudaStream_t)stream;
-    if (ctx->fast && fast_edges_supported(prm))
-        return fast_color_edge(ctx, d_bgr, h, w, pitch, P, prm, bp, low, high, d_labels, lpitch,
-                               d_masks, m_plane_stride, mpitch, d_edges, e_plane_stride, epitch, st);
-    // generic composition
+    if (ctx->fast && fast_edges_supported(prm)) {
+        int rc = fast_color_edge(ctx, d_bgr, h, w, pitch, P, prm, bp, low, high, d_labels, lpitch,
+                                 d_masks, m_plane_stride, mpitch, d_edges, e_plane_stride, epitch, st);
+        if (rc != OMNI_ERR_UNSUPPORTED) return rc;
+    }
+    // composition of the unfused steps (fast kernels where they apply, e.g. edge_kernel_size != 3)
     u8 *labels = d_labels; size_t lp = lpitch;
     if (!labels) {
         lp = ((size_t)w + 15) & ~(size_t)15;
         OMNI_TRY(omni_ws_reserve(ctx, 2, lp * h));
         labels = (u8 *)ctx->ws[2];
     }
-    OMNI_LAUNCH(ctx, st, "assign", g_assign(d_bgr, h, w, pitch, P, 1, labels, lp, st));
-    OMNI_TRY(generic_layer_masks(ctx, labels, h, w, lp, K, 1, 1, d_masks, m_plane_stride, mpitch, st));
+    if (ctx->fast) {
+        OMNI_LAUNCH(ctx, st, "assign", fast_assign(ctx, d_bgr, h, w, pitch, P, 1, labels, lp, st));
+        OMNI_TRY(fast_layer_masks(ctx, labels, h, w, lp, K, 1, 1, d_masks, m_plane_stride, mpitch, st));
+    } else {
+        OMNI_LAUNCH(ctx, st, "assign", g_assign(d_bgr, h, w, pitch, P, 1, labels, lp, st));
+        OMNI_TRY(generic_layer_masks(ctx, labels, h, w, lp, K, 1, 1, d_masks, m_plane_stride, mpitch, st));
+    }
+    if (ctx->fast && fast_edges_supported(prm)) {
+        int rc = fast_edges(ctx, d_masks, K, h, w, m_plane_stride, mpitch, prm, bp, low, high, d_edges, e_plane_stride, epitch, st);
+        if (rc != OMNI_ERR_UNSUPPORTED) return rc;
+    }
     return generic_edges(ctx, d_masks, K, h, w, m_plane_stride, mpitch, prm, bp, low, high, d_edges, e_plane_stride, epitch, st);
 }
 

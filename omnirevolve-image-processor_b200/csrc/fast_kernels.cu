@@ -1,19 +1,828 @@
-// fast_kernels.cu -- placeholder: the fast path is not implemented yet, everything routes to the
-// generic kernels.
+// fast_kernels.cu -- the bit-plane fast path of libomni_b200 (the default for the parameter ranges the
+// pipeline uses; everything else goes to generic_kernels.cu).
+//
+// Data layout.  After the colour assignment every layer is a BIT-PLANE: one u32 word holds 32
+// horizontally adjacent pixels (bit i of word c of row y = pixel x = 32c + i), rows are `ws` words apart
+// (ws = words per row rounded up to 4), planes `plane` words apart.  K=8 planes of a 4096^2 image are
+// 16.8 MB -- they live in the 126 MB L2 between the kernels, so HBM sees only the image read (3 B/px) and
+// the mask / edge byte planes written once each (2K B/px): the algorithmic N*(3+2K) bytes.
+//
+//   fk_assign_bits    image -> [labels] + raw one-hot bit-planes P0           (02:35-36,53-55,121-127,150)
+//   fk_morph<CODE>    P0 -> RECT-3 open/close -> mask BYTES (mask.png content) (02:151-154)
+//                        -> ELLIPSE-3 open/close -> bit-planes M2              (03:23-30)
+//   fk_edges3         M2 -> blur-3 -> Sobel -> NMS -> strong/candidate bit-planes S, C   (03:33-34)
+//   fk_hysteresis     cooperative: E = S; E |= C & dilate8(E) to the global fixed point; E -> edge BYTES
+//
+// Reference call sites are relative to /root/reference/image_processor/.  Arithmetic: SURVEY.md App. A.
 #include "fast_kernels.cuh"
+#include "omni_tables.inc"
+
+#include <cooperative_groups.h>
+namespace cg = cooperative_groups;
+
+#define FK_TRY(expr) do { int rc__ = (expr); if (rc__ != OMNI_OK) return rc__; } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// shared helpers
+// ------------------------------------------------------------------------------------------------
+struct BitGeom {
+    int h, w;
+    int ww;            // words per row that hold pixels
+    int ws;            // row stride in words (multiple of 4)
+    size_t plane;      // words per plane
+};
+
+static BitGeom make_geom(int h, int w)
+{
+    BitGeom g;
+    g.h = h; g.w = w;
+    g.ww = (w + 31) >> 5;
+    g.ws = (g.ww + 3) & ~3;
+    g.plane = (size_t)g.ws * h;
+    return g;
+}
+
+__device__ u16 f_lab_tab[256 + 2048];          // gamma[256] | cbrt[2041]
+static bool f_tab_ready[64] = {false};
+
+static cudaError_t fast_tables()
+{
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 64 && f_tab_ready[dev]) return cudaSuccess;
+    e = cudaMemcpyToSymbol(f_lab_tab, OMNI_LAB_GAMMA, sizeof(OMNI_LAB_GAMMA), 0);
+    if (e != cudaSuccess) return e;
+    e = cudaMemcpyToSymbol(f_lab_tab, OMNI_LAB_CBRT, sizeof(OMNI_LAB_CBRT), 256 * sizeof(u16));
+    if (e != cudaSuccess) return e;
+    if (dev < 64) f_tab_ready[dev] = true;
+    return cudaSuccess;
+}
 
 void fast_ctx_release(omni_ctx *) {}
-bool fast_resize_2x_ok(const u8 *, int, size_t, const u8 *, int, size_t) { return false; }
-cudaError_t fast_resize_2x(const u8 *, size_t, u8 *, int, int, size_t, cudaStream_t) { return cudaErrorNotSupported; }
-cudaError_t fast_assign(omni_ctx *, const u8 *px, int h, int w, size_t pitch, const AssignParams &P, int mode_lab,
+
+// bits i of a 32-bit word whose pixel (start_px + i) lies in [0, w)
+__device__ __forceinline__ u32 range_mask(int start_px, int w)
+{
+    int lo = max(0, -start_px), hi = min(32, w - start_px);
+    if (hi <= lo) return 0u;
+    u32 m = hi >= 32 ? 0xffffffffu : ((1u << hi) - 1u);
+    return m & ~((1u << lo) - 1u);
+}
+
+// 4 mask bits -> 4 bytes of 0x00 / 0xFF
+__device__ __forceinline__ u32 expand4(u32 nib)
+{
+    return ((nib * 0x00204081u) & 0x01010101u) * 255u;
+}
+
+// store 32 pixels (bits of `word`) as 0/255 bytes at dst (pixel x0 = first), only pixels < w
+__device__ __forceinline__ void store_word_bytes(u8 *row, int x0, int w, u32 word, bool aligned16)
+{
+    if (x0 + 32 <= w && aligned16) {
+        uint4 a, b;
+        a.x = expand4(word & 15u);         a.y = expand4((word >> 4) & 15u);
+        a.z = expand4((word >> 8) & 15u);  a.w = expand4((word >> 12) & 15u);
+        b.x = expand4((word >> 16) & 15u); b.y = expand4((word >> 20) & 15u);
+        b.z = expand4((word >> 24) & 15u); b.w = expand4(word >> 28);
+        uint4 *p = reinterpret_cast<uint4 *>(row + x0);
+        p[0] = a; p[1] = b;
+    } else {
+        int n = min(32, w - x0);
+        for (int i = 0; i < n; i++) row[x0 + i] = (word >> i) & 1u ? 255 : 0;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// stage 01: exact 2:1 INTER_AREA, vectorised (01_resize.py:20)
+// Each thread produces 4 destination pixels (12 bytes) from 2 x 24 source bytes.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) fk_resize_2x(const u8 *__restrict__ src, size_t spitch, u8 *__restrict__ dst, int dh, int dw,
+                                                    size_t dpitch)
+{
+    int gx = blockIdx.x * blockDim.x + threadIdx.x;         // group of 4 destination pixels
+    int y = blockIdx.y * blockDim.y + threadIdx.y;
+    int x = gx * 4;
+    if (x >= dw || y >= dh) return;
+    const u8 *r0 = src + (size_t)(2 * y) * spitch + 6 * x, *r1 = r0 + spitch;
+    u8 *o = dst + (size_t)y * dpitch + 3 * x;
+    if (x + 4 <= dw) {
+        // 24 source bytes per row = 3 x 8 B (8-byte aligned: 6*x with x % 4 == 0, pitches % 8 == 0 checked by the host)
+        uint2 a0 = *reinterpret_cast<const uint2 *>(r0), a1 = *reinterpret_cast<const uint2 *>(r0 + 8),
+              a2 = *reinterpret_cast<const uint2 *>(r0 + 16);
+        uint2 b0 = *reinterpret_cast<const uint2 *>(r1), b1 = *reinterpret_cast<const uint2 *>(r1 + 8),
+              b2 = *reinterpret_cast<const uint2 *>(r1 + 16);
+        u32 sa[6] = {a0.x, a0.y, a1.x, a1.y, a2.x, a2.y}, sb[6] = {b0.x, b0.y, b1.x, b1.y, b2.x, b2.y};
+        u8 out[12];
+#pragma unroll
+        for (int p = 0; p < 4; p++)
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+                int i0 = 6 * p + c, i1 = i0 + 3;
+                u32 s = ((sa[i0 >> 2] >> (8 * (i0 & 3))) & 255u) + ((sa[i1 >> 2] >> (8 * (i1 & 3))) & 255u) +
+                        ((sb[i0 >> 2] >> (8 * (i0 & 3))) & 255u) + ((sb[i1 >> 2] >> (8 * (i1 & 3))) & 255u);
+                out[3 * p + c] = (u8)((s + 2u) >> 2);
+            }
+        u32 w0 = out[0] | (out[1] << 8) | (out[2] << 16) | ((u32)out[3] << 24);
+        u32 w1 = out[4] | (out[5] << 8) | (out[6] << 16) | ((u32)out[7] << 24);
+        u32 w2 = out[8] | (out[9] << 8) | (out[10] << 16) | ((u32)out[11] << 24);
+        u32 *po = reinterpret_cast<u32 *>(o);
+        po[0] = w0; po[1] = w1; po[2] = w2;
+    } else {
+        for (int p = 0; x + p < dw; p++)
+            for (int c = 0; c < 3; c++)
+                o[3 * p + c] = (u8)((r0[6 * p + c] + r0[6 * p + c + 3] + r1[6 * p + c] + r1[6 * p + c + 3] + 2) >> 2);
+    }
+}
+
+bool fast_resize_2x_ok(const u8 *src, int sw, size_t spitch, const u8 *dst, int dw, size_t dpitch)
+{
+    (void)sw; (void)dw;
+    return ((uintptr_t)src % 8 == 0) && (spitch % 8 == 0) && ((uintptr_t)dst % 4 == 0) && (dpitch % 4 == 0);
+}
+
+cudaError_t fast_resize_2x(const u8 *src, size_t spitch, u8 *dst, int dh, int dw, size_t dpitch, cudaStream_t st)
+{
+    dim3 b(64, 4), g(((dw + 3) / 4 + 63) / 64, (dh + 3) / 4);
+    fk_resize_2x<<<g, b, 0, st>>>(src, spitch, dst, dh, dw, dpitch);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// stage 02: colour assignment -> labels and/or one-hot bit-planes
+// A warp owns 256 consecutive pixels of a row (lane l: pixels l, l+32, .., l+224); per plane the 8
+// ballots of those pixel groups ARE the 8 bit-plane words, stored as one 32-byte segment per plane.
+// ------------------------------------------------------------------------------------------------
+template <int MODE_LAB>
+__global__ void __launch_bounds__(256) fk_assign_bits(const u8 *__restrict__ px, int h, int w, size_t pitch,
+                                                      const __grid_constant__ AssignParams P, u8 *__restrict__ labels, size_t lpitch,
+                                                      u32 *__restrict__ bits, int ws, size_t plane)
+{
+    __shared__ u16 s_gam[256];
+    __shared__ u16 s_cbrt[2048];
+    __shared__ u8 s_lut[OMNI_MAX_K];
+    if (MODE_LAB) {
+        for (int i = threadIdx.x; i < 2048; i += 256) {
+            s_cbrt[i] = f_lab_tab[256 + i];
+            if (i < 256) s_gam[i] = f_lab_tab[i];
+        }
+    }
+    if (threadIdx.x < OMNI_MAX_K) s_lut[threadIdx.x] = P.lut[threadIdx.x];
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int chunks = (w + 255) >> 8, K = P.K;
+    const long long total = (long long)h * chunks;
+    for (long long u = (long long)blockIdx.x * 8 + warp; u < total; u += (long long)gridDim.x * 8) {
+        const int y = (int)(u / chunks), c = (int)(u - (long long)y * chunks);
+        const int x0 = c * 256 + lane;
+        const u8 *row = px + (size_t)y * pitch;
+        int lab[8];
+#pragma unroll
+        for (int g = 0; g < 8; g++) {
+            const int x = x0 + 32 * g;
+            lab[g] = 255;
+            if (x < w) {
+                const u8 *p = row + 3 * (size_t)x;
+                int v0 = p[0], v1 = p[1], v2 = p[2], best = 0;
+                if (MODE_LAB) {
+                    int L, a, b;
+                    bgr2lab_px(s_gam, s_cbrt, v0, v1, v2, L, a, b);
+                    float f0 = (float)L, f1 = (float)a, f2 = (float)b, bd = 0.f;
+                    for (int k = 0; k < K; k++) {
+                        float d0 = __fsub_rn(f0, P.c[3 * k]), d1 = __fsub_rn(f1, P.c[3 * k + 1]), d2 = __fsub_rn(f2, P.c[3 * k + 2]);
+                        float d = __fadd_rn(__fadd_rn(__fmul_rn(d0, d0), __fmul_rn(d1, d1)), __fmul_rn(d2, d2));
+                        if (k == 0 || d < bd) { bd = d; best = k; }
+                    }
+                } else {
+                    int bd = 0;
+                    for (int k = 0; k < K; k++) {
+                        int d0 = v0 - P.pal[3 * k], d1 = v1 - P.pal[3 * k + 1], d2 = v2 - P.pal[3 * k + 2];
+                        int d = (int)(short)(d0 * d0) + (int)(short)(d1 * d1) + (int)(short)(d2 * d2);
+                        if (k == 0 || d < bd) { bd = d; best = k; }
+                    }
+                }
+                lab[g] = s_lut[best];
+            }
+        }
+        if (labels) {
+            u8 *lrow = labels + (size_t)y * lpitch;
+#pragma unroll
+            for (int g = 0; g < 8; g++)
+                if (x0 + 32 * g < w) lrow[x0 + 32 * g] = (u8)lab[g];
+        }
+        if (bits) {
+            u32 mine = 0;
+            for (int k = 0; k < K; k++) {
+#pragma unroll
+                for (int g = 0; g < 8; g++) {
+                    u32 b = __ballot_sync(0xffffffffu, lab[g] == k);
+                    if (lane == ((k & 3) * 8 + g)) mine = b;
+                }
+                if ((k & 3) == 3 || k == K - 1) {
+                    int kk = (k & ~3) + (lane >> 3), wx = c * 8 + (lane & 7);
+                    if (kk <= k && wx < ws) bits[(size_t)kk * plane + (size_t)y * ws + wx] = mine;
+                    mine = 0;
+                }
+            }
+        }
+    }
+}
+
+// labels u8 -> one-hot bit-planes (omni_layer_masks entry)
+__global__ void __launch_bounds__(256) fk_labels_to_bits(const u8 *__restrict__ labels, int h, int w, size_t lpitch, int K,
+                                                         u32 *__restrict__ bits, int ws, size_t plane)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int chunks = (w + 255) >> 8;
+    const long long total = (long long)h * chunks;
+    for (long long u = (long long)blockIdx.x * 8 + warp; u < total; u += (long long)gridDim.x * 8) {
+        const int y = (int)(u / chunks), c = (int)(u - (long long)y * chunks);
+        const int x0 = c * 256 + lane;
+        const u8 *row = labels + (size_t)y * lpitch;
+        int lab[8];
+#pragma unroll
+        for (int g = 0; g < 8; g++) lab[g] = (x0 + 32 * g < w) ? row[x0 + 32 * g] : 255;
+        u32 mine = 0;
+        for (int k = 0; k < K; k++) {
+#pragma unroll
+            for (int g = 0; g < 8; g++) {
+                u32 b = __ballot_sync(0xffffffffu, lab[g] == k);
+                if (lane == ((k & 3) * 8 + g)) mine = b;
+            }
+            if ((k & 3) == 3 || k == K - 1) {
+                int kk = (k & ~3) + (lane >> 3), wx = c * 8 + (lane & 7);
+                if (kk <= k && wx < ws) bits[(size_t)kk * plane + (size_t)y * ws + wx] = mine;
+                mine = 0;
+            }
+        }
+    }
+}
+
+// mask bytes -> bit-planes; *d_bad set when a byte is neither 0 nor 255 (caller falls back to generic)
+__global__ void __launch_bounds__(256) fk_bytes_to_bits(const u8 *__restrict__ planes, size_t pstride, size_t pitch, int h, int w,
+                                                        u32 *__restrict__ bits, int ws, size_t plane, int *d_bad)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int k = blockIdx.y;
+    const long long total = (long long)h * ws;
+    int bad = 0;
+    for (long long u = (long long)blockIdx.x * 8 + warp; u < total; u += (long long)gridDim.x * 8) {
+        const int y = (int)(u / ws), c = (int)(u - (long long)y * ws);
+        const int x = c * 32 + lane;
+        int v = (x < w) ? planes[(size_t)k * pstride + (size_t)y * pitch + x] : 0;
+        bad |= (v != 0 && v != 255);
+        u32 b = __ballot_sync(0xffffffffu, v != 0);
+        if (lane == 0) bits[(size_t)k * plane + (size_t)y * ws + c] = b;
+    }
+    if (__any_sync(0xffffffffu, bad) && lane == 0) atomicOr(d_bad, 1);
+}
+
+// bit-planes -> 0/255 byte planes
+__global__ void __launch_bounds__(256) fk_expand_bits(const u32 *__restrict__ bits, int ws, size_t plane, int h, int w,
+                                                      u8 *__restrict__ out, size_t ostride, size_t opitch, int aligned16)
+{
+    const int k = blockIdx.y, ww = (w + 31) >> 5;
+    const long long total = (long long)h * ww;
+    for (long long u = (long long)blockIdx.x * blockDim.x + threadIdx.x; u < total; u += (long long)gridDim.x * blockDim.x) {
+        const int y = (int)(u / ww), c = (int)(u - (long long)y * ww);
+        u32 word = bits[(size_t)k * plane + (size_t)y * ws + c];
+        store_word_bytes(out + (size_t)k * ostride + (size_t)y * opitch, c * 32, w, word, aligned16 != 0);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// binary morphology on bit-planes (02:151-154 RECT-3, 03:23-30 ELLIPSE-3 = cross); SURVEY A.0
+//
+// One thread owns one word column and streams down a strip of rows.  It works on a 64-bit WINDOW = its
+// 32 pixels + 16 halo pixels on each side (built from the neighbouring words), so every erode/dilate step
+// of the chain needs no communication: a step only invalidates one more halo bit per side.  All steps of
+// the chain are software-pipelined down the rows (step s lags the input by s rows), state in registers.
+// Pixels outside the image are "ignored" by OpenCV: erode sees 1s, dilate sees 0s -- applied per step.
+// ------------------------------------------------------------------------------------------------
+enum { ST_NONE = 0, ST_ER = 1, ST_DR = 2, ST_EC = 3, ST_DC = 4 };   // erode/dilate x RECT/CROSS
+
+struct W64 { u32 lo, hi; };
+__device__ __forceinline__ W64 w_shl(W64 a) { W64 r; r.lo = a.lo << 1; r.hi = __funnelshift_l(a.lo, a.hi, 1); return r; }
+__device__ __forceinline__ W64 w_shr(W64 a) { W64 r; r.lo = __funnelshift_r(a.lo, a.hi, 1); r.hi = a.hi >> 1; return r; }
+__device__ __forceinline__ W64 w_and3(W64 a, W64 b, W64 c) { W64 r; r.lo = a.lo & b.lo & c.lo; r.hi = a.hi & b.hi & c.hi; return r; }
+__device__ __forceinline__ W64 w_or3(W64 a, W64 b, W64 c) { W64 r; r.lo = a.lo | b.lo | c.lo; r.hi = a.hi | b.hi | c.hi; return r; }
+
+template <int OP>
+__device__ __forceinline__ W64 morph_step(W64 u, W64 m, W64 d)
+{
+    if (OP == ST_ER) { W64 v = w_and3(u, m, d); return w_and3(v, w_shl(v), w_shr(v)); }
+    if (OP == ST_DR) { W64 v = w_or3(u, m, d); return w_or3(v, w_shl(v), w_shr(v)); }
+    if (OP == ST_EC) { W64 v = w_and3(m, w_shl(m), w_shr(m)); return w_and3(v, u, d); }
+    if (OP == ST_DC) { W64 v = w_or3(m, w_shl(m), w_shr(m)); return w_or3(v, u, d); }
+    return m;
+}
+
+__host__ __device__ constexpr int code_op(u32 code, int i) { return (int)((code >> (4 * i)) & 15u); }
+__host__ __device__ constexpr int code_len(u32 code) { int n = 0; while (n < 8 && code_op(code, n) != ST_NONE) n++; return n; }
+__host__ __device__ constexpr bool op_is_erode(int op) { return op == ST_ER || op == ST_EC; }
+
+#define MORPH_TR 64          // rows per strip
+
+// Output-of-range fix-up for a value that the step with opcode `next` will consume: columns outside the
+// image and rows outside the image must read as that step's identity element.
+template <int NEXT>
+__device__ __forceinline__ W64 oob_fix(W64 v, W64 colvalid, bool row_inside)
+{
+    if (NEXT == ST_NONE) { v.lo &= colvalid.lo; v.hi &= colvalid.hi; return v; }
+    if (op_is_erode(NEXT)) {
+        if (!row_inside) { v.lo = v.hi = 0xffffffffu; return v; }
+        v.lo |= ~colvalid.lo; v.hi |= ~colvalid.hi;
+    } else {
+        if (!row_inside) { v.lo = v.hi = 0u; return v; }
+        v.lo &= colvalid.lo; v.hi &= colvalid.hi;
+    }
+    return v;
+}
+
+template <u32 CODE, int S>
+struct MorphChain {
+    // applies steps S.. of CODE to `cur` (= image_S row `t - S`), updating the rolling rows
+    template <int TAP>
+    static __device__ __forceinline__ void run(W64 cur, W64 (&p1)[8], W64 (&p2)[8], int t, int h, W64 colvalid, W64 &tap_out, W64 &fin)
+    {
+        constexpr int N = code_len(CODE);
+        if (S == TAP) tap_out = cur;
+        if constexpr (S < N) {
+            constexpr int OP = code_op(CODE, S);
+            constexpr int NEXT = (S + 1 < N) ? code_op(CODE, S + 1) : ST_NONE;
+            W64 out = morph_step<OP>(p2[S], p1[S], cur);
+            p2[S] = p1[S]; p1[S] = cur;
+            const int r = t - S - 1;                       // row of image_{S+1} just produced
+            out = oob_fix<NEXT>(out, colvalid, r >= 0 && r < h);
+            MorphChain<CODE, S + 1>::template run<TAP>(out, p1, p2, t, h, colvalid, tap_out, fin);
+        } else {
+            fin = cur;
+        }
+    }
+};
+
+// CODE: up to 8 steps, 4 bits each.  TAP: after this many steps the image is the stage-02 mask; it is
+// written as BYTES to `masks` (TAP = -1: nothing).  The final image is written as bits to `out_bits`
+// (may be NULL).
+template <u32 CODE, int TAP>
+__global__ void __launch_bounds__(128) fk_morph(const u32 *__restrict__ in_bits, u32 *__restrict__ out_bits, int ws, size_t plane, int h,
+                                                int w, u8 *__restrict__ masks, size_t mstride, size_t mpitch, int aligned16)
+{
+    constexpr int N = code_len(CODE);
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int ww = (w + 31) >> 5;
+    if (c >= ww) return;
+    const int k = blockIdx.z;
+    const int y0 = blockIdx.y * MORPH_TR, y1 = min(h, y0 + MORPH_TR);
+    const u32 *src = in_bits + (size_t)k * plane;
+    W64 colvalid;
+    colvalid.lo = range_mask(32 * c - 16, w);
+    colvalid.hi = range_mask(32 * c + 16, w);
+    constexpr int OP0 = N > 0 ? code_op(CODE, 0) : ST_NONE;
+    W64 p1[8], p2[8];
+#pragma unroll
+    for (int s = 0; s < 8; s++) { p1[s].lo = p1[s].hi = p2[s].lo = p2[s].hi = 0u; }
+    for (int t = y0 - N; t < y1 + N; t++) {
+        W64 cur;
+        const bool inside = t >= 0 && t < h;
+        if (inside) {
+            const u32 *row = src + (size_t)t * ws;
+            u32 left = c > 0 ? __ldg(row + c - 1) : 0u, own = __ldg(row + c), right = c + 1 < ww ? __ldg(row + c + 1) : 0u;
+            cur.lo = (left >> 16) | (own << 16);
+            cur.hi = (own >> 16) | (right << 16);
+        } else {
+            cur.lo = cur.hi = 0u;
+        }
+        cur = oob_fix<OP0>(cur, colvalid, inside);
+        W64 tap, fin;
+        tap.lo = tap.hi = fin.lo = fin.hi = 0u;
+        MorphChain<CODE, 0>::template run<TAP>(cur, p1, p2, t, h, colvalid, tap, fin);
+        if (TAP >= 0) {
+            const int r = t - TAP;
+            if (r >= y0 && r < y1) {
+                u32 word = (tap.lo >> 16) | (tap.hi << 16);
+                store_word_bytes(masks + (size_t)k * mstride + (size_t)r * mpitch, 32 * c, w, word, aligned16 != 0);
+            }
+        }
+        if (out_bits) {
+            const int r = t - N;
+            if (r >= y0 && r < y1) {
+                u32 word = ((fin.lo >> 16) | (fin.hi << 16)) & range_mask(32 * c, w);
+                out_bits[(size_t)k * plane + (size_t)r * ws + c] = word;
+            }
+        }
+    }
+}
+
+constexpr u32 mk_code(int a, int b = 0, int c = 0, int d = 0, int e = 0, int f = 0, int g = 0, int hh = 0)
+{
+    return (u32)a | ((u32)b << 4) | ((u32)c << 8) | ((u32)d << 12) | ((u32)e << 16) | ((u32)f << 20) | ((u32)g << 24) | ((u32)hh << 28);
+}
+constexpr u32 CODE_R_OC = mk_code(ST_ER, ST_DR, ST_DR, ST_ER);                       // 02: RECT open, close
+constexpr u32 CODE_C_O = mk_code(ST_EC, ST_DC);                                     // 03: cross open
+constexpr u32 CODE_C_C = mk_code(ST_DC, ST_EC);                                     // 03: cross close
+constexpr u32 CODE_C_OC = mk_code(ST_EC, ST_DC, ST_DC, ST_EC);                      // 03: cross open, close
+constexpr u32 CODE_F_O = mk_code(ST_ER, ST_DR, ST_DR, ST_ER, ST_EC, ST_DC);
+constexpr u32 CODE_F_C = mk_code(ST_ER, ST_DR, ST_DR, ST_ER, ST_DC, ST_EC);
+constexpr u32 CODE_F_OC = mk_code(ST_ER, ST_DR, ST_DR, ST_ER, ST_EC, ST_DC, ST_DC, ST_EC);
+
+// morph03: 0 none, 1 open, 2 close, 3 open+close.  with02: prepend the RECT open/close and emit mask bytes.
+static cudaError_t launch_morph(bool with02, int morph03, const u32 *in_bits, u32 *out_bits, const BitGeom &g, int K, u8 *masks,
+                                size_t mstride, size_t mpitch, cudaStream_t st)
+{
+    dim3 b(128), grid((g.ww + 127) / 128, (g.h + MORPH_TR - 1) / MORPH_TR, K);
+    int al = masks && ((uintptr_t)masks % 16 == 0) && (mstride % 16 == 0) && (mpitch % 16 == 0);
+#define LM(CODE, TAP) fk_morph<CODE, TAP><<<grid, b, 0, st>>>(in_bits, out_bits, g.ws, g.plane, g.h, g.w, masks, mstride, mpitch, al)
+    if (with02) {
+        switch (morph03) {
+        case 0: LM(CODE_R_OC, 4); break;
+        case 1: LM(CODE_F_O, 4); break;
+        case 2: LM(CODE_F_C, 4); break;
+        default: LM(CODE_F_OC, 4); break;
+        }
+    } else {
+        switch (morph03) {
+        case 1: LM(CODE_C_O, -1); break;
+        case 2: LM(CODE_C_C, -1); break;
+        case 3: LM(CODE_C_OC, -1); break;
+        default: return cudaErrorInvalidValue;
+        }
+    }
+#undef LM
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// stage 03 on a bit-plane, edge_kernel_size 3:  GaussianBlur(3x3, sigma 0) -> Canny up to the NMS
+// (03:33-34).  On a {0,255} mask the blur is B = (255*S + 32768) >> 16 with
+// S = 4096 * v, v = sum of (1,2,1)x(1,2,1)-weighted BITS in [0,16]  =>  B = 16 v - (v > 8).
+// Borders: blur REFLECT_101 (on the bits), Sobel REPLICATE (on B), magnitude 0 outside the image.
+// Output: bit-planes S (candidate with m > high) and C (candidate: m > low and a directional maximum).
+// ------------------------------------------------------------------------------------------------
+#define E3_TR 16
+#define E3_TWW 8                      // words per tile row = 256 pixels
+#define E3_TW (E3_TWW * 32)
+
+__device__ __forceinline__ int reflect101_dev(int p, int len)
+{
+    if (len == 1) return 0;
+    while (p < 0 || p >= len) p = p < 0 ? -p : 2 * (len - 1) - p;
+    return p;
+}
+
+__global__ void __launch_bounds__(256) fk_edges3(const u32 *__restrict__ m2, int ws, size_t plane, int h, int w, int low, int high,
+                                                 u32 *__restrict__ sbits, u32 *__restrict__ cbits)
+{
+    // bit tile: rows y0-3 .. y0+TR+2 (reflected at the image border), words c0-1 .. c0+TWW
+    __shared__ u32 s_bits[(E3_TR + 6) * (E3_TWW + 2) + 1];   // +1: the funnel shift reads one word ahead
+    __shared__ u8 s_B[(E3_TR + 4) * (E3_TW + 4)];          // B for rows y0-2.., pixels x0-2..
+    __shared__ short s_m[(E3_TR + 2) * (E3_TW + 2)];       // magnitude for rows y0-1.., pixels x0-1..
+    const int k = blockIdx.z, tid = threadIdx.x;
+    const int y0 = blockIdx.y * E3_TR, c0 = blockIdx.x * E3_TWW, x0 = c0 * 32;
+    const int ww = (w + 31) >> 5;
+    const u32 *src = m2 + (size_t)k * plane;
+    constexpr int BW = E3_TWW + 2;
+    for (int i = tid; i < (E3_TR + 6) * BW; i += 256) {
+        int ly = i / BW, lc = i - ly * BW;
+        int gy = y0 - 3 + ly, gc = c0 - 1 + lc;
+        u32 v = 0;
+        if (gy >= -1 && gy <= h && gc >= 0 && gc < ww) {
+            int ry = reflect101_dev(gy, h);
+            v = __ldg(src + (size_t)ry * ws + gc);
+            // REFLECT_101 in x: pixel w := pixel w-2 (or 0 when w == 1)
+            if (gc == (w >> 5) && (w & 31)) {
+                int sx = reflect101_dev(w, w);
+                u32 b = (__ldg(src + (size_t)ry * ws + (sx >> 5)) >> (sx & 31)) & 1u;
+                v |= b << (w & 31);
+            }
+        } else if (gy >= -1 && gy <= h && gc == ww && (w & 31) == 0) {
+            // pixel w is bit 0 of the word after the last one
+            int ry = reflect101_dev(gy, h), sx = reflect101_dev(w, w);
+            v = (__ldg(src + (size_t)ry * ws + (sx >> 5)) >> (sx & 31)) & 1u;
+        }
+        if (gy >= -1 && gy <= h && gc == -1) {
+            // pixel -1 := pixel 1 (or 0 when w == 1): bit 31 of the word left of the image
+            int ry = reflect101_dev(gy, h), sx = reflect101_dev(-1, w);
+            v = ((__ldg(src + (size_t)ry * ws + (sx >> 5)) >> (sx & 31)) & 1u) << 31;
+        }
+        s_bits[i] = v;
+    }
+    __syncthreads();
+    // B tile
+    constexpr int SBW = E3_TW + 4;
+    for (int i = tid; i < (E3_TR + 4) * SBW; i += 256) {
+        int ly = i / SBW, lx = i - ly * SBW;
+        int gy = y0 - 2 + ly, gx = x0 - 2 + lx;
+        int cy = min(max(gy, 0), h - 1), cx = min(max(gx, 0), w - 1);      // Sobel BORDER_REPLICATE on the blurred image
+        // tile-relative position of pixel cx-1 in the bit rows (tile pixel 0 = x0 - 32)
+        int pos = cx - 1 - (x0 - 32);
+        int wd = pos >> 5, sh = pos & 31;
+        int v = 0;
+#pragma unroll
+        for (int dy = -1; dy <= 1; dy++) {
+            const u32 *br = s_bits + (cy + dy - (y0 - 3)) * BW;
+            u32 t3 = __funnelshift_r(br[wd], br[wd + 1], sh) & 7u;
+            int hsum = (0x43213210u >> (4 * t3)) & 15u;               // b0 + 2 b1 + b2
+            v += dy == 0 ? 2 * hsum : hsum;
+        }
+        s_B[i] = (u8)(16 * v - (v > 8 ? 1 : 0));
+    }
+    __syncthreads();
+    constexpr int MW = E3_TW + 2;
+    for (int i = tid; i < (E3_TR + 2) * MW; i += 256) {
+        int ly = i / MW, lx = i - ly * MW;
+        int gy = y0 - 1 + ly, gx = x0 - 1 + lx;
+        int m = 0;
+        if (gy >= 0 && gy < h && gx >= 0 && gx < w) {
+            const u8 *c = s_B + (ly + 1) * SBW + (lx + 1);
+            int dx = (c[-SBW + 1] + 2 * c[1] + c[SBW + 1]) - (c[-SBW - 1] + 2 * c[-1] + c[SBW - 1]);
+            int dy = (c[SBW - 1] + 2 * c[SBW] + c[SBW + 1]) - (c[-SBW - 1] + 2 * c[-SBW] + c[-SBW + 1]);
+            m = abs(dx) + abs(dy);
+        }
+        s_m[i] = (short)m;
+    }
+    __syncthreads();
+    for (int i = tid; i < E3_TR * E3_TW; i += 256) {
+        int ly = i / E3_TW, lx = i - ly * E3_TW;
+        int gy = y0 + ly, gx = x0 + lx;
+        int state = 0;
+        if (gy < h && gx < w) {
+            int mi = (ly + 1) * MW + (lx + 1);
+            int m = s_m[mi];
+            if (m > low) {
+                const u8 *c = s_B + (ly + 2) * SBW + (lx + 2);
+                int xs = (c[-SBW + 1] + 2 * c[1] + c[SBW + 1]) - (c[-SBW - 1] + 2 * c[-1] + c[SBW - 1]);
+                int ys = (c[SBW - 1] + 2 * c[SBW] + c[SBW + 1]) - (c[-SBW - 1] + 2 * c[-SBW] + c[-SBW + 1]);
+                int ax = abs(xs), ay = abs(ys) << 15, tg22 = ax * 13573;
+                bool ok;
+                if (ay < tg22) ok = m > s_m[mi - 1] && m >= s_m[mi + 1];
+                else {
+                    int tg67 = tg22 + (ax << 16);
+                    if (ay > tg67) ok = m > s_m[mi - MW] && m >= s_m[mi + MW];
+                    else { int sg = (xs ^ ys) < 0 ? -1 : 1; ok = m > s_m[mi - MW - sg] && m > s_m[mi + MW + sg]; }
+                }
+                if (ok) state = m > high ? 2 : 1;
+            }
+        }
+        u32 cb = __ballot_sync(0xffffffffu, state != 0), sb = __ballot_sync(0xffffffffu, state == 2);
+        if ((tid & 31) == 0 && gy < h && (gx >> 5) < ww) {
+            size_t o = (size_t)k * plane + (size_t)gy * ws + (gx >> 5);
+            cbits[o] = cb; sbits[o] = sb;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// hysteresis on bit-planes (cv2.Canny's final stage): E = S, then E |= C & dilate8(E) until
+// nothing changes anywhere, then E is written out as 0/255 bytes.  Cooperative persistent kernel: every
+// CTA iterates its tiles to a LOCAL fixed point in shared memory, a grid-wide barrier separates global
+// rounds, and the loop ends after the first round in which no tile changed.  The result set does not
+// depend on the propagation order.
+// ------------------------------------------------------------------------------------------------
+#define HB_TR 32                      // tile rows
+#define HB_TW 32                      // tile words (1024 pixels)
+
+__global__ void __launch_bounds__(256) fk_hysteresis(u32 *__restrict__ ebits, const u32 *__restrict__ cbits, int ws, size_t plane, int h,
+                                                     int w, int K, int *flags /* [0]=rounds, [1..2]=changed ping-pong */,
+                                                     u8 *__restrict__ edges, size_t estride, size_t epitch, int aligned16)
+{
+    cg::grid_group grid = cg::this_grid();
+    __shared__ u32 s_e[(HB_TR + 2) * (HB_TW + 2)];
+    __shared__ u32 s_c[HB_TR * HB_TW];
+    const int ww = (w + 31) >> 5;
+    const int tx_n = (ww + HB_TW - 1) / HB_TW, ty_n = (h + HB_TR - 1) / HB_TR;
+    const int tiles = tx_n * ty_n * K;
+    const int tid = threadIdx.x;
+    constexpr int SW = HB_TW + 2;
+    int round = 0;
+    for (;;) {
+        // flags[1 + round % 3] is this round's "some tile changed" flag (three flags rotate so that the flag of
+        // round r+2 can be cleared right after round r's barrier, when nobody can be setting or reading it)
+        volatile int *chg = flags + 1 + (round % 3);
+        for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
+            const int k = t / (tx_n * ty_n), r = t - k * (tx_n * ty_n);
+            const int ty = r / tx_n, tx = r - ty * tx_n;
+            const int y0 = ty * HB_TR, c0 = tx * HB_TW;
+            u32 *E = ebits + (size_t)k * plane;
+            const u32 *C = cbits + (size_t)k * plane;
+            // load C and E (interior) and test whether anything is still promotable in this tile
+            int pending = 0;
+            for (int i = tid; i < HB_TR * HB_TW; i += 256) {
+                int ly = i / HB_TW, lc = i - ly * HB_TW;
+                int gy = y0 + ly, gc = c0 + lc;
+                u32 cv = 0, ev = 0;
+                if (gy < h && gc < ww) { cv = __ldg(C + (size_t)gy * ws + gc); ev = __ldcg(E + (size_t)gy * ws + gc); }
+                s_c[i] = cv;
+                s_e[(ly + 1) * SW + lc + 1] = ev;
+                pending |= (cv & ~ev) != 0;
+            }
+            if (!__syncthreads_or(pending)) continue;
+            // halo ring of E (other CTAs may be raising bits there concurrently: any snapshot is valid, bits only rise)
+            for (int i = tid; i < 2 * SW + 2 * HB_TR; i += 256) {
+                int ly, lc;
+                if (i < SW) { ly = 0; lc = i; }
+                else if (i < 2 * SW) { ly = HB_TR + 1; lc = i - SW; }
+                else { int j = i - 2 * SW; ly = 1 + (j >> 1); lc = (j & 1) ? HB_TW + 1 : 0; }
+                int gy = y0 - 1 + ly, gc = c0 - 1 + lc;
+                s_e[ly * SW + lc] = (gy >= 0 && gy < h && gc >= 0 && gc < ww) ? __ldcg(E + (size_t)gy * ws + gc) : 0u;
+            }
+            __syncthreads();
+            int any = 0;
+            for (;;) {
+                int changed = 0;
+                for (int i = tid; i < HB_TR * HB_TW; i += 256) {
+                    int ly = i / HB_TW, lc = i - ly * HB_TW;
+                    u32 cv = s_c[i];
+                    int o = (ly + 1) * SW + lc + 1;
+                    u32 ev = s_e[o];
+                    if (cv & ~ev) {
+                        u32 d = 0;
+#pragma unroll
+                        for (int dy = -1; dy <= 1; dy++) {
+                            u32 l = s_e[o + dy * SW - 1], m = s_e[o + dy * SW], rr = s_e[o + dy * SW + 1];
+                            d |= m | (m << 1) | (m >> 1) | (l >> 31) | (rr << 31);
+                        }
+                        u32 nv = ev | (cv & d);
+                        if (nv != ev) { s_e[o] = nv; changed = 1; }
+                    }
+                }
+                if (!__syncthreads_or(changed)) break;
+                any = 1;
+            }
+            if (any) {
+                for (int i = tid; i < HB_TR * HB_TW; i += 256) {
+                    int ly = i / HB_TW, lc = i - ly * HB_TW;
+                    int gy = y0 + ly, gc = c0 + lc;
+                    if (gy < h && gc < ww) E[(size_t)gy * ws + gc] = s_e[(ly + 1) * SW + lc + 1];
+                }
+                if (tid == 0) *chg = 1;
+            }
+            __syncthreads();
+        }
+        __threadfence();
+        grid.sync();
+        const int c = *chg;
+        if (blockIdx.x == 0 && tid == 0) { flags[0] = round + 1; flags[1 + ((round + 2) % 3)] = 0; }
+        round++;
+        if (!c) break;
+    }
+    // E -> bytes
+    if (edges) {
+        const long long total = (long long)K * h * ww;
+        for (long long u = (long long)blockIdx.x * blockDim.x + tid; u < total; u += (long long)gridDim.x * blockDim.x) {
+            int k = (int)(u / ((long long)h * ww));
+            long long r = u - (long long)k * h * ww;
+            int y = (int)(r / ww), c = (int)(r - (long long)y * ww);
+            u32 word = __ldcg(ebits + (size_t)k * plane + (size_t)y * ws + c);
+            store_word_bytes(edges + (size_t)k * estride + (size_t)y * epitch, c * 32, w, word, aligned16 != 0);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host-side drivers
+// ------------------------------------------------------------------------------------------------
+static int persist_blocks(omni_ctx *ctx, int per_sm) { return (ctx->sm_count > 0 ? ctx->sm_count : 148) * per_sm; }
+
+static int bit_planes(omni_ctx *ctx, const BitGeom &g, int K, int n, u32 **out /* n pointers */)
+{
+    size_t one = g.plane * (size_t)K * sizeof(u32);
+    one = (one + 255) & ~(size_t)255;
+    FK_TRY(omni_ws_reserve(ctx, 4, one * n));
+    for (int i = 0; i < n; i++) out[i] = (u32 *)((u8 *)ctx->ws[4] + one * i);
+    return OMNI_OK;
+}
+
+cudaError_t fast_assign(omni_ctx *ctx, const u8 *px, int h, int w, size_t pitch, const AssignParams &P, int mode_lab,
                         u8 *labels, size_t lpitch, cudaStream_t st)
 {
-    return g_assign(px, h, w, pitch, P, mode_lab, labels, lpitch, st);
+    cudaError_t e = fast_tables();
+    if (e != cudaSuccess) return e;
+    int grid = persist_blocks(ctx, 6);
+    if (mode_lab) fk_assign_bits<1><<<grid, 256, 0, st>>>(px, h, w, pitch, P, labels, lpitch, nullptr, 0, 0);
+    else fk_assign_bits<0><<<grid, 256, 0, st>>>(px, h, w, pitch, P, labels, lpitch, nullptr, 0, 0);
+    return cudaGetLastError();
 }
-bool fast_masks_supported(int, int) { return false; }
-int fast_layer_masks(omni_ctx *, const u8 *, int, int, size_t, int, int, int, u8 *, size_t, size_t, cudaStream_t) { return OMNI_ERR_UNSUPPORTED; }
-bool fast_edges_supported(const omni_edge_params *) { return false; }
-int fast_edges(omni_ctx *, const u8 *, int, int, int, size_t, size_t, const omni_edge_params *, const BlurParams &, int, int,
-               u8 *, size_t, size_t, cudaStream_t) { return OMNI_ERR_UNSUPPORTED; }
-int fast_color_edge(omni_ctx *, const u8 *, int, int, size_t, const AssignParams &, const omni_edge_params *, const BlurParams &,
-                    int, int, u8 *, size_t, u8 *, size_t, size_t, u8 *, size_t, size_t, cudaStream_t) { return OMNI_ERR_UNSUPPORTED; }
+
+bool fast_masks_supported(int open_iters, int close_iters)
+{
+    return (open_iters == 1 && close_iters == 1) || (open_iters <= 0 && close_iters <= 0);
+}
+
+int fast_layer_masks(omni_ctx *ctx, const u8 *d_labels, int h, int w, size_t lpitch, int K, int open_iters, int close_iters,
+                     u8 *d_masks, size_t plane_stride, size_t mpitch, cudaStream_t st)
+{
+    BitGeom g = make_geom(h, w);
+    u32 *bp[1];
+    FK_TRY(bit_planes(ctx, g, K, 1, bp));
+    {
+        KScope ks(ctx, "labels_to_bits", st);
+        fk_labels_to_bits<<<persist_blocks(ctx, 8), 256, 0, st>>>(d_labels, h, w, lpitch, K, bp[0], g.ws, g.plane);
+        OMNI_CUDA(cudaGetLastError());
+    }
+    int al = ((uintptr_t)d_masks % 16 == 0) && (plane_stride % 16 == 0) && (mpitch % 16 == 0);
+    if (open_iters == 1 && close_iters == 1) {
+        OMNI_LAUNCH(ctx, st, "morph_bits", launch_morph(true, 0, bp[0], nullptr, g, K, d_masks, plane_stride, mpitch, st));
+    } else {
+        KScope ks(ctx, "expand_bits", st);
+        fk_expand_bits<<<dim3(persist_blocks(ctx, 4), K), 256, 0, st>>>(bp[0], g.ws, g.plane, h, w, d_masks, plane_stride, mpitch, al);
+        OMNI_CUDA(cudaGetLastError());
+    }
+    return OMNI_OK;
+}
+
+// which stage-03 morphology the parameters ask for: 0 none, 1 open, 2 close, 3 both; -1 = not on the fast path
+static int morph03_kind(const omni_edge_params *p)
+{
+    int oi = p->open_iters > 0 ? p->open_iters : 0, ci = p->close_iters > 0 ? p->close_iters : 0;
+    if (p->morph_k == 1) return 0;                    // 1x1 element: identity
+    if (p->morph_k != 3 || oi > 1 || ci > 1) return -1;
+    return oi | (ci << 1);
+}
+
+bool fast_edges_supported(const omni_edge_params *prm)
+{
+    return morph03_kind(prm) >= 0 && prm->ksize == 3;
+}
+
+static int run_hysteresis(omni_ctx *ctx, u32 *ebits, const u32 *cbits, const BitGeom &g, int K, u8 *d_edges, size_t e_plane,
+                          size_t epitch, cudaStream_t st)
+{
+    if (ctx->hyst_blocks == 0) {
+        int per_sm = 0;
+        OMNI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fk_hysteresis, 256, 0));
+        if (per_sm < 1) { omni_set_error("hysteresis kernel cannot be made resident"); return OMNI_ERR_CUDA; }
+        ctx->hyst_blocks = per_sm * (ctx->sm_count > 0 ? ctx->sm_count : 1);
+    }
+    OMNI_CUDA(cudaMemsetAsync(ctx->d_flags, 0, 4 * sizeof(int), st));
+    int ws = g.ws, h = g.h, w = g.w;
+    size_t plane = g.plane;
+    int *flags = ctx->d_flags;
+    int al = ((uintptr_t)d_edges % 16 == 0) && (e_plane % 16 == 0) && (epitch % 16 == 0);
+    void *args[] = {&ebits, &cbits, &ws, &plane, &h, &w, &K, &flags, &d_edges, &e_plane, &epitch, &al};
+    OMNI_LAUNCH(ctx, st, "hysteresis_bits", cudaLaunchCooperativeKernel((const void *)fk_hysteresis, dim3(ctx->hyst_blocks), dim3(256),
+                                                                        args, 0, st));
+    ctx->last_hyst_passes = -1;           // lives in d_flags[0]; fetched lazily by omni_last_hysteresis_passes
+    return OMNI_OK;
+}
+
+static int edges_from_bits(omni_ctx *ctx, const u32 *m2, u32 *sbits, u32 *cbits, const BitGeom &g, int K, int low, int high,
+                           u8 *d_edges, size_t e_plane, size_t epitch, cudaStream_t st)
+{
+    {
+        KScope ks(ctx, "edges3_bits", st);
+        dim3 grid((g.ww + E3_TWW - 1) / E3_TWW, (g.h + E3_TR - 1) / E3_TR, K);
+        fk_edges3<<<grid, 256, 0, st>>>(m2, g.ws, g.plane, g.h, g.w, low, high, sbits, cbits);
+        OMNI_CUDA(cudaGetLastError());
+    }
+    return run_hysteresis(ctx, sbits, cbits, g, K, d_edges, e_plane, epitch, st);
+}
+
+int fast_edges(omni_ctx *ctx, const u8 *d_masks, int K, int h, int w, size_t m_plane, size_t mpitch,
+               const omni_edge_params *prm, const BlurParams &bp, int low, int high,
+               u8 *d_edges, size_t e_plane, size_t epitch, cudaStream_t st)
+{
+    (void)bp;
+    if (low < 0) return OMNI_ERR_UNSUPPORTED;        // m == 0 would be a candidate: generic kernels handle it
+    BitGeom g = make_geom(h, w);
+    u32 *bpp[4];
+    FK_TRY(bit_planes(ctx, g, K, 4, bpp));
+    OMNI_CUDA(cudaMemsetAsync(ctx->d_flags + 8, 0, sizeof(int), st));
+    {
+        KScope ks(ctx, "bytes_to_bits", st);
+        fk_bytes_to_bits<<<dim3(persist_blocks(ctx, 2), K), 256, 0, st>>>(d_masks, m_plane, mpitch, h, w, bpp[0], g.ws, g.plane,
+                                                                         ctx->d_flags + 8);
+        OMNI_CUDA(cudaGetLastError());
+    }
+    OMNI_CUDA(cudaMemcpyAsync(ctx->h_flags + 8, ctx->d_flags + 8, sizeof(int), cudaMemcpyDeviceToHost, st));
+    OMNI_CUDA(cudaStreamSynchronize(st));
+    if (ctx->h_flags[8]) return OMNI_ERR_UNSUPPORTED;     // not a {0,255} mask
+    int kind = morph03_kind(prm);
+    const u32 *m2 = bpp[0];
+    if (kind > 0) {
+        OMNI_LAUNCH(ctx, st, "morph_bits", launch_morph(false, kind, bpp[0], bpp[1], g, K, nullptr, 0, 0, st));
+        m2 = bpp[1];
+    }
+    return edges_from_bits(ctx, m2, bpp[2], bpp[3], g, K, low, high, d_edges, e_plane, epitch, st);
+}
+
+int fast_color_edge(omni_ctx *ctx, const u8 *d_bgr, int h, int w, size_t pitch, const AssignParams &P,
+                    const omni_edge_params *prm, const BlurParams &bp, int low, int high,
+                    u8 *d_labels, size_t lpitch, u8 *d_masks, size_t m_plane, size_t mpitch,
+                    u8 *d_edges, size_t e_plane, size_t epitch, cudaStream_t st)
+{
+    (void)bp;
+    if (low < 0) return OMNI_ERR_UNSUPPORTED;
+    OMNI_CUDA(fast_tables());
+    BitGeom g = make_geom(h, w);
+    u32 *bpp[4];
+    FK_TRY(bit_planes(ctx, g, P.K, 4, bpp));
+    {
+        KScope ks(ctx, "assign_bits", st);
+        fk_assign_bits<1><<<persist_blocks(ctx, 6), 256, 0, st>>>(d_bgr, h, w, pitch, P, d_labels, lpitch, bpp[0], g.ws, g.plane);
+        OMNI_CUDA(cudaGetLastError());
+    }
+    int kind = morph03_kind(prm);
+    OMNI_LAUNCH(ctx, st, "morph_bits", launch_morph(true, kind, bpp[0], bpp[1], g, P.K, d_masks, m_plane, mpitch, st));
+    return edges_from_bits(ctx, bpp[1], bpp[2], bpp[3], g, P.K, low, high, d_edges, e_plane, epitch, st);
+}

@@ -112,19 +112,6 @@ cudaError_t g_resize_area(const u8 *src, int sh, int sw, size_t spitch, u8 *dst,
 // ------------------------------------------------------------------------------------------------
 // 02_color_extract.py:35 (BGR2LAB) + :53-55 (nearest centre, f32)  /  process_colors.py:69-77
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ int descale(int x, int n) { return (x + (1 << (n - 1))) >> n; }
-
-__device__ __forceinline__ void bgr2lab_px(const u16 *gam, const u16 *cbrt, int B8, int G8, int R8, int &L, int &a, int &b)
-{
-    int B = gam[B8], G = gam[G8], R = gam[R8];
-    int fX = cbrt[descale(R * 1777 + G * 1541 + B * 778, 12)];
-    int fY = cbrt[descale(R * 871 + G * 2929 + B * 296, 12)];
-    int fZ = cbrt[descale(R * 73 + G * 448 + B * 3575, 12)];
-    L = min(255, max(0, descale(296 * fY - 1336934, 15)));
-    a = min(255, max(0, descale(500 * (fX - fY) + 128 * 32768, 15)));
-    b = min(255, max(0, descale(200 * (fY - fZ) + 128 * 32768, 15)));
-}
-
 template <int MODE_LAB>
 __global__ void k_assign(const u8 *__restrict__ px, int h, int w, size_t pitch, const __grid_constant__ AssignParams P,
                          u8 *__restrict__ labels, size_t lpitch)

@@ -57,12 +57,13 @@ struct ResizeTab {
     ResizeTabDev dev{};
 };
 
+#define OMNI_WS_SLOTS 6
 struct omni_ctx {
     int device = 0;
     int fast = 1;
     // grow-only device scratch
-    void *ws[4] = {nullptr, nullptr, nullptr, nullptr};
-    size_t ws_bytes[4] = {0, 0, 0, 0};
+    void *ws[OMNI_WS_SLOTS] = {};          // 0-2 generic planes, 3 host staging, 4 bit-planes, 5 misc
+    size_t ws_bytes[OMNI_WS_SLOTS] = {};
     int *d_flags = nullptr;          // 64 ints of device flags / counters
     unsigned long long *d_counts = nullptr;   // 4*OMNI_MAX_K counters
     int *h_flags = nullptr;          // pinned mirror
@@ -76,6 +77,8 @@ struct omni_ctx {
     struct ProfRec { const char *name; cudaEvent_t a, b; };
     std::vector<ProfRec> prof;
     std::vector<cudaEvent_t> ev_pool;
+    int sm_count = 0;
+    int hyst_blocks = 0;             // co-resident CTAs of the cooperative hysteresis kernel (0 = not queried yet)
 };
 
 // Brackets one kernel launch: counts it and, when profiling is on, records a CUDA event pair on the
@@ -115,3 +118,19 @@ cudaError_t g_composite(const u8 *edges, size_t plane, size_t pitch, int K, int 
                         u8 *canvas, size_t cpitch, cudaStream_t st);
 cudaError_t g_copy2d_planes(const u8 *src, size_t s_plane, size_t spitch, u8 *dst, size_t d_plane, size_t dpitch,
                             int K, int h, int w, cudaStream_t st);
+
+#ifdef __CUDACC__
+// cv2.cvtColor(u8 BGR -> Lab) integer pipeline (02_color_extract.py:35); tables: gamma[256], cbrt[2041]
+__device__ __forceinline__ int descale(int x, int n) { return (x + (1 << (n - 1))) >> n; }
+
+__device__ __forceinline__ void bgr2lab_px(const u16 *gam, const u16 *cbrt, int B8, int G8, int R8, int &L, int &a, int &b)
+{
+    int B = gam[B8], G = gam[G8], R = gam[R8];
+    int fX = cbrt[descale(R * 1777 + G * 1541 + B * 778, 12)];
+    int fY = cbrt[descale(R * 871 + G * 2929 + B * 296, 12)];
+    int fZ = cbrt[descale(R * 73 + G * 448 + B * 3575, 12)];
+    L = min(255, max(0, descale(296 * fY - 1336934, 15)));
+    a = min(255, max(0, descale(500 * (fX - fY) + 128 * 32768, 15)));
+    b = min(255, max(0, descale(200 * (fY - fZ) + 128 * 32768, 15)));
+}
+#endif
