@@ -18,6 +18,7 @@
 #include "omni_tables.inc"
 
 #include <cooperative_groups.h>
+#include <stdlib.h>
 namespace cg = cooperative_groups;
 
 #define FK_TRY(expr) do { int rc__ = (expr); if (rc__ != OMNI_OK) return rc__; } while (0)
@@ -769,11 +770,14 @@ static int run_hysteresis(omni_ctx *ctx, u32 *ebits, const u32 *cbits, const Bit
 static int edges_from_bits(omni_ctx *ctx, const u32 *m2, u32 *sbits, u32 *cbits, const BitGeom &g, int K, int low, int high,
                            u8 *d_edges, size_t e_plane, size_t epitch, cudaStream_t st)
 {
-    {
-        KScope ks(ctx, "edges3_bits", st);
+    static const bool use_v1 = getenv("OMNI_EDGES3_V1") != nullptr;       // A/B switch: the simple per-pixel kernel
+    if (use_v1) {
+        KScope ks(ctx, "edges3_bits_v1", st);
         dim3 grid((g.ww + E3_TWW - 1) / E3_TWW, (g.h + E3_TR - 1) / E3_TR, K);
         fk_edges3<<<grid, 256, 0, st>>>(m2, g.ws, g.plane, g.h, g.w, low, high, sbits, cbits);
         OMNI_CUDA(cudaGetLastError());
+    } else {
+        OMNI_LAUNCH(ctx, st, "edges3_bits", launch_edges3_simd(m2, g.ws, g.plane, g.h, g.w, K, low, high, ctx->sm_count, sbits, cbits, st));
     }
     return run_hysteresis(ctx, sbits, cbits, g, K, d_edges, e_plane, epitch, st);
 }

@@ -23,3 +23,7 @@ int fast_color_edge(omni_ctx *ctx, const u8 *d_bgr, int h, int w, size_t pitch, 
                     const omni_edge_params *prm, const BlurParams &bp, int low, int high,
                     u8 *d_labels, size_t lpitch, u8 *d_masks, size_t m_plane, size_t mpitch,
                     u8 *d_edges, size_t e_plane, size_t epitch, cudaStream_t st);
+
+// edges3.cu: SIMD-in-register blur3 + Sobel + NMS on a bit-plane (strong / candidate bit-planes out)
+cudaError_t launch_edges3_simd(const u32 *m2, int ws, size_t plane, int h, int w, int K, int low, int high, int sm_count,
+                               u32 *sbits, u32 *cbits, cudaStream_t st);
