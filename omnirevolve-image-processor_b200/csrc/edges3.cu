@@ -11,7 +11,11 @@
 // Only the ~7 % of pixels with m > low go through the 32-bit direction test + neighbour compare; their
 // m / dx / dy come from a per-warp shared-memory row ring.
 //
-// Borders: blur REFLECT_101 (patched into the bit window), Sobel REPLICATE (patched into B), m = 0 outside.
+// Borders.  Blur uses REFLECT_101 on the mask, Sobel uses REPLICATE on the blurred image, m = 0 outside.  Both
+// are obtained by patching only the BITS that enter the pipeline: with bit(-1) := bit(1) (REFLECT_101) and
+// additionally bit(-2) := bit(0), the blur of position -1 is  b(-2) + 2 b(-1) + b(0) = 2 b(0) + 2 b(1)  = the
+// blur of position 0, i.e. B(-1) = B(0) (REPLICATE) falls out of the normal arithmetic; same at the far side
+// and for rows.
 #include "fast_kernels.cuh"
 
 #include <cuda_fp16.h>
@@ -23,8 +27,8 @@
 // build the rows); the compacted candidate list lets any lane process any lane's candidates.
 struct __align__(16) E3WarpSmem {
     u16 m[3][32 * E3V_LSTRIDE];           // ring of magnitude rows (fp16 bit patterns); lane region index i <-> window pixel e = i + 2
-    u16 dx[2][32 * E3V_LSTRIDE];          // dx, dy of the lane's own 32 pixels (fp16 bit patterns); region index = own pixel
-    u16 dy[2][32 * E3V_LSTRIDE];
+    u16 dx[2][1024];                      // dx, dy of the lanes' own pixels, two rows alternating (fp16 bit patterns):
+    u16 dy[2][1024];                      // index = 32 * lane + pixel
     u16 list[1024];                       // candidates of one row: (owner lane << 5) | pixel
     u32 cw[32], sw[32];                   // result words of the row being resolved
 };
@@ -68,11 +72,7 @@ __global__ void __launch_bounds__(E3V_WARPS * 32) fk_edges3_simd(const u32 *__re
     // the window needs bits up to e = 38 and B up to e = 37, so pixel w matters for eW in [5, 38]: besides the lane
     // that owns pixel w-1 this is the previous lane when w % 32 is 1 or 2
     const bool has_rb = eW >= 5 && eW <= 38;
-    const bool warp_rb = __any_sync(0xffffffffu, has_rb);
     const bool is_lb = c == 0;
-    // PRMT selector that copies byte (eW&3)-1 into byte (eW&3) of the B word holding pixel w (REPLICATE)
-    const u32 rb_sel = (eW & 3) == 0 ? 0x3217u : (eW & 3) == 1 ? 0x3200u : (eW & 3) == 2 ? 0x3110u : 0x2210u;
-    const int rb_q = eW >> 2;
     const int lowc = min(low, 2041), highc = min(high, 2041);
     const __half2 low_h = __floats2half2_rn((float)lowc, (float)lowc);
     const int high_bits = (int)__half_as_ushort(__float2half_rn((float)highc));
@@ -82,25 +82,37 @@ __global__ void __launch_bounds__(E3V_WARPS * 32) fk_edges3_simd(const u32 *__re
     // one pipeline step: consumes bit row t; (hB, hA) = horizontal sums of rows t-1, t-2, hC receives row t;
     // (UB, UA) = blurred rows t-2, t-3 as half2, UC receives row t-1.
     u32 cand_prev = 0u;
-    auto step = [&](const int t, u32 (&hA)[10], u32 (&hB)[10], u32 (&hC)[10], u32 (&UA)[20], u32 (&UB)[20], u32 (&UC)[20]) {
-        // ---- (1) bit row t (REFLECT_101 in y), 40-pixel window: index e <-> pixel 32c - 4 + e --------------------
-        u32 lo = 0u, hi = 0u;
-        if (t >= -1 && t <= h) {
-            int rt = t < 0 ? (h > 1 ? 1 : 0) : (t >= h ? (h > 1 ? h - 2 : 0) : t);
+    u32 pf_l = 0u, pf_o = 0u, pf_r = 0u;                 // words of the next bit row (software prefetch)
+    auto load_row = [&](const int t) {
+        // rows -1 and h mirror rows 1 and h-2 (REFLECT_101); rows -2 and h+1 repeat rows 0 and h-1 (see header)
+        int rt = -1;
+        if (t >= 0 && t < h) rt = t;
+        else if (t == -1) rt = min(1, h - 1);
+        else if (t == -2) rt = 0;
+        else if (t == h) rt = max(h - 2, 0);
+        else if (t == h + 1) rt = h - 1;
+        pf_l = pf_o = pf_r = 0u;
+        if (rt >= 0) {
             const u32 *row = src + (size_t)rt * ws;
-            u32 left = (c > 0 && c - 1 < ww) ? __ldg(row + c - 1) : 0u, own = active ? __ldg(row + c) : 0u,
-                right = (c + 1 < ww) ? __ldg(row + c + 1) : 0u;
-            lo = (left >> 28) | (own << 4);
-            hi = (own >> 28) | (right << 4);
-            if (is_lb) lo = (lo & ~8u) | (((w > 1 ? lo >> 2 : lo >> 1)) & 8u);              // pixel -1 := pixel 1
-            if (has_rb) {                                                                    // pixel w := pixel w-2
-                unsigned long long win = ((unsigned long long)hi << 32) | lo;
-                int se = w > 1 ? eW - 2 : eW - 1;
-                unsigned long long b = (win >> se) & 1ull;
-                win = (win & ~(1ull << eW)) | (b << eW);
-                lo = (u32)win; hi = (u32)(win >> 32);
-            }
+            if (c > 0 && c - 1 < ww) pf_l = __ldg(row + c - 1);
+            if (active) pf_o = __ldg(row + c);
+            if (c + 1 < ww) pf_r = __ldg(row + c + 1);
         }
+    };
+    auto step = [&](const int t, u32 (&hA)[10], u32 (&hB)[10], u32 (&hC)[10], u32 (&UA)[20], u32 (&UB)[20], u32 (&UC)[20]) {
+        // ---- (1) bit row t (prefetched one step ahead), 40-pixel window: index e <-> pixel 32c - 4 + e ---------------
+        u32 lo = (pf_l >> 28) | (pf_o << 4), hi = (pf_o >> 28) | (pf_r << 4);
+        if (is_lb) {                                   // pixels -1, -2 := pixels 1, 0
+            if (w > 1) lo = (lo & ~0xCu) | ((lo >> 2) & 0xCu);
+            else lo = (lo & ~0xCu) | ((lo >> 2) & 4u) | ((lo >> 1) & 8u);
+        }
+        if (has_rb) {                                  // pixels w, w+1 := pixels w-2, w-1
+            unsigned long long win = ((unsigned long long)hi << 32) | lo;
+            unsigned long long two = w > 1 ? (win >> (eW - 2)) & 3ull : ((win >> (eW - 1)) & 1ull) * 3ull;
+            win = (win & ~(3ull << eW)) | (two << eW);
+            lo = (u32)win; hi = (u32)(win >> 32);
+        }
+        load_row(t + 1);
         // ---- (2) horizontal (1,2,1) sums via the 6-bit LUT ---------------------------------------------------------
         hC[0] = s_lut6[(lo << 1) & 63u];
 #pragma unroll
@@ -117,12 +129,6 @@ __global__ void __launch_bounds__(E3V_WARPS * 32) fk_edges3_simd(const u32 *__re
                 u32 cc = ((v + 0x07070707u) >> 4) & 0x01010101u;          // v > 8
                 B[q] = v * 16u - cc;
             }
-            if (is_lb) B[0] = __byte_perm(B[0], B[1], 0x4210);           // B(-1) := B(0)
-            if (warp_rb) {
-#pragma unroll
-                for (int q = 1; q < 10; q++)
-                    if (has_rb && q == rb_q) B[q] = __byte_perm(B[q], B[q - 1], rb_sel);
-            }
 #pragma unroll
             for (int q = 0; q < 10; q++) {                                 // 0x6400 | b is the half 1024 + b
                 UC[2 * q] = as_u32(__hsub2(as_h2(__byte_perm(B[q], 0x64646464u, 0x4140)), k1024));
@@ -136,14 +142,6 @@ __global__ void __launch_bounds__(E3V_WARPS * 32) fk_edges3_simd(const u32 *__re
             const int slot = (r + 3) % 3;
             u16 *mreg = S.m[slot] + lreg;
             if (r >= 0 && r < h) {
-                if (r == 0) {                                              // Sobel BORDER_REPLICATE in y
-#pragma unroll
-                    for (int j = 0; j < 20; j++) UA[j] = UB[j];
-                }
-                if (r == h - 1) {
-#pragma unroll
-                    for (int j = 0; j < 20; j++) UC[j] = UB[j];
-                }
                 u32 V[20], D[20];
 #pragma unroll
                 for (int j = 0; j < 20; j++) {
@@ -175,7 +173,7 @@ __global__ void __launch_bounds__(E3V_WARPS * 32) fk_edges3_simd(const u32 *__re
 #pragma unroll
                 for (int jj = 0; jj < 4; jj++) mv[jj] = make_uint4(mb[4 * jj], mb[4 * jj + 1], mb[4 * jj + 2], mb[4 * jj + 3]);
                 *reinterpret_cast<uint2 *>(mreg + 32) = make_uint2(mb[16], mb[17]);
-                uint4 *dxv = reinterpret_cast<uint4 *>(S.dx[r & 1] + lreg), *dyv = reinterpret_cast<uint4 *>(S.dy[r & 1] + lreg);
+                uint4 *dxv = reinterpret_cast<uint4 *>(S.dx[r & 1] + 32 * lane), *dyv = reinterpret_cast<uint4 *>(S.dy[r & 1] + 32 * lane);
 #pragma unroll
                 for (int jj = 0; jj < 4; jj++) {
                     dxv[jj] = make_uint4(dxb[1 + 4 * jj], dxb[2 + 4 * jj], dxb[3 + 4 * jj], dxb[4 + 4 * jj]);
@@ -222,7 +220,7 @@ __global__ void __launch_bounds__(E3V_WARPS * 32) fk_edges3_simd(const u32 *__re
                 const int o = item >> 5, e = item & 31;
                 const int bi = o * E3V_LSTRIDE + e;
                 const int m0 = mc[bi + 2];
-                const int dx = __half2int_rn(__ushort_as_half(dxr[bi])), dy = __half2int_rn(__ushort_as_half(dyr[bi]));
+                const int dx = __half2int_rn(__ushort_as_half(dxr[item])), dy = __half2int_rn(__ushort_as_half(dyr[item]));
                 const int ax = abs(dx), ay = abs(dy) << 15, tg22 = ax * 13573;
                 const bool hz = ay < tg22, vt = ay > tg22 + (ax << 16);
                 const int s = (dx ^ dy) < 0 ? -1 : 1;
@@ -250,6 +248,7 @@ __global__ void __launch_bounds__(E3V_WARPS * 32) fk_edges3_simd(const u32 *__re
 #pragma unroll
     for (int j = 0; j < 20; j++) UA[j] = UB[j] = UC[j] = 0u;
     const int t_end = y1 + 2;
+    load_row(y0 - 3);
     for (int t = y0 - 3; t <= t_end; t += 3) {
         step(t, hA, hB, hC, UA, UB, UC);
         if (t + 1 > t_end) break;
