@@ -19,6 +19,7 @@
 
 #include <cooperative_groups.h>
 #include <stdlib.h>
+#include <string.h>
 namespace cg = cooperative_groups;
 
 #define FK_TRY(expr) do { int rc__ = (expr); if (rc__ != OMNI_OK) return rc__; } while (0)
@@ -151,16 +152,70 @@ cudaError_t fast_resize_2x(const u8 *src, size_t spitch, u8 *dst, int dh, int dw
 
 // ------------------------------------------------------------------------------------------------
 // stage 02: colour assignment -> labels and/or one-hot bit-planes
-// A warp owns 256 consecutive pixels of a row (lane l: pixels l, l+32, .., l+224); per plane the 8
-// ballots of those pixel groups ARE the 8 bit-plane words, stored as one 32-byte segment per plane.
+//
+// Exact pruning of the centre loop.  Lab space is cut into 8x8x8 cells; fk_build_cells gives every cell the
+// set of centres that can be the nearest one for SOME point of the cell: with dmin_k / dmax_k the smallest /
+// largest true squared distance from centre k to the cell's box, centre k is kept iff
+// dmin_k <= min_j dmax_j + 1.  A dropped centre is more than 1 farther (squared) than the true nearest centre
+// of every point in the cell, and the float32 evaluation (02:53-55 order, every operation rounded) is off by
+// < 0.05, so it can never win or tie the argmin.  The kept centres are evaluated with the reference's exact
+// float32 sequence in ascending k with a strict '<', i.e. np.argmin's first-minimum rule.  A pixel visits ~1.3
+// (K=8) .. 1.5 (K=16) centres instead of K.
+//
+// A warp owns 256 consecutive pixels of a row (lane l: pixels l, l+32, .., l+224).  Bit-plane words come from
+// __match_any_sync on the labels of a 32-pixel group: the mask a lane gets back IS the word of its label's
+// plane; the lowest lane of each label stores it (the planes are zeroed beforehand).
 // ------------------------------------------------------------------------------------------------
+#define CELL_SHIFT 3
+#define CELL_N (256 >> CELL_SHIFT)                 // 32 cells per axis
+#define CELL_COUNT (CELL_N * CELL_N * CELL_N)
+
+__global__ void __launch_bounds__(256) fk_build_cells(const __grid_constant__ AssignParams P, u32 *__restrict__ cells)
+{
+    // float32 is enough here: coordinates <= 255 and |centre| < 1e4 (checked), so dmin/dmax carry an absolute
+    // error far below the slack of 2 used in the test (1 for the argument above + 1 for this arithmetic)
+    const int ci = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ci >= CELL_COUNT) return;
+    const int K = P.K;
+    const float lo[3] = {(float)((ci >> (2 * 5)) << CELL_SHIFT), (float)(((ci >> 5) & 31) << CELL_SHIFT), (float)((ci & 31) << CELL_SHIFT)};
+    const float span = (float)((1 << CELL_SHIFT) - 1);
+    float U = 3.0e38f;
+    bool sane = true;
+    for (int k = 0; k < K; k++) {
+        float dmax = 0.f;
+#pragma unroll
+        for (int d = 0; d < 3; d++) {
+            float c = P.c[3 * k + d];
+            sane = sane && (fabsf(c) < 1.0e4f);                 // also false for NaN
+            float m = fmaxf(fabsf(lo[d] - c), fabsf(lo[d] + span - c));
+            dmax += m * m;
+        }
+        U = fminf(U, dmax);
+    }
+    u32 mask = 0u;
+    for (int k = 0; k < K; k++) {
+        float dmin = 0.f;
+#pragma unroll
+        for (int d = 0; d < 3; d++) {
+            float c = P.c[3 * k + d];
+            float n = fminf(fmaxf(c, lo[d]), lo[d] + span);
+            dmin += (n - c) * (n - c);
+        }
+        if (dmin <= U + 2.0f) mask |= 1u << k;
+    }
+    if (!sane || mask == 0u) mask = K >= 32 ? 0xffffffffu : ((1u << K) - 1u);
+    cells[ci] = mask;
+}
+
 template <int MODE_LAB>
 __global__ void __launch_bounds__(256) fk_assign_bits(const u8 *__restrict__ px, int h, int w, size_t pitch,
-                                                      const __grid_constant__ AssignParams P, u8 *__restrict__ labels, size_t lpitch,
+                                                      const __grid_constant__ AssignParams P, const u32 *__restrict__ cells,
+                                                      u8 *__restrict__ labels, size_t lpitch,
                                                       u32 *__restrict__ bits, int ws, size_t plane)
 {
     __shared__ u16 s_gam[256];
     __shared__ u16 s_cbrt[2048];
+    __shared__ float4 s_ctr[OMNI_MAX_K];
     __shared__ u8 s_lut[OMNI_MAX_K];
     if (MODE_LAB) {
         for (int i = threadIdx.x; i < 2048; i += 256) {
@@ -168,7 +223,10 @@ __global__ void __launch_bounds__(256) fk_assign_bits(const u8 *__restrict__ px,
             if (i < 256) s_gam[i] = f_lab_tab[i];
         }
     }
-    if (threadIdx.x < OMNI_MAX_K) s_lut[threadIdx.x] = P.lut[threadIdx.x];
+    if (threadIdx.x < OMNI_MAX_K) {
+        s_lut[threadIdx.x] = P.lut[threadIdx.x];
+        s_ctr[threadIdx.x] = make_float4(P.c[3 * threadIdx.x], P.c[3 * threadIdx.x + 1], P.c[3 * threadIdx.x + 2], 0.f);
+    }
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int chunks = (w + 255) >> 8, K = P.K;
@@ -188,12 +246,16 @@ __global__ void __launch_bounds__(256) fk_assign_bits(const u8 *__restrict__ px,
                 if (MODE_LAB) {
                     int L, a, b;
                     bgr2lab_px(s_gam, s_cbrt, v0, v1, v2, L, a, b);
-                    float f0 = (float)L, f1 = (float)a, f2 = (float)b, bd = 0.f;
-                    for (int k = 0; k < K; k++) {
-                        float d0 = __fsub_rn(f0, P.c[3 * k]), d1 = __fsub_rn(f1, P.c[3 * k + 1]), d2 = __fsub_rn(f2, P.c[3 * k + 2]);
+                    u32 mk = __ldg(cells + (((L >> CELL_SHIFT) * CELL_N + (a >> CELL_SHIFT)) * CELL_N + (b >> CELL_SHIFT)));
+                    float f0 = (float)L, f1 = (float)a, f2 = (float)b, bd = 3.0e38f;
+                    do {
+                        const int k = __ffs(mk) - 1;
+                        mk &= mk - 1u;
+                        const float4 ck = s_ctr[k];
+                        float d0 = __fsub_rn(f0, ck.x), d1 = __fsub_rn(f1, ck.y), d2 = __fsub_rn(f2, ck.z);
                         float d = __fadd_rn(__fadd_rn(__fmul_rn(d0, d0), __fmul_rn(d1, d1)), __fmul_rn(d2, d2));
-                        if (k == 0 || d < bd) { bd = d; best = k; }
-                    }
+                        if (d < bd) { bd = d; best = k; }
+                    } while (mk);
                 } else {
                     int bd = 0;
                     for (int k = 0; k < K; k++) {
@@ -212,18 +274,11 @@ __global__ void __launch_bounds__(256) fk_assign_bits(const u8 *__restrict__ px,
                 if (x0 + 32 * g < w) lrow[x0 + 32 * g] = (u8)lab[g];
         }
         if (bits) {
-            u32 mine = 0;
-            for (int k = 0; k < K; k++) {
+            u32 *brow = bits + (size_t)y * ws + c * 8;
 #pragma unroll
-                for (int g = 0; g < 8; g++) {
-                    u32 b = __ballot_sync(0xffffffffu, lab[g] == k);
-                    if (lane == ((k & 3) * 8 + g)) mine = b;
-                }
-                if ((k & 3) == 3 || k == K - 1) {
-                    int kk = (k & ~3) + (lane >> 3), wx = c * 8 + (lane & 7);
-                    if (kk <= k && wx < ws) bits[(size_t)kk * plane + (size_t)y * ws + wx] = mine;
-                    mine = 0;
-                }
+            for (int g = 0; g < 8; g++) {
+                const u32 same = __match_any_sync(0xffffffffu, lab[g]);
+                if (lab[g] < K && lane == __ffs(same) - 1 && c * 8 + g < ws) brow[(size_t)lab[g] * plane + g] = same;
             }
         }
     }
@@ -694,14 +749,37 @@ static int bit_planes(omni_ctx *ctx, const BitGeom &g, int K, int n, u32 **out /
     return OMNI_OK;
 }
 
+// candidate-cell table for the centres of this call (workspace slot 5), built on the device
+static int assign_cells(omni_ctx *ctx, const AssignParams &P, u32 **cells, cudaStream_t st)
+{
+    FK_TRY(omni_ws_reserve(ctx, 5, CELL_COUNT * sizeof(u32)));
+    *cells = (u32 *)ctx->ws[5];
+    // same centres as the previous call on this ctx (a batch of frames): the table in the workspace is still valid
+    // (calls on one ctx are serialised and go to one stream at a time, see omni_b200.h)
+    if (ctx->cells_valid && ctx->cells_stream == (void *)st && ctx->cells_K == P.K &&
+        memcmp(ctx->cells_c, P.c, sizeof(float) * 3 * P.K) == 0)
+        return OMNI_OK;
+    memcpy(ctx->cells_c, P.c, sizeof(float) * 3 * P.K);
+    ctx->cells_K = P.K; ctx->cells_stream = (void *)st; ctx->cells_valid = 1;
+    KScope ks(ctx, "build_cells", st);
+    fk_build_cells<<<CELL_COUNT / 256, 256, 0, st>>>(P, *cells);
+    OMNI_CUDA(cudaGetLastError());
+    return OMNI_OK;
+}
+
 cudaError_t fast_assign(omni_ctx *ctx, const u8 *px, int h, int w, size_t pitch, const AssignParams &P, int mode_lab,
                         u8 *labels, size_t lpitch, cudaStream_t st)
 {
     cudaError_t e = fast_tables();
     if (e != cudaSuccess) return e;
     int grid = persist_blocks(ctx, 6);
-    if (mode_lab) fk_assign_bits<1><<<grid, 256, 0, st>>>(px, h, w, pitch, P, labels, lpitch, nullptr, 0, 0);
-    else fk_assign_bits<0><<<grid, 256, 0, st>>>(px, h, w, pitch, P, labels, lpitch, nullptr, 0, 0);
+    if (mode_lab) {
+        u32 *cells = nullptr;
+        if (assign_cells(ctx, P, &cells, st) != OMNI_OK) return cudaErrorMemoryAllocation;
+        fk_assign_bits<1><<<grid, 256, 0, st>>>(px, h, w, pitch, P, cells, labels, lpitch, nullptr, 0, 0);
+    } else {
+        fk_assign_bits<0><<<grid, 256, 0, st>>>(px, h, w, pitch, P, nullptr, labels, lpitch, nullptr, 0, 0);
+    }
     return cudaGetLastError();
 }
 
@@ -821,9 +899,12 @@ int fast_color_edge(omni_ctx *ctx, const u8 *d_bgr, int h, int w, size_t pitch, 
     BitGeom g = make_geom(h, w);
     u32 *bpp[4];
     FK_TRY(bit_planes(ctx, g, P.K, 4, bpp));
+    u32 *cells = nullptr;
+    FK_TRY(assign_cells(ctx, P, &cells, st));
+    OMNI_CUDA(cudaMemsetAsync(bpp[0], 0, g.plane * (size_t)P.K * sizeof(u32), st));      // match_any stores only non-empty words
     {
         KScope ks(ctx, "assign_bits", st);
-        fk_assign_bits<1><<<persist_blocks(ctx, 6), 256, 0, st>>>(d_bgr, h, w, pitch, P, d_labels, lpitch, bpp[0], g.ws, g.plane);
+        fk_assign_bits<1><<<persist_blocks(ctx, 6), 256, 0, st>>>(d_bgr, h, w, pitch, P, cells, d_labels, lpitch, bpp[0], g.ws, g.plane);
         OMNI_CUDA(cudaGetLastError());
     }
     int kind = morph03_kind(prm);

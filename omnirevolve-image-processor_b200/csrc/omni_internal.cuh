@@ -78,7 +78,11 @@ struct omni_ctx {
     std::vector<ProfRec> prof;
     std::vector<cudaEvent_t> ev_pool;
     int sm_count = 0;
-    int hyst_blocks = 0;             // co-resident CTAs of the cooperative hysteresis kernel (0 = not queried yet)
+    int hyst_blocks = 0;
+    // centres the candidate-cell table in ws[5] was built for (fast colour assignment)
+    int cells_valid = 0, cells_K = 0;
+    void *cells_stream = nullptr;
+    float cells_c[OMNI_MAX_K * 3];             // co-resident CTAs of the cooperative hysteresis kernel (0 = not queried yet)
 };
 
 // Brackets one kernel launch: counts it and, when profiling is on, records a CUDA event pair on the
