@@ -181,7 +181,8 @@ def cpu_baseline_leg(wl, img, centers):
 # our arm
 # ------------------------------------------------------------------------------------------------------
 KERNEL_BYTES = {
-    # algorithmic bytes per launch, N = H*W pixels, K planes (u8 in + u8 out, intermediates zero)
+    # algorithmic bytes per launch: the u8 image / mask / edge tensors a kernel must read or write in HBM
+    # (N = H*W pixels, K planes; bit-plane intermediates count zero -- SURVEY 8d)
     "assign": lambda N, K: N * (3 + 1),
     "onehot": lambda N, K: N * (1 + K),
     "morph": lambda N, K: N * 2 * K,
@@ -189,10 +190,15 @@ KERNEL_BYTES = {
     "canny_nms": lambda N, K: N * 2 * K,
     "hyst_pass": lambda N, K: N * 2 * K,
     "hyst_final": lambda N, K: N * 2 * K,
-    "color_masks": lambda N, K: N * (3 + K),           # image -> K masks (fast path)
-    "edge_planes": lambda N, K: N * 2 * K,             # K masks -> K edges (fast path)
-    "color_edge": lambda N, K: N * (3 + 2 * K),        # fused image -> K masks + K edges
+    "assign_bits": lambda N, K: N * 3,               # image read; one-hot bit-planes stay in L2
+    "morph_bits": lambda N, K: N * K,                # mask byte planes written
+    "edges3_bits": lambda N, K: N * K,               # bit-planes in; edge byte planes (strong set) written
+    "hysteresis_bits": lambda N, K: 0,               # bit-planes only + a few promoted pixels
+    "build_cells": lambda N, K: 0,
 }
+# stage grouping for the report: colour = image -> K masks, edge = K masks -> K edges (masks are not re-read)
+STAGES = {"color": ("build_cells", "assign_bits", "morph_bits", "assign", "onehot"),
+          "edge": ("edges3_bits", "hysteresis_bits", "morph", "blur", "canny_nms", "hyst_pass", "hyst_final")}
 
 
 def run_ours(args, wl):
@@ -298,7 +304,7 @@ def run_ours(args, wl):
             per_launch_ms = ms / n_l
             bytes_fn = KERNEL_BYTES.get(name)
             alg = bytes_fn(N, K) if bytes_fn else None
-            ach = alg / (per_launch_ms / 1e3) / 1e9 if alg else None
+            ach = alg / (per_launch_ms / 1e3) / 1e9 if alg is not None else None
             traffic = None
             tp = os.path.join(ROOT, "profiles", "traffic.json")
             if os.path.exists(tp):
@@ -307,13 +313,17 @@ def run_ours(args, wl):
                 except Exception:
                     traffic = None
             roof = {"bound": "hbm", "kernel": name, "achieved": ach, "peak": peak, "unit": "GB/s",
-                    "frac": (ach / peak) if ach else None, "traffic": traffic, "peak_source": peak_src,
+                    "frac": (ach / peak) if ach is not None else None, "traffic": traffic, "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": alg, "launches_per_step": n_l / args.steps,
                     "ms_per_launch": per_launch_ms, "share_of_step": ms / total_ms,
                     "step": {"algorithmic_bytes": N * (3 + 2 * K),
                              "achieved": N * (3 + 2 * K) / (ms_per_step / 1e3) / 1e9,
                              "frac": N * (3 + 2 * K) / (ms_per_step / 1e3) / 1e9 / peak},
-                    "kernels_ms_per_step": {k: v[1] / args.steps for k, v in prof.items()}}
+                    "kernels_ms_per_step": {k: v[1] / args.steps for k, v in prof.items()},
+                    "kernels_frac_of_peak": {k: (KERNEL_BYTES[k](N, K) / (v[1] / v[0] / 1e3) / 1e9 / peak)
+                                             for k, v in prof.items() if k in KERNEL_BYTES and KERNEL_BYTES[k](N, K)},
+                    "stages_ms_per_step": {sname: sum(v[1] for k, v in prof.items() if k in members) / args.steps
+                                           for sname, members in STAGES.items()}}
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

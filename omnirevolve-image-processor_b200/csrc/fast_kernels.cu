@@ -63,38 +63,6 @@ static cudaError_t fast_tables()
 
 void fast_ctx_release(omni_ctx *) {}
 
-// bits i of a 32-bit word whose pixel (start_px + i) lies in [0, w)
-__device__ __forceinline__ u32 range_mask(int start_px, int w)
-{
-    int lo = max(0, -start_px), hi = min(32, w - start_px);
-    if (hi <= lo) return 0u;
-    u32 m = hi >= 32 ? 0xffffffffu : ((1u << hi) - 1u);
-    return m & ~((1u << lo) - 1u);
-}
-
-// 4 mask bits -> 4 bytes of 0x00 / 0xFF
-__device__ __forceinline__ u32 expand4(u32 nib)
-{
-    return ((nib * 0x00204081u) & 0x01010101u) * 255u;
-}
-
-// store 32 pixels (bits of `word`) as 0/255 bytes at dst (pixel x0 = first), only pixels < w
-__device__ __forceinline__ void store_word_bytes(u8 *row, int x0, int w, u32 word, bool aligned16)
-{
-    if (x0 + 32 <= w && aligned16) {
-        uint4 a, b;
-        a.x = expand4(word & 15u);         a.y = expand4((word >> 4) & 15u);
-        a.z = expand4((word >> 8) & 15u);  a.w = expand4((word >> 12) & 15u);
-        b.x = expand4((word >> 16) & 15u); b.y = expand4((word >> 20) & 15u);
-        b.z = expand4((word >> 24) & 15u); b.w = expand4(word >> 28);
-        uint4 *p = reinterpret_cast<uint4 *>(row + x0);
-        p[0] = a; p[1] = b;
-    } else {
-        int n = min(32, w - x0);
-        for (int i = 0; i < n; i++) row[x0 + i] = (word >> i) & 1u ? 255 : 0;
-    }
-}
-
 // ------------------------------------------------------------------------------------------------
 // stage 01: exact 2:1 INTER_AREA, vectorised (01_resize.py:20)
 // Each thread produces 4 destination pixels (12 bytes) from 2 x 24 source bytes.
@@ -509,128 +477,9 @@ static cudaError_t launch_morph(bool with02, int morph03, const u32 *in_bits, u3
 }
 
 // ------------------------------------------------------------------------------------------------
-// stage 03 on a bit-plane, edge_kernel_size 3:  GaussianBlur(3x3, sigma 0) -> Canny up to the NMS
-// (03:33-34).  On a {0,255} mask the blur is B = (255*S + 32768) >> 16 with
-// S = 4096 * v, v = sum of (1,2,1)x(1,2,1)-weighted BITS in [0,16]  =>  B = 16 v - (v > 8).
-// Borders: blur REFLECT_101 (on the bits), Sobel REPLICATE (on B), magnitude 0 outside the image.
-// Output: bit-planes S (candidate with m > high) and C (candidate: m > low and a directional maximum).
-// ------------------------------------------------------------------------------------------------
-#define E3_TR 16
-#define E3_TWW 8                      // words per tile row = 256 pixels
-#define E3_TW (E3_TWW * 32)
-
-__device__ __forceinline__ int reflect101_dev(int p, int len)
-{
-    if (len == 1) return 0;
-    while (p < 0 || p >= len) p = p < 0 ? -p : 2 * (len - 1) - p;
-    return p;
-}
-
-__global__ void __launch_bounds__(256) fk_edges3(const u32 *__restrict__ m2, int ws, size_t plane, int h, int w, int low, int high,
-                                                 u32 *__restrict__ sbits, u32 *__restrict__ cbits)
-{
-    // bit tile: rows y0-3 .. y0+TR+2 (reflected at the image border), words c0-1 .. c0+TWW
-    __shared__ u32 s_bits[(E3_TR + 6) * (E3_TWW + 2) + 1];   // +1: the funnel shift reads one word ahead
-    __shared__ u8 s_B[(E3_TR + 4) * (E3_TW + 4)];          // B for rows y0-2.., pixels x0-2..
-    __shared__ short s_m[(E3_TR + 2) * (E3_TW + 2)];       // magnitude for rows y0-1.., pixels x0-1..
-    const int k = blockIdx.z, tid = threadIdx.x;
-    const int y0 = blockIdx.y * E3_TR, c0 = blockIdx.x * E3_TWW, x0 = c0 * 32;
-    const int ww = (w + 31) >> 5;
-    const u32 *src = m2 + (size_t)k * plane;
-    constexpr int BW = E3_TWW + 2;
-    for (int i = tid; i < (E3_TR + 6) * BW; i += 256) {
-        int ly = i / BW, lc = i - ly * BW;
-        int gy = y0 - 3 + ly, gc = c0 - 1 + lc;
-        u32 v = 0;
-        if (gy >= -1 && gy <= h && gc >= 0 && gc < ww) {
-            int ry = reflect101_dev(gy, h);
-            v = __ldg(src + (size_t)ry * ws + gc);
-            // REFLECT_101 in x: pixel w := pixel w-2 (or 0 when w == 1)
-            if (gc == (w >> 5) && (w & 31)) {
-                int sx = reflect101_dev(w, w);
-                u32 b = (__ldg(src + (size_t)ry * ws + (sx >> 5)) >> (sx & 31)) & 1u;
-                v |= b << (w & 31);
-            }
-        } else if (gy >= -1 && gy <= h && gc == ww && (w & 31) == 0) {
-            // pixel w is bit 0 of the word after the last one
-            int ry = reflect101_dev(gy, h), sx = reflect101_dev(w, w);
-            v = (__ldg(src + (size_t)ry * ws + (sx >> 5)) >> (sx & 31)) & 1u;
-        }
-        if (gy >= -1 && gy <= h && gc == -1) {
-            // pixel -1 := pixel 1 (or 0 when w == 1): bit 31 of the word left of the image
-            int ry = reflect101_dev(gy, h), sx = reflect101_dev(-1, w);
-            v = ((__ldg(src + (size_t)ry * ws + (sx >> 5)) >> (sx & 31)) & 1u) << 31;
-        }
-        s_bits[i] = v;
-    }
-    __syncthreads();
-    // B tile
-    constexpr int SBW = E3_TW + 4;
-    for (int i = tid; i < (E3_TR + 4) * SBW; i += 256) {
-        int ly = i / SBW, lx = i - ly * SBW;
-        int gy = y0 - 2 + ly, gx = x0 - 2 + lx;
-        int cy = min(max(gy, 0), h - 1), cx = min(max(gx, 0), w - 1);      // Sobel BORDER_REPLICATE on the blurred image
-        // tile-relative position of pixel cx-1 in the bit rows (tile pixel 0 = x0 - 32)
-        int pos = cx - 1 - (x0 - 32);
-        int wd = pos >> 5, sh = pos & 31;
-        int v = 0;
-#pragma unroll
-        for (int dy = -1; dy <= 1; dy++) {
-            const u32 *br = s_bits + (cy + dy - (y0 - 3)) * BW;
-            u32 t3 = __funnelshift_r(br[wd], br[wd + 1], sh) & 7u;
-            int hsum = (0x43213210u >> (4 * t3)) & 15u;               // b0 + 2 b1 + b2
-            v += dy == 0 ? 2 * hsum : hsum;
-        }
-        s_B[i] = (u8)(16 * v - (v > 8 ? 1 : 0));
-    }
-    __syncthreads();
-    constexpr int MW = E3_TW + 2;
-    for (int i = tid; i < (E3_TR + 2) * MW; i += 256) {
-        int ly = i / MW, lx = i - ly * MW;
-        int gy = y0 - 1 + ly, gx = x0 - 1 + lx;
-        int m = 0;
-        if (gy >= 0 && gy < h && gx >= 0 && gx < w) {
-            const u8 *c = s_B + (ly + 1) * SBW + (lx + 1);
-            int dx = (c[-SBW + 1] + 2 * c[1] + c[SBW + 1]) - (c[-SBW - 1] + 2 * c[-1] + c[SBW - 1]);
-            int dy = (c[SBW - 1] + 2 * c[SBW] + c[SBW + 1]) - (c[-SBW - 1] + 2 * c[-SBW] + c[-SBW + 1]);
-            m = abs(dx) + abs(dy);
-        }
-        s_m[i] = (short)m;
-    }
-    __syncthreads();
-    for (int i = tid; i < E3_TR * E3_TW; i += 256) {
-        int ly = i / E3_TW, lx = i - ly * E3_TW;
-        int gy = y0 + ly, gx = x0 + lx;
-        int state = 0;
-        if (gy < h && gx < w) {
-            int mi = (ly + 1) * MW + (lx + 1);
-            int m = s_m[mi];
-            if (m > low) {
-                const u8 *c = s_B + (ly + 2) * SBW + (lx + 2);
-                int xs = (c[-SBW + 1] + 2 * c[1] + c[SBW + 1]) - (c[-SBW - 1] + 2 * c[-1] + c[SBW - 1]);
-                int ys = (c[SBW - 1] + 2 * c[SBW] + c[SBW + 1]) - (c[-SBW - 1] + 2 * c[-SBW] + c[-SBW + 1]);
-                int ax = abs(xs), ay = abs(ys) << 15, tg22 = ax * 13573;
-                bool ok;
-                if (ay < tg22) ok = m > s_m[mi - 1] && m >= s_m[mi + 1];
-                else {
-                    int tg67 = tg22 + (ax << 16);
-                    if (ay > tg67) ok = m > s_m[mi - MW] && m >= s_m[mi + MW];
-                    else { int sg = (xs ^ ys) < 0 ? -1 : 1; ok = m > s_m[mi - MW - sg] && m > s_m[mi + MW + sg]; }
-                }
-                if (ok) state = m > high ? 2 : 1;
-            }
-        }
-        u32 cb = __ballot_sync(0xffffffffu, state != 0), sb = __ballot_sync(0xffffffffu, state == 2);
-        if ((tid & 31) == 0 && gy < h && (gx >> 5) < ww) {
-            size_t o = (size_t)k * plane + (size_t)gy * ws + (gx >> 5);
-            cbits[o] = cb; sbits[o] = sb;
-        }
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
 // hysteresis on bit-planes (cv2.Canny's final stage): E = S, then E |= C & dilate8(E) until
-// nothing changes anywhere, then E is written out as 0/255 bytes.  Cooperative persistent kernel: every
+// nothing changes anywhere.  The edge kernel has already written the byte planes for E = S (on pipeline data
+// nearly every candidate is strong), so at the end only the promoted pixels E & ~S are patched to 255.  Cooperative persistent kernel: every
 // CTA iterates its tiles to a LOCAL fixed point in shared memory, a grid-wide barrier separates global
 // rounds, and the loop ends after the first round in which no tile changed.  The result set does not
 // depend on the propagation order.
@@ -638,9 +487,10 @@ __global__ void __launch_bounds__(256) fk_edges3(const u32 *__restrict__ m2, int
 #define HB_TR 32                      // tile rows
 #define HB_TW 32                      // tile words (1024 pixels)
 
-__global__ void __launch_bounds__(256) fk_hysteresis(u32 *__restrict__ ebits, const u32 *__restrict__ cbits, int ws, size_t plane, int h,
-                                                     int w, int K, int *flags /* [0]=rounds, [1..2]=changed ping-pong */,
-                                                     u8 *__restrict__ edges, size_t estride, size_t epitch, int aligned16)
+__global__ void __launch_bounds__(256) fk_hysteresis(u32 *__restrict__ ebits, const u32 *__restrict__ cbits,
+                                                     const u32 *__restrict__ sbits, int ws, size_t plane, int h,
+                                                     int w, int K, int *flags /* [0]=rounds, [1..3]=rotating "changed" flags */,
+                                                     u8 *__restrict__ edges, size_t estride, size_t epitch)
 {
     cg::grid_group grid = cg::this_grid();
     __shared__ u32 s_e[(HB_TR + 2) * (HB_TW + 2)];
@@ -722,15 +572,21 @@ __global__ void __launch_bounds__(256) fk_hysteresis(u32 *__restrict__ ebits, co
         round++;
         if (!c) break;
     }
-    // E -> bytes
+    // The edge kernel already wrote the byte planes for E = S; only the promoted pixels (E & ~S) remain.
     if (edges) {
         const long long total = (long long)K * h * ww;
         for (long long u = (long long)blockIdx.x * blockDim.x + tid; u < total; u += (long long)gridDim.x * blockDim.x) {
             int k = (int)(u / ((long long)h * ww));
             long long r = u - (long long)k * h * ww;
             int y = (int)(r / ww), c = (int)(r - (long long)y * ww);
-            u32 word = __ldcg(ebits + (size_t)k * plane + (size_t)y * ws + c);
-            store_word_bytes(edges + (size_t)k * estride + (size_t)y * epitch, c * 32, w, word, aligned16 != 0);
+            size_t o = (size_t)k * plane + (size_t)y * ws + c;
+            u32 d = __ldcg(ebits + o) & ~__ldg(sbits + o);
+            u8 *row = edges + (size_t)k * estride + (size_t)y * epitch + c * 32;
+            while (d) {
+                int e = __ffs(d) - 1;
+                d &= d - 1u;
+                row[e] = 255;
+            }
         }
     }
 }
@@ -824,8 +680,8 @@ bool fast_edges_supported(const omni_edge_params *prm)
     return morph03_kind(prm) >= 0 && prm->ksize == 3;
 }
 
-static int run_hysteresis(omni_ctx *ctx, u32 *ebits, const u32 *cbits, const BitGeom &g, int K, u8 *d_edges, size_t e_plane,
-                          size_t epitch, cudaStream_t st)
+static int run_hysteresis(omni_ctx *ctx, u32 *ebits, const u32 *cbits, const u32 *sbits, const BitGeom &g, int K, u8 *d_edges,
+                          size_t e_plane, size_t epitch, cudaStream_t st)
 {
     if (ctx->hyst_blocks == 0) {
         int per_sm = 0;
@@ -837,27 +693,21 @@ static int run_hysteresis(omni_ctx *ctx, u32 *ebits, const u32 *cbits, const Bit
     int ws = g.ws, h = g.h, w = g.w;
     size_t plane = g.plane;
     int *flags = ctx->d_flags;
-    int al = ((uintptr_t)d_edges % 16 == 0) && (e_plane % 16 == 0) && (epitch % 16 == 0);
-    void *args[] = {&ebits, &cbits, &ws, &plane, &h, &w, &K, &flags, &d_edges, &e_plane, &epitch, &al};
+    void *args[] = {&ebits, &cbits, &sbits, &ws, &plane, &h, &w, &K, &flags, &d_edges, &e_plane, &epitch};
     OMNI_LAUNCH(ctx, st, "hysteresis_bits", cudaLaunchCooperativeKernel((const void *)fk_hysteresis, dim3(ctx->hyst_blocks), dim3(256),
                                                                         args, 0, st));
     ctx->last_hyst_passes = -1;           // lives in d_flags[0]; fetched lazily by omni_last_hysteresis_passes
     return OMNI_OK;
 }
 
-static int edges_from_bits(omni_ctx *ctx, const u32 *m2, u32 *sbits, u32 *cbits, const BitGeom &g, int K, int low, int high,
+// bit-planes M2 -> edge byte planes.  bp: [sbits, cbits, ebits] workspace planes.
+static int edges_from_bits(omni_ctx *ctx, const u32 *m2, u32 *sbits, u32 *cbits, u32 *ebits, const BitGeom &g, int K, int low, int high,
                            u8 *d_edges, size_t e_plane, size_t epitch, cudaStream_t st)
 {
-    static const bool use_v1 = getenv("OMNI_EDGES3_V1") != nullptr;       // A/B switch: the simple per-pixel kernel
-    if (use_v1) {
-        KScope ks(ctx, "edges3_bits_v1", st);
-        dim3 grid((g.ww + E3_TWW - 1) / E3_TWW, (g.h + E3_TR - 1) / E3_TR, K);
-        fk_edges3<<<grid, 256, 0, st>>>(m2, g.ws, g.plane, g.h, g.w, low, high, sbits, cbits);
-        OMNI_CUDA(cudaGetLastError());
-    } else {
-        OMNI_LAUNCH(ctx, st, "edges3_bits", launch_edges3_simd(m2, g.ws, g.plane, g.h, g.w, K, low, high, ctx->sm_count, sbits, cbits, st));
-    }
-    return run_hysteresis(ctx, sbits, cbits, g, K, d_edges, e_plane, epitch, st);
+    int al = ((uintptr_t)d_edges % 16 == 0) && (e_plane % 16 == 0) && (epitch % 16 == 0);
+    OMNI_LAUNCH(ctx, st, "edges3_bits", launch_edges3_simd(m2, g.ws, g.plane, g.h, g.w, K, low, high, ctx->sm_count, sbits, cbits, ebits,
+                                                           d_edges, e_plane, epitch, al, st));
+    return run_hysteresis(ctx, ebits, cbits, sbits, g, K, d_edges, e_plane, epitch, st);
 }
 
 int fast_edges(omni_ctx *ctx, const u8 *d_masks, int K, int h, int w, size_t m_plane, size_t mpitch,
@@ -867,8 +717,8 @@ int fast_edges(omni_ctx *ctx, const u8 *d_masks, int K, int h, int w, size_t m_p
     (void)bp;
     if (low < 0) return OMNI_ERR_UNSUPPORTED;        // m == 0 would be a candidate: generic kernels handle it
     BitGeom g = make_geom(h, w);
-    u32 *bpp[4];
-    FK_TRY(bit_planes(ctx, g, K, 4, bpp));
+    u32 *bpp[5];
+    FK_TRY(bit_planes(ctx, g, K, 5, bpp));
     OMNI_CUDA(cudaMemsetAsync(ctx->d_flags + 8, 0, sizeof(int), st));
     {
         KScope ks(ctx, "bytes_to_bits", st);
@@ -885,7 +735,7 @@ int fast_edges(omni_ctx *ctx, const u8 *d_masks, int K, int h, int w, size_t m_p
         OMNI_LAUNCH(ctx, st, "morph_bits", launch_morph(false, kind, bpp[0], bpp[1], g, K, nullptr, 0, 0, st));
         m2 = bpp[1];
     }
-    return edges_from_bits(ctx, m2, bpp[2], bpp[3], g, K, low, high, d_edges, e_plane, epitch, st);
+    return edges_from_bits(ctx, m2, bpp[2], bpp[3], bpp[4], g, K, low, high, d_edges, e_plane, epitch, st);
 }
 
 int fast_color_edge(omni_ctx *ctx, const u8 *d_bgr, int h, int w, size_t pitch, const AssignParams &P,
@@ -897,8 +747,8 @@ int fast_color_edge(omni_ctx *ctx, const u8 *d_bgr, int h, int w, size_t pitch, 
     if (low < 0) return OMNI_ERR_UNSUPPORTED;
     OMNI_CUDA(fast_tables());
     BitGeom g = make_geom(h, w);
-    u32 *bpp[4];
-    FK_TRY(bit_planes(ctx, g, P.K, 4, bpp));
+    u32 *bpp[5];
+    FK_TRY(bit_planes(ctx, g, P.K, 5, bpp));
     u32 *cells = nullptr;
     FK_TRY(assign_cells(ctx, P, &cells, st));
     OMNI_CUDA(cudaMemsetAsync(bpp[0], 0, g.plane * (size_t)P.K * sizeof(u32), st));      // match_any stores only non-empty words
@@ -909,5 +759,5 @@ int fast_color_edge(omni_ctx *ctx, const u8 *d_bgr, int h, int w, size_t pitch, 
     }
     int kind = morph03_kind(prm);
     OMNI_LAUNCH(ctx, st, "morph_bits", launch_morph(true, kind, bpp[0], bpp[1], g, P.K, d_masks, m_plane, mpitch, st));
-    return edges_from_bits(ctx, bpp[1], bpp[2], bpp[3], g, P.K, low, high, d_edges, e_plane, epitch, st);
+    return edges_from_bits(ctx, bpp[1], bpp[2], bpp[3], bpp[4], g, P.K, low, high, d_edges, e_plane, epitch, st);
 }

@@ -124,6 +124,38 @@ cudaError_t g_copy2d_planes(const u8 *src, size_t s_plane, size_t spitch, u8 *ds
                             int K, int h, int w, cudaStream_t st);
 
 #ifdef __CUDACC__
+// bits i of a 32-bit word whose pixel (start_px + i) lies in [0, w)
+__device__ __forceinline__ u32 range_mask(int start_px, int w)
+{
+    int lo = max(0, -start_px), hi = min(32, w - start_px);
+    if (hi <= lo) return 0u;
+    u32 m = hi >= 32 ? 0xffffffffu : ((1u << hi) - 1u);
+    return m & ~((1u << lo) - 1u);
+}
+
+// 4 mask bits -> 4 bytes of 0x00 / 0xFF
+__device__ __forceinline__ u32 expand4(u32 nib)
+{
+    return ((nib * 0x00204081u) & 0x01010101u) * 255u;
+}
+
+// store 32 pixels (bits of `word`) as 0/255 bytes at dst (pixel x0 = first), only pixels < w
+__device__ __forceinline__ void store_word_bytes(u8 *row, int x0, int w, u32 word, bool aligned16)
+{
+    if (x0 + 32 <= w && aligned16) {
+        uint4 a, b;
+        a.x = expand4(word & 15u);         a.y = expand4((word >> 4) & 15u);
+        a.z = expand4((word >> 8) & 15u);  a.w = expand4((word >> 12) & 15u);
+        b.x = expand4((word >> 16) & 15u); b.y = expand4((word >> 20) & 15u);
+        b.z = expand4((word >> 24) & 15u); b.w = expand4(word >> 28);
+        uint4 *p = reinterpret_cast<uint4 *>(row + x0);
+        p[0] = a; p[1] = b;
+    } else {
+        int n = min(32, w - x0);
+        for (int i = 0; i < n; i++) row[x0 + i] = (word >> i) & 1u ? 255 : 0;
+    }
+}
+
 // cv2.cvtColor(u8 BGR -> Lab) integer pipeline (02_color_extract.py:35); tables: gamma[256], cbrt[2041]
 __device__ __forceinline__ int descale(int x, int n) { return (x + (1 << (n - 1))) >> n; }
 
