@@ -345,7 +345,7 @@ __host__ __device__ constexpr int code_op(u32 code, int i) { return (int)((code 
 __host__ __device__ constexpr int code_len(u32 code) { int n = 0; while (n < 8 && code_op(code, n) != ST_NONE) n++; return n; }
 __host__ __device__ constexpr bool op_is_erode(int op) { return op == ST_ER || op == ST_EC; }
 
-#define MORPH_TR 64          // rows per strip
+#define MORPH_TR 32          // rows per strip
 
 // Output-of-range fix-up for a value that the step with opcode `next` will consume: columns outside the
 // image and rows outside the image must read as that step's identity element.
@@ -406,17 +406,24 @@ __global__ void __launch_bounds__(128) fk_morph(const u32 *__restrict__ in_bits,
     W64 p1[8], p2[8];
 #pragma unroll
     for (int s = 0; s < 8; s++) { p1[s].lo = p1[s].hi = p2[s].lo = p2[s].hi = 0u; }
+    // the three words of the next input row are loaded one iteration ahead (the row is consumed ~250 instructions later)
+    u32 nl = 0u, no = 0u, nr = 0u;
+    auto fetch = [&](int t) {
+        nl = no = nr = 0u;
+        if (t >= 0 && t < h) {
+            const u32 *row = src + (size_t)t * ws;
+            if (c > 0) nl = __ldg(row + c - 1);
+            no = __ldg(row + c);
+            if (c + 1 < ww) nr = __ldg(row + c + 1);
+        }
+    };
+    fetch(y0 - N);
     for (int t = y0 - N; t < y1 + N; t++) {
         W64 cur;
         const bool inside = t >= 0 && t < h;
-        if (inside) {
-            const u32 *row = src + (size_t)t * ws;
-            u32 left = c > 0 ? __ldg(row + c - 1) : 0u, own = __ldg(row + c), right = c + 1 < ww ? __ldg(row + c + 1) : 0u;
-            cur.lo = (left >> 16) | (own << 16);
-            cur.hi = (own >> 16) | (right << 16);
-        } else {
-            cur.lo = cur.hi = 0u;
-        }
+        cur.lo = (nl >> 16) | (no << 16);
+        cur.hi = (no >> 16) | (nr << 16);
+        fetch(t + 1);
         cur = oob_fix<OP0>(cur, colvalid, inside);
         W64 tap, fin;
         tap.lo = tap.hi = fin.lo = fin.hi = 0u;
@@ -479,16 +486,29 @@ static cudaError_t launch_morph(bool with02, int morph03, const u32 *in_bits, u3
 // ------------------------------------------------------------------------------------------------
 // hysteresis on bit-planes (cv2.Canny's final stage): E = S, then E |= C & dilate8(E) until
 // nothing changes anywhere.  The edge kernel has already written the byte planes for E = S (on pipeline data
-// nearly every candidate is strong), so at the end only the promoted pixels E & ~S are patched to 255.  Cooperative persistent kernel: every
-// CTA iterates its tiles to a LOCAL fixed point in shared memory, a grid-wide barrier separates global
-// rounds, and the loop ends after the first round in which no tile changed.  The result set does not
-// depend on the propagation order.
+// nearly every candidate is strong), so a promoted pixel is patched to 255 the moment it is promoted.
+//
+// Cooperative persistent kernel; grid.sync() separates global rounds; three rotating "changed" flags let one
+// barrier per round suffice.  Rounds 0..HY_WORD_ROUNDS-1 are WORD rounds: one thread per word, a word with
+// promotable bits looks at its 8 neighbour words and closes the chain inside the word (pipeline data: done
+// after 1-2 such rounds, each a single pass over the L2-resident bit-planes).  Longer chains escalate to TILE
+// rounds: a CTA iterates a 32-row x 1024-pixel tile to its local fixed point in shared memory, so a chain
+// advances by a tile, not a pixel, per round.  The result set does not depend on the propagation order.
 // ------------------------------------------------------------------------------------------------
 #define HB_TR 32                      // tile rows
 #define HB_TW 32                      // tile words (1024 pixels)
+#define HY_WORD_ROUNDS 4
 
-__global__ void __launch_bounds__(256) fk_hysteresis(u32 *__restrict__ ebits, const u32 *__restrict__ cbits,
-                                                     const u32 *__restrict__ sbits, int ws, size_t plane, int h,
+__device__ __forceinline__ void hy_patch_bytes(u8 *row, u32 promoted)
+{
+    while (promoted) {
+        int e = __ffs(promoted) - 1;
+        promoted &= promoted - 1u;
+        row[e] = 255;
+    }
+}
+
+__global__ void __launch_bounds__(256) fk_hysteresis(u32 *__restrict__ ebits, const u32 *__restrict__ cbits, int ws, size_t plane, int h,
                                                      int w, int K, int *flags /* [0]=rounds, [1..3]=rotating "changed" flags */,
                                                      u8 *__restrict__ edges, size_t estride, size_t epitch)
 {
@@ -496,74 +516,113 @@ __global__ void __launch_bounds__(256) fk_hysteresis(u32 *__restrict__ ebits, co
     __shared__ u32 s_e[(HB_TR + 2) * (HB_TW + 2)];
     __shared__ u32 s_c[HB_TR * HB_TW];
     const int ww = (w + 31) >> 5;
-    const int tx_n = (ww + HB_TW - 1) / HB_TW, ty_n = (h + HB_TR - 1) / HB_TR;
-    const int tiles = tx_n * ty_n * K;
     const int tid = threadIdx.x;
     constexpr int SW = HB_TW + 2;
     int round = 0;
     for (;;) {
-        // flags[1 + round % 3] is this round's "some tile changed" flag (three flags rotate so that the flag of
-        // round r+2 can be cleared right after round r's barrier, when nobody can be setting or reading it)
         volatile int *chg = flags + 1 + (round % 3);
-        for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
-            const int k = t / (tx_n * ty_n), r = t - k * (tx_n * ty_n);
-            const int ty = r / tx_n, tx = r - ty * tx_n;
-            const int y0 = ty * HB_TR, c0 = tx * HB_TW;
-            u32 *E = ebits + (size_t)k * plane;
-            const u32 *C = cbits + (size_t)k * plane;
-            // load C and E (interior) and test whether anything is still promotable in this tile
-            int pending = 0;
-            for (int i = tid; i < HB_TR * HB_TW; i += 256) {
-                int ly = i / HB_TW, lc = i - ly * HB_TW;
-                int gy = y0 + ly, gc = c0 + lc;
-                u32 cv = 0, ev = 0;
-                if (gy < h && gc < ww) { cv = __ldg(C + (size_t)gy * ws + gc); ev = __ldcg(E + (size_t)gy * ws + gc); }
-                s_c[i] = cv;
-                s_e[(ly + 1) * SW + lc + 1] = ev;
-                pending |= (cv & ~ev) != 0;
-            }
-            if (!__syncthreads_or(pending)) continue;
-            // halo ring of E (other CTAs may be raising bits there concurrently: any snapshot is valid, bits only rise)
-            for (int i = tid; i < 2 * SW + 2 * HB_TR; i += 256) {
-                int ly, lc;
-                if (i < SW) { ly = 0; lc = i; }
-                else if (i < 2 * SW) { ly = HB_TR + 1; lc = i - SW; }
-                else { int j = i - 2 * SW; ly = 1 + (j >> 1); lc = (j & 1) ? HB_TW + 1 : 0; }
-                int gy = y0 - 1 + ly, gc = c0 - 1 + lc;
-                s_e[ly * SW + lc] = (gy >= 0 && gy < h && gc >= 0 && gc < ww) ? __ldcg(E + (size_t)gy * ws + gc) : 0u;
-            }
-            __syncthreads();
-            int any = 0;
-            for (;;) {
-                int changed = 0;
-                for (int i = tid; i < HB_TR * HB_TW; i += 256) {
-                    int ly = i / HB_TW, lc = i - ly * HB_TW;
-                    u32 cv = s_c[i];
-                    int o = (ly + 1) * SW + lc + 1;
-                    u32 ev = s_e[o];
-                    if (cv & ~ev) {
-                        u32 d = 0;
+        if (round < HY_WORD_ROUNDS) {
+            // ---- word round: rows are walked by warps (coalesced 128-byte row segments) ----
+            const long long rows = (long long)K * h;
+            const int lane = tid & 31;
+            const long long warp0 = ((long long)blockIdx.x * blockDim.x + tid) >> 5, nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+            for (long long R = warp0; R < rows; R += nwarps) {
+                const int k = (int)(R / h), y = (int)(R - (long long)k * h);
+                u32 *E = ebits + (size_t)k * plane + (size_t)y * ws;
+                const u32 *C = cbits + (size_t)k * plane + (size_t)y * ws;
+                for (int c = lane; c < ww; c += 32) {
+                    const u32 cv = __ldg(C + c), ev = __ldcg(E + c);
+                    if ((cv & ~ev) == 0u) continue;
+                    u32 d = 0u;
 #pragma unroll
-                        for (int dy = -1; dy <= 1; dy++) {
-                            u32 l = s_e[o + dy * SW - 1], m = s_e[o + dy * SW], rr = s_e[o + dy * SW + 1];
-                            d |= m | (m << 1) | (m >> 1) | (l >> 31) | (rr << 31);
-                        }
-                        u32 nv = ev | (cv & d);
-                        if (nv != ev) { s_e[o] = nv; changed = 1; }
+                    for (int dy = -1; dy <= 1; dy++) {
+                        if (y + dy < 0 || y + dy >= h) continue;
+                        const u32 *Er = E + (ptrdiff_t)dy * ws;
+                        u32 m = __ldcg(Er + c), l = c > 0 ? __ldcg(Er + c - 1) : 0u, r = c + 1 < ww ? __ldcg(Er + c + 1) : 0u;
+                        d |= m | (m << 1) | (m >> 1) | (l >> 31) | (r << 31);
+                    }
+                    u32 nv = ev | (cv & d);
+                    for (;;) {                                   // close the chain inside the word
+                        u32 t = nv | (cv & ((nv << 1) | (nv >> 1)));
+                        if (t == nv) break;
+                        nv = t;
+                    }
+                    if (nv != ev) {
+                        E[c] = nv;
+                        *chg = 1;
+                        hy_patch_bytes(edges + (size_t)k * estride + (size_t)y * epitch + 32 * c, nv & ~ev);
                     }
                 }
-                if (!__syncthreads_or(changed)) break;
-                any = 1;
             }
-            if (any) {
+        } else {
+            // ---- tile round ----
+            const int tx_n = (ww + HB_TW - 1) / HB_TW, ty_n = (h + HB_TR - 1) / HB_TR;
+            const int tiles = tx_n * ty_n * K;
+            for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
+                const int k = t / (tx_n * ty_n), r = t - k * (tx_n * ty_n);
+                const int ty = r / tx_n, tx = r - ty * tx_n;
+                const int y0 = ty * HB_TR, c0 = tx * HB_TW;
+                u32 *E = ebits + (size_t)k * plane;
+                const u32 *C = cbits + (size_t)k * plane;
+                int pending = 0;
                 for (int i = tid; i < HB_TR * HB_TW; i += 256) {
                     int ly = i / HB_TW, lc = i - ly * HB_TW;
                     int gy = y0 + ly, gc = c0 + lc;
-                    if (gy < h && gc < ww) E[(size_t)gy * ws + gc] = s_e[(ly + 1) * SW + lc + 1];
+                    u32 cv = 0, ev = 0;
+                    if (gy < h && gc < ww) { cv = __ldg(C + (size_t)gy * ws + gc); ev = __ldcg(E + (size_t)gy * ws + gc); }
+                    s_c[i] = cv;
+                    s_e[(ly + 1) * SW + lc + 1] = ev;
+                    pending |= (cv & ~ev) != 0;
                 }
-                if (tid == 0) *chg = 1;
+                if (!__syncthreads_or(pending)) continue;
+                // halo ring of E (other CTAs may be raising bits there concurrently: any snapshot is valid, bits only rise)
+                for (int i = tid; i < 2 * SW + 2 * HB_TR; i += 256) {
+                    int ly, lc;
+                    if (i < SW) { ly = 0; lc = i; }
+                    else if (i < 2 * SW) { ly = HB_TR + 1; lc = i - SW; }
+                    else { int j = i - 2 * SW; ly = 1 + (j >> 1); lc = (j & 1) ? HB_TW + 1 : 0; }
+                    int gy = y0 - 1 + ly, gc = c0 - 1 + lc;
+                    s_e[ly * SW + lc] = (gy >= 0 && gy < h && gc >= 0 && gc < ww) ? __ldcg(E + (size_t)gy * ws + gc) : 0u;
+                }
+                __syncthreads();
+                int any = 0;
+                for (;;) {
+                    int changed = 0;
+                    for (int i = tid; i < HB_TR * HB_TW; i += 256) {
+                        int ly = i / HB_TW, lc = i - ly * HB_TW;
+                        u32 cv = s_c[i];
+                        int o = (ly + 1) * SW + lc + 1;
+                        u32 ev = s_e[o];
+                        if (cv & ~ev) {
+                            u32 d = 0;
+#pragma unroll
+                            for (int dy = -1; dy <= 1; dy++) {
+                                u32 l = s_e[o + dy * SW - 1], m = s_e[o + dy * SW], rr = s_e[o + dy * SW + 1];
+                                d |= m | (m << 1) | (m >> 1) | (l >> 31) | (rr << 31);
+                            }
+                            u32 nv = ev | (cv & d);
+                            if (nv != ev) { s_e[o] = nv; changed = 1; }
+                        }
+                    }
+                    if (!__syncthreads_or(changed)) break;
+                    any = 1;
+                }
+                if (any) {
+                    for (int i = tid; i < HB_TR * HB_TW; i += 256) {
+                        int ly = i / HB_TW, lc = i - ly * HB_TW;
+                        int gy = y0 + ly, gc = c0 + lc;
+                        if (gy < h && gc < ww) {
+                            u32 nv = s_e[(ly + 1) * SW + lc + 1], old = __ldcg(E + (size_t)gy * ws + gc);
+                            if (nv & ~old) {
+                                E[(size_t)gy * ws + gc] = nv | old;
+                                hy_patch_bytes(edges + (size_t)k * estride + (size_t)gy * epitch + 32 * gc, nv & ~old);
+                            }
+                        }
+                    }
+                    if (tid == 0) *chg = 1;
+                }
+                __syncthreads();
             }
-            __syncthreads();
         }
         __threadfence();
         grid.sync();
@@ -571,23 +630,6 @@ __global__ void __launch_bounds__(256) fk_hysteresis(u32 *__restrict__ ebits, co
         if (blockIdx.x == 0 && tid == 0) { flags[0] = round + 1; flags[1 + ((round + 2) % 3)] = 0; }
         round++;
         if (!c) break;
-    }
-    // The edge kernel already wrote the byte planes for E = S; only the promoted pixels (E & ~S) remain.
-    if (edges) {
-        const long long total = (long long)K * h * ww;
-        for (long long u = (long long)blockIdx.x * blockDim.x + tid; u < total; u += (long long)gridDim.x * blockDim.x) {
-            int k = (int)(u / ((long long)h * ww));
-            long long r = u - (long long)k * h * ww;
-            int y = (int)(r / ww), c = (int)(r - (long long)y * ww);
-            size_t o = (size_t)k * plane + (size_t)y * ws + c;
-            u32 d = __ldcg(ebits + o) & ~__ldg(sbits + o);
-            u8 *row = edges + (size_t)k * estride + (size_t)y * epitch + c * 32;
-            while (d) {
-                int e = __ffs(d) - 1;
-                d &= d - 1u;
-                row[e] = 255;
-            }
-        }
     }
 }
 
@@ -680,7 +722,7 @@ bool fast_edges_supported(const omni_edge_params *prm)
     return morph03_kind(prm) >= 0 && prm->ksize == 3;
 }
 
-static int run_hysteresis(omni_ctx *ctx, u32 *ebits, const u32 *cbits, const u32 *sbits, const BitGeom &g, int K, u8 *d_edges,
+static int run_hysteresis(omni_ctx *ctx, u32 *ebits, const u32 *cbits, const BitGeom &g, int K, u8 *d_edges,
                           size_t e_plane, size_t epitch, cudaStream_t st)
 {
     if (ctx->hyst_blocks == 0) {
@@ -693,21 +735,21 @@ static int run_hysteresis(omni_ctx *ctx, u32 *ebits, const u32 *cbits, const u32
     int ws = g.ws, h = g.h, w = g.w;
     size_t plane = g.plane;
     int *flags = ctx->d_flags;
-    void *args[] = {&ebits, &cbits, &sbits, &ws, &plane, &h, &w, &K, &flags, &d_edges, &e_plane, &epitch};
+    void *args[] = {&ebits, &cbits, &ws, &plane, &h, &w, &K, &flags, &d_edges, &e_plane, &epitch};
     OMNI_LAUNCH(ctx, st, "hysteresis_bits", cudaLaunchCooperativeKernel((const void *)fk_hysteresis, dim3(ctx->hyst_blocks), dim3(256),
                                                                         args, 0, st));
     ctx->last_hyst_passes = -1;           // lives in d_flags[0]; fetched lazily by omni_last_hysteresis_passes
     return OMNI_OK;
 }
 
-// bit-planes M2 -> edge byte planes.  bp: [sbits, cbits, ebits] workspace planes.
-static int edges_from_bits(omni_ctx *ctx, const u32 *m2, u32 *sbits, u32 *cbits, u32 *ebits, const BitGeom &g, int K, int low, int high,
+// bit-planes M2 -> edge byte planes.  sbits doubles as the working set E of the hysteresis.
+static int edges_from_bits(omni_ctx *ctx, const u32 *m2, u32 *sbits, u32 *cbits, const BitGeom &g, int K, int low, int high,
                            u8 *d_edges, size_t e_plane, size_t epitch, cudaStream_t st)
 {
     int al = ((uintptr_t)d_edges % 16 == 0) && (e_plane % 16 == 0) && (epitch % 16 == 0);
-    OMNI_LAUNCH(ctx, st, "edges3_bits", launch_edges3_simd(m2, g.ws, g.plane, g.h, g.w, K, low, high, ctx->sm_count, sbits, cbits, ebits,
+    OMNI_LAUNCH(ctx, st, "edges3_bits", launch_edges3_simd(m2, g.ws, g.plane, g.h, g.w, K, low, high, ctx->sm_count, sbits, cbits,
                                                            d_edges, e_plane, epitch, al, st));
-    return run_hysteresis(ctx, ebits, cbits, sbits, g, K, d_edges, e_plane, epitch, st);
+    return run_hysteresis(ctx, sbits, cbits, g, K, d_edges, e_plane, epitch, st);
 }
 
 int fast_edges(omni_ctx *ctx, const u8 *d_masks, int K, int h, int w, size_t m_plane, size_t mpitch,
@@ -717,8 +759,8 @@ int fast_edges(omni_ctx *ctx, const u8 *d_masks, int K, int h, int w, size_t m_p
     (void)bp;
     if (low < 0) return OMNI_ERR_UNSUPPORTED;        // m == 0 would be a candidate: generic kernels handle it
     BitGeom g = make_geom(h, w);
-    u32 *bpp[5];
-    FK_TRY(bit_planes(ctx, g, K, 5, bpp));
+    u32 *bpp[4];
+    FK_TRY(bit_planes(ctx, g, K, 4, bpp));
     OMNI_CUDA(cudaMemsetAsync(ctx->d_flags + 8, 0, sizeof(int), st));
     {
         KScope ks(ctx, "bytes_to_bits", st);
@@ -735,7 +777,7 @@ int fast_edges(omni_ctx *ctx, const u8 *d_masks, int K, int h, int w, size_t m_p
         OMNI_LAUNCH(ctx, st, "morph_bits", launch_morph(false, kind, bpp[0], bpp[1], g, K, nullptr, 0, 0, st));
         m2 = bpp[1];
     }
-    return edges_from_bits(ctx, m2, bpp[2], bpp[3], bpp[4], g, K, low, high, d_edges, e_plane, epitch, st);
+    return edges_from_bits(ctx, m2, bpp[2], bpp[3], g, K, low, high, d_edges, e_plane, epitch, st);
 }
 
 int fast_color_edge(omni_ctx *ctx, const u8 *d_bgr, int h, int w, size_t pitch, const AssignParams &P,
@@ -747,8 +789,8 @@ int fast_color_edge(omni_ctx *ctx, const u8 *d_bgr, int h, int w, size_t pitch, 
     if (low < 0) return OMNI_ERR_UNSUPPORTED;
     OMNI_CUDA(fast_tables());
     BitGeom g = make_geom(h, w);
-    u32 *bpp[5];
-    FK_TRY(bit_planes(ctx, g, P.K, 5, bpp));
+    u32 *bpp[4];
+    FK_TRY(bit_planes(ctx, g, P.K, 4, bpp));
     u32 *cells = nullptr;
     FK_TRY(assign_cells(ctx, P, &cells, st));
     OMNI_CUDA(cudaMemsetAsync(bpp[0], 0, g.plane * (size_t)P.K * sizeof(u32), st));      // match_any stores only non-empty words
@@ -759,5 +801,5 @@ int fast_color_edge(omni_ctx *ctx, const u8 *d_bgr, int h, int w, size_t pitch, 
     }
     int kind = morph03_kind(prm);
     OMNI_LAUNCH(ctx, st, "morph_bits", launch_morph(true, kind, bpp[0], bpp[1], g, P.K, d_masks, m_plane, mpitch, st));
-    return edges_from_bits(ctx, bpp[1], bpp[2], bpp[3], bpp[4], g, P.K, low, high, d_edges, e_plane, epitch, st);
+    return edges_from_bits(ctx, bpp[1], bpp[2], bpp[3], g, P.K, low, high, d_edges, e_plane, epitch, st);
 }

@@ -322,3 +322,32 @@ def test_no_cpu_fallback_error_paths(eng):
         eng.edges(dev(blob_mask(64, 64, 0)[None]), omni_b200.EdgeConfig(ksize=33))
     with pytest.raises(omni_b200.OmniError):
         eng.assign_lab(dev(synth(64, 64, 0)), np.zeros((40, 3), np.float32))
+
+
+def _spiral_binary(n=384, pitch=8):
+    img = np.zeros((n, n), np.uint8)
+    y = x = 6
+    dy, dx, run = 0, 1, n - 13
+    while run > 2 * pitch:
+        for _ in range(run):
+            img[y, x] = 255
+            y, x = y + dy, x + dx
+        dy, dx = dx, -dy
+        run -= pitch
+    img[3:10, 3:10] = 255
+    return img
+
+
+def test_edges_binary_spiral_long_chain(eng_mode):
+    """A {0,255} mask (fast bit-plane path) whose weak chain is ~8700 pixels deep from 4-8 strong seeds: the
+    cooperative hysteresis must escalate from word rounds to tile rounds and still reach the fixed point."""
+    import omni_b200
+    cm = _cm()
+    img = _spiral_binary()
+    masks = np.stack([img, np.ascontiguousarray(img.T), np.ascontiguousarray(img[::-1])])
+    ec = omni_b200.EdgeConfig(low=100, high=900, ksize=3, open_iters=0, close_iters=0)
+    got = host(eng_mode.edges(dev(masks), ec))
+    want = np.stack([cm.edge_chain(m, 3, 0, 0, 3, 100, 900) for m in masks])
+    assert want[0].sum() > 15000 * 255
+    assert np.array_equal(got, want)
+    assert eng_mode.last_hysteresis_passes() > 4
