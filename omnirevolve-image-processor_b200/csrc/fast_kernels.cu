@@ -175,6 +175,20 @@ __global__ void __launch_bounds__(256) fk_build_cells(const __grid_constant__ As
     cells[ci] = mask;
 }
 
+// cv2 BGR->Lab (8-bit) for one pixel, without the final saturate_cast: with OpenCV's tables L, a, b stay
+// inside [0,255] for every input (L 0..255, a 42..226, b 20..223 over all 2^24 colours -- the exhaustive GPU test
+// covers it), so the clamps of the generic kernel are no-ops here.
+__device__ __forceinline__ void lab_noclamp(const u16 *gam, const u16 *cbrt, int B8, int G8, int R8, int &L, int &a, int &b)
+{
+    const int B = gam[B8], G = gam[G8], R = gam[R8];
+    const int fX = cbrt[(R * 1777 + G * 1541 + B * 778 + 2048) >> 12];
+    const int fY = cbrt[(R * 871 + G * 2929 + B * 296 + 2048) >> 12];
+    const int fZ = cbrt[(R * 73 + G * 448 + B * 3575 + 2048) >> 12];
+    L = (296 * fY - 1336934 + 16384) >> 15;
+    a = (500 * (fX - fY) + 128 * 32768 + 16384) >> 15;
+    b = (200 * (fY - fZ) + 128 * 32768 + 16384) >> 15;
+}
+
 template <int MODE_LAB>
 __global__ void __launch_bounds__(256) fk_assign_bits(const u8 *__restrict__ px, int h, int w, size_t pitch,
                                                       const __grid_constant__ AssignParams P, const u32 *__restrict__ cells,
@@ -185,6 +199,7 @@ __global__ void __launch_bounds__(256) fk_assign_bits(const u8 *__restrict__ px,
     __shared__ u16 s_cbrt[2048];
     __shared__ float4 s_ctr[OMNI_MAX_K];
     __shared__ u8 s_lut[OMNI_MAX_K];
+    __shared__ __align__(16) u8 s_px[8][768];                 // per warp: the 256 pixels of the current chunk
     if (MODE_LAB) {
         for (int i = threadIdx.x; i < 2048; i += 256) {
             s_cbrt[i] = f_lab_tab[256 + i];
@@ -198,22 +213,48 @@ __global__ void __launch_bounds__(256) fk_assign_bits(const u8 *__restrict__ px,
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int chunks = (w + 255) >> 8, K = P.K;
-    const long long total = (long long)h * chunks;
-    for (long long u = (long long)blockIdx.x * 8 + warp; u < total; u += (long long)gridDim.x * 8) {
+    const long long total = (long long)h * chunks, stride = (long long)gridDim.x * 8;
+    // rows can be moved with 16-byte loads when the image base and pitch allow it
+    const bool vec_ok = (((uintptr_t)px | pitch) & 15) == 0;
+    u8 *spx = s_px[warp];
+    uint4 pf0 = make_uint4(0, 0, 0, 0), pf1 = pf0;
+    auto chunk_full = [&](long long u) { int c = (int)(u % chunks); return vec_ok && c * 256 + 256 <= w; };
+    auto prefetch = [&](long long u) {
+        if (u < total && chunk_full(u)) {
+            const int y = (int)(u / chunks), c = (int)(u - (long long)y * chunks);
+            const uint4 *src = reinterpret_cast<const uint4 *>(px + (size_t)y * pitch + (size_t)c * 768);
+            pf0 = __ldg(src + lane);
+            if (lane < 16) pf1 = __ldg(src + 32 + lane);
+        }
+    };
+    long long u = (long long)blockIdx.x * 8 + warp;
+    prefetch(u);
+    for (; u < total; u += stride) {
         const int y = (int)(u / chunks), c = (int)(u - (long long)y * chunks);
         const int x0 = c * 256 + lane;
-        const u8 *row = px + (size_t)y * pitch;
+        const bool full = chunk_full(u);
+        __syncwarp();                                          // the previous chunk has been consumed
+        if (full) {
+            reinterpret_cast<uint4 *>(spx)[lane] = pf0;
+            if (lane < 16) reinterpret_cast<uint4 *>(spx)[32 + lane] = pf1;
+        } else {
+            const u8 *row = px + (size_t)y * pitch + (size_t)c * 768;
+            const int nb = 3 * min(256, w - c * 256);
+            for (int i = lane; i < nb; i += 32) spx[i] = row[i];
+        }
+        prefetch(u + stride);
+        __syncwarp();
         int lab[8];
 #pragma unroll
         for (int g = 0; g < 8; g++) {
             const int x = x0 + 32 * g;
             lab[g] = 255;
             if (x < w) {
-                const u8 *p = row + 3 * (size_t)x;
+                const u8 *p = spx + 3 * lane + 96 * g;
                 int v0 = p[0], v1 = p[1], v2 = p[2], best = 0;
                 if (MODE_LAB) {
                     int L, a, b;
-                    bgr2lab_px(s_gam, s_cbrt, v0, v1, v2, L, a, b);
+                    lab_noclamp(s_gam, s_cbrt, v0, v1, v2, L, a, b);
                     u32 mk = __ldg(cells + (((L >> CELL_SHIFT) * CELL_N + (a >> CELL_SHIFT)) * CELL_N + (b >> CELL_SHIFT)));
                     float f0 = (float)L, f1 = (float)a, f2 = (float)b, bd = 3.0e38f;
                     do {
@@ -638,6 +679,21 @@ __global__ void __launch_bounds__(256) fk_hysteresis(u32 *__restrict__ ebits, co
 // ------------------------------------------------------------------------------------------------
 static int persist_blocks(omni_ctx *ctx, int per_sm) { return (ctx->sm_count > 0 ? ctx->sm_count : 148) * per_sm; }
 
+// persistent grid of a kernel = SM count x the number of its CTAs that are resident per SM (queried once)
+template <typename Kern>
+static int resident_grid(omni_ctx *ctx, Kern kern, int block, int *cache)
+{
+    if (*cache == 0) {
+        int per_sm = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, block, 0) != cudaSuccess || per_sm < 1) {
+            cudaGetLastError();
+            per_sm = 1;
+        }
+        *cache = per_sm;
+    }
+    return persist_blocks(ctx, *cache);
+}
+
 static int bit_planes(omni_ctx *ctx, const BitGeom &g, int K, int n, u32 **out /* n pointers */)
 {
     size_t one = g.plane * (size_t)K * sizeof(u32);
@@ -670,7 +726,8 @@ cudaError_t fast_assign(omni_ctx *ctx, const u8 *px, int h, int w, size_t pitch,
 {
     cudaError_t e = fast_tables();
     if (e != cudaSuccess) return e;
-    int grid = persist_blocks(ctx, 6);
+    int grid = mode_lab ? resident_grid(ctx, fk_assign_bits<1>, 256, &ctx->occ_assign_lab)
+                        : resident_grid(ctx, fk_assign_bits<0>, 256, &ctx->occ_assign_pal);
     if (mode_lab) {
         u32 *cells = nullptr;
         if (assign_cells(ctx, P, &cells, st) != OMNI_OK) return cudaErrorMemoryAllocation;
@@ -796,7 +853,8 @@ int fast_color_edge(omni_ctx *ctx, const u8 *d_bgr, int h, int w, size_t pitch, 
     OMNI_CUDA(cudaMemsetAsync(bpp[0], 0, g.plane * (size_t)P.K * sizeof(u32), st));      // match_any stores only non-empty words
     {
         KScope ks(ctx, "assign_bits", st);
-        fk_assign_bits<1><<<persist_blocks(ctx, 6), 256, 0, st>>>(d_bgr, h, w, pitch, P, cells, d_labels, lpitch, bpp[0], g.ws, g.plane);
+        fk_assign_bits<1><<<resident_grid(ctx, fk_assign_bits<1>, 256, &ctx->occ_assign_lab), 256, 0, st>>>(
+            d_bgr, h, w, pitch, P, cells, d_labels, lpitch, bpp[0], g.ws, g.plane);
         OMNI_CUDA(cudaGetLastError());
     }
     int kind = morph03_kind(prm);

@@ -79,6 +79,7 @@ struct omni_ctx {
     std::vector<cudaEvent_t> ev_pool;
     int sm_count = 0;
     int hyst_blocks = 0;
+    int occ_assign_lab = 0, occ_assign_pal = 0;   // resident CTAs per SM of the persistent assignment kernels
     // centres the candidate-cell table in ws[5] was built for (fast colour assignment)
     int cells_valid = 0, cells_K = 0;
     void *cells_stream = nullptr;
