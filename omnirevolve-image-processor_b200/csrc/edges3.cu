@@ -48,7 +48,8 @@ __device__ __forceinline__ u32 as_u32(__half2 x) { return *reinterpret_cast<u32 
 __global__ void __launch_bounds__(E3V_WARPS * 32) fk_edges3_simd(const u32 *__restrict__ m2, int ws, size_t plane, int h, int w, int low,
                                                                  int high, int tr, int wcols, u32 *__restrict__ sbits,
                                                                  u32 *__restrict__ cbits, u8 *__restrict__ edges,
-                                                                 size_t estride, size_t epitch, int aligned16)
+                                                                 size_t estride, size_t epitch, int aligned16, int *__restrict__ wl_count,
+                                                                 u32 *__restrict__ worklist, int wl_cap)
 {
     __shared__ E3WarpSmem sm[E3V_WARPS];
     __shared__ u32 s_lut6[64];
@@ -240,8 +241,14 @@ __global__ void __launch_bounds__(E3V_WARPS * 32) fk_edges3_simd(const u32 *__re
         if (do_nms && active) {
             size_t o = (size_t)k * plane + (size_t)rn * ws + c;
             const u32 sw = S.sw[lane];
-            cbits[o] = S.cw[lane]; sbits[o] = sw;
+            const u32 cwv = S.cw[lane];
+            cbits[o] = cwv; sbits[o] = sw;
+            if (cwv & ~sw) {                                   // a weak candidate: the hysteresis kernel must look at this word
+                int i = atomicAdd(wl_count, 1);
+                if (i < wl_cap) worklist[i] = (u32)o;
+            }
             // edge bytes for E = S; the hysteresis kernel patches the (rare) promoted weak pixels afterwards
+            // (arithmetic bit->byte expansion: a 2 KB table would cost the 6th resident CTA per SM)
             store_word_bytes(edges + (size_t)k * estride + (size_t)rn * epitch, 32 * c, w, sw, aligned16 != 0);
         }
         cand_prev = cand;
@@ -264,7 +271,8 @@ __global__ void __launch_bounds__(E3V_WARPS * 32) fk_edges3_simd(const u32 *__re
 }
 
 cudaError_t launch_edges3_simd(const u32 *m2, int ws, size_t plane, int h, int w, int K, int low, int high, int sm_count,
-                               u32 *sbits, u32 *cbits, u8 *edges, size_t estride, size_t epitch, int aligned16, cudaStream_t st)
+                               u32 *sbits, u32 *cbits, u8 *edges, size_t estride, size_t epitch, int aligned16, int *wl_count, u32 *worklist, int wl_cap,
+                               cudaStream_t st)
 {
     const int ww = (w + 31) >> 5, wcols = (ww + 31) / 32;
     // strip height: enough warps for ~2 waves of the machine (12 resident warps per SM), at most 64 rows
@@ -278,6 +286,6 @@ cudaError_t launch_edges3_simd(const u32 *m2, int ws, size_t plane, int h, int w
     strips = (h + tr - 1) / tr;
     long long warps = (long long)strips * wcols;
     dim3 grid((unsigned)((warps + E3V_WARPS - 1) / E3V_WARPS), K);
-    fk_edges3_simd<<<grid, E3V_WARPS * 32, 0, st>>>(m2, ws, plane, h, w, low, high, tr, wcols, sbits, cbits, edges, estride, epitch, aligned16);
+    fk_edges3_simd<<<grid, E3V_WARPS * 32, 0, st>>>(m2, ws, plane, h, w, low, high, tr, wcols, sbits, cbits, edges, estride, epitch, aligned16, wl_count, worklist, wl_cap);
     return cudaGetLastError();
 }

@@ -137,6 +137,9 @@ cudaError_t fast_resize_2x(const u8 *src, size_t spitch, u8 *dst, int dh, int dw
 #define CELL_SHIFT 3
 #define CELL_N (256 >> CELL_SHIFT)                 // 32 cells per axis
 #define CELL_COUNT (CELL_N * CELL_N * CELL_N)
+// workspace slot 5: [candidate-cell table | hysteresis worklist]
+#define HYST_WL_OFFSET CELL_COUNT
+#define WS5_BYTES ((size_t)(CELL_COUNT + 8192) * sizeof(u32))
 
 __global__ void __launch_bounds__(256) fk_build_cells(const __grid_constant__ AssignParams P, u32 *__restrict__ cells)
 {
@@ -434,6 +437,11 @@ __global__ void __launch_bounds__(128) fk_morph(const u32 *__restrict__ in_bits,
                                                 int w, u8 *__restrict__ masks, size_t mstride, size_t mpitch, int aligned16)
 {
     constexpr int N = code_len(CODE);
+    __shared__ uint2 s_lut8[256];
+    if (TAP >= 0) {
+        expand_lut_init(s_lut8, threadIdx.x, blockDim.x);
+        __syncthreads();
+    }
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     const int ww = (w + 31) >> 5;
     if (c >= ww) return;
@@ -473,7 +481,7 @@ __global__ void __launch_bounds__(128) fk_morph(const u32 *__restrict__ in_bits,
             const int r = t - TAP;
             if (r >= y0 && r < y1) {
                 u32 word = (tap.lo >> 16) | (tap.hi << 16);
-                store_word_bytes(masks + (size_t)k * mstride + (size_t)r * mpitch, 32 * c, w, word, aligned16 != 0);
+                store_word_bytes_lut(masks + (size_t)k * mstride + (size_t)r * mpitch, 32 * c, w, word, aligned16 != 0, s_lut8);
             }
         }
         if (out_bits) {
@@ -539,6 +547,7 @@ static cudaError_t launch_morph(bool with02, int morph03, const u32 *in_bits, u3
 #define HB_TR 32                      // tile rows
 #define HB_TW 32                      // tile words (1024 pixels)
 #define HY_WORD_ROUNDS 4
+#define HY_WL_CAP 8192                 // words holding weak candidates; more than this -> full sweeps
 
 __device__ __forceinline__ void hy_patch_bytes(u8 *row, u32 promoted)
 {
@@ -550,10 +559,54 @@ __device__ __forceinline__ void hy_patch_bytes(u8 *row, u32 promoted)
 }
 
 __global__ void __launch_bounds__(256) fk_hysteresis(u32 *__restrict__ ebits, const u32 *__restrict__ cbits, int ws, size_t plane, int h,
-                                                     int w, int K, int *flags /* [0]=rounds, [1..3]=rotating "changed" flags */,
+                                                     int w, int K, int *flags /* [0]=rounds, [1..3]=rotating "changed" flags, [4]=worklist count */,
+                                                     const u32 *__restrict__ worklist,
                                                      u8 *__restrict__ edges, size_t estride, size_t epitch)
 {
     cg::grid_group grid = cg::this_grid();
+    // ---- worklist mode: the edge kernel listed every word that holds a weak candidate (C & ~S); on pipeline data
+    // that is a few hundred words, so ONE CTA resolves them and the rest of the grid leaves at once ----
+    const int n_weak = flags[4];
+    if (n_weak <= HY_WL_CAP) {
+        if (blockIdx.x != 0) return;
+        const int wwl = (w + 31) >> 5;
+        int rounds = 0;
+        for (;;) {
+            int changed = 0;
+            for (int i = threadIdx.x; i < n_weak; i += 256) {
+                const u32 o = worklist[i];
+                const int k = (int)(o / plane), rem = (int)(o - (size_t)k * plane);
+                const int y = rem / ws, c = rem - y * ws;
+                u32 *E = ebits + (size_t)k * plane + (size_t)y * ws;
+                const u32 cv = __ldg(cbits + o), ev = __ldcg(E + c);
+                if ((cv & ~ev) == 0u) continue;
+                u32 d = 0u;
+#pragma unroll
+                for (int dy = -1; dy <= 1; dy++) {
+                    if (y + dy < 0 || y + dy >= h) continue;
+                    const u32 *Er = E + (ptrdiff_t)dy * ws;
+                    u32 m = __ldcg(Er + c), l = c > 0 ? __ldcg(Er + c - 1) : 0u, r = c + 1 < wwl ? __ldcg(Er + c + 1) : 0u;
+                    d |= m | (m << 1) | (m >> 1) | (l >> 31) | (r << 31);
+                }
+                u32 nv = ev | (cv & d);
+                for (;;) {
+                    u32 t = nv | (cv & ((nv << 1) | (nv >> 1)));
+                    if (t == nv) break;
+                    nv = t;
+                }
+                if (nv != ev) {
+                    E[c] = nv;
+                    changed = 1;
+                    hy_patch_bytes(edges + (size_t)k * estride + (size_t)y * epitch + 32 * c, nv & ~ev);
+                }
+            }
+            rounds++;
+            __threadfence_block();
+            if (!__syncthreads_or(changed)) break;
+        }
+        if (threadIdx.x == 0) flags[0] = rounds;
+        return;
+    }
     __shared__ u32 s_e[(HB_TR + 2) * (HB_TW + 2)];
     __shared__ u32 s_c[HB_TR * HB_TW];
     const int ww = (w + 31) >> 5;
@@ -706,7 +759,7 @@ static int bit_planes(omni_ctx *ctx, const BitGeom &g, int K, int n, u32 **out /
 // candidate-cell table for the centres of this call (workspace slot 5), built on the device
 static int assign_cells(omni_ctx *ctx, const AssignParams &P, u32 **cells, cudaStream_t st)
 {
-    FK_TRY(omni_ws_reserve(ctx, 5, CELL_COUNT * sizeof(u32)));
+    FK_TRY(omni_ws_reserve(ctx, 5, WS5_BYTES));
     *cells = (u32 *)ctx->ws[5];
     // same centres as the previous call on this ctx (a batch of frames): the table in the workspace is still valid
     // (calls on one ctx are serialised and go to one stream at a time, see omni_b200.h)
@@ -788,11 +841,11 @@ static int run_hysteresis(omni_ctx *ctx, u32 *ebits, const u32 *cbits, const Bit
         if (per_sm < 1) { omni_set_error("hysteresis kernel cannot be made resident"); return OMNI_ERR_CUDA; }
         ctx->hyst_blocks = per_sm * (ctx->sm_count > 0 ? ctx->sm_count : 1);
     }
-    OMNI_CUDA(cudaMemsetAsync(ctx->d_flags, 0, 4 * sizeof(int), st));
     int ws = g.ws, h = g.h, w = g.w;
     size_t plane = g.plane;
     int *flags = ctx->d_flags;
-    void *args[] = {&ebits, &cbits, &ws, &plane, &h, &w, &K, &flags, &d_edges, &e_plane, &epitch};
+    const u32 *worklist = (const u32 *)ctx->ws[5] + HYST_WL_OFFSET;
+    void *args[] = {&ebits, &cbits, &ws, &plane, &h, &w, &K, &flags, &worklist, &d_edges, &e_plane, &epitch};
     OMNI_LAUNCH(ctx, st, "hysteresis_bits", cudaLaunchCooperativeKernel((const void *)fk_hysteresis, dim3(ctx->hyst_blocks), dim3(256),
                                                                         args, 0, st));
     ctx->last_hyst_passes = -1;           // lives in d_flags[0]; fetched lazily by omni_last_hysteresis_passes
@@ -804,8 +857,11 @@ static int edges_from_bits(omni_ctx *ctx, const u32 *m2, u32 *sbits, u32 *cbits,
                            u8 *d_edges, size_t e_plane, size_t epitch, cudaStream_t st)
 {
     int al = ((uintptr_t)d_edges % 16 == 0) && (e_plane % 16 == 0) && (epitch % 16 == 0);
+    FK_TRY(omni_ws_reserve(ctx, 5, WS5_BYTES));
+    OMNI_CUDA(cudaMemsetAsync(ctx->d_flags, 0, 8 * sizeof(int), st));     // rounds, 3 changed flags, worklist count
     OMNI_LAUNCH(ctx, st, "edges3_bits", launch_edges3_simd(m2, g.ws, g.plane, g.h, g.w, K, low, high, ctx->sm_count, sbits, cbits,
-                                                           d_edges, e_plane, epitch, al, st));
+                                                           d_edges, e_plane, epitch, al, ctx->d_flags + 4,
+                                                           (u32 *)ctx->ws[5] + HYST_WL_OFFSET, HY_WL_CAP, st));
     return run_hysteresis(ctx, sbits, cbits, g, K, d_edges, e_plane, epitch, st);
 }
 

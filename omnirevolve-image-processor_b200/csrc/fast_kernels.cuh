@@ -26,4 +26,5 @@ int fast_color_edge(omni_ctx *ctx, const u8 *d_bgr, int h, int w, size_t pitch, 
 
 // edges3.cu: SIMD-in-register blur3 + Sobel + NMS on a bit-plane (strong / candidate bit-planes out)
 cudaError_t launch_edges3_simd(const u32 *m2, int ws, size_t plane, int h, int w, int K, int low, int high, int sm_count,
-                               u32 *sbits, u32 *cbits, u8 *edges, size_t estride, size_t epitch, int aligned16, cudaStream_t st);
+                               u32 *sbits, u32 *cbits, u8 *edges, size_t estride, size_t epitch, int aligned16, int *wl_count, u32 *worklist, int wl_cap,
+                               cudaStream_t st);

@@ -157,6 +157,24 @@ __device__ __forceinline__ void store_word_bytes(u8 *row, int x0, int w, u32 wor
     }
 }
 
+// same, with the bit -> byte expansion done by a 256-entry shared-memory table (8 mask bits -> 8 bytes)
+__device__ __forceinline__ void expand_lut_init(uint2 *lut8, int tid, int nthreads)
+{
+    for (int b = tid; b < 256; b += nthreads) lut8[b] = make_uint2(expand4(b & 15u), expand4((u32)b >> 4));
+}
+__device__ __forceinline__ void store_word_bytes_lut(u8 *row, int x0, int w, u32 word, bool aligned16, const uint2 *lut8)
+{
+    if (x0 + 32 <= w && aligned16) {
+        const uint2 a = lut8[word & 255u], b = lut8[(word >> 8) & 255u], c = lut8[(word >> 16) & 255u], d = lut8[word >> 24];
+        uint4 *p = reinterpret_cast<uint4 *>(row + x0);
+        p[0] = make_uint4(a.x, a.y, b.x, b.y);
+        p[1] = make_uint4(c.x, c.y, d.x, d.y);
+    } else {
+        int n = min(32, w - x0);
+        for (int i = 0; i < n; i++) row[x0 + i] = (word >> i) & 1u ? 255 : 0;
+    }
+}
+
 // cv2.cvtColor(u8 BGR -> Lab) integer pipeline (02_color_extract.py:35); tables: gamma[256], cbrt[2041]
 __device__ __forceinline__ int descale(int x, int n) { return (x + (1 << (n - 1))) >> n; }
 
