@@ -253,7 +253,6 @@ def run_ours(args, wl):
     sampler.start()
     time.sleep(0.05)
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    eng.profile(True)
     n_launch0 = eng.launch_count()
     barrier()
     t_wall0 = time.perf_counter()
@@ -265,8 +264,19 @@ def run_ours(args, wl):
     barrier()
     t_wall = time.perf_counter() - t_wall0
     launches = eng.launch_count() - n_launch0
+    # per-kernel CUDA events cost ~20 us per step, so they run in a second pass of the same K steps (same inputs,
+    # same L2 flush) right after the timed region instead of inside it
+    eng.profile(True)
+    pev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for a, b in pev:
+        flush.fill_(1)
+        a.record()
+        step()
+        b.record()
+    torch.cuda.synchronize()
     prof = eng.profile_summary()
     eng.profile(False)
+    prof_step_ms = sum(a.elapsed_time(b) for a, b in pev) / args.steps
     clocks = sampler.result()
     step_ms = [a.elapsed_time(b) for a, b in ev]
     total_ms = sum(step_ms)
@@ -339,7 +349,9 @@ def run_ours(args, wl):
             roof = {"bound": "hbm", "kernel": name, "achieved": ach, "peak": peak, "unit": "GB/s",
                     "frac": (ach / peak) if ach is not None else None, "traffic": traffic, "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": alg, "launches_per_step": n_l / args.steps,
-                    "ms_per_launch": per_launch_ms, "share_of_step": ms / total_ms,
+                    "ms_per_launch": per_launch_ms, "share_of_step": ms / (prof_step_ms * args.steps),
+                    "timing": "CUDA events around every kernel launch, second pass of the same K steps (%.4f ms/step with the "
+                              "events vs %.4f without)" % (prof_step_ms, ms_per_step),
                     "step": {"algorithmic_bytes": N * (3 + 2 * K),
                              "achieved": N * (3 + 2 * K) / (ms_per_step / 1e3) / 1e9,
                              "frac": N * (3 + 2 * K) / (ms_per_step / 1e3) / 1e9 / peak},

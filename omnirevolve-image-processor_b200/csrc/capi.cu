@@ -413,9 +413,10 @@ static int generic_hysteresis(omni_ctx *ctx, u8 *state, size_t plane, size_t pit
     return OMNI_OK;
 }
 
+// skip_morph: d_masks already holds the planes AFTER the stage-03 open/close (fast bit morphology wrote them)
 static int generic_edges(omni_ctx *ctx, const uint8_t *d_masks, int K, int h, int w, size_t m_plane, size_t mpitch,
                          const omni_edge_params *prm, const BlurParams &bp, int low, int high,
-                         uint8_t *d_edges, size_t e_plane, size_t epitch, cudaStream_t st)
+                         uint8_t *d_edges, size_t e_plane, size_t epitch, cudaStream_t st, bool skip_morph = false)
 {
     size_t wp = ((size_t)w + 15) & ~(size_t)15, wplane = wp * h;
     OMNI_TRY(omni_ws_reserve(ctx, 0, wplane * K));
@@ -424,6 +425,7 @@ static int generic_edges(omni_ctx *ctx, const uint8_t *d_masks, int K, int h, in
     MorphSE se;
     omni_build_se(1, prm->morph_k, &se);
     int oi = prm->open_iters > 0 ? prm->open_iters : 0, ci = prm->close_iters > 0 ? prm->close_iters : 0;
+    if (skip_morph) oi = ci = 0;
     int seq_n = 0, seq[4 * 64];
     for (int i = 0; i < oi; i++) seq[seq_n++] = 0;
     for (int i = 0; i < oi; i++) seq[seq_n++] = 1;
@@ -441,6 +443,28 @@ static int generic_edges(omni_ctx *ctx, const uint8_t *d_masks, int K, int h, in
     return generic_hysteresis(ctx, d_edges, e_plane, epitch, K, h, w, st);
 }
 
+// masks (byte planes) -> edges with the best available kernels:
+//   fast bit-plane path (edge_kernel_size 3) > fast bit morphology + generic blur/Canny (other sizes) > generic
+static int edges_dispatch(omni_ctx *ctx, const uint8_t *d_masks, int K, int h, int w, size_t m_plane, size_t mpitch,
+                          const omni_edge_params *prm, const BlurParams &bp, int low, int high,
+                          uint8_t *d_edges, size_t e_plane, size_t epitch, cudaStream_t st)
+{
+    if (ctx->fast && fast_edges_supported(prm)) {
+        int rc = fast_edges(ctx, d_masks, K, h, w, m_plane, mpitch, prm, bp, low, high, d_edges, e_plane, epitch, st);
+        if (rc != OMNI_ERR_UNSUPPORTED) return rc;       // non-binary masks fall through to the generic kernels
+    } else if (ctx->fast && fast_morph03_supported(prm)) {
+        size_t wp = ((size_t)w + 15) & ~(size_t)15, wplane = wp * h;
+        OMNI_TRY(omni_ws_reserve(ctx, 0, wplane * K));
+        OMNI_TRY(omni_ws_reserve(ctx, 1, wplane * K));
+        u8 *m2 = (u8 *)ctx->ws[1];                       // generic_edges blurs from here into slot 0
+        int rc = fast_morph03_bytes(ctx, d_masks, K, h, w, m_plane, mpitch, prm, m2, wplane, wp, st);
+        if (rc == OMNI_OK)
+            return generic_edges(ctx, m2, K, h, w, wplane, wp, prm, bp, low, high, d_edges, e_plane, epitch, st, true);
+        if (rc != OMNI_ERR_UNSUPPORTED) return rc;
+    }
+    return generic_edges(ctx, d_masks, K, h, w, m_plane, mpitch, prm, bp, low, high, d_edges, e_plane, epitch, st);
+}
+
 extern "C" int omni_edges(omni_ctx *ctx, const uint8_t *d_masks, int K, int h, int w, size_t m_plane_stride, size_t mpitch,
                           const omni_edge_params *prm,
                           uint8_t *d_edges, size_t e_plane_stride, size_t epitch, void *stream)
@@ -451,12 +475,8 @@ extern "C" int omni_edges(omni_ctx *ctx, const uint8_t *d_masks, int K, int h, i
     OMNI_REQUIRE(h > 0 && w > 0 && mpitch >= (size_t)w && epitch >= (size_t)w, "omni_edges: bad geometry");
     BlurParams bp; int low, high;
     OMNI_TRY(check_edge_params(prm, &bp, &low, &high));
-    cudaStream_t st = (cudaStream_t)stream;
-    if (ctx->fast && fast_edges_supported(prm)) {
-        int rc = fast_edges(ctx, d_masks, K, h, w, m_plane_stride, mpitch, prm, bp, low, high, d_edges, e_plane_stride, epitch, st);
-        if (rc != OMNI_ERR_UNSUPPORTED) return rc;       // non-binary masks fall through to the generic kernels
-    }
-    return generic_edges(ctx, d_masks, K, h, w, m_plane_stride, mpitch, prm, bp, low, high, d_edges, e_plane_stride, epitch, st);
+    return edges_dispatch(ctx, d_masks, K, h, w, m_plane_stride, mpitch, prm, bp, low, high, d_edges, e_plane_stride, epitch,
+                          (cudaStream_t)stream);
 }
 
 // ---- fused hot path -------------------------------------------------------------------------------------
@@ -494,11 +514,7 @@ extern "C" int omni_color_edge(omni_ctx *ctx, const uint8_t *d_bgr, int h, int w
         OMNI_LAUNCH(ctx, st, "assign", g_assign(d_bgr, h, w, pitch, P, 1, labels, lp, st));
         OMNI_TRY(generic_layer_masks(ctx, labels, h, w, lp, K, 1, 1, d_masks, m_plane_stride, mpitch, st));
     }
-    if (ctx->fast && fast_edges_supported(prm)) {
-        int rc = fast_edges(ctx, d_masks, K, h, w, m_plane_stride, mpitch, prm, bp, low, high, d_edges, e_plane_stride, epitch, st);
-        if (rc != OMNI_ERR_UNSUPPORTED) return rc;
-    }
-    return generic_edges(ctx, d_masks, K, h, w, m_plane_stride, mpitch, prm, bp, low, high, d_edges, e_plane_stride, epitch, st);
+    return edges_dispatch(ctx, d_masks, K, h, w, m_plane_stride, mpitch, prm, bp, low, high, d_edges, e_plane_stride, epitch, st);
 }
 
 // ---- counts / composite -----------------------------------------------------------------------------------

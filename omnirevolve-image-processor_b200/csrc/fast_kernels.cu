@@ -832,6 +832,37 @@ bool fast_edges_supported(const omni_edge_params *prm)
     return morph03_kind(prm) >= 0 && prm->ksize == 3;
 }
 
+bool fast_morph03_supported(const omni_edge_params *prm) { return morph03_kind(prm) >= 0; }
+
+int fast_morph03_bytes(omni_ctx *ctx, const u8 *d_masks, int K, int h, int w, size_t m_plane, size_t mpitch,
+                       const omni_edge_params *prm, u8 *d_out, size_t o_plane, size_t opitch, cudaStream_t st)
+{
+    BitGeom g = make_geom(h, w);
+    u32 *bpp[2];
+    FK_TRY(bit_planes(ctx, g, K, 2, bpp));
+    OMNI_CUDA(cudaMemsetAsync(ctx->d_flags + 8, 0, sizeof(int), st));
+    {
+        KScope ks(ctx, "bytes_to_bits", st);
+        fk_bytes_to_bits<<<dim3(persist_blocks(ctx, 2), K), 256, 0, st>>>(d_masks, m_plane, mpitch, h, w, bpp[0], g.ws, g.plane,
+                                                                         ctx->d_flags + 8);
+        OMNI_CUDA(cudaGetLastError());
+    }
+    OMNI_CUDA(cudaMemcpyAsync(ctx->h_flags + 8, ctx->d_flags + 8, sizeof(int), cudaMemcpyDeviceToHost, st));
+    OMNI_CUDA(cudaStreamSynchronize(st));
+    if (ctx->h_flags[8]) return OMNI_ERR_UNSUPPORTED;     // not a {0,255} mask
+    const int kind = morph03_kind(prm);
+    const u32 *m2 = bpp[0];
+    if (kind > 0) {
+        OMNI_LAUNCH(ctx, st, "morph_bits", launch_morph(false, kind, bpp[0], bpp[1], g, K, nullptr, 0, 0, st));
+        m2 = bpp[1];
+    }
+    int al = ((uintptr_t)d_out % 16 == 0) && (o_plane % 16 == 0) && (opitch % 16 == 0);
+    KScope ks(ctx, "expand_bits", st);
+    fk_expand_bits<<<dim3(persist_blocks(ctx, 4), K), 256, 0, st>>>(m2, g.ws, g.plane, h, w, d_out, o_plane, opitch, al);
+    OMNI_CUDA(cudaGetLastError());
+    return OMNI_OK;
+}
+
 static int run_hysteresis(omni_ctx *ctx, u32 *ebits, const u32 *cbits, const BitGeom &g, int K, u8 *d_edges,
                           size_t e_plane, size_t epitch, cudaStream_t st)
 {

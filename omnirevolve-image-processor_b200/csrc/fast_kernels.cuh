@@ -15,6 +15,11 @@ int fast_layer_masks(omni_ctx *ctx, const u8 *d_labels, int h, int w, size_t lpi
                      u8 *d_masks, size_t plane_stride, size_t mpitch, cudaStream_t st);
 
 bool fast_edges_supported(const omni_edge_params *prm);
+// stage-03 morphology alone on the bit-plane kernels (any edge_kernel_size): masks (bytes) -> opened/closed planes (bytes).
+// OMNI_ERR_UNSUPPORTED when the masks are not strictly {0,255}.
+bool fast_morph03_supported(const omni_edge_params *prm);
+int fast_morph03_bytes(omni_ctx *ctx, const u8 *d_masks, int K, int h, int w, size_t m_plane, size_t mpitch,
+                       const omni_edge_params *prm, u8 *d_out, size_t o_plane, size_t opitch, cudaStream_t st);
 // returns OMNI_ERR_UNSUPPORTED when the masks are not strictly {0,255} (caller falls back to the generic kernels)
 int fast_edges(omni_ctx *ctx, const u8 *d_masks, int K, int h, int w, size_t m_plane, size_t mpitch,
                const omni_edge_params *prm, const BlurParams &bp, int low, int high,
