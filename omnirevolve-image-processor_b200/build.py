@@ -24,8 +24,14 @@ def _deps():
     return d
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, out: str | None = None, defines=()) -> str:
+    """out / defines: build an experimental variant (e.g. -DE3V_MINBLOCKS=4) next to the product library."""
     os.makedirs(LIB_DIR, exist_ok=True)
+    if out is not None:
+        nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+        cmd = [nvcc] + NVCC_FLAGS + ["-D" + d for d in defines] + ["-o", out] + [os.path.join(CSRC, s) for s in SOURCES]
+        subprocess.check_call(cmd)
+        return out
     if not force and os.path.exists(LIB) and all(os.path.getmtime(LIB) >= os.path.getmtime(p) for p in _deps()):
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")

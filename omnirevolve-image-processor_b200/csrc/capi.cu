@@ -625,11 +625,25 @@ extern "C" int omni_host_color_edge(omni_ctx *ctx, const uint8_t *h_bgr, int h, 
     OMNI_TRY(omni_ws_reserve(ctx, 3, i_bytes + l_bytes + m_bytes + e_bytes));
     u8 *di = (u8 *)ctx->ws[3], *dl = di + i_bytes, *dm = dl + l_bytes, *de = dm + m_bytes;
     cudaStream_t st = ctx->stream;
-    OMNI_CUDA(cudaMemcpy2DAsync(di, ip, h_bgr, pitch, (size_t)w * 3, h, cudaMemcpyHostToDevice, st));
-    OMNI_TRY(omni_color_edge(ctx, di, h, w, ip, h_centers, K, h_lut, prm, dl, lp, dm, mplane, mp, de, eplane, ep, st));
-    if (h_labels) OMNI_CUDA(cudaMemcpy2DAsync(h_labels, lpitch, dl, lp, (size_t)w, h, cudaMemcpyDeviceToHost, st));
-    OMNI_TRY(copy_planes_d2h(h_masks, m_plane_stride, mpitch, dm, mplane, mp, K, h, w, st));
-    OMNI_TRY(copy_planes_d2h(h_edges, e_plane_stride, epitch, de, eplane, ep, K, h, w, st));
+    int rc = OMNI_ERR_UNSUPPORTED;
+    if (ctx->fast && h_centers) {
+        // pipelined path: band-wise H2D / kernels / D2H on three streams
+        BlurParams bp; int low, high;
+        OMNI_TRY(check_edge_params(prm, &bp, &low, &high));
+        AssignParams P;
+        OMNI_TRY(fill_assign(&P, h_centers, nullptr, K, h_lut));
+        rc = fast_host_color_edge(ctx, h_bgr, h, w, pitch, P, prm, low, high, h_labels, lpitch, h_masks, m_plane_stride, mpitch,
+                                  h_edges, e_plane_stride, epitch, di, ip, dl, lp, dm, mplane, mp, de, eplane, ep,
+                                  h_labels != nullptr || h_counts != nullptr);
+        if (rc != OMNI_OK && rc != OMNI_ERR_UNSUPPORTED) return rc;
+    }
+    if (rc == OMNI_ERR_UNSUPPORTED) {
+        OMNI_CUDA(cudaMemcpy2DAsync(di, ip, h_bgr, pitch, (size_t)w * 3, h, cudaMemcpyHostToDevice, st));
+        OMNI_TRY(omni_color_edge(ctx, di, h, w, ip, h_centers, K, h_lut, prm, dl, lp, dm, mplane, mp, de, eplane, ep, st));
+        if (h_labels) OMNI_CUDA(cudaMemcpy2DAsync(h_labels, lpitch, dl, lp, (size_t)w, h, cudaMemcpyDeviceToHost, st));
+        OMNI_TRY(copy_planes_d2h(h_masks, m_plane_stride, mpitch, dm, mplane, mp, K, h, w, st));
+        OMNI_TRY(copy_planes_d2h(h_edges, e_plane_stride, epitch, de, eplane, ep, K, h, w, st));
+    }
     if (h_counts) {
         OMNI_CUDA(cudaMemsetAsync(ctx->d_counts, 0, 3 * OMNI_MAX_K * sizeof(unsigned long long), st));
         OMNI_LAUNCH(ctx, st, "count_labels", g_count_labels(dl, lp, h, w, K, ctx->d_counts, st));

@@ -61,7 +61,6 @@ static cudaError_t fast_tables()
     return cudaSuccess;
 }
 
-void fast_ctx_release(omni_ctx *) {}
 
 // ------------------------------------------------------------------------------------------------
 // stage 01: exact 2:1 INTER_AREA, vectorised (01_resize.py:20)
@@ -434,7 +433,8 @@ struct MorphChain {
 // (may be NULL).
 template <u32 CODE, int TAP>
 __global__ void __launch_bounds__(128) fk_morph(const u32 *__restrict__ in_bits, u32 *__restrict__ out_bits, int ws, size_t plane, int h,
-                                                int w, u8 *__restrict__ masks, size_t mstride, size_t mpitch, int aligned16)
+                                                int w, u8 *__restrict__ masks, size_t mstride, size_t mpitch, int aligned16,
+                                                int y_lo, int y_hi /* rows [y_lo, y_hi) are produced; input rows around them must exist */)
 {
     constexpr int N = code_len(CODE);
     __shared__ uint2 s_lut8[256];
@@ -446,7 +446,7 @@ __global__ void __launch_bounds__(128) fk_morph(const u32 *__restrict__ in_bits,
     const int ww = (w + 31) >> 5;
     if (c >= ww) return;
     const int k = blockIdx.z;
-    const int y0 = blockIdx.y * MORPH_TR, y1 = min(h, y0 + MORPH_TR);
+    const int y0 = y_lo + blockIdx.y * MORPH_TR, y1 = min(y_hi, y0 + MORPH_TR);
     const u32 *src = in_bits + (size_t)k * plane;
     W64 colvalid;
     colvalid.lo = range_mask(32 * c - 16, w);
@@ -508,11 +508,13 @@ constexpr u32 CODE_F_OC = mk_code(ST_ER, ST_DR, ST_DR, ST_ER, ST_EC, ST_DC, ST_D
 
 // morph03: 0 none, 1 open, 2 close, 3 open+close.  with02: prepend the RECT open/close and emit mask bytes.
 static cudaError_t launch_morph(bool with02, int morph03, const u32 *in_bits, u32 *out_bits, const BitGeom &g, int K, u8 *masks,
-                                size_t mstride, size_t mpitch, cudaStream_t st)
+                                size_t mstride, size_t mpitch, cudaStream_t st, int y_lo = 0, int y_hi = -1)
 {
-    dim3 b(128), grid((g.ww + 127) / 128, (g.h + MORPH_TR - 1) / MORPH_TR, K);
+    if (y_hi < 0) y_hi = g.h;
+    if (y_hi <= y_lo) return cudaSuccess;
+    dim3 b(128), grid((g.ww + 127) / 128, (y_hi - y_lo + MORPH_TR - 1) / MORPH_TR, K);
     int al = masks && ((uintptr_t)masks % 16 == 0) && (mstride % 16 == 0) && (mpitch % 16 == 0);
-#define LM(CODE, TAP) fk_morph<CODE, TAP><<<grid, b, 0, st>>>(in_bits, out_bits, g.ws, g.plane, g.h, g.w, masks, mstride, mpitch, al)
+#define LM(CODE, TAP) fk_morph<CODE, TAP><<<grid, b, 0, st>>>(in_bits, out_bits, g.ws, g.plane, g.h, g.w, masks, mstride, mpitch, al, y_lo, y_hi)
     if (with02) {
         switch (morph03) {
         case 0: LM(CODE_R_OC, 4); break;
@@ -947,4 +949,122 @@ int fast_color_edge(omni_ctx *ctx, const u8 *d_bgr, int h, int w, size_t pitch, 
     int kind = morph03_kind(prm);
     OMNI_LAUNCH(ctx, st, "morph_bits", launch_morph(true, kind, bpp[0], bpp[1], g, P.K, d_masks, m_plane, mpitch, st));
     return edges_from_bits(ctx, bpp[1], bpp[2], bpp[3], g, P.K, low, high, d_edges, e_plane, epitch, st);
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// Host-buffer fused call, pipelined over row bands (omni_host_color_edge when the fast path applies).
+// PCIe is the bound of this call (3 B/px in, 2K B/px out), so copies and kernels are overlapped:
+//   copy-in stream : band b of the image                                   (H2D)
+//   compute stream : assign(b) as soon as band b has landed; morph(b-1) once assign(b) is done (its 8-row halo);
+//                    after the last band: edge kernel + hysteresis on the whole image
+//   copy-out stream: mask planes of band b as soon as morph(b) is done; labels; edge planes at the end   (D2H)
+// ------------------------------------------------------------------------------------------------
+#define HP_MAX_BANDS 8
+
+static int pipe_init(omni_ctx *ctx)
+{
+    if (ctx->pipe_ready) return OMNI_OK;
+    OMNI_CUDA(cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking));
+    OMNI_CUDA(cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking));
+    for (int i = 0; i < 2 * HP_MAX_BANDS + 4; i++) OMNI_CUDA(cudaEventCreateWithFlags(&ctx->pipe_ev[i], cudaEventDisableTiming));
+    ctx->pipe_ready = 1;
+    return OMNI_OK;
+}
+
+void fast_ctx_release(omni_ctx *ctx)
+{
+    if (!ctx || !ctx->pipe_ready) return;
+    cudaStreamDestroy(ctx->s_in);
+    cudaStreamDestroy(ctx->s_out);
+    for (int i = 0; i < 2 * HP_MAX_BANDS + 4; i++) cudaEventDestroy(ctx->pipe_ev[i]);
+    ctx->pipe_ready = 0;
+}
+
+int fast_host_color_edge(omni_ctx *ctx, const u8 *h_bgr, int h, int w, size_t pitch, const AssignParams &P,
+                         const omni_edge_params *prm, int low, int high,
+                         u8 *h_labels, size_t lpitch, u8 *h_masks, size_t h_mplane, size_t h_mpitch,
+                         u8 *h_edges, size_t h_eplane, size_t h_epitch,
+                         u8 *d_img, size_t ip, u8 *d_labels, size_t lp, u8 *d_masks, size_t mplane, size_t mp,
+                         u8 *d_edges, size_t eplane, size_t ep, bool want_labels)
+{
+    if (low < 0 || !fast_edges_supported(prm)) return OMNI_ERR_UNSUPPORTED;
+    FK_TRY(pipe_init(ctx));
+    OMNI_CUDA(fast_tables());
+    const int K = P.K;
+    BitGeom g = make_geom(h, w);
+    u32 *bpp[4];
+    FK_TRY(bit_planes(ctx, g, K, 4, bpp));
+    cudaStream_t sc = ctx->stream, si = ctx->s_in, so = ctx->s_out;
+    cudaEvent_t *evH = ctx->pipe_ev, *evM = ctx->pipe_ev + HP_MAX_BANDS, *evX = ctx->pipe_ev + 2 * HP_MAX_BANDS;
+    // bands: multiples of the morphology strip height, at least 256 rows each
+    int nb = HP_MAX_BANDS;
+    while (nb > 1 && (h + nb - 1) / nb < 256) nb--;
+    int rows_per = ((h + nb - 1) / nb + MORPH_TR - 1) / MORPH_TR * MORPH_TR;
+    nb = (h + rows_per - 1) / rows_per;
+    const int kind = morph03_kind(prm);
+    // everything queued on the side streams must wait for what the caller queued before on the ctx stream -- nothing:
+    // omni_host_* calls own ctx->stream; a start event orders the side streams after earlier work of this ctx
+    OMNI_CUDA(cudaEventRecord(evX[0], sc));
+    OMNI_CUDA(cudaStreamWaitEvent(si, evX[0], 0));
+    OMNI_CUDA(cudaStreamWaitEvent(so, evX[0], 0));
+    for (int b = 0; b < nb; b++) {
+        int y0 = b * rows_per, rows = min(rows_per, h - y0);
+        OMNI_CUDA(cudaMemcpy2DAsync(d_img + (size_t)y0 * ip, ip, h_bgr + (size_t)y0 * pitch, pitch, (size_t)w * 3, rows,
+                                    cudaMemcpyHostToDevice, si));
+        OMNI_CUDA(cudaEventRecord(evH[b], si));
+    }
+    u32 *cells = nullptr;
+    FK_TRY(assign_cells(ctx, P, &cells, sc));
+    OMNI_CUDA(cudaMemsetAsync(bpp[0], 0, g.plane * (size_t)K * sizeof(u32), sc));
+    const int agrid = resident_grid(ctx, fk_assign_bits<1>, 256, &ctx->occ_assign_lab);
+    auto morph_band = [&](int b) -> int {
+        int y0 = b * rows_per, y1 = min(h, y0 + rows_per);
+        OMNI_LAUNCH(ctx, sc, "morph_bits", launch_morph(true, kind, bpp[0], bpp[1], g, K, d_masks, mplane, mp, sc, y0, y1));
+        OMNI_CUDA(cudaEventRecord(evM[b], sc));
+        OMNI_CUDA(cudaStreamWaitEvent(so, evM[b], 0));
+        const bool contiguous = (h_mpitch == mp);
+        for (int k = 0; k < K; k++) {
+            if (contiguous)
+                OMNI_CUDA(cudaMemcpyAsync(h_masks + (size_t)k * h_mplane + (size_t)y0 * h_mpitch, d_masks + (size_t)k * mplane + (size_t)y0 * mp,
+                                          (size_t)(y1 - y0 - 1) * mp + w, cudaMemcpyDeviceToHost, so));
+            else
+                OMNI_CUDA(cudaMemcpy2DAsync(h_masks + (size_t)k * h_mplane + (size_t)y0 * h_mpitch, h_mpitch,
+                                            d_masks + (size_t)k * mplane + (size_t)y0 * mp, mp, (size_t)w, y1 - y0, cudaMemcpyDeviceToHost, so));
+        }
+        return OMNI_OK;
+    };
+    for (int b = 0; b < nb; b++) {
+        int y0 = b * rows_per, rows = min(rows_per, h - y0);
+        OMNI_CUDA(cudaStreamWaitEvent(sc, evH[b], 0));
+        {
+            KScope ks(ctx, "assign_bits", sc);
+            fk_assign_bits<1><<<agrid, 256, 0, sc>>>(d_img + (size_t)y0 * ip, rows, w, ip, P, cells,
+                                                    want_labels ? d_labels + (size_t)y0 * lp : nullptr, lp,
+                                                    bpp[0] + (size_t)y0 * g.ws, g.ws, g.plane);
+            OMNI_CUDA(cudaGetLastError());
+        }
+        if (b > 0) FK_TRY(morph_band(b - 1));             // its halo rows (band b) are assigned now
+    }
+    FK_TRY(morph_band(nb - 1));
+    if (want_labels && h_labels) {
+        OMNI_CUDA(cudaEventRecord(evX[1], sc));
+        OMNI_CUDA(cudaStreamWaitEvent(so, evX[1], 0));
+        OMNI_CUDA(cudaMemcpy2DAsync(h_labels, lpitch, d_labels, lp, (size_t)w, h, cudaMemcpyDeviceToHost, so));
+    }
+    FK_TRY(edges_from_bits(ctx, bpp[1], bpp[2], bpp[3], g, K, low, high, d_edges, eplane, ep, sc));
+    OMNI_CUDA(cudaEventRecord(evX[2], sc));
+    OMNI_CUDA(cudaStreamWaitEvent(so, evX[2], 0));
+    for (int k = 0; k < K; k++) {
+        if (h_epitch == ep)
+            OMNI_CUDA(cudaMemcpyAsync(h_edges + (size_t)k * h_eplane, d_edges + (size_t)k * eplane, (size_t)(h - 1) * ep + w,
+                                      cudaMemcpyDeviceToHost, so));
+        else
+            OMNI_CUDA(cudaMemcpy2DAsync(h_edges + (size_t)k * h_eplane, h_epitch, d_edges + (size_t)k * eplane, ep, (size_t)w, h,
+                                        cudaMemcpyDeviceToHost, so));
+    }
+    // the caller continues on ctx->stream (counts) and synchronises it: make it wait for the copy-out stream
+    OMNI_CUDA(cudaEventRecord(evX[3], so));
+    OMNI_CUDA(cudaStreamWaitEvent(sc, evX[3], 0));
+    return OMNI_OK;
 }

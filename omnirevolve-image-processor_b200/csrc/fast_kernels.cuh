@@ -33,3 +33,12 @@ int fast_color_edge(omni_ctx *ctx, const u8 *d_bgr, int h, int w, size_t pitch, 
 cudaError_t launch_edges3_simd(const u32 *m2, int ws, size_t plane, int h, int w, int K, int low, int high, int sm_count,
                                u32 *sbits, u32 *cbits, u8 *edges, size_t estride, size_t epitch, int aligned16, int *wl_count, u32 *worklist, int wl_cap,
                                cudaStream_t st);
+
+// host-buffer fused call with H2D / kernels / D2H overlapped over row bands; OMNI_ERR_UNSUPPORTED when the parameters
+// are outside the fast path.  On success all work is ordered before later work on ctx->stream.
+int fast_host_color_edge(omni_ctx *ctx, const u8 *h_bgr, int h, int w, size_t pitch, const AssignParams &P,
+                         const omni_edge_params *prm, int low, int high,
+                         u8 *h_labels, size_t lpitch, u8 *h_masks, size_t h_mplane, size_t h_mpitch,
+                         u8 *h_edges, size_t h_eplane, size_t h_epitch,
+                         u8 *d_img, size_t ip, u8 *d_labels, size_t lp, u8 *d_masks, size_t mplane, size_t mp,
+                         u8 *d_edges, size_t eplane, size_t ep, bool want_labels);

@@ -79,6 +79,10 @@ struct omni_ctx {
     std::vector<cudaEvent_t> ev_pool;
     int sm_count = 0;
     int hyst_blocks = 0;
+    // side streams + events of the pipelined host-buffer call (fast_host_color_edge)
+    int pipe_ready = 0;
+    cudaStream_t s_in = nullptr, s_out = nullptr;
+    cudaEvent_t pipe_ev[20] = {};
     int occ_assign_lab = 0, occ_assign_pal = 0;   // resident CTAs per SM of the persistent assignment kernels
     // centres the candidate-cell table in ws[5] was built for (fast colour assignment)
     int cells_valid = 0, cells_K = 0;

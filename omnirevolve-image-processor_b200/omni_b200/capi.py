@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libomni_b200.so")
+LIB_PATH = os.environ.get("OMNI_B200_LIB") or os.path.join(os.path.dirname(_HERE), "lib", "libomni_b200.so")
 
 OMNI_MAX_K = 32
 OMNI_MAX_BLUR_K = 31
