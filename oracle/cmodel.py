@@ -33,6 +33,8 @@ def lib():
         L.orc_edge_chain.argtypes = [u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                      C.c_double, C.c_double, u8p]
         L.orc_edge_chain.restype = C.c_int
+        L.orc_thin_zhangsuen.argtypes = [u8p, C.c_int, C.c_int, u8p, C.c_int, i32p]
+        L.orc_thin_zhangsuen.restype = C.c_int
         _lib = L
     return _lib
 
@@ -146,3 +148,12 @@ def edge_chain(mask, morph_k=3, open_iters=1, close_iters=1, ks=3, t1=50, t2=150
     if rc:
         raise ValueError(f"edge_chain rc={rc}")
     return out
+
+
+def thin_zhangsuen(img, max_iter=120, with_log=False):
+    """04_find_contours.py:35-99 thinning_zhangsuen: u8 (>0 = foreground) -> skeleton {0,255}."""
+    img = _u8(img)
+    out = np.empty_like(img)
+    removed = np.zeros(max(1, max_iter), np.int32)
+    it = lib().orc_thin_zhangsuen(_p(img), img.shape[0], img.shape[1], _p(out), max_iter, _p(removed, C.c_int32))
+    return (out, removed[:it].copy()) if with_log else out

@@ -383,3 +383,54 @@ ORC_API int orc_edge_chain(const uint8_t *mask, int h, int w, int morph_k, int o
     free(se); free(m); free(bl);
     return 0;
 }
+
+
+/* ------------------------------------------------------------------------------------------ */
+/* 04_find_contours.py:35-99  thinning_zhangsuen(bin_0_255, layer)  (row "next" of SURVEY 8f)   */
+/* ------------------------------------------------------------------------------------------ */
+/* The reference works on the bounding box of the non-zero pixels padded by 2 with zero fill
+ * outside -- identical to zero padding around the whole image.  Its neighbour names are rotated
+ * by 180 degrees against the textbook (P2 = pixel BELOW): _shift(roi, dy, dx)[y, x] = roi[y - dy, x - dx].
+ *   P2 = (y+1, x)   P3 = (y+1, x-1)  P4 = (y, x-1)   P5 = (y-1, x-1)
+ *   P6 = (y-1, x)   P7 = (y-1, x+1)  P8 = (y, x+1)   P9 = (y+1, x+1)
+ * Each iteration: sub-step 1 deletes (A==1, 2<=B<=6, P2*P4*P6==0, P4*P6*P8==0) simultaneously, sub-step 2
+ * (P2*P4*P8==0, P2*P6*P8==0) on the result; stops when an iteration removes nothing or after 120 iterations.
+ * in/out: h x w u8, in > 0 is foreground, out in {0,255}.  removed (optional): removed[i] = pixels deleted in
+ * iteration i+1 (the number the reference logs).  Returns the number of iterations executed. */
+static int orc_zs_substep(uint8_t *roi, int h, int w, int step, uint8_t *del)
+{
+    int n = 0;
+#define ZS(y, x) (((y) >= 0 && (y) < h && (x) >= 0 && (x) < w) ? roi[(size_t)(y) * w + (x)] : 0)
+    for (int y = 0; y < h; y++)
+        for (int x = 0; x < w; x++) {
+            del[(size_t)y * w + x] = 0;
+            if (!roi[(size_t)y * w + x]) continue;
+            int P2 = ZS(y + 1, x), P3 = ZS(y + 1, x - 1), P4 = ZS(y, x - 1), P5 = ZS(y - 1, x - 1);
+            int P6 = ZS(y - 1, x), P7 = ZS(y - 1, x + 1), P8 = ZS(y, x + 1), P9 = ZS(y + 1, x + 1);
+            int B = P2 + P3 + P4 + P5 + P6 + P7 + P8 + P9;
+            int A = (!P2 && P3) + (!P3 && P4) + (!P4 && P5) + (!P5 && P6) + (!P6 && P7) + (!P7 && P8) + (!P8 && P9) + (!P9 && P2);
+            int c = step == 1 ? ((P2 * P4 * P6) == 0 && (P4 * P6 * P8) == 0) : ((P2 * P4 * P8) == 0 && (P2 * P6 * P8) == 0);
+            if (A == 1 && B >= 2 && B <= 6 && c) { del[(size_t)y * w + x] = 1; n++; }
+        }
+#undef ZS
+    for (size_t i = 0; i < (size_t)h * w; i++) if (del[i]) roi[i] = 0;
+    return n;
+}
+
+ORC_API int orc_thin_zhangsuen(const uint8_t *in, int h, int w, uint8_t *out, int max_iter, int32_t *removed)
+{
+    size_t n = (size_t)h * w;
+    uint8_t *roi = (uint8_t *)malloc(n ? n : 1), *del = (uint8_t *)malloc(n ? n : 1);
+    for (size_t i = 0; i < n; i++) roi[i] = in[i] > 0;
+    int it = 0, changed = 1;
+    while (changed && it < max_iter) {
+        it++;
+        int n1 = orc_zs_substep(roi, h, w, 1, del);
+        int n2 = orc_zs_substep(roi, h, w, 2, del);
+        if (removed) removed[it - 1] = n1 + n2;
+        changed = (n1 + n2) > 0;
+    }
+    for (size_t i = 0; i < n; i++) out[i] = roi[i] ? 255 : 0;
+    free(roi); free(del);
+    return it;
+}

@@ -156,3 +156,36 @@ def assign_labels_rgb_chunked(img_rgb, palette_rgb, rows: int = 256):
     for y in range(0, img_rgb.shape[0], rows):
         out[y:y + rows] = assign_labels_rgb(np.ascontiguousarray(img_rgb[y:y + rows]), palette_rgb)
     return out
+
+
+# ---- 04_find_contours.py:14-22,35-99 (row "next" of SURVEY 8f) ------------------------------------
+def _shift(img, dy, dx):
+    h, w = img.shape
+    out = np.zeros_like(img)
+    out[max(0, dy):min(h, h + dy), max(0, dx):min(w, w + dx)] = img[max(0, -dy):min(h, h - dy), max(0, -dx):min(w, w - dx)]
+    return out
+
+
+def thinning_zhangsuen(bin_0_255: np.ndarray, max_iter: int = 120) -> np.ndarray:
+    """The reference's NumPy Zhang-Suen (same shifts, same conditions, same stop rule), without the bounding-box
+    crop (zero fill outside makes it equivalent) and without the progress prints."""
+    roi = (bin_0_255 > 0).astype(np.uint8)
+    changed, it = True, 0
+    while changed and it < max_iter:
+        it += 1
+        changed = False
+        for step in (1, 2):
+            P2 = _shift(roi, -1, 0); P3 = _shift(roi, -1, 1); P4 = _shift(roi, 0, 1); P5 = _shift(roi, 1, 1)
+            P6 = _shift(roi, 1, 0); P7 = _shift(roi, 1, -1); P8 = _shift(roi, 0, -1); P9 = _shift(roi, -1, -1)
+            B = P2 + P3 + P4 + P5 + P6 + P7 + P8 + P9
+            seq = [P2, P3, P4, P5, P6, P7, P8, P9, P2]
+            A = sum(((a == 0) & (b == 1)).astype(np.uint8) for a, b in zip(seq[:-1], seq[1:]))
+            if step == 1:
+                cond = ((P2 * P4 * P6) == 0) & ((P4 * P6 * P8) == 0)
+            else:
+                cond = ((P2 * P4 * P8) == 0) & ((P2 * P6 * P8) == 0)
+            dele = (roi == 1) & (A == 1) & (B >= 2) & (B <= 6) & cond
+            if dele.any():
+                roi[dele] = 0
+                changed = True
+    return (roi * 255).astype(np.uint8)

@@ -72,3 +72,29 @@ def test_function_cases():
         dims = rp.resize_dims(src.shape[0], src.shape[1], md)
         got = src if dims is None else cm.resize_area(src, dims[0], dims[1])
         assert np.array_equal(got, dst), tag
+
+
+def _thin_cases():
+    z = np.load(f"{GOLDEN}/thinning.npz")
+    return z, sorted(k[:-3] for k in z.files if k.endswith("_in"))
+
+
+def test_thinning_golden():
+    """04_find_contours.py:35-99: C model and NumPy replay vs outputs frozen from the
+    unmodified reference (tools/make_golden_thinning.py)."""
+    z, names = _thin_cases()
+    assert len(names) >= 8
+    for n in names:
+        src, want = z[n + "_in"], z[n + "_out"]
+        assert np.array_equal(cm.thin_zhangsuen(src), want), n
+        if src.size <= 300 * 300:                              # the NumPy replay is slow on thick masks
+            assert np.array_equal(rp.thinning_zhangsuen(src), want), n
+
+
+def test_thinning_iteration_cap():
+    """max_iter is honoured (the reference stops after 120 iterations even when pixels were still removed)."""
+    img = np.full((64, 64), 255, np.uint8)
+    full, log = cm.thin_zhangsuen(img, with_log=True)
+    cut = cm.thin_zhangsuen(img, max_iter=3)
+    assert len(log) > 4 and log[-1] == 0 and (cut > 0).sum() > (full > 0).sum()
+    assert np.array_equal(cut, rp.thinning_zhangsuen(img, max_iter=3))
