@@ -62,7 +62,9 @@ int omni_version(void);
 const char *omni_last_error_string(void);
 int omni_device_count(void);
 /* Which implementation serves the calls: 0 = generic kernels only, 1 = fast bit-plane kernels where
- * the parameters allow (default).  For tests and A/B measurements. */
+ * the parameters allow (default; the edge kernel walks only the tile runs that can hold an edge),
+ * 2 = as 1 with the dense edge kernel (every tile).  All three give identical bytes.  For tests and
+ * A/B measurements. */
 int omni_set_fast_path(omni_ctx *ctx, int enable);
 int omni_ctx_create(int device, omni_ctx **out);
 int omni_ctx_destroy(omni_ctx *ctx);
@@ -141,6 +143,21 @@ int omni_count_nonzero(omni_ctx *ctx, const uint8_t *d_planes, int K, int h, int
  * edges > 0 (later planes overwrite earlier ones). */
 int omni_edges_composite(omni_ctx *ctx, const uint8_t *d_edges, int K, int h, int w, size_t e_plane_stride, size_t epitch,
                          const uint8_t *h_colors_bgr, uint8_t *d_canvas, size_t cpitch, void *stream);
+
+/* ---- stage 04 (first step): 04_find_contours.py:35-99  thinning_zhangsuen(bin_0_255, layer) ---- */
+/* K independent planes; a pixel > 0 is foreground (`(roi > 0)`, 04:43).  Zhang-Suen thinning with the reference's
+ * neighbour naming, both sub-steps per iteration, until an iteration deletes nothing or max_iter (the reference
+ * uses 120) iterations have run.  Output {0,255} (04:97).  In and out may alias.
+ * h_removed (optional, K*max_iter int32): pixels deleted from plane p in iteration i+1 at [p*max_iter + i] -- the
+ * `removed=` number of the reference's progress lines (04:90-92); h_iters (optional, K int32): iterations the
+ * reference's loop would have executed on plane p.  Either one makes the call synchronise the stream.
+ * There is no generic (byte-plane) variant of this kernel: omni_set_fast_path does not affect it. */
+int omni_thin_zhangsuen(omni_ctx *ctx, const uint8_t *d_in, int K, int h, int w, size_t in_plane_stride, size_t in_pitch,
+                        int max_iter, uint8_t *d_out, size_t out_plane_stride, size_t out_pitch,
+                        int32_t *h_removed, int32_t *h_iters, void *stream);
+int omni_host_thin_zhangsuen(omni_ctx *ctx, const uint8_t *h_in, int K, int h, int w, size_t in_plane_stride, size_t in_pitch,
+                             int max_iter, uint8_t *h_out, size_t out_plane_stride, size_t out_pitch,
+                             int32_t *h_removed, int32_t *h_iters);
 
 /* Diagnostics of the last omni_edges / omni_color_edge call on this ctx: number of global
  * hysteresis passes that were needed (>= 1). */

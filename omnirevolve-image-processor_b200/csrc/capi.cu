@@ -1,4 +1,5 @@
 // capi.cu -- extern "C" entry points of libomni_b200.so (declared in include/omni_b200.h).
+#include <stdlib.h>
 #include "omni_internal.cuh"
 #include "fast_kernels.cuh"
 
@@ -43,6 +44,12 @@ extern "C" int omni_ctx_create(int device, omni_ctx **out)
     OMNI_CUDA(cudaSetDevice(device));
     omni_ctx *c = new omni_ctx();
     c->device = device;
+    {   // A/B switch for measurements only: both edge kernels are bit-identical (tests run both)
+        const char *ev = getenv("OMNI_B200_EDGE_DENSE");
+        c->edge_sparse = (ev && ev[0] == '1') ? 0 : 1;
+        ev = getenv("OMNI_B200_ASSIGN_LABCELL");
+        c->assign_rgbcell = (ev && ev[0] == '1') ? 0 : 1;
+    }
     OMNI_CUDA(cudaMalloc(&c->d_flags, 64 * sizeof(int)));
     OMNI_CUDA(cudaMemset(c->d_flags, 0, 64 * sizeof(int)));
     OMNI_CUDA(cudaMalloc(&c->d_counts, 4 * OMNI_MAX_K * sizeof(unsigned long long)));
@@ -76,6 +83,7 @@ extern "C" int omni_set_fast_path(omni_ctx *ctx, int enable)
 {
     OMNI_REQUIRE(ctx != nullptr, "omni_set_fast_path: ctx is NULL");
     ctx->fast = enable ? 1 : 0;
+    if (enable) ctx->edge_sparse = ctx->assign_rgbcell = (enable == 2) ? 0 : 1;
     return OMNI_OK;
 }
 
@@ -109,6 +117,7 @@ extern "C" int omni_last_hysteresis_passes(omni_ctx *ctx)
 // ---- launch accounting / per-kernel timing ----------------------------------------------------------
 KScope::KScope(omni_ctx *ctx, const char *name, cudaStream_t s) : c(ctx), st(s)
 {
+    if (!c) return;                       // unscoped launch (the caller brackets it)
     c->launches++;
     if (!c->prof_on) return;
     cudaEvent_t a = nullptr;
@@ -283,7 +292,15 @@ extern "C" int omni_resize_area_u8c3(omni_ctx *ctx, const uint8_t *d_src, int sh
     } else {
         const ResizeTab *t = omni_get_resize_tab(ctx, sh, sw, dh, dw, st);
         if (!t) { omni_set_error("omni_resize_area_u8c3: cannot build resize tables"); return OMNI_ERR_NOMEM; }
-        OMNI_LAUNCH(ctx, st, "resize_area", g_resize_area(d_src, sh, sw, spitch, d_dst, dh, dw, dpitch, &t->dev, st));
+        bool done = false;
+        if (ctx->fast) {
+            KScope ks(ctx, "resize_frac_v", st);
+            cudaError_t e = fast_resize_frac(d_src, sh, sw, spitch, d_dst, dh, dw, dpitch, &t->dev, st);
+            if (e == cudaSuccess) done = true;
+            else if (e != cudaErrorNotSupported) OMNI_CUDA(e);
+            else ctx->launches--;                      // nothing was launched
+        }
+        if (!done) OMNI_LAUNCH(ctx, st, "resize_area", g_resize_area(d_src, sh, sw, spitch, d_dst, dh, dw, dpitch, &t->dev, st));
     }
     return OMNI_OK;
 }
@@ -605,6 +622,36 @@ extern "C" int omni_host_edges(omni_ctx *ctx, const uint8_t *h_masks, int K, int
         OMNI_CUDA(cudaMemcpy2DAsync(dm + k * dplane, dp, h_masks + k * m_plane_stride, mpitch, (size_t)w, h, cudaMemcpyHostToDevice, ctx->stream));
     OMNI_TRY(omni_edges(ctx, dm, K, h, w, dplane, dp, prm, de, eplane, ep, ctx->stream));
     OMNI_TRY(copy_planes_d2h(h_edges, e_plane_stride, epitch, de, eplane, ep, K, h, w, ctx->stream));
+    OMNI_CUDA(cudaStreamSynchronize(ctx->stream));
+    return OMNI_OK;
+}
+
+// ---- stage 04: thinning ------------------------------------------------------------------------------------
+extern "C" int omni_thin_zhangsuen(omni_ctx *ctx, const uint8_t *d_in, int K, int h, int w, size_t in_plane_stride, size_t in_pitch,
+                                   int max_iter, uint8_t *d_out, size_t out_plane_stride, size_t out_pitch,
+                                   int32_t *h_removed, int32_t *h_iters, void *stream)
+{
+    OMNI_TRY(set_device(ctx));
+    OMNI_REQUIRE(d_in && d_out && K >= 1 && K <= OMNI_MAX_K && h > 0 && w > 0, "omni_thin_zhangsuen: bad arguments");
+    OMNI_REQUIRE(in_pitch >= (size_t)w && out_pitch >= (size_t)w, "omni_thin_zhangsuen: pitch smaller than a row");
+    OMNI_REQUIRE(max_iter >= 0 && max_iter <= 100000, "omni_thin_zhangsuen: max_iter %d out of range", max_iter);
+    return fast_thin(ctx, d_in, K, h, w, in_plane_stride, in_pitch, max_iter, d_out, out_plane_stride, out_pitch, h_removed, h_iters,
+                     (cudaStream_t)stream);
+}
+
+extern "C" int omni_host_thin_zhangsuen(omni_ctx *ctx, const uint8_t *h_in, int K, int h, int w, size_t in_plane_stride, size_t in_pitch,
+                                        int max_iter, uint8_t *h_out, size_t out_plane_stride, size_t out_pitch,
+                                        int32_t *h_removed, int32_t *h_iters)
+{
+    OMNI_TRY(set_device(ctx));
+    OMNI_REQUIRE(h_in && h_out && K >= 1 && K <= OMNI_MAX_K && h > 0 && w > 0, "omni_host_thin_zhangsuen: bad arguments");
+    size_t dp = pad16((size_t)w), dplane = dp * h, bytes = pad16(dplane * K);
+    OMNI_TRY(omni_ws_reserve(ctx, 3, bytes));
+    u8 *d = (u8 *)ctx->ws[3];
+    for (int k = 0; k < K; k++)
+        OMNI_CUDA(cudaMemcpy2DAsync(d + k * dplane, dp, h_in + k * in_plane_stride, in_pitch, (size_t)w, h, cudaMemcpyHostToDevice, ctx->stream));
+    OMNI_TRY(omni_thin_zhangsuen(ctx, d, K, h, w, dplane, dp, max_iter, d, dplane, dp, h_removed, h_iters, ctx->stream));
+    OMNI_TRY(copy_planes_d2h(h_out, out_plane_stride, out_pitch, d, dplane, dp, K, h, w, ctx->stream));
     OMNI_CUDA(cudaStreamSynchronize(ctx->stream));
     return OMNI_OK;
 }

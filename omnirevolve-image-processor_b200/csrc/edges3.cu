@@ -22,6 +22,8 @@
 #include <cuda_fp16.h>
 
 #define E3V_WARPS 2
+#define ET_R 8                            // tile rows of the sparse variant
+struct E3RunOff { unsigned v[ET_MAXT]; };
 #define E3V_LSTRIDE 40                    // u16 per lane region (80 bytes: conflict-free uint4 stores)
 
 // Per-warp shared memory.  Every lane stores ITS OWN window of a row (no cross-lane exchange is needed to
@@ -45,11 +47,22 @@ __device__ __forceinline__ u32 e3_range_mask(int start_px, int w)
 __device__ __forceinline__ __half2 as_h2(u32 x) { return *reinterpret_cast<__half2 *>(&x); }
 __device__ __forceinline__ u32 as_u32(__half2 x) { return *reinterpret_cast<u32 *>(&x); }
 
-__global__ void __launch_bounds__(E3V_WARPS * 32) fk_edges3_simd(const u32 *__restrict__ m2, int ws, size_t plane, int h, int w, int low,
-                                                                 int high, int tr, int wcols, u32 *__restrict__ sbits,
-                                                                 u32 *__restrict__ cbits, u8 *__restrict__ edges,
-                                                                 size_t estride, size_t epitch, int aligned16, int *__restrict__ wl_count,
-                                                                 u32 *__restrict__ worklist, int wl_cap)
+// Work items.  DENSE: a warp = 32 adjacent word columns x one strip of `tr` rows of plane blockIdx.y.
+// SPARSE: a lane = one RUN from the run lists of fk_edge_runs (below): word column c of plane k, rows
+// [8 j0, 8 j0 + 8 nt) -- only runs whose 5x5 neighbourhoods are not uniform can hold an edge pixel; the 32 lanes of a
+// warp take 32 runs of the same length nt (lists are bucketed by nt) and walk them in lock step.  Everything in the
+// row pipeline is lane-private (own 40-pixel window, own shared-memory regions), so the lanes of a warp may sit
+// anywhere in the image; only the candidate list of the NMS step is shared, to balance the per-pixel work.
+struct E3Args {
+    const u32 *m2; int ws; size_t plane; int h, w, low, high;
+    int tr, wcols;                                    // dense: strip height, warp columns
+    u32 *sbits, *cbits; u8 *edges; size_t estride, epitch; int aligned16;
+    int *wl_count; u32 *worklist; int wl_cap;         // words with weak candidates, for the hysteresis kernel
+    const int *run_counts; int *run_next; const u32 *run_items; unsigned run_off[ET_MAXT];   // sparse: run lists
+};
+
+template <bool SPARSE>
+__global__ void __launch_bounds__(E3V_WARPS * 32) fk_edges3_simd(const __grid_constant__ E3Args A)
 {
     __shared__ E3WarpSmem sm[E3V_WARPS];
     __shared__ u32 s_lut6[64];
@@ -61,14 +74,24 @@ __global__ void __launch_bounds__(E3V_WARPS * 32) fk_edges3_simd(const u32 *__re
     __syncthreads();
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     E3WarpSmem &S = sm[wid];
+    const u32 *__restrict__ m2 = A.m2;
+    u32 *__restrict__ sbits = A.sbits, *__restrict__ cbits = A.cbits;
+    u8 *__restrict__ edges = A.edges;
+    const int ws = A.ws, h = A.h, w = A.w;
+    const size_t plane = A.plane, estride = A.estride, epitch = A.epitch;
+    const int aligned16 = A.aligned16, wl_cap = A.wl_cap;
+    int *__restrict__ wl_count = A.wl_count;
+    u32 *__restrict__ worklist = A.worklist;
     const int ww = (w + 31) >> 5;
-    const int gw = blockIdx.x * E3V_WARPS + wid;
-    const int wx = gw % wcols, strip = gw / wcols;
-    const int k = blockIdx.y;
-    const int y0 = strip * tr, y1 = min(h, y0 + tr);
-    if (y0 >= h) return;
-    const int c = wx * 32 + lane;
-    const bool active = c < ww;
+    const int lowc = min(A.low, 2041), highc = min(A.high, 2041);
+    const __half2 low_h = __floats2half2_rn((float)lowc, (float)lowc);
+    const int high_bits = (int)__half_as_ushort(__float2half_rn((float)highc));
+    const __half2 k1024 = __floats2half2_rn(1024.f, 1024.f), k2 = __floats2half2_rn(2.f, 2.f);
+    const int lreg = lane * E3V_LSTRIDE;                 // this lane's region (u16 units)
+
+    // rows [y0, y1) of word column c of plane k (this lane's item); `nrows` is the warp-uniform row count of the item
+    // (y1 <= y0 + nrows); lanes without an item run along with `active` false.
+    auto process = [&](const int k, const int c, const int y0, const int y1, const int nrows, const bool active) {
     const u32 *src = m2 + (size_t)k * plane;
     const u32 pv = active ? e3_range_mask(32 * c, w) : 0u;
     const int eW = 4 + w - 32 * c;                       // window index of pixel w (the first one right of the image)
@@ -76,14 +99,10 @@ __global__ void __launch_bounds__(E3V_WARPS * 32) fk_edges3_simd(const u32 *__re
     // that owns pixel w-1 this is the previous lane when w % 32 is 1 or 2
     const bool has_rb = eW >= 5 && eW <= 38;
     const bool is_lb = c == 0;
-    const int lowc = min(low, 2041), highc = min(high, 2041);
-    const __half2 low_h = __floats2half2_rn((float)lowc, (float)lowc);
-    const int high_bits = (int)__half_as_ushort(__float2half_rn((float)highc));
-    const __half2 k1024 = __floats2half2_rn(1024.f, 1024.f), k2 = __floats2half2_rn(2.f, 2.f);
-    const int lreg = lane * E3V_LSTRIDE;                 // this lane's region (u16 units)
 
-    // one pipeline step: consumes bit row t; (hB, hA) = horizontal sums of rows t-1, t-2, hC receives row t;
-    // (UB, UA) = blurred rows t-2, t-3 as half2, UC receives row t-1.
+    // one pipeline step: consumes bit row t = y0 + tt; (hB, hA) = horizontal sums of rows t-1, t-2, hC receives row t;
+    // (UB, UA) = blurred rows t-2, t-3 as half2, UC receives row t-1.  Ring slots are indexed by the RELATIVE row
+    // (the same for every lane of the warp).
     u32 cand_prev = 0u;
     u32 pf_l = 0u, pf_o = 0u, pf_r = 0u;                 // words of the next bit row (software prefetch)
     auto load_row = [&](const int t) {
@@ -95,14 +114,15 @@ __global__ void __launch_bounds__(E3V_WARPS * 32) fk_edges3_simd(const u32 *__re
         else if (t == h) rt = max(h - 2, 0);
         else if (t == h + 1) rt = h - 1;
         pf_l = pf_o = pf_r = 0u;
-        if (rt >= 0) {
+        if (rt >= 0 && (active || !SPARSE)) {
             const u32 *row = src + (size_t)rt * ws;
             if (c > 0 && c - 1 < ww) pf_l = __ldg(row + c - 1);
             if (active) pf_o = __ldg(row + c);
             if (c + 1 < ww) pf_r = __ldg(row + c + 1);
         }
     };
-    auto step = [&](const int t, u32 (&hA)[10], u32 (&hB)[10], u32 (&hC)[10], u32 (&UA)[20], u32 (&UB)[20], u32 (&UC)[20]) {
+    auto step = [&](const int tt, u32 (&hA)[10], u32 (&hB)[10], u32 (&hC)[10], u32 (&UA)[20], u32 (&UB)[20], u32 (&UC)[20]) {
+        const int t = y0 + tt;
         // ---- (1) bit row t (prefetched one step ahead), 40-pixel window: index e <-> pixel 32c - 4 + e ---------------
         u32 lo = (pf_l >> 28) | (pf_o << 4), hi = (pf_o >> 28) | (pf_r << 4);
         if (is_lb) {                                   // pixels -1, -2 := pixels 1, 0
@@ -139,10 +159,10 @@ __global__ void __launch_bounds__(E3V_WARPS * 32) fk_edges3_simd(const u32 *__re
             }
         }
         // ---- (4) row r = t-2: Sobel, magnitude, candidate mask; rows into shared memory ----------------------------
-        const int r = t - 2;
+        const int r = t - 2, rr = tt - 2;                                   // absolute / relative
         u32 cand = 0u;
-        if (r >= y0 - 1 && r <= y1) {
-            const int slot = (r + 3) % 3;
+        if (rr >= -1 && rr <= nrows) {
+            const int slot = (rr + 6) % 3;
             u16 *mreg = S.m[slot] + lreg;
             if (r >= 0 && r < h) {
                 u32 V[20], D[20];
@@ -176,7 +196,7 @@ __global__ void __launch_bounds__(E3V_WARPS * 32) fk_edges3_simd(const u32 *__re
 #pragma unroll
                 for (int jj = 0; jj < 4; jj++) mv[jj] = make_uint4(mb[4 * jj], mb[4 * jj + 1], mb[4 * jj + 2], mb[4 * jj + 3]);
                 *reinterpret_cast<uint2 *>(mreg + 32) = make_uint2(mb[16], mb[17]);
-                uint4 *dxv = reinterpret_cast<uint4 *>(S.dx[r & 1] + 32 * lane), *dyv = reinterpret_cast<uint4 *>(S.dy[r & 1] + 32 * lane);
+                uint4 *dxv = reinterpret_cast<uint4 *>(S.dx[rr & 1] + 32 * lane), *dyv = reinterpret_cast<uint4 *>(S.dy[rr & 1] + 32 * lane);
 #pragma unroll
                 for (int jj = 0; jj < 4; jj++) {
                     dxv[jj] = make_uint4(dxb[1 + 4 * jj], dxb[2 + 4 * jj], dxb[3 + 4 * jj], dxb[4 + 4 * jj]);
@@ -193,11 +213,12 @@ __global__ void __launch_bounds__(E3V_WARPS * 32) fk_edges3_simd(const u32 *__re
             }
         }
         // ---- (5) NMS + thresholds for row t-3: candidates compacted over the warp, one per lane and round -----------
-        const int rn = t - 3;
-        const bool do_nms = rn >= y0 && rn < y1;
+        const int rn = t - 3, rnr = tt - 3;
+        const bool do_nms = rnr >= 0 && rnr < nrows;                        // warp-uniform
+        const bool mine = active && rn < y1;                                // this lane has a row to resolve
         int total = 0;
         if (do_nms) {
-            u32 mk = cand_prev;
+            u32 mk = mine ? cand_prev : 0u;
             const int cnt = __popc(mk);
             int x = cnt;
 #pragma unroll
@@ -207,38 +228,58 @@ __global__ void __launch_bounds__(E3V_WARPS * 32) fk_edges3_simd(const u32 *__re
             }
             total = __shfl_sync(0xffffffffu, x, 31);
             int pos = x - cnt;
+            const u32 tag = (u32)lane << 5;
             while (mk) {
                 const int e = __ffs(mk) - 1;
                 mk &= mk - 1u;
-                S.list[pos++] = (u16)((lane << 5) | e);
+                S.list[pos++] = (u16)(tag | e);
             }
             S.cw[lane] = 0u; S.sw[lane] = 0u;
         }
         __syncwarp();
         if (do_nms) {
-            const u16 *mu = S.m[(rn + 2) % 3], *mc = S.m[rn % 3], *md = S.m[(rn + 1) % 3];
-            const u16 *dxr = S.dx[rn & 1], *dyr = S.dy[rn & 1];
-            for (int i = lane; i < total; i += 32) {
-                const int item = S.list[i];
-                const int o = item >> 5, e = item & 31;
+            const u16 *mu = S.m[(rnr + 5) % 3], *mc = S.m[(rnr + 6) % 3], *md = S.m[(rnr + 7) % 3];
+            const u16 *dxr = S.dx[rnr & 1], *dyr = S.dy[rnr & 1];
+            // two candidates per lane and round (independent dependency chains); a lane whose second index falls off the
+            // list repeats the last entry -- the result bits are OR-ed in, so a repeat is harmless
+            auto nms_one = [&](const int item, int &o, u32 &bit, bool &ok, bool &strong) {
+                o = item >> 5;
+                const int e = item & 31;
                 const int bi = o * E3V_LSTRIDE + e;
                 const int m0 = mc[bi + 2];
-                const int dx = __half2int_rn(__ushort_as_half(dxr[item])), dy = __half2int_rn(__ushort_as_half(dyr[item]));
-                const int ax = abs(dx), ay = abs(dy) << 15, tg22 = ax * 13573;
-                const bool hz = ay < tg22, vt = ay > tg22 + (ax << 16);
-                const int s = (dx ^ dy) < 0 ? -1 : 1;
+                // cv2.Canny's direction test  |dy| * 2^15 < |dx| * TG22  /  > |dx| * (TG22 + 2^16), TG22 = 13573, in float32:
+                // |dx|, |dy| <= 1020 are integers, so |dx| * 13573 < 2^24 and (|dy| - 2|dx|) * 2^15 are exact
+                const u32 dxb = dxr[item], dyb = dyr[item];
+                const float ax = fabsf(__half2float(__ushort_as_half((u16)dxb))), ay = fabsf(__half2float(__ushort_as_half((u16)dyb)));
+                const float tg = __fmul_rn(ax, 13573.f);
+                const bool hz = __fmul_rn(ay, 32768.f) < tg, vt = __fmul_rn(__fsub_rn(ay, __fadd_rn(ax, ax)), 32768.f) > tg;
+                const int s = ((dxb ^ dyb) & 0x8000u) ? -1 : 1;             // fp16 differences are never -0
                 const int off = hz ? 1 : (vt ? 0 : s);                    // a = (row above|same)[x - off], b = (row below|same)[x + off]
                 const u16 *ra = hz ? mc : mu, *rb = hz ? mc : md;
                 const int a = ra[bi + 2 - off], b = rb[bi + 2 + off];
-                const bool ok = m0 > a && (m0 > b || ((hz || vt) && m0 == b));
-                if (ok) {
-                    atomicOr(&S.cw[o], 1u << e);
-                    if (m0 > high_bits) atomicOr(&S.sw[o], 1u << e);
+                ok = m0 > a && (m0 > b || ((hz || vt) && m0 == b));
+                strong = m0 > high_bits;
+                bit = 1u << e;
+            };
+            for (int i = lane; i < total; i += 64) {
+                const int item0 = S.list[i], item1 = S.list[min(i + 32, total - 1)];
+                int o0, o1;
+                u32 b0, b1;
+                bool ok0, ok1, st0, st1;
+                nms_one(item0, o0, b0, ok0, st0);
+                nms_one(item1, o1, b1, ok1, st1);
+                if (ok0) {
+                    atomicOr(&S.cw[o0], b0);
+                    if (st0) atomicOr(&S.sw[o0], b0);
+                }
+                if (ok1) {
+                    atomicOr(&S.cw[o1], b1);
+                    if (st1) atomicOr(&S.sw[o1], b1);
                 }
             }
         }
         __syncwarp();
-        if (do_nms && active) {
+        if (do_nms && mine) {
             size_t o = (size_t)k * plane + (size_t)rn * ws + c;
             const u32 sw = S.sw[lane];
             const u32 cwv = S.cw[lane];
@@ -259,22 +300,189 @@ __global__ void __launch_bounds__(E3V_WARPS * 32) fk_edges3_simd(const u32 *__re
     for (int q = 0; q < 10; q++) hA[q] = hB[q] = hC[q] = 0u;
 #pragma unroll
     for (int j = 0; j < 20; j++) UA[j] = UB[j] = UC[j] = 0u;
-    const int t_end = y1 + 2;
+    const int tt_end = nrows + 2;
     load_row(y0 - 3);
-    for (int t = y0 - 3; t <= t_end; t += 3) {
-        step(t, hA, hB, hC, UA, UB, UC);
-        if (t + 1 > t_end) break;
-        step(t + 1, hB, hC, hA, UB, UC, UA);
-        if (t + 2 > t_end) break;
-        step(t + 2, hC, hA, hB, UC, UA, UB);
+    for (int tt = -3; tt <= tt_end; tt += 3) {
+        step(tt, hA, hB, hC, UA, UB, UC);
+        if (tt + 1 > tt_end) break;
+        step(tt + 1, hB, hC, hA, UB, UC, UA);
+        if (tt + 2 > tt_end) break;
+        step(tt + 2, hC, hA, hB, UC, UA, UB);
+    }
+    };  // process
+
+    if (!SPARSE) {
+        const int gw = blockIdx.x * E3V_WARPS + wid;
+        const int wx = gw % A.wcols, strip = gw / A.wcols;
+        const int y0 = strip * A.tr;
+        if (y0 >= h) return;
+        const int c = wx * 32 + lane;
+        process(blockIdx.y, c, y0, min(h, y0 + A.tr), A.tr, c < ww);
+    } else {
+        // run lists, longest runs first; a warp item = 32 consecutive entries of ONE list
+        int cnt[ET_MAXT], wcum[ET_MAXT + 1];
+        wcum[0] = 0;
+#pragma unroll
+        for (int b = 0; b < ET_MAXT; b++) {
+            cnt[b] = A.run_counts[ET_MAXT - 1 - b];                         // b = 0 <-> nt = ET_MAXT
+            wcum[b + 1] = wcum[b] + ((cnt[b] + 31) >> 5);
+        }
+        for (;;) {
+            int wi = 0;
+            if (lane == 0) wi = atomicAdd(A.run_next, 1);
+            wi = __shfl_sync(0xffffffffu, wi, 0);
+            if (wi >= wcum[ET_MAXT]) break;
+            int b = 0;
+#pragma unroll
+            for (int q = 1; q < ET_MAXT; q++) if (wi >= wcum[q]) b = q;
+            int cb = cnt[0], wb = wcum[0];
+#pragma unroll
+            for (int q = 1; q < ET_MAXT; q++) if (b == q) { cb = cnt[q]; wb = wcum[q]; }
+            const int nt = ET_MAXT - b;
+            const int idx = (wi - wb) * 32 + lane;
+            const bool valid = idx < cb;
+            const u32 item = valid ? __ldg(A.run_items + A.run_off[nt - 1] + idx) : 0u;
+            const int k = (int)(item >> 27), j0 = (int)((item >> 13) & 0x3fffu), c = (int)(item & 0x1fffu);
+            const int y0 = j0 * ET_R, nrows = nt * ET_R;
+            __syncwarp();
+            process(k, c, y0, min(h, y0 + nrows), nrows, valid);
+        }
     }
 }
 
-cudaError_t launch_edges3_simd(const u32 *m2, int ws, size_t plane, int h, int w, int K, int low, int high, int sm_count,
-                               u32 *sbits, u32 *cbits, u8 *edges, size_t estride, size_t epitch, int aligned16, int *wl_count, u32 *worklist, int wl_cap,
-                               cudaStream_t st)
+// ------------------------------------------------------------------------------------------------
+// Run lists for the sparse edge kernel.  A TILE is one word column x ET_R rows of one plane.  It is DEAD when the
+// tile grown by 2 pixels on every side (clipped to the image) is all 0 or all 1: every 5x5 neighbourhood of its
+// pixels is then uniform, so the blurred image is constant there (REFLECT_101 / REPLICATE only mirror pixels of the
+// same neighbourhood), dx = dy = 0 and no pixel can exceed `low` >= 0.  Dead tiles get their zeros (candidate /
+// strong words, edge bytes) written right here.  Vertically adjacent live tiles are merged into runs of at most
+// ET_MAXT tiles (the 6 extra pipeline rows are paid per run); runs are listed per length so that a warp of the edge
+// kernel works on 32 equally long runs.
+// One lane walks one word column down a strip of ER_STRIP_TILES tiles; a warp = 32 adjacent word columns.
+// ------------------------------------------------------------------------------------------------
+#define ER_STRIP_TILES 4
+#define ER_WARPS 4
+#define ER_MAXITEMS ER_STRIP_TILES          // maxt = 1: every live tile is an item
+
+__global__ void __launch_bounds__(ER_WARPS * 32) fk_edge_runs(const u32 *__restrict__ m2, int ws, size_t plane, int h, int w, int wcols,
+                                                               u32 *__restrict__ sbits, u32 *__restrict__ cbits, u8 *__restrict__ edges,
+                                                               size_t estride, size_t epitch, int aligned16, int *__restrict__ run_counts,
+                                                               u32 *__restrict__ run_items, const __grid_constant__ E3RunOff off, int maxt)
 {
-    const int ww = (w + 31) >> 5, wcols = (ww + 31) / 32;
+    __shared__ u32 s_item[ER_WARPS][ER_MAXITEMS][32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int gw = blockIdx.x * ER_WARPS + wid;
+    const int wx = gw % wcols, strip = gw / wcols;
+    const int k = blockIdx.y;
+    const int ww = (w + 31) >> 5;
+    const int tiles_y = (h + ET_R - 1) / ET_R;
+    const int j_lo = strip * ER_STRIP_TILES, j_hi = min(tiles_y, j_lo + ER_STRIP_TILES);
+    if (j_lo >= tiles_y) return;
+    const int c = wx * 32 + lane;
+    const bool active = c < ww;
+    const u32 *src = m2 + (size_t)k * plane;
+    // validity of the 36 window pixels 32c-2 .. 32c+33
+    const u32 pv = active ? e3_range_mask(32 * c, w) : 0u;
+    const u32 lv = (active && c > 0) ? 0xC0000000u : 0u;                    // pixels 32c-2, 32c-1 = bits 30, 31 of word c-1
+    const u32 rv = active ? (e3_range_mask(32 * c + 32, w) & 3u) : 0u;      // pixels 32c+32, 32c+33
+    // "has a 1" / "has a 0" over the 36-pixel windows of the ET_R rows of tile row j: all rows (A), the first two (F),
+    // the last two (L).  The rows are fetched as one batch of independent loads.  Tile j grown by 2 rows is L(j-1) | A(j) | F(j+1).
+    struct Fl { u32 a1, a0, f1, f0, l1, l0; };
+    auto row_group = [&](const int j) {
+        Fl f = {0u, 0u, 0u, 0u, 0u, 0u};
+        if (!active || j < 0 || j >= tiles_y) return f;
+        u32 o[ET_R], l[ET_R], r[ET_R];
+        bool in[ET_R];
+#pragma unroll
+        for (int i = 0; i < ET_R; i++) {
+            const int y = j * ET_R + i;
+            in[i] = y < h;
+            const u32 *row = src + (size_t)(in[i] ? y : 0) * ws;
+            o[i] = __ldg(row + c);
+            l[i] = lv ? __ldg(row + c - 1) : 0u;
+            r[i] = rv ? __ldg(row + c + 1) : 0u;
+        }
+        const int last = min(h, j * ET_R + ET_R) - j * ET_R - 1;             // index of the tile's last row inside the image
+#pragma unroll
+        for (int i = 0; i < ET_R; i++) {
+            if (!in[i]) continue;
+            const u32 h1 = (o[i] & pv) | (l[i] & lv) | (r[i] & rv), h0 = (~o[i] & pv) | (~l[i] & lv) | (~r[i] & rv);
+            f.a1 |= h1; f.a0 |= h0;
+            if (i < 2) { f.f1 |= h1; f.f0 |= h0; }
+            if (i >= last - 1) { f.l1 |= h1; f.l0 |= h0; }
+        }
+        return f;
+    };
+    int n_items = 0, run = 0, run_j0 = 0;
+    u32 lens = 0u;                                                          // 3 bits per emitted item: its run length nt
+    auto emit = [&]() { s_item[wid][n_items++][lane] = ((u32)k << 27) | ((u32)run_j0 << 13) | (u32)c; };
+    Fl prev = row_group(j_lo - 1), cur = row_group(j_lo);
+#pragma unroll
+    for (int jj = 0; jj < ER_STRIP_TILES; jj++) {
+        const int j = j_lo + jj;
+        if (j >= j_hi) break;
+        const Fl next = row_group(j + 1);
+        const u32 has1 = prev.l1 | cur.a1 | next.f1, has0 = prev.l0 | cur.a0 | next.f0;
+        const bool live = has1 != 0u && has0 != 0u;
+        if (live) {
+            if (run == 0) run_j0 = j;
+            if (++run == maxt) { lens |= (u32)run << (3 * n_items); emit(); run = 0; }
+        } else {
+            if (run) { lens |= (u32)run << (3 * n_items); emit(); run = 0; }
+            if (active) {
+                const int y1 = min(h, j * ET_R + ET_R);
+                for (int y = j * ET_R; y < y1; y++) {
+                    const size_t o = (size_t)k * plane + (size_t)y * ws + c;
+                    cbits[o] = 0u; sbits[o] = 0u;
+                    store_word_bytes(edges + (size_t)k * estride + (size_t)y * epitch, 32 * c, w, 0u, aligned16 != 0);
+                }
+            }
+        }
+        prev = cur; cur = next;
+    }
+    if (run) { lens |= (u32)run << (3 * n_items); emit(); run = 0; }
+    // flush: per run length one warp-aggregated reservation
+#pragma unroll
+    for (int nt = 1; nt <= ET_MAXT; nt++) {
+        int mine = 0;
+        for (int i = 0; i < n_items; i++) mine += ((lens >> (3 * i)) & 7u) == (u32)nt;
+        int x = mine;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            int y = __shfl_up_sync(0xffffffffu, x, d);
+            if (lane >= d) x += y;
+        }
+        const int total = __shfl_sync(0xffffffffu, x, 31);
+        if (total == 0) continue;
+        int base = 0;
+        if (lane == 31) base = atomicAdd(run_counts + nt - 1, total);
+        base = __shfl_sync(0xffffffffu, base, 31);
+        int pos = base + x - mine;
+        for (int i = 0; i < n_items; i++)
+            if (((lens >> (3 * i)) & 7u) == (u32)nt) run_items[off.v[nt - 1] + pos++] = s_item[wid][i][lane];
+    }
+}
+
+size_t edges3_run_words(int h, int w, int K, unsigned off[ET_MAXT])
+{
+    const size_t tiles = (size_t)K * ((h + ET_R - 1) / ET_R) * ((w + 31) / 32);
+    size_t at = 0;
+    for (int nt = 1; nt <= ET_MAXT; nt++) {
+        off[nt - 1] = (unsigned)at;
+        at += tiles / nt + 64;                      // a run of nt tiles uses nt tiles; strip seams only shorten runs
+    }
+    return at;
+}
+
+bool edges3_sparse_ok(int h, int w, int K)
+{
+    unsigned off[ET_MAXT];
+    return K <= 32 && (w + 31) / 32 <= 0x2000 && (h + ET_R - 1) / ET_R <= 0x4000 && edges3_run_words(h, w, K, off) < 0xffffffffull;
+}
+
+static void e3_dense_grid(int h, int ww, int K, int sm_count, int *tr_out, int *wcols_out, dim3 *grid)
+{
+    const int wcols = (ww + 31) / 32;
     // strip height: enough warps for ~2 waves of the machine (12 resident warps per SM), at most 64 rows
     long long target = (long long)(sm_count > 0 ? sm_count : 148) * 12 * 2;
     long long per_row_strips = (long long)wcols * K;
@@ -285,7 +493,65 @@ cudaError_t launch_edges3_simd(const u32 *m2, int ws, size_t plane, int h, int w
     if (tr > 64) tr = 64;
     strips = (h + tr - 1) / tr;
     long long warps = (long long)strips * wcols;
-    dim3 grid((unsigned)((warps + E3V_WARPS - 1) / E3V_WARPS), K);
-    fk_edges3_simd<<<grid, E3V_WARPS * 32, 0, st>>>(m2, ws, plane, h, w, low, high, tr, wcols, sbits, cbits, edges, estride, epitch, aligned16, wl_count, worklist, wl_cap);
+    *tr_out = tr; *wcols_out = wcols;
+    *grid = dim3((unsigned)((warps + E3V_WARPS - 1) / E3V_WARPS), K);
+}
+
+cudaError_t launch_edges3_simd(const u32 *m2, int ws, size_t plane, int h, int w, int K, int low, int high, int sm_count,
+                               u32 *sbits, u32 *cbits, u8 *edges, size_t estride, size_t epitch, int aligned16, int *wl_count, u32 *worklist, int wl_cap,
+                               cudaStream_t st)
+{
+    E3Args A{};
+    A.m2 = m2; A.ws = ws; A.plane = plane; A.h = h; A.w = w; A.low = low; A.high = high;
+    A.sbits = sbits; A.cbits = cbits; A.edges = edges; A.estride = estride; A.epitch = epitch; A.aligned16 = aligned16;
+    A.wl_count = wl_count; A.worklist = worklist; A.wl_cap = wl_cap;
+    dim3 grid;
+    e3_dense_grid(h, (w + 31) >> 5, K, sm_count, &A.tr, &A.wcols, &grid);
+    fk_edges3_simd<false><<<grid, E3V_WARPS * 32, 0, st>>>(A);
     return cudaGetLastError();
+}
+
+// run lists (fk_edge_runs; zero-fills the dead tiles).  run_counts: ET_MAXT ints + 1 int "next warp item", zeroed by the caller.
+cudaError_t launch_edge_runs(const u32 *m2, int ws, size_t plane, int h, int w, int K, u32 *sbits, u32 *cbits, u8 *edges,
+                             size_t estride, size_t epitch, int aligned16, int *run_counts, u32 *run_items, int resident_warps, cudaStream_t st)
+{
+    // Longest run, in tiles: long runs pay the 6 extra pipeline rows less often, short runs give more warp items.  On
+    // pipeline-like masks about a third of the tiles is live and a run holds (1, 1.6, 2, 2.4) tiles on average for
+    // maxt = 1..4; take the longest runs that still give every resident warp of the edge kernel an item.
+    const double live = 0.35 * (double)K * ((h + ET_R - 1) / ET_R) * ((w + 31) / 32);
+    const double avg[ET_MAXT] = {1.0, 1.6, 2.0, 2.4};
+    int maxt = ET_MAXT;
+    while (maxt > 1 && live / avg[maxt - 1] / 32.0 < (double)resident_warps) maxt--;
+    const int ww = (w + 31) >> 5, wcols = (ww + 31) / 32;
+    const int tiles_y = (h + ET_R - 1) / ET_R, strips = (tiles_y + ER_STRIP_TILES - 1) / ER_STRIP_TILES;
+    E3RunOff off;
+    edges3_run_words(h, w, K, off.v);
+    dim3 grid((unsigned)(((long long)strips * wcols + ER_WARPS - 1) / ER_WARPS), K);
+    fk_edge_runs<<<grid, ER_WARPS * 32, 0, st>>>(m2, ws, plane, h, w, wcols, sbits, cbits, edges, estride, epitch, aligned16, run_counts,
+                                                 run_items, off, maxt);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_edges3_sparse(const u32 *m2, int ws, size_t plane, int h, int w, int K, int low, int high, int grid_blocks,
+                                 u32 *sbits, u32 *cbits, u8 *edges, size_t estride, size_t epitch, int aligned16, int *wl_count,
+                                 u32 *worklist, int wl_cap, const int *run_counts, int *run_next, const u32 *run_items, cudaStream_t st)
+{
+    E3Args A{};
+    A.m2 = m2; A.ws = ws; A.plane = plane; A.h = h; A.w = w; A.low = low; A.high = high;
+    A.sbits = sbits; A.cbits = cbits; A.edges = edges; A.estride = estride; A.epitch = epitch; A.aligned16 = aligned16;
+    A.wl_count = wl_count; A.worklist = worklist; A.wl_cap = wl_cap;
+    A.run_counts = run_counts; A.run_next = run_next; A.run_items = run_items;
+    edges3_run_words(h, w, K, A.run_off);
+    fk_edges3_simd<true><<<grid_blocks, E3V_WARPS * 32, 0, st>>>(A);
+    return cudaGetLastError();
+}
+
+int edges3_sparse_blocks_per_sm()
+{
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fk_edges3_simd<true>, E3V_WARPS * 32, 0) != cudaSuccess || per_sm < 1) {
+        cudaGetLastError();
+        per_sm = 1;
+    }
+    return per_sm;
 }

@@ -17,6 +17,7 @@
 #include "fast_kernels.cuh"
 #include "omni_tables.inc"
 
+#include <algorithm>
 #include <cooperative_groups.h>
 #include <stdlib.h>
 #include <string.h>
@@ -118,6 +119,103 @@ cudaError_t fast_resize_2x(const u8 *src, size_t spitch, u8 *dst, int dh, int dw
 }
 
 // ------------------------------------------------------------------------------------------------
+// stage 01: fractional INTER_AREA (the default max_dimension=2000 path, e.g. 4096 -> 2000), SURVEY A.1 (iii).
+// A CTA produces a tile of RF_TX x RF_TY destination pixels: the source rectangle the tile touches is staged in
+// shared memory with coalesced 16-byte row segments (every source byte crosses HBM once), then each thread walks
+// OpenCV's tables for its destination pixels exactly like the generic kernel (same float32 operation order:
+// per source row a sequential horizontal sum, then sum = beta * buf / sum += beta * buf).
+// ------------------------------------------------------------------------------------------------
+#define RF_TX 64
+#define RF_THREADS 256
+
+__global__ void __launch_bounds__(RF_THREADS) fk_resize_frac(const u8 *__restrict__ src, int sh, int sw, size_t spitch, u8 *__restrict__ dst,
+                                                             int dh, int dw, size_t dpitch, const ResizeTabDev t, int ty_rows, int spitch_s,
+                                                             int vec_ok)
+{
+    extern __shared__ __align__(16) u8 s_src[];
+    const int x0 = blockIdx.x * RF_TX, y0 = blockIdx.y * ty_rows;
+    const int x1 = min(dw, x0 + RF_TX), y1 = min(dh, y0 + ty_rows);
+    const int xs0 = t.xsi[t.xofs[x0]], xs1 = t.xsi[t.xofs[x1] - 1];          // source columns [xs0, xs1]
+    const int ys0 = t.ysi[t.yofs[y0]], ys1 = t.ysi[t.yofs[y1] - 1];          // source rows    [ys0, ys1]
+    const int b0 = (3 * xs0) & ~15;                                            // first staged byte of a row (16-aligned)
+    const int nbytes = 3 * (xs1 + 1) - b0;
+    const int nrows = ys1 - ys0 + 1;
+    if (vec_ok) {
+        const int nv = (nbytes + 15) >> 4;
+        for (int i = threadIdx.x; i < nrows * nv; i += RF_THREADS) {
+            const int r = i / nv, v = i - r * nv;
+            const u8 *g = src + (size_t)(ys0 + r) * spitch + b0 + 16 * v;
+            u8 *d = s_src + (size_t)r * spitch_s + 16 * v;
+            if (b0 + 16 * v + 16 <= 3 * sw) *reinterpret_cast<uint4 *>(d) = __ldg(reinterpret_cast<const uint4 *>(g));
+            else for (int q = 0; b0 + 16 * v + q < 3 * sw; q++) d[q] = g[q];       // never read past the row's pixels
+        }
+    } else {
+        for (int i = threadIdx.x; i < nrows * nbytes; i += RF_THREADS) {
+            const int r = i / nbytes, v = i - r * nbytes;
+            s_src[(size_t)r * spitch_s + v] = src[(size_t)(ys0 + r) * spitch + b0 + v];
+        }
+    }
+    __syncthreads();
+    const int tw = x1 - x0, n = tw * (y1 - y0);
+    for (int i = threadIdx.x; i < n; i += RF_THREADS) {
+        const int ly = i / tw, lx = i - ly * tw;
+        const int x = x0 + lx, y = y0 + ly;
+        const int xb = t.xofs[x], xe = t.xofs[x + 1], yb = t.yofs[y], ye = t.yofs[y + 1];
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+        for (int j = yb; j < ye; j++) {
+            const u8 *r = s_src + (size_t)(t.ysi[j] - ys0) * spitch_s - b0;
+            const float beta = t.yal[j];
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+            for (int k = xb; k < xe; k++) {
+                const u8 *p = r + 3 * t.xsi[k];
+                const float a = t.xal[k];
+                a0 = __fadd_rn(a0, __fmul_rn((float)p[0], a));
+                a1 = __fadd_rn(a1, __fmul_rn((float)p[1], a));
+                a2 = __fadd_rn(a2, __fmul_rn((float)p[2], a));
+            }
+            if (j == yb) { s0 = __fmul_rn(beta, a0); s1 = __fmul_rn(beta, a1); s2 = __fmul_rn(beta, a2); }
+            else {
+                s0 = __fadd_rn(s0, __fmul_rn(beta, a0)); s1 = __fadd_rn(s1, __fmul_rn(beta, a1)); s2 = __fadd_rn(s2, __fmul_rn(beta, a2));
+            }
+        }
+        u8 *o = dst + (size_t)y * dpitch + 3 * x;
+        o[0] = (u8)min(255, max(0, __float2int_rn(s0)));
+        o[1] = (u8)min(255, max(0, __float2int_rn(s1)));
+        o[2] = (u8)min(255, max(0, __float2int_rn(s2)));
+    }
+}
+
+// returns cudaErrorNotSupported when the staged rectangle would not fit (very large ratios): caller uses the generic kernel
+cudaError_t fast_resize_frac(const u8 *src, int sh, int sw, size_t spitch, u8 *dst, int dh, int dw, size_t dpitch, const ResizeTabDev *tab,
+                             cudaStream_t st)
+{
+    const double scx = (double)sw / dw, scy = (double)sh / dh;
+    const int vec_ok = (((uintptr_t)src | spitch) & 15) == 0;
+    // widest source span of a tile: (RF_TX + 1) destination pixels worth of source columns, plus alignment slack
+    const int span_px = (int)(scx * RF_TX) + 3;
+    const int spitch_s = ((3 * span_px + 15 + 15) & ~15) + 16;
+    int ty = 16;
+    size_t smem = 0;
+    for (;; ty >>= 1) {
+        const int rows = (int)(scy * ty) + 3;
+        smem = (size_t)rows * spitch_s;
+        if (smem <= 96 * 1024 || ty == 4) break;
+    }
+    if (smem > 200 * 1024) return cudaErrorNotSupported;
+    static bool attr_set[64] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 64 && !attr_set[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(fk_resize_frac, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (e != cudaSuccess) return e;
+        attr_set[dev] = true;
+    }
+    dim3 grid((dw + RF_TX - 1) / RF_TX, (dh + ty - 1) / ty);
+    fk_resize_frac<<<grid, RF_THREADS, smem, st>>>(src, sh, sw, spitch, dst, dh, dw, dpitch, *tab, ty, spitch_s, vec_ok);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
 // stage 02: colour assignment -> labels and/or one-hot bit-planes
 //
 // Exact pruning of the centre loop.  Lab space is cut into 8x8x8 cells; fk_build_cells gives every cell the
@@ -136,9 +234,14 @@ cudaError_t fast_resize_2x(const u8 *src, size_t spitch, u8 *dst, int dh, int dw
 #define CELL_SHIFT 3
 #define CELL_N (256 >> CELL_SHIFT)                 // 32 cells per axis
 #define CELL_COUNT (CELL_N * CELL_N * CELL_N)
-// workspace slot 5: [candidate-cell table | hysteresis worklist]
+// RGB cells (fk_build_rgbcells): 4x4x4 colours each, 64 per axis
+#define RC_SHIFT 2
+#define RC_N (256 >> RC_SHIFT)
+#define RC_COUNT (RC_N * RC_N * RC_N)
+// workspace slot 5: [Lab candidate-cell table (u32) | hysteresis worklist | RGB cell table (u8)]
 #define HYST_WL_OFFSET CELL_COUNT
-#define WS5_BYTES ((size_t)(CELL_COUNT + 8192) * sizeof(u32))
+#define RGBCELL_OFFSET (CELL_COUNT + 8192)
+#define WS5_BYTES ((size_t)(CELL_COUNT + 8192 + RC_COUNT / 4) * sizeof(u32))
 
 __global__ void __launch_bounds__(256) fk_build_cells(const __grid_constant__ AssignParams P, u32 *__restrict__ cells)
 {
@@ -189,6 +292,195 @@ __device__ __forceinline__ void lab_noclamp(const u16 *gam, const u16 *cbrt, int
     L = (296 * fY - 1336934 + 16384) >> 15;
     a = (500 * (fX - fY) + 128 * 32768 + 16384) >> 15;
     b = (200 * (fY - fZ) + 128 * 32768 + 16384) >> 15;
+}
+
+// ---- RGB-cell variant (the default for Lab centres) -------------------------------------------------------
+// The same exact pruning, one level earlier: the RGB cube is cut into 64^3 cells of 4x4x4 colours and every cell gets
+// the set of centres that can be nearest for SOME colour of the cell.  OpenCV's integer Lab pipeline is monotone where
+// it matters: gamma[] and cbrt[] are non-decreasing tables and X, Y, Z are sums with positive coefficients, so over a
+// cell fX, fY, fZ lie between their values at the cell's low and high corner; L rises with fY, a with fX - fY, b with
+// fY - fZ, which bounds the cell's image by a Lab box (tight in L, conservative in a and b).  The box goes through
+// the dmin / dmax test of fk_build_cells.  ~79 % (K=8) / ~69 % (K=16) of the pixels of the benchmark images fall
+// into a cell with ONE candidate: their label is a one-byte table lookup, no Lab conversion at all.  The others
+// (table value RC_MULTI) are compacted over the warp (shared-memory queue) and take the Lab-cell path of
+// fk_assign_bits: Lab conversion, candidate set of their Lab cell, the reference's float32 evaluation.
+// The byte table is stored in blocks of 4x4x2 cells = one 32-byte sector per 16x16x8 colours, so that the 32 lookups
+// of a warp (neighbouring pixels: similar colours + noise) touch a handful of sectors instead of one each.
+#define RC_MULTI 255
+__host__ __device__ __forceinline__ u32 rc_index(u32 cb, u32 cg, u32 cr)     // cell coordinates (6 bits each)
+{
+    return ((((cb >> 2) * 16u + (cg >> 2)) * 32u + (cr >> 1)) << 5) | (((cb & 3u) * 4u + (cg & 3u)) * 2u + (cr & 1u));
+}
+__device__ __forceinline__ void lab_f(const u16 *gam, const u16 *cbrt, int B8, int G8, int R8, int &fX, int &fY, int &fZ)
+{
+    const int B = gam[B8], G = gam[G8], R = gam[R8];
+    fX = cbrt[(R * 1777 + G * 1541 + B * 778 + 2048) >> 12];
+    fY = cbrt[(R * 871 + G * 2929 + B * 296 + 2048) >> 12];
+    fZ = cbrt[(R * 73 + G * 448 + B * 3575 + 2048) >> 12];
+}
+
+__global__ void __launch_bounds__(256) fk_build_rgbcells(const __grid_constant__ AssignParams P, u8 *__restrict__ cells)
+{
+    const int ci = blockIdx.x * blockDim.x + threadIdx.x;               // (B >> 2, G >> 2, R >> 2), B slowest
+    if (ci >= RC_COUNT) return;
+    const int K = P.K;
+    const int b0 = (ci >> (2 * 6)) << RC_SHIFT, g0 = ((ci >> 6) & (RC_N - 1)) << RC_SHIFT, r0 = (ci & (RC_N - 1)) << RC_SHIFT;
+    const int span = (1 << RC_SHIFT) - 1;
+    int xl, yl, zl, xh, yh, zh;
+    lab_f(f_lab_tab, f_lab_tab + 256, b0, g0, r0, xl, yl, zl);
+    lab_f(f_lab_tab, f_lab_tab + 256, b0 + span, g0 + span, r0 + span, xh, yh, zh);
+    const float lo[3] = {(float)((296 * yl - 1336934 + 16384) >> 15), (float)((500 * (xl - yh) + 128 * 32768 + 16384) >> 15),
+                         (float)((200 * (yl - zh) + 128 * 32768 + 16384) >> 15)};
+    const float hi[3] = {(float)((296 * yh - 1336934 + 16384) >> 15), (float)((500 * (xh - yl) + 128 * 32768 + 16384) >> 15),
+                         (float)((200 * (yh - zl) + 128 * 32768 + 16384) >> 15)};
+    float U = 3.0e38f;
+    bool sane = true;
+    for (int k = 0; k < K; k++) {
+        float dmax = 0.f;
+#pragma unroll
+        for (int d = 0; d < 3; d++) {
+            float c = P.c[3 * k + d];
+            sane = sane && (fabsf(c) < 1.0e4f);                 // also false for NaN
+            float m = fmaxf(fabsf(lo[d] - c), fabsf(hi[d] - c));
+            dmax += m * m;
+        }
+        U = fminf(U, dmax);
+    }
+    u32 mask = 0u;
+    for (int k = 0; k < K; k++) {
+        float dmin = 0.f;
+#pragma unroll
+        for (int d = 0; d < 3; d++) {
+            float c = P.c[3 * k + d];
+            float n = fminf(fmaxf(c, lo[d]), hi[d]);
+            dmin += (n - c) * (n - c);
+        }
+        if (dmin <= U + 2.0f) mask |= 1u << k;                  // slack: see fk_build_cells
+    }
+    const bool single = sane && mask != 0u && (mask & (mask - 1u)) == 0u;
+    cells[rc_index(b0 >> RC_SHIFT, g0 >> RC_SHIFT, r0 >> RC_SHIFT)] = single ? P.lut[__ffs(mask) - 1] : (u8)RC_MULTI;
+}
+
+__global__ void __launch_bounds__(256) fk_assign_rgbcell(const u8 *__restrict__ px, int h, int w, size_t pitch,
+                                                         const __grid_constant__ AssignParams P, const u8 *__restrict__ rcells,
+                                                         const u32 *__restrict__ cells,
+                                                         u8 *__restrict__ labels, size_t lpitch,
+                                                         u32 *__restrict__ bits, int ws, size_t plane)
+{
+    __shared__ u16 s_gam[256];
+    __shared__ u16 s_cbrt[2048];
+    __shared__ float4 s_ctr[OMNI_MAX_K];
+    __shared__ u8 s_lut[OMNI_MAX_K];
+    __shared__ __align__(16) u8 s_px[8][768];                 // per warp: the 256 pixels of the current chunk
+    __shared__ u8 s_q[8][256];                                // per warp: queued pixel indices
+    __shared__ u8 s_lab[8][256];                              // per warp: labels of the queued pixels
+    for (int i = threadIdx.x; i < 2048; i += 256) {
+        s_cbrt[i] = f_lab_tab[256 + i];
+        if (i < 256) s_gam[i] = f_lab_tab[i];
+    }
+    if (threadIdx.x < OMNI_MAX_K) {
+        s_lut[threadIdx.x] = P.lut[threadIdx.x];
+        s_ctr[threadIdx.x] = make_float4(P.c[3 * threadIdx.x], P.c[3 * threadIdx.x + 1], P.c[3 * threadIdx.x + 2], 0.f);
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int chunks = (w + 255) >> 8, K = P.K;
+    const int total = h * chunks, stride = gridDim.x * 8;     // h * chunks < 2^31 for every image the ABI accepts
+    const bool vec_ok = (((uintptr_t)px | pitch) & 15) == 0;
+    u8 *spx = s_px[warp];
+    u8 *sq = s_q[warp], *slab = s_lab[warp];
+    const u32 lt = (1u << lane) - 1u;
+    uint4 pf0 = make_uint4(0, 0, 0, 0), pf1 = pf0;
+    auto prefetch = [&](int u) {
+        if (u < total) {
+            const int y = u / chunks, c = u - y * chunks;
+            if (vec_ok && c * 256 + 256 <= w) {
+                const uint4 *src = reinterpret_cast<const uint4 *>(px + (size_t)y * pitch + (size_t)c * 768);
+                pf0 = __ldg(src + lane);
+                if (lane < 16) pf1 = __ldg(src + 32 + lane);
+            }
+        }
+    };
+    int u = blockIdx.x * 8 + warp;
+    prefetch(u);
+    for (; u < total; u += stride) {
+        const int y = u / chunks, c = u - y * chunks;
+        const int x0 = c * 256 + lane;
+        const bool full = vec_ok && c * 256 + 256 <= w;
+        __syncwarp();                                          // the previous chunk has been consumed
+        if (full) {
+            reinterpret_cast<uint4 *>(spx)[lane] = pf0;
+            if (lane < 16) reinterpret_cast<uint4 *>(spx)[32 + lane] = pf1;
+        } else {
+            const u8 *row = px + (size_t)y * pitch + (size_t)c * 768;
+            const int nb = 3 * min(256, w - c * 256);
+            for (int i = lane; i < nb; i += 32) spx[i] = row[i];
+        }
+        prefetch(u + stride);
+        __syncwarp();
+        // ---- phase 1: one-byte table lookup; pixels of cells with several candidates are queued ----
+        int lab[8];
+        int nq = 0;
+        u32 und = 0u;
+#pragma unroll
+        for (int g = 0; g < 8; g++) {
+            const int x = x0 + 32 * g;
+            lab[g] = 255;
+            bool multi = false;
+            if (x < w) {
+                const u8 *p = spx + 3 * lane + 96 * g;
+                const u32 v0 = p[0], v1 = p[1], v2 = p[2];
+                lab[g] = __ldg(rcells + rc_index(v0 >> RC_SHIFT, v1 >> RC_SHIFT, v2 >> RC_SHIFT));
+                multi = lab[g] == RC_MULTI;
+            }
+            const u32 bal = __ballot_sync(0xffffffffu, multi);
+            if (multi) {
+                sq[nq + __popc(bal & lt)] = (u8)(32 * g + lane);
+                und |= 1u << g;
+            }
+            nq += __popc(bal);
+        }
+        __syncwarp();
+        // ---- phase 2: Lab conversion + the reference's float32 argmin over the Lab cell's candidates, one queued pixel
+        //      per lane and round ----
+        for (int i = lane; i < nq; i += 32) {
+            const int pi = sq[i];
+            const u8 *p = spx + 3 * pi;
+            int L, a, b, best = 0;
+            lab_noclamp(s_gam, s_cbrt, p[0], p[1], p[2], L, a, b);
+            u32 mk = __ldg(cells + (((L >> CELL_SHIFT) * CELL_N + (a >> CELL_SHIFT)) * CELL_N + (b >> CELL_SHIFT)));
+            const float f0 = (float)L, f1 = (float)a, f2 = (float)b;
+            float bd = 3.0e38f;
+            do {
+                const int k = __ffs(mk) - 1;
+                mk &= mk - 1u;
+                const float4 ck = s_ctr[k];
+                float d0 = __fsub_rn(f0, ck.x), d1 = __fsub_rn(f1, ck.y), d2 = __fsub_rn(f2, ck.z);
+                float d = __fadd_rn(__fadd_rn(__fmul_rn(d0, d0), __fmul_rn(d1, d1)), __fmul_rn(d2, d2));
+                if (d < bd) { bd = d; best = k; }
+            } while (mk);
+            slab[pi] = s_lut[best];
+        }
+        __syncwarp();
+#pragma unroll
+        for (int g = 0; g < 8; g++)
+            if ((und >> g) & 1u) lab[g] = slab[32 * g + lane];
+        // ---- phase 3: outputs ----
+        if (labels) {
+            u8 *lrow = labels + (size_t)y * lpitch;
+#pragma unroll
+            for (int g = 0; g < 8; g++)
+                if (x0 + 32 * g < w) lrow[x0 + 32 * g] = (u8)lab[g];
+        }
+        if (bits) {
+            u32 *brow = bits + (size_t)y * ws + c * 8;
+#pragma unroll
+            for (int g = 0; g < 8; g++) {
+                const u32 same = __match_any_sync(0xffffffffu, lab[g]);
+                if (lab[g] < K && lane == __ffs(same) - 1 && c * 8 + g < ws) brow[(size_t)lab[g] * plane + g] = same;
+            }
+        }
+    }
 }
 
 template <int MODE_LAB>
@@ -758,20 +1050,49 @@ static int bit_planes(omni_ctx *ctx, const BitGeom &g, int K, int n, u32 **out /
     return OMNI_OK;
 }
 
-// candidate-cell table for the centres of this call (workspace slot 5), built on the device
-static int assign_cells(omni_ctx *ctx, const AssignParams &P, u32 **cells, cudaStream_t st)
+// candidate-cell tables for the centres of this call (workspace slot 5), built on the device
+static int assign_cells(omni_ctx *ctx, const AssignParams &P, u32 **cells, u8 **rcells, cudaStream_t st)
 {
     FK_TRY(omni_ws_reserve(ctx, 5, WS5_BYTES));
+    const int variant = ctx->assign_rgbcell ? 2 : 1;
     *cells = (u32 *)ctx->ws[5];
-    // same centres as the previous call on this ctx (a batch of frames): the table in the workspace is still valid
-    // (calls on one ctx are serialised and go to one stream at a time, see omni_b200.h)
-    if (ctx->cells_valid && ctx->cells_stream == (void *)st && ctx->cells_K == P.K &&
-        memcmp(ctx->cells_c, P.c, sizeof(float) * 3 * P.K) == 0)
+    *rcells = (u8 *)((u32 *)ctx->ws[5] + RGBCELL_OFFSET);
+    // same centres (and label map) as the previous call on this ctx (a batch of frames): the tables in the workspace are
+    // still valid (calls on one ctx are serialised and go to one stream at a time, see omni_b200.h)
+    if (ctx->cells_valid == variant && ctx->cells_stream == (void *)st && ctx->cells_K == P.K &&
+        memcmp(ctx->cells_c, P.c, sizeof(float) * 3 * P.K) == 0 && memcmp(ctx->cells_lut, P.lut, P.K) == 0)
         return OMNI_OK;
     memcpy(ctx->cells_c, P.c, sizeof(float) * 3 * P.K);
-    ctx->cells_K = P.K; ctx->cells_stream = (void *)st; ctx->cells_valid = 1;
-    KScope ks(ctx, "build_cells", st);
-    fk_build_cells<<<CELL_COUNT / 256, 256, 0, st>>>(P, *cells);
+    memcpy(ctx->cells_lut, P.lut, P.K);
+    ctx->cells_K = P.K; ctx->cells_stream = (void *)st; ctx->cells_valid = variant;
+    {
+        KScope ks(ctx, "build_cells", st);
+        fk_build_cells<<<CELL_COUNT / 256, 256, 0, st>>>(P, *cells);
+        OMNI_CUDA(cudaGetLastError());
+    }
+    if (variant == 2) {
+        KScope ks(ctx, "build_rgbcells", st);
+        fk_build_rgbcells<<<RC_COUNT / 256, 256, 0, st>>>(P, *rcells);
+        OMNI_CUDA(cudaGetLastError());
+    }
+    return OMNI_OK;
+}
+
+// Lab-centre assignment of rows [0, h) at px: labels and/or one-hot bit-plane words (either may be NULL)
+static int launch_assign_lab(omni_ctx *ctx, const u8 *px, int h, int w, size_t pitch, const AssignParams &P, u8 *labels, size_t lpitch,
+                             u32 *bits, int ws, size_t plane, cudaStream_t st, bool scoped = true)
+{
+    u32 *cells = nullptr;
+    u8 *rcells = nullptr;
+    FK_TRY(assign_cells(ctx, P, &cells, &rcells, st));
+    KScope ks(scoped ? ctx : nullptr, "assign_bits", st);
+    if (ctx->assign_rgbcell && (long long)h * ((w + 255) >> 8) < (1ll << 30)) {       // the kernel counts chunks in 32 bits
+        const int grid = resident_grid(ctx, fk_assign_rgbcell, 256, &ctx->occ_assign_rgb);
+        fk_assign_rgbcell<<<grid, 256, 0, st>>>(px, h, w, pitch, P, rcells, cells, labels, lpitch, bits, ws, plane);
+    } else {
+        const int grid = resident_grid(ctx, fk_assign_bits<1>, 256, &ctx->occ_assign_lab);
+        fk_assign_bits<1><<<grid, 256, 0, st>>>(px, h, w, pitch, P, cells, labels, lpitch, bits, ws, plane);
+    }
     OMNI_CUDA(cudaGetLastError());
     return OMNI_OK;
 }
@@ -781,13 +1102,10 @@ cudaError_t fast_assign(omni_ctx *ctx, const u8 *px, int h, int w, size_t pitch,
 {
     cudaError_t e = fast_tables();
     if (e != cudaSuccess) return e;
-    int grid = mode_lab ? resident_grid(ctx, fk_assign_bits<1>, 256, &ctx->occ_assign_lab)
-                        : resident_grid(ctx, fk_assign_bits<0>, 256, &ctx->occ_assign_pal);
     if (mode_lab) {
-        u32 *cells = nullptr;
-        if (assign_cells(ctx, P, &cells, st) != OMNI_OK) return cudaErrorMemoryAllocation;
-        fk_assign_bits<1><<<grid, 256, 0, st>>>(px, h, w, pitch, P, cells, labels, lpitch, nullptr, 0, 0);
+        if (launch_assign_lab(ctx, px, h, w, pitch, P, labels, lpitch, nullptr, 0, 0, st, false) != OMNI_OK) return cudaErrorUnknown;
     } else {
+        int grid = resident_grid(ctx, fk_assign_bits<0>, 256, &ctx->occ_assign_pal);
         fk_assign_bits<0><<<grid, 256, 0, st>>>(px, h, w, pitch, P, nullptr, labels, lpitch, nullptr, 0, 0);
     }
     return cudaGetLastError();
@@ -891,10 +1209,23 @@ static int edges_from_bits(omni_ctx *ctx, const u32 *m2, u32 *sbits, u32 *cbits,
 {
     int al = ((uintptr_t)d_edges % 16 == 0) && (e_plane % 16 == 0) && (epitch % 16 == 0);
     FK_TRY(omni_ws_reserve(ctx, 5, WS5_BYTES));
-    OMNI_CUDA(cudaMemsetAsync(ctx->d_flags, 0, 8 * sizeof(int), st));     // rounds, 3 changed flags, worklist count
-    OMNI_LAUNCH(ctx, st, "edges3_bits", launch_edges3_simd(m2, g.ws, g.plane, g.h, g.w, K, low, high, ctx->sm_count, sbits, cbits,
-                                                           d_edges, e_plane, epitch, al, ctx->d_flags + 4,
-                                                           (u32 *)ctx->ws[5] + HYST_WL_OFFSET, HY_WL_CAP, st));
+    // d_flags: [0] rounds, [1..3] changed flags, [4] weak-word count, [16..19] run counts per length, [20] next warp item
+    OMNI_CUDA(cudaMemsetAsync(ctx->d_flags, 0, 24 * sizeof(int), st));
+    if (ctx->edge_sparse && edges3_sparse_ok(g.h, g.w, K)) {
+        unsigned off[ET_MAXT];
+        FK_TRY(omni_ws_reserve(ctx, 6, edges3_run_words(g.h, g.w, K, off) * sizeof(u32)));
+        if (ctx->e3s_per_sm == 0) ctx->e3s_per_sm = edges3_sparse_blocks_per_sm();
+        OMNI_LAUNCH(ctx, st, "edge_runs", launch_edge_runs(m2, g.ws, g.plane, g.h, g.w, K, sbits, cbits, d_edges, e_plane, epitch, al,
+                                                           ctx->d_flags + 16, (u32 *)ctx->ws[6], 2 * persist_blocks(ctx, ctx->e3s_per_sm), st));
+        OMNI_LAUNCH(ctx, st, "edges3_bits", launch_edges3_sparse(m2, g.ws, g.plane, g.h, g.w, K, low, high, persist_blocks(ctx, ctx->e3s_per_sm),
+                                                                 sbits, cbits, d_edges, e_plane, epitch, al, ctx->d_flags + 4,
+                                                                 (u32 *)ctx->ws[5] + HYST_WL_OFFSET, HY_WL_CAP, ctx->d_flags + 16,
+                                                                 ctx->d_flags + 20, (const u32 *)ctx->ws[6], st));
+    } else {
+        OMNI_LAUNCH(ctx, st, "edges3_bits", launch_edges3_simd(m2, g.ws, g.plane, g.h, g.w, K, low, high, ctx->sm_count, sbits, cbits,
+                                                               d_edges, e_plane, epitch, al, ctx->d_flags + 4,
+                                                               (u32 *)ctx->ws[5] + HYST_WL_OFFSET, HY_WL_CAP, st));
+    }
     return run_hysteresis(ctx, sbits, cbits, g, K, d_edges, e_plane, epitch, st);
 }
 
@@ -937,15 +1268,8 @@ int fast_color_edge(omni_ctx *ctx, const u8 *d_bgr, int h, int w, size_t pitch, 
     BitGeom g = make_geom(h, w);
     u32 *bpp[4];
     FK_TRY(bit_planes(ctx, g, P.K, 4, bpp));
-    u32 *cells = nullptr;
-    FK_TRY(assign_cells(ctx, P, &cells, st));
     OMNI_CUDA(cudaMemsetAsync(bpp[0], 0, g.plane * (size_t)P.K * sizeof(u32), st));      // match_any stores only non-empty words
-    {
-        KScope ks(ctx, "assign_bits", st);
-        fk_assign_bits<1><<<resident_grid(ctx, fk_assign_bits<1>, 256, &ctx->occ_assign_lab), 256, 0, st>>>(
-            d_bgr, h, w, pitch, P, cells, d_labels, lpitch, bpp[0], g.ws, g.plane);
-        OMNI_CUDA(cudaGetLastError());
-    }
+    FK_TRY(launch_assign_lab(ctx, d_bgr, h, w, pitch, P, d_labels, lpitch, bpp[0], g.ws, g.plane, st));
     int kind = morph03_kind(prm);
     OMNI_LAUNCH(ctx, st, "morph_bits", launch_morph(true, kind, bpp[0], bpp[1], g, P.K, d_masks, m_plane, mpitch, st));
     return edges_from_bits(ctx, bpp[1], bpp[2], bpp[3], g, P.K, low, high, d_edges, e_plane, epitch, st);
@@ -1014,10 +1338,7 @@ int fast_host_color_edge(omni_ctx *ctx, const u8 *h_bgr, int h, int w, size_t pi
                                     cudaMemcpyHostToDevice, si));
         OMNI_CUDA(cudaEventRecord(evH[b], si));
     }
-    u32 *cells = nullptr;
-    FK_TRY(assign_cells(ctx, P, &cells, sc));
     OMNI_CUDA(cudaMemsetAsync(bpp[0], 0, g.plane * (size_t)K * sizeof(u32), sc));
-    const int agrid = resident_grid(ctx, fk_assign_bits<1>, 256, &ctx->occ_assign_lab);
     auto morph_band = [&](int b) -> int {
         int y0 = b * rows_per, y1 = min(h, y0 + rows_per);
         OMNI_LAUNCH(ctx, sc, "morph_bits", launch_morph(true, kind, bpp[0], bpp[1], g, K, d_masks, mplane, mp, sc, y0, y1));
@@ -1037,13 +1358,8 @@ int fast_host_color_edge(omni_ctx *ctx, const u8 *h_bgr, int h, int w, size_t pi
     for (int b = 0; b < nb; b++) {
         int y0 = b * rows_per, rows = min(rows_per, h - y0);
         OMNI_CUDA(cudaStreamWaitEvent(sc, evH[b], 0));
-        {
-            KScope ks(ctx, "assign_bits", sc);
-            fk_assign_bits<1><<<agrid, 256, 0, sc>>>(d_img + (size_t)y0 * ip, rows, w, ip, P, cells,
-                                                    want_labels ? d_labels + (size_t)y0 * lp : nullptr, lp,
-                                                    bpp[0] + (size_t)y0 * g.ws, g.ws, g.plane);
-            OMNI_CUDA(cudaGetLastError());
-        }
+        FK_TRY(launch_assign_lab(ctx, d_img + (size_t)y0 * ip, rows, w, ip, P, want_labels ? d_labels + (size_t)y0 * lp : nullptr, lp,
+                                 bpp[0] + (size_t)y0 * g.ws, g.ws, g.plane, sc));
         if (b > 0) FK_TRY(morph_band(b - 1));             // its halo rows (band b) are assigned now
     }
     FK_TRY(morph_band(nb - 1));
@@ -1066,5 +1382,180 @@ int fast_host_color_edge(omni_ctx *ctx, const u8 *h_bgr, int h, int w, size_t pi
     // the caller continues on ctx->stream (counts) and synchronises it: make it wait for the copy-out stream
     OMNI_CUDA(cudaEventRecord(evX[3], so));
     OMNI_CUDA(cudaStreamWaitEvent(sc, evX[3], 0));
+    return OMNI_OK;
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// stage 04: Zhang-Suen thinning of the edge planes, 04_find_contours.py:35-99.
+//
+// The reference runs the two sub-iterations with NumPy shifts over the bounding box of the non-zero pixels (zero
+// outside -- the same as zero outside the image) until an iteration deletes nothing, at most 120 iterations.  Its
+// neighbour names are rotated against the textbook:  P2 = (y+1, x)  P3 = (y+1, x-1)  P4 = (y, x-1)  P5 = (y-1, x-1)
+// P6 = (y-1, x)  P7 = (y-1, x+1)  P8 = (y, x+1)  P9 = (y+1, x+1);  a pixel is deleted when  A == 1  (0 -> 1 transitions
+// around P2..P9,P2),  2 <= B <= 6  (neighbour count)  and  P2 P4 P6 == 0, P4 P6 P8 == 0  (sub-step 1)  resp.
+// P2 P4 P8 == 0, P2 P6 P8 == 0  (sub-step 2).
+//
+// Here a sub-step is ~60 bit operations per 32-pixel word: the eight neighbour planes are shifted words, B comes
+// from a bit-sliced adder tree, "exactly one transition" from a one/two-or-more pair.  All K planes are thinned by ONE
+// cooperative kernel: sub-step 1 reads plane set A and writes B, sub-step 2 reads B and writes A (a deletion must not
+// be seen by its neighbours inside a sub-step), grid.sync() between them; three rotating "changed" flags give the
+// stop test without a second barrier.  A plane that has converged stays unchanged in later iterations, so running
+// all planes until the last one converges (or to max_iter) gives every plane the reference's result;
+// removed[k * max_iter + i] = pixels deleted from plane k in iteration i + 1 (the number the reference logs).
+// ------------------------------------------------------------------------------------------------
+#define TH_ROWS 16
+
+__device__ __forceinline__ u32 th_xor3(u32 a, u32 b, u32 c) { return a ^ b ^ c; }
+__device__ __forceinline__ u32 th_maj(u32 a, u32 b, u32 c) { return (a & b) | (c & (a | b)); }
+
+template <int STEP>
+__device__ __forceinline__ u32 thin_delete_mask(u32 ul, u32 um, u32 ur, u32 ml, u32 mm, u32 mr, u32 dl, u32 dm, u32 dr)
+{
+    // u* = row y-1, m* = row y, d* = row y+1; *l / *m / *r = words c-1, c, c+1
+    const u32 P2 = dm, P3 = __funnelshift_l(dl, dm, 1), P4 = __funnelshift_l(ml, mm, 1), P5 = __funnelshift_l(ul, um, 1);
+    const u32 P6 = um, P7 = __funnelshift_r(um, ur, 1), P8 = __funnelshift_r(mm, mr, 1), P9 = __funnelshift_r(dm, dr, 1);
+    // B = P2 + .. + P9, bit-sliced
+    const u32 s1 = th_xor3(P2, P3, P4), c1 = th_maj(P2, P3, P4);
+    const u32 s2 = th_xor3(P5, P6, P7), c2 = th_maj(P5, P6, P7);
+    const u32 s3 = P8 ^ P9, c3 = P8 & P9;
+    const u32 b0 = th_xor3(s1, s2, s3), c4 = th_maj(s1, s2, s3);
+    const u32 t0 = th_xor3(c1, c2, c3), d1 = th_maj(c1, c2, c3);
+    const u32 b1 = t0 ^ c4, d2 = t0 & c4;
+    const u32 b2 = d1 ^ d2, b3 = d1 & d2;
+    const u32 b_ok = (b1 | b2 | b3) & ~b3 & ~(b2 & b1 & b0);            // 2 <= B <= 6
+    // A == 1: exactly one of the eight (0 -> 1) transitions
+    u32 one = 0u, two = 0u, t;
+    t = ~P2 & P3; two |= one & t; one |= t;
+    t = ~P3 & P4; two |= one & t; one |= t;
+    t = ~P4 & P5; two |= one & t; one |= t;
+    t = ~P5 & P6; two |= one & t; one |= t;
+    t = ~P6 & P7; two |= one & t; one |= t;
+    t = ~P7 & P8; two |= one & t; one |= t;
+    t = ~P8 & P9; two |= one & t; one |= t;
+    t = ~P9 & P2; two |= one & t; one |= t;
+    const u32 a_ok = one & ~two;
+    const u32 c_ok = STEP == 1 ? (~(P2 & P4 & P6) & ~(P4 & P6 & P8)) : (~(P2 & P4 & P8) & ~(P2 & P6 & P8));
+    return mm & a_ok & b_ok & c_ok;
+}
+
+template <int STEP>
+__device__ __forceinline__ void thin_substep(const u32 *__restrict__ src, u32 *__restrict__ dst, int ws, size_t plane, int h, int ww, int K,
+                                             int *removed_it /* + k * max_iter */, int max_iter, volatile int *chg)
+{
+    const int lane = threadIdx.x & 31;
+    const int wcols = (ww + 31) / 32, strips = (h + TH_ROWS - 1) / TH_ROWS;
+    const long long units = (long long)K * strips * wcols;
+    const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long u = warp0; u < units; u += nwarps) {
+        const int wx = (int)(u % wcols);
+        const long long r0 = u / wcols;
+        const int strip = (int)(r0 % strips), k = (int)(r0 / strips);
+        const int c = wx * 32 + lane;
+        const bool active = c < ww;
+        const int y0 = strip * TH_ROWS, y1 = min(h, y0 + TH_ROWS);
+        const u32 *S = src + (size_t)k * plane;
+        u32 *D = dst + (size_t)k * plane;
+        // a row as (left, own, right) words; the neighbours' words come from the neighbouring lanes
+        auto fetch = [&](const int y, u32 &l, u32 &m, u32 &r) {
+            const bool in = y >= 0 && y < h;
+            m = (in && active) ? __ldcg(S + (size_t)y * ws + c) : 0u;
+            l = __shfl_up_sync(0xffffffffu, m, 1);
+            r = __shfl_down_sync(0xffffffffu, m, 1);
+            if (lane == 0) l = (in && c > 0 && c - 1 < ww) ? __ldcg(S + (size_t)y * ws + c - 1) : 0u;
+            if (lane == 31) r = (in && c + 1 < ww) ? __ldcg(S + (size_t)y * ws + c + 1) : 0u;
+        };
+        u32 ul, um, ur, ml, mm, mr, dl, dm, dr;
+        fetch(y0 - 1, ul, um, ur);
+        fetch(y0, ml, mm, mr);
+        int cnt = 0;
+        for (int y = y0; y < y1; y++) {
+            fetch(y + 1, dl, dm, dr);
+            u32 del = 0u;
+            if (mm) del = thin_delete_mask<STEP>(ul, um, ur, ml, mm, mr, dl, dm, dr);
+            if (active) D[(size_t)y * ws + c] = mm & ~del;
+            cnt += __popc(del);
+            ul = ml; um = mm; ur = mr; ml = dl; mm = dm; mr = dr;
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, d);
+        if (lane == 0 && cnt) { atomicAdd(removed_it + (size_t)k * max_iter, cnt); *chg = 1; }
+    }
+}
+
+__global__ void __launch_bounds__(256) fk_thin(u32 *__restrict__ A, u32 *__restrict__ B, int ws, size_t plane, int h, int w, int K, int max_iter,
+                                               int *__restrict__ removed, int *flags /* [0] iterations run, [1..3] rotating changed flags */)
+{
+    cg::grid_group grid = cg::this_grid();
+    const int ww = (w + 31) >> 5;
+    for (int it = 0; it < max_iter; it++) {
+        volatile int *chg = flags + 1 + (it % 3);
+        thin_substep<1>(A, B, ws, plane, h, ww, K, removed + it, max_iter, chg);
+        __threadfence();
+        grid.sync();
+        thin_substep<2>(B, A, ws, plane, h, ww, K, removed + it, max_iter, chg);
+        __threadfence();
+        grid.sync();
+        const int c = *chg;
+        if (blockIdx.x == 0 && threadIdx.x == 0) { flags[0] = it + 1; flags[1 + ((it + 2) % 3)] = 0; }
+        if (!c) break;
+    }
+}
+
+// planes of u8 (> 0 = foreground) -> skeleton planes {0,255}; h_removed (K * max_iter ints, may be NULL) and h_iters (K ints,
+// may be NULL: iterations the reference would have run on that plane) are filled after a stream synchronisation.
+int fast_thin(omni_ctx *ctx, const u8 *d_in, int K, int h, int w, size_t in_plane, size_t in_pitch, int max_iter,
+              u8 *d_out, size_t out_plane, size_t out_pitch, int32_t *h_removed, int32_t *h_iters, cudaStream_t st)
+{
+    BitGeom g = make_geom(h, w);
+    u32 *bpp[2];
+    FK_TRY(bit_planes(ctx, g, K, 2, bpp));
+    int al = ((uintptr_t)d_out % 16 == 0) && (out_plane % 16 == 0) && (out_pitch % 16 == 0);
+    if (max_iter < 0) max_iter = 0;
+    const size_t n_rem = (size_t)K * (max_iter > 0 ? max_iter : 1);
+    FK_TRY(omni_ws_reserve(ctx, 6, n_rem * sizeof(int)));
+    int *d_removed = (int *)ctx->ws[6];
+    OMNI_CUDA(cudaMemsetAsync(d_removed, 0, n_rem * sizeof(int), st));
+    OMNI_CUDA(cudaMemsetAsync(ctx->d_flags, 0, 8 * sizeof(int), st));
+    OMNI_CUDA(cudaMemsetAsync(ctx->d_flags + 8, 0, sizeof(int), st));
+    {
+        KScope ks(ctx, "bytes_to_bits", st);
+        fk_bytes_to_bits<<<dim3(persist_blocks(ctx, 2), K), 256, 0, st>>>(d_in, in_plane, in_pitch, h, w, bpp[0], g.ws, g.plane, ctx->d_flags + 8);
+        OMNI_CUDA(cudaGetLastError());
+    }
+    if (max_iter > 0) {
+        if (ctx->thin_blocks == 0) {
+            int per_sm = 0;
+            OMNI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fk_thin, 256, 0));
+            if (per_sm < 1) { omni_set_error("thinning kernel cannot be made resident"); return OMNI_ERR_CUDA; }
+            ctx->thin_blocks = per_sm * (ctx->sm_count > 0 ? ctx->sm_count : 1);
+        }
+        // no more CTAs than warp units (8 warps per CTA): barriers get cheaper on small inputs
+        const long long units = (long long)K * ((h + TH_ROWS - 1) / TH_ROWS) * ((g.ww + 31) / 32);
+        int blocks = (int)std::min<long long>(ctx->thin_blocks, (units + 7) / 8);
+        if (blocks < 1) blocks = 1;
+        int ws = g.ws;
+        size_t plane = g.plane;
+        int *flags = ctx->d_flags;
+        void *args[] = {&bpp[0], &bpp[1], &ws, &plane, &h, &w, &K, &max_iter, &d_removed, &flags};
+        OMNI_LAUNCH(ctx, st, "thin_zhangsuen", cudaLaunchCooperativeKernel((const void *)fk_thin, dim3(blocks), dim3(256), args, 0, st));
+    }
+    {
+        KScope ks(ctx, "expand_bits", st);
+        fk_expand_bits<<<dim3(persist_blocks(ctx, 4), K), 256, 0, st>>>(bpp[0], g.ws, g.plane, h, w, d_out, out_plane, out_pitch, al);
+        OMNI_CUDA(cudaGetLastError());
+    }
+    if (h_removed || h_iters) {
+        std::vector<int> rem(n_rem, 0);
+        if (max_iter > 0) OMNI_CUDA(cudaMemcpyAsync(rem.data(), d_removed, n_rem * sizeof(int), cudaMemcpyDeviceToHost, st));
+        OMNI_CUDA(cudaStreamSynchronize(st));
+        for (int k = 0; k < K; k++) {
+            int it = 0;
+            while (it < max_iter) { it++; if (rem[(size_t)k * max_iter + it - 1] == 0) break; }   // 04:50-94: stops after the first empty iteration
+            if (h_iters) h_iters[k] = it;
+            if (h_removed)
+                for (int i = 0; i < max_iter; i++) h_removed[(size_t)k * max_iter + i] = i < it ? rem[(size_t)k * max_iter + i] : 0;
+        }
+    }
     return OMNI_OK;
 }

@@ -6,6 +6,10 @@ void fast_ctx_release(omni_ctx *ctx);
 
 bool fast_resize_2x_ok(const u8 *src, int sw, size_t spitch, const u8 *dst, int dw, size_t dpitch);
 cudaError_t fast_resize_2x(const u8 *src, size_t spitch, u8 *dst, int dh, int dw, size_t dpitch, cudaStream_t st);
+// fractional INTER_AREA with the source rectangle of each destination tile staged in shared memory;
+// cudaErrorNotSupported when the ratio is too large for the staging buffer (use g_resize_area then)
+cudaError_t fast_resize_frac(const u8 *src, int sh, int sw, size_t spitch, u8 *dst, int dh, int dw, size_t dpitch, const ResizeTabDev *tab,
+                             cudaStream_t st);
 
 cudaError_t fast_assign(omni_ctx *ctx, const u8 *px, int h, int w, size_t pitch, const AssignParams &P, int mode_lab,
                         u8 *labels, size_t lpitch, cudaStream_t st);
@@ -29,7 +33,18 @@ int fast_color_edge(omni_ctx *ctx, const u8 *d_bgr, int h, int w, size_t pitch, 
                     u8 *d_labels, size_t lpitch, u8 *d_masks, size_t m_plane, size_t mpitch,
                     u8 *d_edges, size_t e_plane, size_t epitch, cudaStream_t st);
 
-// edges3.cu: SIMD-in-register blur3 + Sobel + NMS on a bit-plane (strong / candidate bit-planes out)
+// edges3.cu: SIMD-in-register blur3 + Sobel + NMS on a bit-plane (strong / candidate bit-planes out).
+// Dense variant: every word of every plane.  Sparse variant: fk_edge_runs lists the runs of tiles that can hold an
+// edge pixel (and zero-fills the rest), the edge kernel walks only those.
+#define ET_MAXT 4                         // longest run, in tiles
+size_t edges3_run_words(int h, int w, int K, unsigned off[ET_MAXT]);
+bool edges3_sparse_ok(int h, int w, int K);
+int edges3_sparse_blocks_per_sm();
+cudaError_t launch_edge_runs(const u32 *m2, int ws, size_t plane, int h, int w, int K, u32 *sbits, u32 *cbits, u8 *edges,
+                             size_t estride, size_t epitch, int aligned16, int *run_counts, u32 *run_items, int resident_warps, cudaStream_t st);
+cudaError_t launch_edges3_sparse(const u32 *m2, int ws, size_t plane, int h, int w, int K, int low, int high, int grid_blocks,
+                                 u32 *sbits, u32 *cbits, u8 *edges, size_t estride, size_t epitch, int aligned16, int *wl_count,
+                                 u32 *worklist, int wl_cap, const int *run_counts, int *run_next, const u32 *run_items, cudaStream_t st);
 cudaError_t launch_edges3_simd(const u32 *m2, int ws, size_t plane, int h, int w, int K, int low, int high, int sm_count,
                                u32 *sbits, u32 *cbits, u8 *edges, size_t estride, size_t epitch, int aligned16, int *wl_count, u32 *worklist, int wl_cap,
                                cudaStream_t st);
@@ -42,3 +57,7 @@ int fast_host_color_edge(omni_ctx *ctx, const u8 *h_bgr, int h, int w, size_t pi
                          u8 *h_edges, size_t h_eplane, size_t h_epitch,
                          u8 *d_img, size_t ip, u8 *d_labels, size_t lp, u8 *d_masks, size_t mplane, size_t mp,
                          u8 *d_edges, size_t eplane, size_t ep, bool want_labels);
+
+// stage 04 thinning (04_find_contours.py:35-99) on bit-planes; see fast_kernels.cu
+int fast_thin(omni_ctx *ctx, const u8 *d_in, int K, int h, int w, size_t in_plane, size_t in_pitch, int max_iter,
+              u8 *d_out, size_t out_plane, size_t out_pitch, int32_t *h_removed, int32_t *h_iters, cudaStream_t st);

@@ -57,12 +57,12 @@ struct ResizeTab {
     ResizeTabDev dev{};
 };
 
-#define OMNI_WS_SLOTS 6
+#define OMNI_WS_SLOTS 7
 struct omni_ctx {
     int device = 0;
     int fast = 1;
     // grow-only device scratch
-    void *ws[OMNI_WS_SLOTS] = {};          // 0-2 generic planes, 3 host staging, 4 bit-planes, 5 misc
+    void *ws[OMNI_WS_SLOTS] = {};          // 0-2 generic planes, 3 host staging, 4 bit-planes, 5 misc, 6 edge run lists
     size_t ws_bytes[OMNI_WS_SLOTS] = {};
     int *d_flags = nullptr;          // 64 ints of device flags / counters
     unsigned long long *d_counts = nullptr;   // 4*OMNI_MAX_K counters
@@ -79,15 +79,20 @@ struct omni_ctx {
     std::vector<cudaEvent_t> ev_pool;
     int sm_count = 0;
     int hyst_blocks = 0;
+    int thin_blocks = 0;             // co-resident CTAs of the cooperative thinning kernel (0 = not queried yet)
+    int e3s_per_sm = 0;              // resident CTAs per SM of the sparse edge kernel (0 = not queried yet)
+    int assign_rgbcell = 1;          // 0: Lab-cell assignment kernel (the previous generation; set_fast_path mode 2)
+    int edge_sparse = 1;             // 0: dense edge kernel (A/B runs, OMNI_B200_EDGE_DENSE=1)
     // side streams + events of the pipelined host-buffer call (fast_host_color_edge)
     int pipe_ready = 0;
     cudaStream_t s_in = nullptr, s_out = nullptr;
     cudaEvent_t pipe_ev[20] = {};
-    int occ_assign_lab = 0, occ_assign_pal = 0;   // resident CTAs per SM of the persistent assignment kernels
+    int occ_assign_lab = 0, occ_assign_pal = 0, occ_assign_rgb = 0;   // resident CTAs per SM of the persistent assignment kernels
     // centres the candidate-cell table in ws[5] was built for (fast colour assignment)
     int cells_valid = 0, cells_K = 0;
     void *cells_stream = nullptr;
-    float cells_c[OMNI_MAX_K * 3];             // co-resident CTAs of the cooperative hysteresis kernel (0 = not queried yet)
+    float cells_c[OMNI_MAX_K * 3];
+    u8 cells_lut[OMNI_MAX_K] = {};             // co-resident CTAs of the cooperative hysteresis kernel (0 = not queried yet)
 };
 
 // Brackets one kernel launch: counts it and, when profiling is on, records a CUDA event pair on the

@@ -20,7 +20,7 @@ EXPORTS = [
     "omni_assign_lab_f32", "omni_assign_rgb_i16wrap", "omni_host_assign_rgb_i16wrap", "omni_layer_masks",
     "omni_edges", "omni_host_edges", "omni_color_edge", "omni_host_color_edge", "omni_count_nonzero",
     "omni_edges_composite", "omni_last_hysteresis_passes", "omni_launch_count", "omni_profile_enable",
-    "omni_profile_summary",
+    "omni_profile_summary", "omni_thin_zhangsuen", "omni_host_thin_zhangsuen",
 ]
 
 
@@ -50,6 +50,7 @@ def lib():
     vp, sz, i, u8p = C.c_void_p, C.c_size_t, C.c_int, C.c_void_p
     f32p, i64p, epp = C.POINTER(C.c_float), C.POINTER(C.c_int64), C.POINTER(EdgeParams)
     hu8 = C.POINTER(C.c_uint8)
+    i32p = C.POINTER(C.c_int32)
     sig = {
         "omni_version": ([], i),
         "omni_last_error_string": ([], C.c_char_p),
@@ -75,6 +76,8 @@ def lib():
         "omni_launch_count": ([vp], C.c_longlong),
         "omni_profile_enable": ([vp, i], i),
         "omni_profile_summary": ([vp, C.c_char_p, sz], i),
+        "omni_thin_zhangsuen": ([vp, u8p, i, i, i, sz, sz, i, u8p, sz, sz, i32p, i32p, vp], i),
+        "omni_host_thin_zhangsuen": ([vp, u8p, i, i, i, sz, sz, i, u8p, sz, sz, i32p, i32p], i),
     }
     for name, (args, res) in sig.items():
         fn = getattr(L, name)

@@ -90,8 +90,9 @@ class Engine:
         except Exception:
             pass
 
-    def set_fast_path(self, enable: bool):
-        capi.check(self._L.omni_set_fast_path(self._h, 1 if enable else 0))
+    def set_fast_path(self, enable):
+        """False/0: generic kernels; True/1: bit-plane fast path (default); 2: fast path with the dense edge kernel."""
+        capi.check(self._L.omni_set_fast_path(self._h, int(enable)))
 
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
@@ -200,6 +201,38 @@ class Engine:
         capi.check(self._L.omni_edges_composite(self._h, edges.data_ptr(), K, h, w, edges.stride(0), edges.stride(1),
                                                 _u8p(col), out.data_ptr(), out.stride(0), self._stream()))
         return out
+
+    # ---- stage 04: thinning ----------------------------------------------------------------------
+    def thin_zhangsuen(self, planes: torch.Tensor, max_iter: int = 120, out: torch.Tensor | None = None,
+                       with_log: bool = False):
+        """04_find_contours.py:35-99 on K planes at once: [K,H,W] u8 (> 0 = foreground) -> skeletons {0,255}.
+        with_log: also returns (removed[K, max_iter] int32, iters[K] int32) -- what the reference prints per iteration."""
+        _check_planes(planes)
+        K, h, w = planes.shape
+        if out is None:
+            out = torch.empty((K, h, w), dtype=torch.uint8, device=planes.device)
+        _check_planes(out)
+        removed = np.zeros((K, max(1, max_iter)), np.int32) if with_log else None
+        iters = np.zeros(K, np.int32) if with_log else None
+        i32p = C.POINTER(C.c_int32)
+        capi.check(self._L.omni_thin_zhangsuen(
+            self._h, planes.data_ptr(), K, h, w, planes.stride(0), planes.stride(1), int(max_iter),
+            out.data_ptr(), out.stride(0), out.stride(1),
+            removed.ctypes.data_as(i32p) if with_log else None, iters.ctypes.data_as(i32p) if with_log else None, self._stream()))
+        return (out, removed[:, :max_iter], iters) if with_log else out
+
+    def host_thin_zhangsuen(self, planes: np.ndarray, max_iter: int = 120):
+        """Host-buffer form: NumPy [K,H,W] u8 in, (skeletons, removed[K,max_iter], iters[K]) out."""
+        planes = np.ascontiguousarray(planes, dtype=np.uint8)
+        K, h, w = planes.shape
+        out = np.empty_like(planes)
+        removed = np.zeros((K, max(1, max_iter)), np.int32)
+        iters = np.zeros(K, np.int32)
+        i32p = C.POINTER(C.c_int32)
+        capi.check(self._L.omni_host_thin_zhangsuen(
+            self._h, planes.ctypes.data, K, h, w, planes.strides[0], planes.strides[1], int(max_iter),
+            out.ctypes.data, out.strides[0], out.strides[1], removed.ctypes.data_as(i32p), iters.ctypes.data_as(i32p)))
+        return out, removed[:, :max_iter], iters
 
     def last_hysteresis_passes(self) -> int:
         return int(self._L.omni_last_hysteresis_passes(self._h))

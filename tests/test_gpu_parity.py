@@ -20,9 +20,9 @@ def eng():
     e.close()
 
 
-@pytest.fixture(scope="module", params=[1, 0], ids=["fast", "generic"])
+@pytest.fixture(scope="module", params=[1, 2, 0], ids=["fast", "fast_dense_edges", "generic"])
 def eng_mode(request, eng):
-    eng.set_fast_path(bool(request.param))
+    eng.set_fast_path(request.param)
     yield eng
     eng.set_fast_path(True)
 
@@ -200,6 +200,36 @@ def test_edges_spiral_worst_case(eng_mode):
     assert want.any()
 
 
+def _sparse_cases(h, w):
+    """Masks built to stress the tile-run lists of the sparse edge kernel: uniform planes, shapes touching every
+    border, features on tile seams (rows 8j, words 32c), isolated pixels, long vertical runs."""
+    z = np.zeros((h, w), np.uint8)
+    cases = [z.copy(), np.full((h, w), 255, np.uint8)]
+    a = z.copy(); a[: max(1, h // 3)] = 255; cases.append(a)                     # top band (row seam somewhere)
+    a = z.copy(); a[:, : max(1, w // 2)] = 255; cases.append(a)                  # left half: one long vertical boundary
+    a = z.copy(); a[:, -3:] = 255; a[-2:] = 255; cases.append(a)                 # right / bottom border strips
+    a = z.copy(); a[::16, ::64] = 255; a[7::24, 31::96] = 255; cases.append(a)   # isolated pixels on seams
+    a = z.copy()
+    for y0 in range(0, h, 40):
+        for x0 in range(0, w, 100):
+            a[y0 + 6:y0 + 18, x0 + 28:x0 + 70] = 255                             # boxes straddling tile rows and words
+    cases.append(a)
+    a = np.full((h, w), 255, np.uint8); a[h // 2, w // 2] = 0; a[0, 0] = 0; a[-1, -1] = 0; cases.append(a)
+    return np.stack(cases)
+
+
+@pytest.mark.parametrize("hw", [(8, 32), (9, 33), (63, 250), (130, 517), (257, 96), (300, 1100)])
+def test_edges_sparse_tile_runs(eng_mode, hw):
+    import omni_b200
+    masks = _sparse_cases(*hw)
+    for oi, ci in ((0, 0), (1, 1)):
+        for lo, hi in ((50, 150), (0, 10), (200, 2000)):
+            ec = omni_b200.EdgeConfig(low=lo, high=hi, ksize=3, open_iters=oi, close_iters=ci)
+            out = torch.full((masks.shape[0],) + hw, 7, dtype=torch.uint8, device="cuda")   # stale bytes must be overwritten
+            got = host(eng_mode.edges(dev(masks), ec, out=out))
+            assert np.array_equal(got, _edge_want(masks, open_iters=oi, close_iters=ci, low=lo, high=hi)), (oi, ci, lo, hi)
+
+
 def test_edges_strided_planes(eng):
     import omni_b200
     masks = np.stack([blob_mask(200, 300, s) for s in (7, 8, 9)])
@@ -351,3 +381,78 @@ def test_edges_binary_spiral_long_chain(eng_mode):
     assert want[0].sum() > 15000 * 255
     assert np.array_equal(got, want)
     assert eng_mode.last_hysteresis_passes() > 4
+
+
+# ---- stage 04: thinning -----------------------------------------------------------------------
+def test_thinning_golden(eng):
+    """Skeletons frozen from the unmodified reference (tools/make_golden_thinning.py), incl. thick masks (many iterations)."""
+    z = np.load(f"{GOLDEN}/thinning.npz")
+    names = sorted(k[:-3] for k in z.files if k.endswith("_in"))
+    cm = _cm()
+    for n in names:
+        src, want = z[n + "_in"], z[n + "_out"]
+        got, removed, iters = eng.thin_zhangsuen(dev(src[None]), with_log=True)
+        assert np.array_equal(host(got)[0], want), n
+        _sk, log = cm.thin_zhangsuen(src, with_log=True)
+        assert int(iters[0]) == len(log) and np.array_equal(removed[0, :len(log)], log), n     # the reference's log numbers
+
+
+@pytest.mark.parametrize("hw", [(1, 1), (1, 70), (70, 1), (2, 2), (31, 33), (64, 64), (97, 161), (300, 515)])
+def test_thinning_shapes_vs_oracle(eng, hw):
+    cm = _cm()
+    h, w = hw
+    rng = np.random.default_rng(h * 1000 + w)
+    planes = np.stack([blob_mask(h, w, 11, 0.5, k=5) if min(h, w) > 12 else (rng.random((h, w)) < 0.6).astype(np.uint8) * 255,
+                       (rng.random((h, w)) < 0.7).astype(np.uint8) * 200,                   # any value > 0 is foreground
+                       np.full((h, w), 255, np.uint8), np.zeros((h, w), np.uint8)])
+    got, removed, iters = eng.thin_zhangsuen(dev(planes), with_log=True)
+    got = host(got)
+    for k in range(planes.shape[0]):
+        want, log = cm.thin_zhangsuen(planes[k], with_log=True)
+        assert np.array_equal(got[k], want), k
+        assert int(iters[k]) == len(log) and np.array_equal(removed[k, :len(log)], log), k
+    # host-buffer form and the iteration cap
+    out_h, _r, _i = eng.host_thin_zhangsuen(planes)
+    assert np.array_equal(out_h, got)
+    cut = host(eng.thin_zhangsuen(dev(planes), max_iter=2))
+    for k in range(planes.shape[0]):
+        assert np.array_equal(cut[k], cm.thin_zhangsuen(planes[k], max_iter=2)), k
+
+
+def test_thinning_in_place_and_strided(eng):
+    cm = _cm()
+    planes = np.stack([blob_mask(120, 200, s, 0.4, k=7) for s in (3, 4)])
+    big = torch.zeros((2, 140, 256), dtype=torch.uint8, device="cuda")
+    big[:, 7:127, 19:219] = dev(planes)
+    view = big[:, 7:127, 19:219]
+    eng.thin_zhangsuen(view, out=view)                                                      # in and out alias
+    want = np.stack([cm.thin_zhangsuen(p) for p in planes])
+    assert np.array_equal(host(view), want)
+    assert int(big[:, :7].sum()) == 0 and int(big[:, :, :19].sum()) == 0 and int(big[:, :, 219:].sum()) == 0
+
+
+def test_thinning_edges_of_fused_path(eng):
+    """Stage 03 -> 04 hand-off on the device: thin the edge planes of a synthetic image, compare with the oracle chain."""
+    import omni_b200
+    cm, rp = _cm(), _rp()
+    img = synth(512, 768, 5)
+    K = 4
+    centers = rp.kmeans_lab_centers(img, K)
+    _order, lut = rp.darkness_order(centers)
+    _l, _m, edges = eng.color_edge(dev(img), centers, lut.astype(np.uint8), omni_b200.EdgeConfig())
+    sk = host(eng.thin_zhangsuen(edges))
+    e = host(edges)
+    for k in range(K):
+        assert np.array_equal(sk[k], cm.thin_zhangsuen(e[k])), k
+    assert (sk > 0).sum() < (e > 0).sum()
+
+
+def test_thinning_function_mirror(eng, capsys):
+    from omni_b200 import contours
+    cm = _cm()
+    img = blob_mask(90, 130, 21, 0.3, k=7)
+    out = contours.thinning_zhangsuen(img, "layer_x")
+    assert np.array_equal(out, cm.thin_zhangsuen(img))
+    log = capsys.readouterr().out
+    assert "[layer_x] Thinning ROI" in log and "Thin 01: removed=" in log and "Thinning done" in log
+    assert np.array_equal(contours.thinning_zhangsuen(np.zeros((5, 5), np.uint8), "e"), np.zeros((5, 5), np.uint8))
