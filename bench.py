@@ -197,8 +197,8 @@ KERNEL_BYTES = {
     "build_cells": lambda N, K: 0,
 }
 # stage grouping for the report: colour = image -> K masks, edge = K masks -> K edges (masks are not re-read)
-STAGES = {"color": ("build_cells", "assign_bits", "morph_bits", "assign", "onehot"),
-          "edge": ("edges3_bits", "hysteresis_bits", "morph", "blur", "canny_nms", "hyst_pass", "hyst_final")}
+STAGES = {"color": ("build_cells", "build_rgbcells", "assign_bits", "morph_bits", "assign", "onehot"),
+          "edge": ("edge_runs", "edges3_bits", "hysteresis_bits", "morph", "blur", "canny_nms", "hyst_pass", "hyst_final")}
 
 
 def run_ours(args, wl):
@@ -329,6 +329,26 @@ def run_ours(args, wl):
                                  "MP/s_src": sh * sw / ms / 1e3}
             del src, dst
 
+    # ---- stage 04 thinning of the K edge planes the step just produced (not part of the step) ----
+    thin_extra = None
+    if rank == 0 and world == 1:
+        peak0, _src0 = peaks()
+        d_skel = torch.empty_like(d_edges)
+        _o, removed, iters = eng.thin_zhangsuen(d_edges, out=d_skel, with_log=True)
+        tms = []
+        for _ in range(5):
+            flush.fill_(3)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); eng.thin_zhangsuen(d_edges, out=d_skel); b.record()
+            torch.cuda.synchronize()
+            tms.append(a.elapsed_time(b))
+        ms = statistics.median(tms)
+        thin_extra = {"ms": ms, "iterations_max": int(iters.max()), "removed_px": int(removed.sum()),
+                      "algorithmic_bytes": 2 * K * N, "GB/s": 2 * K * N / ms / 1e6, "frac_of_peak": 2 * K * N / ms / 1e6 / peak0,
+                      "layer_MP/s": K * N / ms / 1e3,
+                      "what": "omni_thin_zhangsuen on the K edge planes (bytes in -> bit-planes -> cooperative Zhang-Suen -> bytes out)"}
+        del d_skel
+
     if rank == 0:
         peak, peak_src = peaks()
         dom = max(prof.items(), key=lambda kv: kv[1][1]) if prof else None
@@ -376,6 +396,7 @@ def run_ours(args, wl):
             "step_ms": {"min": min(step_ms), "median": statistics.median(step_ms), "max": max(step_ms)},
             "wall_s_timed_region": t_wall,
             "resize_kernel": resize_extra,
+            "thinning_kernel": thin_extra,
         }
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline_leg(wl, img, centers)

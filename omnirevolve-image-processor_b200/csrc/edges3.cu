@@ -22,8 +22,6 @@
 #include <cuda_fp16.h>
 
 #define E3V_WARPS 2
-#define ET_R 8                            // tile rows of the sparse variant
-struct E3RunOff { unsigned v[ET_MAXT]; };
 #define E3V_LSTRIDE 40                    // u16 per lane region (80 bytes: conflict-free uint4 stores)
 
 // Per-warp shared memory.  Every lane stores ITS OWN window of a row (no cross-lane exchange is needed to
@@ -511,17 +509,23 @@ cudaError_t launch_edges3_simd(const u32 *m2, int ws, size_t plane, int h, int w
     return cudaGetLastError();
 }
 
-// run lists (fk_edge_runs; zero-fills the dead tiles).  run_counts: ET_MAXT ints + 1 int "next warp item", zeroed by the caller.
-cudaError_t launch_edge_runs(const u32 *m2, int ws, size_t plane, int h, int w, int K, u32 *sbits, u32 *cbits, u8 *edges,
-                             size_t estride, size_t epitch, int aligned16, int *run_counts, u32 *run_items, int resident_warps, cudaStream_t st)
+// Longest run, in tiles: long runs pay the 6 extra pipeline rows less often, short runs give more warp items.  On
+// pipeline-like masks about a third of the tiles is live and a run holds (1, 1.6, 2, 2.4) tiles on average for
+// maxt = 1..4; take the longest runs that still give every resident warp of the edge kernel an item.
+int edges3_pick_maxt(int h, int w, int K, int resident_warps)
 {
-    // Longest run, in tiles: long runs pay the 6 extra pipeline rows less often, short runs give more warp items.  On
-    // pipeline-like masks about a third of the tiles is live and a run holds (1, 1.6, 2, 2.4) tiles on average for
-    // maxt = 1..4; take the longest runs that still give every resident warp of the edge kernel an item.
     const double live = 0.35 * (double)K * ((h + ET_R - 1) / ET_R) * ((w + 31) / 32);
     const double avg[ET_MAXT] = {1.0, 1.6, 2.0, 2.4};
     int maxt = ET_MAXT;
     while (maxt > 1 && live / avg[maxt - 1] / 32.0 < (double)resident_warps) maxt--;
+    return maxt;
+}
+
+// run lists (fk_edge_runs; zero-fills the dead tiles).  run_counts: ET_MAXT ints + 1 int "next warp item", zeroed by the caller.
+cudaError_t launch_edge_runs(const u32 *m2, int ws, size_t plane, int h, int w, int K, u32 *sbits, u32 *cbits, u8 *edges,
+                             size_t estride, size_t epitch, int aligned16, int *run_counts, u32 *run_items, int resident_warps, cudaStream_t st)
+{
+    const int maxt = edges3_pick_maxt(h, w, K, resident_warps);
     const int ww = (w + 31) >> 5, wcols = (ww + 31) / 32;
     const int tiles_y = (h + ET_R - 1) / ET_R, strips = (tiles_y + ER_STRIP_TILES - 1) / ER_STRIP_TILES;
     E3RunOff off;

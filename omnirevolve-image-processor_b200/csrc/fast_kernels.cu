@@ -19,6 +19,7 @@
 
 #include <algorithm>
 #include <cooperative_groups.h>
+#include <math.h>
 #include <stdlib.h>
 #include <string.h>
 namespace cg = cooperative_groups;
@@ -125,57 +126,97 @@ cudaError_t fast_resize_2x(const u8 *src, size_t spitch, u8 *dst, int dh, int dw
 // OpenCV's tables for its destination pixels exactly like the generic kernel (same float32 operation order:
 // per source row a sequential horizontal sum, then sum = beta * buf / sum += beta * buf).
 // ------------------------------------------------------------------------------------------------
-#define RF_TX 64
+#define RF_TX 128                         // destination columns per CTA (one per thread of a half)
+#define RF_TY 16                          // destination rows per CTA (RF_TY / 2 per half)
 #define RF_THREADS 256
+#define RF_MAXTAPS 8                      // source pixels per destination pixel and axis the register path holds
 
+// A thread owns one destination column of the tile: its horizontal taps (shared-memory byte offsets + weights) sit in
+// registers for all its destination rows, and the horizontal sum of a source row is reused when the next destination
+// row shares that source row (the fractional rows do).
 __global__ void __launch_bounds__(RF_THREADS) fk_resize_frac(const u8 *__restrict__ src, int sh, int sw, size_t spitch, u8 *__restrict__ dst,
-                                                             int dh, int dw, size_t dpitch, const ResizeTabDev t, int ty_rows, int spitch_s,
-                                                             int vec_ok)
+                                                             int dh, int dw, size_t dpitch, const ResizeTabDev t, int spitch_s, int vec_ok)
 {
     extern __shared__ __align__(16) u8 s_src[];
-    const int x0 = blockIdx.x * RF_TX, y0 = blockIdx.y * ty_rows;
-    const int x1 = min(dw, x0 + RF_TX), y1 = min(dh, y0 + ty_rows);
+    const int x0 = blockIdx.x * RF_TX, y0 = blockIdx.y * RF_TY;
+    const int x1 = min(dw, x0 + RF_TX), y1 = min(dh, y0 + RF_TY);
     const int xs0 = t.xsi[t.xofs[x0]], xs1 = t.xsi[t.xofs[x1] - 1];          // source columns [xs0, xs1]
     const int ys0 = t.ysi[t.yofs[y0]], ys1 = t.ysi[t.yofs[y1] - 1];          // source rows    [ys0, ys1]
     const int b0 = (3 * xs0) & ~15;                                            // first staged byte of a row (16-aligned)
     const int nbytes = 3 * (xs1 + 1) - b0;
     const int nrows = ys1 - ys0 + 1;
     if (vec_ok) {
-        const int nv = (nbytes + 15) >> 4;
-        for (int i = threadIdx.x; i < nrows * nv; i += RF_THREADS) {
-            const int r = i / nv, v = i - r * nv;
-            const u8 *g = src + (size_t)(ys0 + r) * spitch + b0 + 16 * v;
-            u8 *d = s_src + (size_t)r * spitch_s + 16 * v;
-            if (b0 + 16 * v + 16 <= 3 * sw) *reinterpret_cast<uint4 *>(d) = __ldg(reinterpret_cast<const uint4 *>(g));
-            else for (int q = 0; b0 + 16 * v + q < 3 * sw; q++) d[q] = g[q];       // never read past the row's pixels
+        // 16-byte vectors, four independent loads in flight per thread (the staging is latency-bound otherwise)
+        const int nv = (nbytes + 15) >> 4, total = nrows * nv;
+        for (int i0 = threadIdx.x; i0 < total; i0 += 4 * RF_THREADS) {
+            uint4 val[4];
+            bool vec[4];
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const int i = i0 + q * RF_THREADS;
+                vec[q] = false;
+                if (i < total) {
+                    const int r = i / nv, v = i - r * nv;
+                    vec[q] = b0 + 16 * v + 16 <= 3 * sw;
+                    if (vec[q]) val[q] = __ldg(reinterpret_cast<const uint4 *>(src + (size_t)(ys0 + r) * spitch + b0 + 16 * v));
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const int i = i0 + q * RF_THREADS;
+                if (i < total) {
+                    const int r = i / nv, v = i - r * nv;
+                    u8 *d = s_src + (size_t)r * spitch_s + 16 * v;
+                    if (vec[q]) *reinterpret_cast<uint4 *>(d) = val[q];
+                    else {                                                     // never read past the row's pixels
+                        const u8 *g = src + (size_t)(ys0 + r) * spitch + b0 + 16 * v;
+                        for (int e = 0; b0 + 16 * v + e < 3 * sw; e++) d[e] = g[e];
+                    }
+                }
+            }
         }
     } else {
-        for (int i = threadIdx.x; i < nrows * nbytes; i += RF_THREADS) {
-            const int r = i / nbytes, v = i - r * nbytes;
-            s_src[(size_t)r * spitch_s + v] = src[(size_t)(ys0 + r) * spitch + b0 + v];
-        }
+        for (int r = threadIdx.x / 64; r < nrows; r += RF_THREADS / 64)
+            for (int v = threadIdx.x & 63; v < nbytes; v += 64)
+                s_src[(size_t)r * spitch_s + v] = src[(size_t)(ys0 + r) * spitch + b0 + v];
     }
     __syncthreads();
-    const int tw = x1 - x0, n = tw * (y1 - y0);
-    for (int i = threadIdx.x; i < n; i += RF_THREADS) {
-        const int ly = i / tw, lx = i - ly * tw;
-        const int x = x0 + lx, y = y0 + ly;
-        const int xb = t.xofs[x], xe = t.xofs[x + 1], yb = t.yofs[y], ye = t.yofs[y + 1];
+    const int lx = threadIdx.x & (RF_TX - 1), half = threadIdx.x / RF_TX;
+    const int x = x0 + lx;
+    if (x >= x1) return;
+    const int xb = t.xofs[x], nt = t.xofs[x + 1] - xb;
+    int off[RF_MAXTAPS];
+    float wgt[RF_MAXTAPS];
+#pragma unroll
+    for (int q = 0; q < RF_MAXTAPS; q++) {
+        off[q] = q < nt ? 3 * t.xsi[xb + q] - b0 : 0;
+        wgt[q] = q < nt ? t.xal[xb + q] : 0.f;
+    }
+    const int ya = y0 + half * (RF_TY / 2), yb = min(y1, ya + RF_TY / 2);
+    int cached = -1;
+    float h0 = 0.f, h1 = 0.f, h2 = 0.f;
+    for (int y = ya; y < yb; y++) {
+        const int jb = t.yofs[y], je = t.yofs[y + 1];
         float s0 = 0.f, s1 = 0.f, s2 = 0.f;
-        for (int j = yb; j < ye; j++) {
-            const u8 *r = s_src + (size_t)(t.ysi[j] - ys0) * spitch_s - b0;
+        for (int j = jb; j < je; j++) {
+            const int sr = t.ysi[j];
             const float beta = t.yal[j];
-            float a0 = 0.f, a1 = 0.f, a2 = 0.f;
-            for (int k = xb; k < xe; k++) {
-                const u8 *p = r + 3 * t.xsi[k];
-                const float a = t.xal[k];
-                a0 = __fadd_rn(a0, __fmul_rn((float)p[0], a));
-                a1 = __fadd_rn(a1, __fmul_rn((float)p[1], a));
-                a2 = __fadd_rn(a2, __fmul_rn((float)p[2], a));
+            if (sr != cached) {
+                const u8 *r = s_src + (size_t)(sr - ys0) * spitch_s;
+                h0 = h1 = h2 = 0.f;
+#pragma unroll
+                for (int q = 0; q < RF_MAXTAPS; q++)
+                    if (q < nt) {                                              // same order as OpenCV: k ascending, 0 + p*a first
+                        const u8 *p = r + off[q];
+                        h0 = __fadd_rn(h0, __fmul_rn((float)p[0], wgt[q]));
+                        h1 = __fadd_rn(h1, __fmul_rn((float)p[1], wgt[q]));
+                        h2 = __fadd_rn(h2, __fmul_rn((float)p[2], wgt[q]));
+                    }
+                cached = sr;
             }
-            if (j == yb) { s0 = __fmul_rn(beta, a0); s1 = __fmul_rn(beta, a1); s2 = __fmul_rn(beta, a2); }
+            if (j == jb) { s0 = __fmul_rn(beta, h0); s1 = __fmul_rn(beta, h1); s2 = __fmul_rn(beta, h2); }
             else {
-                s0 = __fadd_rn(s0, __fmul_rn(beta, a0)); s1 = __fadd_rn(s1, __fmul_rn(beta, a1)); s2 = __fadd_rn(s2, __fmul_rn(beta, a2));
+                s0 = __fadd_rn(s0, __fmul_rn(beta, h0)); s1 = __fadd_rn(s1, __fmul_rn(beta, h1)); s2 = __fadd_rn(s2, __fmul_rn(beta, h2));
             }
         }
         u8 *o = dst + (size_t)y * dpitch + 3 * x;
@@ -191,16 +232,13 @@ cudaError_t fast_resize_frac(const u8 *src, int sh, int sw, size_t spitch, u8 *d
 {
     const double scx = (double)sw / dw, scy = (double)sh / dh;
     const int vec_ok = (((uintptr_t)src | spitch) & 15) == 0;
-    // widest source span of a tile: (RF_TX + 1) destination pixels worth of source columns, plus alignment slack
+    // a destination pixel covers at most ceil(scale) + 1 source pixels per axis: the register path holds RF_MAXTAPS
+    if ((int)ceil(scx) + 1 > RF_MAXTAPS) return cudaErrorNotSupported;
+    // widest source span of a tile: RF_TX destination pixels worth of source columns, plus alignment slack
     const int span_px = (int)(scx * RF_TX) + 3;
     const int spitch_s = ((3 * span_px + 15 + 15) & ~15) + 16;
-    int ty = 16;
-    size_t smem = 0;
-    for (;; ty >>= 1) {
-        const int rows = (int)(scy * ty) + 3;
-        smem = (size_t)rows * spitch_s;
-        if (smem <= 96 * 1024 || ty == 4) break;
-    }
+    const int rows = (int)(scy * RF_TY) + 3;
+    const size_t smem = (size_t)rows * spitch_s;
     if (smem > 200 * 1024) return cudaErrorNotSupported;
     static bool attr_set[64] = {false};
     int dev = 0;
@@ -210,8 +248,8 @@ cudaError_t fast_resize_frac(const u8 *src, int sh, int sw, size_t spitch, u8 *d
         if (e != cudaSuccess) return e;
         attr_set[dev] = true;
     }
-    dim3 grid((dw + RF_TX - 1) / RF_TX, (dh + ty - 1) / ty);
-    fk_resize_frac<<<grid, RF_THREADS, smem, st>>>(src, sh, sw, spitch, dst, dh, dw, dpitch, *tab, ty, spitch_s, vec_ok);
+    dim3 grid((dw + RF_TX - 1) / RF_TX, (dh + RF_TY - 1) / RF_TY);
+    fk_resize_frac<<<grid, RF_THREADS, smem, st>>>(src, sh, sw, spitch, dst, dh, dw, dpitch, *tab, spitch_s, vec_ok);
     return cudaGetLastError();
 }
 
@@ -238,10 +276,10 @@ cudaError_t fast_resize_frac(const u8 *src, int sh, int sw, size_t spitch, u8 *d
 #define RC_SHIFT 2
 #define RC_N (256 >> RC_SHIFT)
 #define RC_COUNT (RC_N * RC_N * RC_N)
-// workspace slot 5: [Lab candidate-cell table (u32) | hysteresis worklist | RGB cell table (u8)]
+// workspace slot 5: [Lab candidate-cell table (u32) | hysteresis worklist | RGB cell tables: label nibbles, flags]
 #define HYST_WL_OFFSET CELL_COUNT
 #define RGBCELL_OFFSET (CELL_COUNT + 8192)
-#define WS5_BYTES ((size_t)(CELL_COUNT + 8192 + RC_COUNT / 4) * sizeof(u32))
+#define WS5_BYTES ((size_t)(CELL_COUNT + 8192) * sizeof(u32) + (size_t)RC_COUNT / 2 + (size_t)RC_COUNT / 8)
 
 __global__ void __launch_bounds__(256) fk_build_cells(const __grid_constant__ AssignParams P, u32 *__restrict__ cells)
 {
@@ -301,16 +339,15 @@ __device__ __forceinline__ void lab_noclamp(const u16 *gam, const u16 *cbrt, int
 // cell fX, fY, fZ lie between their values at the cell's low and high corner; L rises with fY, a with fX - fY, b with
 // fY - fZ, which bounds the cell's image by a Lab box (tight in L, conservative in a and b).  The box goes through
 // the dmin / dmax test of fk_build_cells.  ~79 % (K=8) / ~69 % (K=16) of the pixels of the benchmark images fall
-// into a cell with ONE candidate: their label is a one-byte table lookup, no Lab conversion at all.  The others
-// (table value RC_MULTI) are compacted over the warp (shared-memory queue) and take the Lab-cell path of
+// into a cell with ONE candidate: their label is a table lookup, no Lab conversion at all.  The others (flagged
+// in a second, one-bit table) are compacted over the warp (shared-memory queue) and take the Lab-cell path of
 // fk_assign_bits: Lab conversion, candidate set of their Lab cell, the reference's float32 evaluation.
-// The byte table is stored in blocks of 4x4x2 cells = one 32-byte sector per 16x16x8 colours, so that the 32 lookups
-// of a warp (neighbouring pixels: similar colours + noise) touch a handful of sectors instead of one each.
-#define RC_MULTI 255
-__host__ __device__ __forceinline__ u32 rc_index(u32 cb, u32 cg, u32 cr)     // cell coordinates (6 bits each)
-{
-    return ((((cb >> 2) * 16u + (cg >> 2)) * 32u + (cr >> 1)) << 5) | (((cb & 3u) * 4u + (cg & 3u)) * 2u + (cr & 1u));
-}
+// The tables are 4 bits (label, K <= 16) + 1 bit (several candidates) per cell = 160 KB and live in SHARED memory: one
+// 1024-thread CTA per SM copies them in once and then streams pixels (random lookups from global memory were bound
+// by L1 sector traffic: the +-12 noise of neighbouring pixels scatters a warp's 32 lookups over ~20 sectors).
+#define RC_NIB_BYTES (RC_COUNT / 2)
+#define RC_MB_BYTES (RC_COUNT / 8)
+#define RC_MAX_K 16
 __device__ __forceinline__ void lab_f(const u16 *gam, const u16 *cbrt, int B8, int G8, int R8, int &fX, int &fY, int &fZ)
 {
     const int B = gam[B8], G = gam[G8], R = gam[R8];
@@ -319,62 +356,83 @@ __device__ __forceinline__ void lab_f(const u16 *gam, const u16 *cbrt, int B8, i
     fZ = cbrt[(R * 73 + G * 448 + B * 3575 + 2048) >> 12];
 }
 
-__global__ void __launch_bounds__(256) fk_build_rgbcells(const __grid_constant__ AssignParams P, u8 *__restrict__ cells)
+// one thread = 8 cells consecutive in R: one u32 of label nibbles + one byte of "several candidates" flags
+__global__ void __launch_bounds__(256) fk_build_rgbcells(const __grid_constant__ AssignParams P, u32 *__restrict__ nib, u8 *__restrict__ mb)
 {
-    const int ci = blockIdx.x * blockDim.x + threadIdx.x;               // (B >> 2, G >> 2, R >> 2), B slowest
-    if (ci >= RC_COUNT) return;
+    const int gi = blockIdx.x * blockDim.x + threadIdx.x;               // cell index / 8; cell = (B >> 2, G >> 2, R >> 2), B slowest
+    if (gi >= RC_COUNT / 8) return;
     const int K = P.K;
-    const int b0 = (ci >> (2 * 6)) << RC_SHIFT, g0 = ((ci >> 6) & (RC_N - 1)) << RC_SHIFT, r0 = (ci & (RC_N - 1)) << RC_SHIFT;
-    const int span = (1 << RC_SHIFT) - 1;
-    int xl, yl, zl, xh, yh, zh;
-    lab_f(f_lab_tab, f_lab_tab + 256, b0, g0, r0, xl, yl, zl);
-    lab_f(f_lab_tab, f_lab_tab + 256, b0 + span, g0 + span, r0 + span, xh, yh, zh);
-    const float lo[3] = {(float)((296 * yl - 1336934 + 16384) >> 15), (float)((500 * (xl - yh) + 128 * 32768 + 16384) >> 15),
-                         (float)((200 * (yl - zh) + 128 * 32768 + 16384) >> 15)};
-    const float hi[3] = {(float)((296 * yh - 1336934 + 16384) >> 15), (float)((500 * (xh - yl) + 128 * 32768 + 16384) >> 15),
-                         (float)((200 * (yh - zl) + 128 * 32768 + 16384) >> 15)};
-    float U = 3.0e38f;
-    bool sane = true;
-    for (int k = 0; k < K; k++) {
-        float dmax = 0.f;
+    u32 nibbles = 0u, multi = 0u;
+    for (int q = 0; q < 8; q++) {
+        const int ci = gi * 8 + q;
+        const int b0 = (ci >> (2 * 6)) << RC_SHIFT, g0 = ((ci >> 6) & (RC_N - 1)) << RC_SHIFT, r0 = (ci & (RC_N - 1)) << RC_SHIFT;
+        const int span = (1 << RC_SHIFT) - 1;
+        int xl, yl, zl, xh, yh, zh;
+        lab_f(f_lab_tab, f_lab_tab + 256, b0, g0, r0, xl, yl, zl);
+        lab_f(f_lab_tab, f_lab_tab + 256, b0 + span, g0 + span, r0 + span, xh, yh, zh);
+        const float lo[3] = {(float)((296 * yl - 1336934 + 16384) >> 15), (float)((500 * (xl - yh) + 128 * 32768 + 16384) >> 15),
+                             (float)((200 * (yl - zh) + 128 * 32768 + 16384) >> 15)};
+        const float hi[3] = {(float)((296 * yh - 1336934 + 16384) >> 15), (float)((500 * (xh - yl) + 128 * 32768 + 16384) >> 15),
+                             (float)((200 * (yh - zl) + 128 * 32768 + 16384) >> 15)};
+        float U = 3.0e38f;
+        bool sane = true;
+        for (int k = 0; k < K; k++) {
+            float dmax = 0.f;
 #pragma unroll
-        for (int d = 0; d < 3; d++) {
-            float c = P.c[3 * k + d];
-            sane = sane && (fabsf(c) < 1.0e4f);                 // also false for NaN
-            float m = fmaxf(fabsf(lo[d] - c), fabsf(hi[d] - c));
-            dmax += m * m;
+            for (int d = 0; d < 3; d++) {
+                float c = P.c[3 * k + d];
+                sane = sane && (fabsf(c) < 1.0e4f);                 // also false for NaN
+                float m = fmaxf(fabsf(lo[d] - c), fabsf(hi[d] - c));
+                dmax += m * m;
+            }
+            U = fminf(U, dmax);
         }
-        U = fminf(U, dmax);
-    }
-    u32 mask = 0u;
-    for (int k = 0; k < K; k++) {
-        float dmin = 0.f;
+        u32 mask = 0u;
+        for (int k = 0; k < K; k++) {
+            float dmin = 0.f;
 #pragma unroll
-        for (int d = 0; d < 3; d++) {
-            float c = P.c[3 * k + d];
-            float n = fminf(fmaxf(c, lo[d]), hi[d]);
-            dmin += (n - c) * (n - c);
+            for (int d = 0; d < 3; d++) {
+                float c = P.c[3 * k + d];
+                float n = fminf(fmaxf(c, lo[d]), hi[d]);
+                dmin += (n - c) * (n - c);
+            }
+            if (dmin <= U + 2.0f) mask |= 1u << k;                  // slack: see fk_build_cells
         }
-        if (dmin <= U + 2.0f) mask |= 1u << k;                  // slack: see fk_build_cells
+        const bool single = sane && mask != 0u && (mask & (mask - 1u)) == 0u;
+        if (single) nibbles |= (u32)(P.lut[__ffs(mask) - 1] & 15u) << (4 * q);
+        else multi |= 1u << q;
     }
-    const bool single = sane && mask != 0u && (mask & (mask - 1u)) == 0u;
-    cells[rc_index(b0 >> RC_SHIFT, g0 >> RC_SHIFT, r0 >> RC_SHIFT)] = single ? P.lut[__ffs(mask) - 1] : (u8)RC_MULTI;
+    nib[gi] = nibbles;
+    mb[gi] = (u8)multi;
 }
 
-__global__ void __launch_bounds__(256) fk_assign_rgbcell(const u8 *__restrict__ px, int h, int w, size_t pitch,
-                                                         const __grid_constant__ AssignParams P, const u8 *__restrict__ rcells,
-                                                         const u32 *__restrict__ cells,
-                                                         u8 *__restrict__ labels, size_t lpitch,
-                                                         u32 *__restrict__ bits, int ws, size_t plane)
+#define RA_THREADS 1024
+#define RA_WARPS (RA_THREADS / 32)
+// dynamic shared memory: [label nibbles | flags | cbrt | gamma | centres | lut | per warp: pixels 768, queue 256, labels 256]
+#define RA_OFF_MB RC_NIB_BYTES
+#define RA_OFF_CBRT (RA_OFF_MB + RC_MB_BYTES)
+#define RA_OFF_GAM (RA_OFF_CBRT + 2048 * 2)
+#define RA_OFF_CTR (RA_OFF_GAM + 256 * 2)
+#define RA_OFF_LUT (RA_OFF_CTR + OMNI_MAX_K * 16)
+#define RA_OFF_WARP (RA_OFF_LUT + 64)
+#define RA_WARP_BYTES (768 + 256 + 256)
+#define RA_SMEM (RA_OFF_WARP + RA_WARPS * RA_WARP_BYTES)
+
+__global__ void __launch_bounds__(RA_THREADS, 1) fk_assign_rgbcell(const u8 *__restrict__ px, int h, int w, size_t pitch,
+                                                                   const __grid_constant__ AssignParams P, const uint4 *__restrict__ rtab,
+                                                                   const u32 *__restrict__ cells,
+                                                                   u8 *__restrict__ labels, size_t lpitch,
+                                                                   u32 *__restrict__ bits, int ws, size_t plane)
 {
-    __shared__ u16 s_gam[256];
-    __shared__ u16 s_cbrt[2048];
-    __shared__ float4 s_ctr[OMNI_MAX_K];
-    __shared__ u8 s_lut[OMNI_MAX_K];
-    __shared__ __align__(16) u8 s_px[8][768];                 // per warp: the 256 pixels of the current chunk
-    __shared__ u8 s_q[8][256];                                // per warp: queued pixel indices
-    __shared__ u8 s_lab[8][256];                              // per warp: labels of the queued pixels
-    for (int i = threadIdx.x; i < 2048; i += 256) {
+    extern __shared__ __align__(16) u8 smem[];
+    const u32 *s_nib = reinterpret_cast<const u32 *>(smem);
+    const u32 *s_mb = reinterpret_cast<const u32 *>(smem + RA_OFF_MB);
+    u16 *s_cbrt = reinterpret_cast<u16 *>(smem + RA_OFF_CBRT);
+    u16 *s_gam = reinterpret_cast<u16 *>(smem + RA_OFF_GAM);
+    float4 *s_ctr = reinterpret_cast<float4 *>(smem + RA_OFF_CTR);
+    u8 *s_lut = smem + RA_OFF_LUT;
+    for (int i = threadIdx.x; i < (RC_NIB_BYTES + RC_MB_BYTES) / 16; i += RA_THREADS) reinterpret_cast<uint4 *>(smem)[i] = __ldg(rtab + i);
+    for (int i = threadIdx.x; i < 2048; i += RA_THREADS) {
         s_cbrt[i] = f_lab_tab[256 + i];
         if (i < 256) s_gam[i] = f_lab_tab[i];
     }
@@ -385,10 +443,10 @@ __global__ void __launch_bounds__(256) fk_assign_rgbcell(const u8 *__restrict__ 
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int chunks = (w + 255) >> 8, K = P.K;
-    const int total = h * chunks, stride = gridDim.x * 8;     // h * chunks < 2^31 for every image the ABI accepts
+    const int total = h * chunks, stride = gridDim.x * RA_WARPS;     // h * chunks < 2^30 (checked by the host)
     const bool vec_ok = (((uintptr_t)px | pitch) & 15) == 0;
-    u8 *spx = s_px[warp];
-    u8 *sq = s_q[warp], *slab = s_lab[warp];
+    u8 *spx = smem + RA_OFF_WARP + warp * RA_WARP_BYTES;              // per warp: the 256 pixels of the current chunk
+    u8 *sq = spx + 768, *slab = sq + 256;                             //           queued pixel indices, their labels
     const u32 lt = (1u << lane) - 1u;
     uint4 pf0 = make_uint4(0, 0, 0, 0), pf1 = pf0;
     auto prefetch = [&](int u) {
@@ -401,7 +459,7 @@ __global__ void __launch_bounds__(256) fk_assign_rgbcell(const u8 *__restrict__ 
             }
         }
     };
-    int u = blockIdx.x * 8 + warp;
+    int u = blockIdx.x * RA_WARPS + warp;
     prefetch(u);
     for (; u < total; u += stride) {
         const int y = u / chunks, c = u - y * chunks;
@@ -418,7 +476,7 @@ __global__ void __launch_bounds__(256) fk_assign_rgbcell(const u8 *__restrict__ 
         }
         prefetch(u + stride);
         __syncwarp();
-        // ---- phase 1: one-byte table lookup; pixels of cells with several candidates are queued ----
+        // ---- phase 1: table lookup in shared memory; pixels of cells with several candidates are queued ----
         int lab[8];
         int nq = 0;
         u32 und = 0u;
@@ -430,8 +488,9 @@ __global__ void __launch_bounds__(256) fk_assign_rgbcell(const u8 *__restrict__ 
             if (x < w) {
                 const u8 *p = spx + 3 * lane + 96 * g;
                 const u32 v0 = p[0], v1 = p[1], v2 = p[2];
-                lab[g] = __ldg(rcells + rc_index(v0 >> RC_SHIFT, v1 >> RC_SHIFT, v2 >> RC_SHIFT));
-                multi = lab[g] == RC_MULTI;
+                const u32 ci = ((v0 >> RC_SHIFT) << 12) | ((v1 >> RC_SHIFT) << 6) | (v2 >> RC_SHIFT);
+                lab[g] = (s_nib[ci >> 3] >> ((ci & 7u) * 4u)) & 15u;
+                multi = (s_mb[ci >> 5] >> (ci & 31u)) & 1u;
             }
             const u32 bal = __ballot_sync(0xffffffffu, multi);
             if (multi) {
@@ -617,23 +676,46 @@ __global__ void __launch_bounds__(256) fk_labels_to_bits(const u8 *__restrict__ 
     }
 }
 
-// mask bytes -> bit-planes; *d_bad set when a byte is neither 0 nor 255 (caller falls back to generic)
+// mask bytes -> bit-planes; *d_bad set when a byte is neither 0 nor 255 (caller falls back to generic).
+// A warp packs 512 pixels per step: every lane reads 16 bytes with one load, turns them into 16 bits (high bit of
+// "byte != 0" per byte, gathered with shifts), lane pairs are joined into words by a shuffle.  All ws words of a row
+// are written (the padding words as zeros).
+__device__ __forceinline__ u32 nz4(u32 v, u32 &bad)            // 4 bytes -> 4 bits "byte != 0"
+{
+    const u32 t = ((((v & 0x7f7f7f7fu) + 0x7f7f7f7fu) | v) & 0x80808080u) >> 7;      // 0x01 per non-zero byte
+    bad |= v ^ (t * 255u);                                                           // a non-zero byte that is not 0xFF
+    return (t | (t >> 7) | (t >> 14) | (t >> 21)) & 15u;
+}
+
 __global__ void __launch_bounds__(256) fk_bytes_to_bits(const u8 *__restrict__ planes, size_t pstride, size_t pitch, int h, int w,
                                                         u32 *__restrict__ bits, int ws, size_t plane, int *d_bad)
 {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int k = blockIdx.y;
-    const long long total = (long long)h * ws;
-    int bad = 0;
+    const int chunks = (ws + 15) >> 4;                         // 16 words = 512 pixels per warp step
+    const long long total = (long long)h * chunks;
+    const bool vec_ok = (((uintptr_t)(planes + (size_t)k * pstride) | pitch) & 15) == 0;
+    u32 bad = 0u;
     for (long long u = (long long)blockIdx.x * 8 + warp; u < total; u += (long long)gridDim.x * 8) {
-        const int y = (int)(u / ws), c = (int)(u - (long long)y * ws);
-        const int x = c * 32 + lane;
-        int v = (x < w) ? planes[(size_t)k * pstride + (size_t)y * pitch + x] : 0;
-        bad |= (v != 0 && v != 255);
-        u32 b = __ballot_sync(0xffffffffu, v != 0);
-        if (lane == 0) bits[(size_t)k * plane + (size_t)y * ws + c] = b;
+        const int y = (int)(u / chunks), ch = (int)(u - (long long)y * chunks);
+        const int x = ch * 512 + 16 * lane;
+        const u8 *row = planes + (size_t)k * pstride + (size_t)y * pitch;
+        u32 m16 = 0u;
+        if (vec_ok && x + 16 <= w) {
+            const uint4 v = __ldg(reinterpret_cast<const uint4 *>(row + x));
+            m16 = nz4(v.x, bad) | (nz4(v.y, bad) << 4) | (nz4(v.z, bad) << 8) | (nz4(v.w, bad) << 12);
+        } else {
+            for (int i = 0; i < 16 && x + i < w; i++) {
+                const u32 v = row[x + i];
+                bad |= (v != 0u && v != 255u);
+                m16 |= (u32)(v != 0u) << i;
+            }
+        }
+        const u32 other = __shfl_xor_sync(0xffffffffu, m16, 1);
+        const int c = ch * 16 + (lane >> 1);
+        if (!(lane & 1) && c < ws) bits[(size_t)k * plane + (size_t)y * ws + c] = m16 | (other << 16);
     }
-    if (__any_sync(0xffffffffu, bad) && lane == 0) atomicOr(d_bad, 1);
+    if (__any_sync(0xffffffffu, bad != 0u) && lane == 0) atomicOr(d_bad, 1);
 }
 
 // bit-planes -> 0/255 byte planes
@@ -680,7 +762,8 @@ __host__ __device__ constexpr int code_op(u32 code, int i) { return (int)((code 
 __host__ __device__ constexpr int code_len(u32 code) { int n = 0; while (n < 8 && code_op(code, n) != ST_NONE) n++; return n; }
 __host__ __device__ constexpr bool op_is_erode(int op) { return op == ST_ER || op == ST_EC; }
 
-#define MORPH_TR 32          // rows per strip
+#define MORPH_TR 32          // rows per strip (default)
+#define MORPH_TR_BIG 64      // ... when the grid is large enough: 16+TR rows are processed for TR produced
 
 // Output-of-range fix-up for a value that the step with opcode `next` will consume: columns outside the
 // image and rows outside the image must read as that step's identity element.
@@ -720,25 +803,40 @@ struct MorphChain {
     }
 };
 
+// Run lists of the sparse edge kernel, produced by the morphology kernel itself (RUNS = true): the final image rows
+// pass through this lane's registers with 8 valid halo pixels per side, which is all fk_edge_runs (edges3.cu) needs
+// to classify the lane's MORPH_TR / ET_R tiles -- see the comment there for the rule and the list layout.  The strip is
+// extended by 2 final rows at each end for the tiles' 2-row halo.
+struct MorphRuns {
+    u32 *sbits, *cbits; u8 *edges; size_t estride, epitch; int aligned16;
+    int *run_counts; u32 *run_items; E3RunOff off; int maxt;
+    int zero_fill;                    // 1: the kernel writes the zeros of the dead tiles; 0: the planes were cleared beforehand
+};
+
 // CODE: up to 8 steps, 4 bits each.  TAP: after this many steps the image is the stage-02 mask; it is
 // written as BYTES to `masks` (TAP = -1: nothing).  The final image is written as bits to `out_bits`
 // (may be NULL).
-template <u32 CODE, int TAP>
+template <u32 CODE, int TAP, bool RUNS, int TR>
 __global__ void __launch_bounds__(128) fk_morph(const u32 *__restrict__ in_bits, u32 *__restrict__ out_bits, int ws, size_t plane, int h,
                                                 int w, u8 *__restrict__ masks, size_t mstride, size_t mpitch, int aligned16,
-                                                int y_lo, int y_hi /* rows [y_lo, y_hi) are produced; input rows around them must exist */)
+                                                int y_lo, int y_hi /* rows [y_lo, y_hi) are produced; input rows around them must exist */,
+                                                const __grid_constant__ MorphRuns R)
 {
     constexpr int N = code_len(CODE);
+    constexpr int EXT = RUNS ? 2 : 0;
+    constexpr int TILES = TR / ET_R;
     __shared__ uint2 s_lut8[256];
+    __shared__ u32 s_item[RUNS ? 4 : 1][RUNS ? TILES : 1][32];
     if (TAP >= 0) {
         expand_lut_init(s_lut8, threadIdx.x, blockDim.x);
         __syncthreads();
     }
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     const int ww = (w + 31) >> 5;
-    if (c >= ww) return;
+    const bool active = c < ww;
+    if (!RUNS && !active) return;                          // with RUNS every lane stays for the warp-wide list flush
     const int k = blockIdx.z;
-    const int y0 = y_lo + blockIdx.y * MORPH_TR, y1 = min(y_hi, y0 + MORPH_TR);
+    const int y0 = y_lo + blockIdx.y * TR, y1 = min(y_hi, y0 + TR);
     const u32 *src = in_bits + (size_t)k * plane;
     W64 colvalid;
     colvalid.lo = range_mask(32 * c - 16, w);
@@ -751,15 +849,16 @@ __global__ void __launch_bounds__(128) fk_morph(const u32 *__restrict__ in_bits,
     u32 nl = 0u, no = 0u, nr = 0u;
     auto fetch = [&](int t) {
         nl = no = nr = 0u;
-        if (t >= 0 && t < h) {
+        if (t >= 0 && t < h && active) {
             const u32 *row = src + (size_t)t * ws;
             if (c > 0) nl = __ldg(row + c - 1);
             no = __ldg(row + c);
             if (c + 1 < ww) nr = __ldg(row + c + 1);
         }
     };
-    fetch(y0 - N);
-    for (int t = y0 - N; t < y1 + N; t++) {
+    u32 live1 = 0u, live0 = 0u;                            // per tile of the strip: "has a 1" / "has a 0" in the grown tile
+    fetch(y0 - N - EXT);
+    for (int t = y0 - N - EXT; t < y1 + N + EXT; t++) {
         W64 cur;
         const bool inside = t >= 0 && t < h;
         cur.lo = (nl >> 16) | (no << 16);
@@ -771,17 +870,81 @@ __global__ void __launch_bounds__(128) fk_morph(const u32 *__restrict__ in_bits,
         MorphChain<CODE, 0>::template run<TAP>(cur, p1, p2, t, h, colvalid, tap, fin);
         if (TAP >= 0) {
             const int r = t - TAP;
-            if (r >= y0 && r < y1) {
+            if (r >= y0 && r < y1 && active) {
                 u32 word = (tap.lo >> 16) | (tap.hi << 16);
                 store_word_bytes_lut(masks + (size_t)k * mstride + (size_t)r * mpitch, 32 * c, w, word, aligned16 != 0, s_lut8);
             }
         }
+        const int r = t - N;
         if (out_bits) {
-            const int r = t - N;
-            if (r >= y0 && r < y1) {
+            if (r >= y0 && r < y1 && active) {
                 u32 word = ((fin.lo >> 16) | (fin.hi << 16)) & range_mask(32 * c, w);
                 out_bits[(size_t)k * plane + (size_t)r * ws + c] = word;
             }
+        }
+        if (RUNS) {
+            if (r >= y0 - 2 && r < y1 + 2 && r >= 0 && r < h) {
+                // window bits 14..49 = pixels 32c-2 .. 32c+33; fin is already 0 outside the image
+                const u32 m_lo = 0xFFFFC000u & colvalid.lo, m_hi = 0x0003FFFFu & colvalid.hi;
+                const bool h1 = ((fin.lo & m_lo) | (fin.hi & m_hi)) != 0u, h0 = ((~fin.lo & m_lo) | (~fin.hi & m_hi)) != 0u;
+                const int rr = r - y0, sub = rr & 7;
+                u32 m = 1u << ((rr >> 3) + 1);                          // tile rr / 8 (floor), biased by one
+                if (sub < 2) m |= m >> 1;                                // also the 2-row halo of the tile above
+                if (sub >= 6) m |= m << 1;                               // ... of the tile below
+                m = (m >> 1) & ((1u << TILES) - 1u);
+                if (h1) live1 |= m;
+                if (h0) live0 |= m;
+            }
+        }
+    }
+    if (RUNS) {
+        const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+        const u32 live = active ? (live1 & live0) : 0u;
+        int n_items = 0, run = 0, run_j0 = 0;
+        u32 lens = 0u;                                                   // 3 bits per emitted item: its run length
+        auto emit = [&]() {
+            lens |= (u32)run << (3 * n_items);
+            s_item[wid][n_items++][lane] = ((u32)k << 27) | ((u32)run_j0 << 13) | (u32)c;
+            run = 0;
+        };
+#pragma unroll
+        for (int tl = 0; tl < TILES; tl++) {
+            const int ty0 = y0 + tl * ET_R;
+            if (ty0 >= y1) break;
+            if ((live >> tl) & 1u) {
+                if (run == 0) run_j0 = ty0 / ET_R;
+                if (++run == R.maxt) emit();
+            } else {
+                if (run) emit();
+                if (active && R.zero_fill) {
+                    const int ty1 = min(y1, ty0 + ET_R);
+                    for (int y = ty0; y < ty1; y++) {
+                        const size_t o = (size_t)k * plane + (size_t)y * ws + c;
+                        R.cbits[o] = 0u; R.sbits[o] = 0u;
+                        store_word_bytes(R.edges + (size_t)k * R.estride + (size_t)y * R.epitch, 32 * c, w, 0u, R.aligned16 != 0);
+                    }
+                }
+            }
+        }
+        if (run) emit();
+#pragma unroll
+        for (int nt = 1; nt <= ET_MAXT; nt++) {
+            int mine = 0;
+            for (int i = 0; i < n_items; i++) mine += ((lens >> (3 * i)) & 7u) == (u32)nt;
+            int x = mine;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                int y = __shfl_up_sync(0xffffffffu, x, d);
+                if (lane >= d) x += y;
+            }
+            const int total = __shfl_sync(0xffffffffu, x, 31);
+            if (total == 0) continue;
+            int base = 0;
+            if (lane == 31) base = atomicAdd(R.run_counts + nt - 1, total);
+            base = __shfl_sync(0xffffffffu, base, 31);
+            int pos = base + x - mine;
+            for (int i = 0; i < n_items; i++)
+                if (((lens >> (3 * i)) & 7u) == (u32)nt) R.run_items[R.off.v[nt - 1] + pos++] = s_item[wid][i][lane];
         }
     }
 }
@@ -799,14 +962,26 @@ constexpr u32 CODE_F_C = mk_code(ST_ER, ST_DR, ST_DR, ST_ER, ST_DC, ST_EC);
 constexpr u32 CODE_F_OC = mk_code(ST_ER, ST_DR, ST_DR, ST_ER, ST_EC, ST_DC, ST_DC, ST_EC);
 
 // morph03: 0 none, 1 open, 2 close, 3 open+close.  with02: prepend the RECT open/close and emit mask bytes.
+// runs != NULL: also classify the tiles of the final image for the sparse edge kernel (MorphRuns).
 static cudaError_t launch_morph(bool with02, int morph03, const u32 *in_bits, u32 *out_bits, const BitGeom &g, int K, u8 *masks,
-                                size_t mstride, size_t mpitch, cudaStream_t st, int y_lo = 0, int y_hi = -1)
+                                size_t mstride, size_t mpitch, cudaStream_t st, int y_lo = 0, int y_hi = -1, const MorphRuns *runs = nullptr)
 {
     if (y_hi < 0) y_hi = g.h;
     if (y_hi <= y_lo) return cudaSuccess;
-    dim3 b(128), grid((g.ww + 127) / 128, (y_hi - y_lo + MORPH_TR - 1) / MORPH_TR, K);
+    // taller strips (less halo work) once there are plenty of warps: 128-thread CTAs, 4 warps each
+    const long long warps_big = (long long)((g.ww + 127) / 128) * 4 * ((y_hi - y_lo + MORPH_TR_BIG - 1) / MORPH_TR_BIG) * K;
+    const bool big = warps_big >= 8192 && (y_lo % MORPH_TR_BIG) == 0;
+    const int tr = big ? MORPH_TR_BIG : MORPH_TR;
+    dim3 b(128), grid((g.ww + 127) / 128, (y_hi - y_lo + tr - 1) / tr, K);
     int al = masks && ((uintptr_t)masks % 16 == 0) && (mstride % 16 == 0) && (mpitch % 16 == 0);
-#define LM(CODE, TAP) fk_morph<CODE, TAP><<<grid, b, 0, st>>>(in_bits, out_bits, g.ws, g.plane, g.h, g.w, masks, mstride, mpitch, al, y_lo, y_hi)
+    MorphRuns R{};
+    if (runs) R = *runs;
+#define LM2(CODE, TAP, RUNS, TR) fk_morph<CODE, TAP, RUNS, TR><<<grid, b, 0, st>>>(in_bits, out_bits, g.ws, g.plane, g.h, g.w, masks, mstride, mpitch, al, y_lo, y_hi, R)
+#define LM(CODE, TAP)                                                                  \
+    do {                                                                               \
+        if (runs) { if (big) LM2(CODE, TAP, true, MORPH_TR_BIG); else LM2(CODE, TAP, true, MORPH_TR); }   \
+        else { if (big) LM2(CODE, TAP, false, MORPH_TR_BIG); else LM2(CODE, TAP, false, MORPH_TR); }      \
+    } while (0)
     if (with02) {
         switch (morph03) {
         case 0: LM(CODE_R_OC, 4); break;
@@ -823,6 +998,7 @@ static cudaError_t launch_morph(bool with02, int morph03, const u32 *in_bits, u3
         }
     }
 #undef LM
+#undef LM2
     return cudaGetLastError();
 }
 
@@ -841,6 +1017,7 @@ static cudaError_t launch_morph(bool with02, int morph03, const u32 *in_bits, u3
 #define HB_TR 32                      // tile rows
 #define HB_TW 32                      // tile words (1024 pixels)
 #define HY_WORD_ROUNDS 4
+#define HY_THREADS 1024                // one CTA resolves the whole worklist in the common case: make it a big one
 #define HY_WL_CAP 8192                 // words holding weak candidates; more than this -> full sweeps
 
 __device__ __forceinline__ void hy_patch_bytes(u8 *row, u32 promoted)
@@ -852,7 +1029,7 @@ __device__ __forceinline__ void hy_patch_bytes(u8 *row, u32 promoted)
     }
 }
 
-__global__ void __launch_bounds__(256) fk_hysteresis(u32 *__restrict__ ebits, const u32 *__restrict__ cbits, int ws, size_t plane, int h,
+__global__ void __launch_bounds__(HY_THREADS) fk_hysteresis(u32 *__restrict__ ebits, const u32 *__restrict__ cbits, int ws, size_t plane, int h,
                                                      int w, int K, int *flags /* [0]=rounds, [1..3]=rotating "changed" flags, [4]=worklist count */,
                                                      const u32 *__restrict__ worklist,
                                                      u8 *__restrict__ edges, size_t estride, size_t epitch)
@@ -867,7 +1044,7 @@ __global__ void __launch_bounds__(256) fk_hysteresis(u32 *__restrict__ ebits, co
         int rounds = 0;
         for (;;) {
             int changed = 0;
-            for (int i = threadIdx.x; i < n_weak; i += 256) {
+            for (int i = threadIdx.x; i < n_weak; i += HY_THREADS) {
                 const u32 o = worklist[i];
                 const int k = (int)(o / plane), rem = (int)(o - (size_t)k * plane);
                 const int y = rem / ws, c = rem - y * ws;
@@ -953,7 +1130,7 @@ __global__ void __launch_bounds__(256) fk_hysteresis(u32 *__restrict__ ebits, co
                 u32 *E = ebits + (size_t)k * plane;
                 const u32 *C = cbits + (size_t)k * plane;
                 int pending = 0;
-                for (int i = tid; i < HB_TR * HB_TW; i += 256) {
+                for (int i = tid; i < HB_TR * HB_TW; i += HY_THREADS) {
                     int ly = i / HB_TW, lc = i - ly * HB_TW;
                     int gy = y0 + ly, gc = c0 + lc;
                     u32 cv = 0, ev = 0;
@@ -964,7 +1141,7 @@ __global__ void __launch_bounds__(256) fk_hysteresis(u32 *__restrict__ ebits, co
                 }
                 if (!__syncthreads_or(pending)) continue;
                 // halo ring of E (other CTAs may be raising bits there concurrently: any snapshot is valid, bits only rise)
-                for (int i = tid; i < 2 * SW + 2 * HB_TR; i += 256) {
+                for (int i = tid; i < 2 * SW + 2 * HB_TR; i += HY_THREADS) {
                     int ly, lc;
                     if (i < SW) { ly = 0; lc = i; }
                     else if (i < 2 * SW) { ly = HB_TR + 1; lc = i - SW; }
@@ -976,7 +1153,7 @@ __global__ void __launch_bounds__(256) fk_hysteresis(u32 *__restrict__ ebits, co
                 int any = 0;
                 for (;;) {
                     int changed = 0;
-                    for (int i = tid; i < HB_TR * HB_TW; i += 256) {
+                    for (int i = tid; i < HB_TR * HB_TW; i += HY_THREADS) {
                         int ly = i / HB_TW, lc = i - ly * HB_TW;
                         u32 cv = s_c[i];
                         int o = (ly + 1) * SW + lc + 1;
@@ -996,7 +1173,7 @@ __global__ void __launch_bounds__(256) fk_hysteresis(u32 *__restrict__ ebits, co
                     any = 1;
                 }
                 if (any) {
-                    for (int i = tid; i < HB_TR * HB_TW; i += 256) {
+                    for (int i = tid; i < HB_TR * HB_TW; i += HY_THREADS) {
                         int ly = i / HB_TW, lc = i - ly * HB_TW;
                         int gy = y0 + ly, gc = c0 + lc;
                         if (gy < h && gc < ww) {
@@ -1024,6 +1201,8 @@ __global__ void __launch_bounds__(256) fk_hysteresis(u32 *__restrict__ ebits, co
 // ------------------------------------------------------------------------------------------------
 // host-side drivers
 // ------------------------------------------------------------------------------------------------
+#define HP_MAX_BANDS 8
+static int pipe_init(omni_ctx *ctx);
 static int persist_blocks(omni_ctx *ctx, int per_sm) { return (ctx->sm_count > 0 ? ctx->sm_count : 148) * per_sm; }
 
 // persistent grid of a kernel = SM count x the number of its CTAs that are resident per SM (queried once)
@@ -1054,7 +1233,7 @@ static int bit_planes(omni_ctx *ctx, const BitGeom &g, int K, int n, u32 **out /
 static int assign_cells(omni_ctx *ctx, const AssignParams &P, u32 **cells, u8 **rcells, cudaStream_t st)
 {
     FK_TRY(omni_ws_reserve(ctx, 5, WS5_BYTES));
-    const int variant = ctx->assign_rgbcell ? 2 : 1;
+    const int variant = (ctx->assign_rgbcell && P.K <= RC_MAX_K) ? 2 : 1;
     *cells = (u32 *)ctx->ws[5];
     *rcells = (u8 *)((u32 *)ctx->ws[5] + RGBCELL_OFFSET);
     // same centres (and label map) as the previous call on this ctx (a batch of frames): the tables in the workspace are
@@ -1072,7 +1251,7 @@ static int assign_cells(omni_ctx *ctx, const AssignParams &P, u32 **cells, u8 **
     }
     if (variant == 2) {
         KScope ks(ctx, "build_rgbcells", st);
-        fk_build_rgbcells<<<RC_COUNT / 256, 256, 0, st>>>(P, *rcells);
+        fk_build_rgbcells<<<RC_COUNT / 8 / 256, 256, 0, st>>>(P, (u32 *)*rcells, *rcells + RC_NIB_BYTES);
         OMNI_CUDA(cudaGetLastError());
     }
     return OMNI_OK;
@@ -1086,9 +1265,15 @@ static int launch_assign_lab(omni_ctx *ctx, const u8 *px, int h, int w, size_t p
     u8 *rcells = nullptr;
     FK_TRY(assign_cells(ctx, P, &cells, &rcells, st));
     KScope ks(scoped ? ctx : nullptr, "assign_bits", st);
-    if (ctx->assign_rgbcell && (long long)h * ((w + 255) >> 8) < (1ll << 30)) {       // the kernel counts chunks in 32 bits
-        const int grid = resident_grid(ctx, fk_assign_rgbcell, 256, &ctx->occ_assign_rgb);
-        fk_assign_rgbcell<<<grid, 256, 0, st>>>(px, h, w, pitch, P, rcells, cells, labels, lpitch, bits, ws, plane);
+    if (ctx->assign_rgbcell && P.K <= RC_MAX_K && (long long)h * ((w + 255) >> 8) < (1ll << 30)) {   // the kernel counts chunks in 32 bits
+        if (!ctx->occ_assign_rgb) {
+            OMNI_CUDA(cudaFuncSetAttribute(fk_assign_rgbcell, cudaFuncAttributeMaxDynamicSharedMemorySize, RA_SMEM));
+            ctx->occ_assign_rgb = 1;
+        }
+        // one CTA per SM (its tables fill most of the shared memory); no more CTAs than chunks of 32 warps
+        const long long chunks = (long long)h * ((w + 255) >> 8);
+        const int grid = (int)std::max<long long>(1, std::min<long long>(persist_blocks(ctx, 1), (chunks + RA_WARPS - 1) / RA_WARPS));
+        fk_assign_rgbcell<<<grid, RA_THREADS, RA_SMEM, st>>>(px, h, w, pitch, P, (const uint4 *)rcells, cells, labels, lpitch, bits, ws, plane);
     } else {
         const int grid = resident_grid(ctx, fk_assign_bits<1>, 256, &ctx->occ_assign_lab);
         fk_assign_bits<1><<<grid, 256, 0, st>>>(px, h, w, pitch, P, cells, labels, lpitch, bits, ws, plane);
@@ -1188,7 +1373,7 @@ static int run_hysteresis(omni_ctx *ctx, u32 *ebits, const u32 *cbits, const Bit
 {
     if (ctx->hyst_blocks == 0) {
         int per_sm = 0;
-        OMNI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fk_hysteresis, 256, 0));
+        OMNI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fk_hysteresis, HY_THREADS, 0));
         if (per_sm < 1) { omni_set_error("hysteresis kernel cannot be made resident"); return OMNI_ERR_CUDA; }
         ctx->hyst_blocks = per_sm * (ctx->sm_count > 0 ? ctx->sm_count : 1);
     }
@@ -1197,26 +1382,65 @@ static int run_hysteresis(omni_ctx *ctx, u32 *ebits, const u32 *cbits, const Bit
     int *flags = ctx->d_flags;
     const u32 *worklist = (const u32 *)ctx->ws[5] + HYST_WL_OFFSET;
     void *args[] = {&ebits, &cbits, &ws, &plane, &h, &w, &K, &flags, &worklist, &d_edges, &e_plane, &epitch};
-    OMNI_LAUNCH(ctx, st, "hysteresis_bits", cudaLaunchCooperativeKernel((const void *)fk_hysteresis, dim3(ctx->hyst_blocks), dim3(256),
+    OMNI_LAUNCH(ctx, st, "hysteresis_bits", cudaLaunchCooperativeKernel((const void *)fk_hysteresis, dim3(ctx->hyst_blocks), dim3(HY_THREADS),
                                                                         args, 0, st));
     ctx->last_hyst_passes = -1;           // lives in d_flags[0]; fetched lazily by omni_last_hysteresis_passes
     return OMNI_OK;
 }
 
-// bit-planes M2 -> edge byte planes.  sbits doubles as the working set E of the hysteresis.
+// Zeroes the device flags of an edge pass -- d_flags: [0] rounds, [1..3] changed flags, [4] weak-word count, [16..19] run
+// counts per length, [20] next warp item -- and, when the sparse edge kernel will run, fills the MorphRuns block that lets
+// the morphology kernel produce the run lists (returns false: dense edge kernel, nothing to prepare).
+static int edge_pass_begin(omni_ctx *ctx, const BitGeom &g, int K, u32 *sbits, u32 *cbits, u8 *d_edges, size_t e_plane, size_t epitch,
+                           cudaStream_t st, MorphRuns *R, bool *sparse, bool side_fill)
+{
+    FK_TRY(omni_ws_reserve(ctx, 5, WS5_BYTES));
+    OMNI_CUDA(cudaMemsetAsync(ctx->d_flags, 0, 24 * sizeof(int), st));
+    ctx->edge_join = nullptr;
+    *sparse = ctx->edge_sparse && edges3_sparse_ok(g.h, g.w, K);
+    if (!*sparse) return OMNI_OK;
+    if (ctx->e3s_per_sm == 0) ctx->e3s_per_sm = edges3_sparse_blocks_per_sm();
+    FK_TRY(omni_ws_reserve(ctx, 6, edges3_run_words(g.h, g.w, K, R->off.v) * sizeof(u32)));
+    R->sbits = sbits; R->cbits = cbits; R->edges = d_edges; R->estride = e_plane; R->epitch = epitch;
+    R->aligned16 = ((uintptr_t)d_edges % 16 == 0) && (e_plane % 16 == 0) && (epitch % 16 == 0);
+    R->run_counts = ctx->d_flags + 16; R->run_items = (u32 *)ctx->ws[6];
+    R->maxt = edges3_pick_maxt(g.h, g.w, K, 2 * persist_blocks(ctx, ctx->e3s_per_sm));
+    R->zero_fill = side_fill ? 0 : 1;
+    if (side_fill) {
+        // The zeros of the dead tiles (most of the 2K bytes per pixel the edge pass writes) do not depend on anything: clear
+        // the edge byte planes and the candidate / strong bit-planes on a side stream while the colour assignment and the
+        // morphology (both bound by instruction issue, not by HBM) run; the edge kernel joins before it writes the live tiles.
+        FK_TRY(pipe_init(ctx));
+        cudaEvent_t fork = ctx->pipe_ev[2 * HP_MAX_BANDS + 4], join = ctx->pipe_ev[2 * HP_MAX_BANDS + 5];
+        cudaStream_t ss = ctx->s_in;
+        OMNI_CUDA(cudaEventRecord(fork, st));
+        OMNI_CUDA(cudaStreamWaitEvent(ss, fork, 0));
+        if (epitch == (size_t)g.w && e_plane == epitch * (size_t)g.h) OMNI_CUDA(cudaMemsetAsync(d_edges, 0, e_plane * (size_t)K, ss));
+        else                                        // strided views: only the pixels of the planes may be touched
+            for (int k = 0; k < K; k++) OMNI_CUDA(cudaMemset2DAsync(d_edges + (size_t)k * e_plane, epitch, 0, (size_t)g.w, g.h, ss));
+        const size_t pbytes = g.plane * (size_t)K * sizeof(u32);
+        OMNI_CUDA(cudaMemsetAsync(sbits, 0, pbytes, ss));
+        OMNI_CUDA(cudaMemsetAsync(cbits, 0, pbytes, ss));
+        OMNI_CUDA(cudaEventRecord(join, ss));
+        ctx->edge_join = join;
+    }
+    return OMNI_OK;
+}
+
+// bit-planes M2 -> edge byte planes.  sbits doubles as the working set E of the hysteresis.  edge_pass_begin has run;
+// runs_done: the morphology kernel has already produced the run lists and zero-filled the dead tiles.
 static int edges_from_bits(omni_ctx *ctx, const u32 *m2, u32 *sbits, u32 *cbits, const BitGeom &g, int K, int low, int high,
-                           u8 *d_edges, size_t e_plane, size_t epitch, cudaStream_t st)
+                           u8 *d_edges, size_t e_plane, size_t epitch, cudaStream_t st, bool sparse, bool runs_done)
 {
     int al = ((uintptr_t)d_edges % 16 == 0) && (e_plane % 16 == 0) && (epitch % 16 == 0);
-    FK_TRY(omni_ws_reserve(ctx, 5, WS5_BYTES));
-    // d_flags: [0] rounds, [1..3] changed flags, [4] weak-word count, [16..19] run counts per length, [20] next warp item
-    OMNI_CUDA(cudaMemsetAsync(ctx->d_flags, 0, 24 * sizeof(int), st));
-    if (ctx->edge_sparse && edges3_sparse_ok(g.h, g.w, K)) {
-        unsigned off[ET_MAXT];
-        FK_TRY(omni_ws_reserve(ctx, 6, edges3_run_words(g.h, g.w, K, off) * sizeof(u32)));
-        if (ctx->e3s_per_sm == 0) ctx->e3s_per_sm = edges3_sparse_blocks_per_sm();
-        OMNI_LAUNCH(ctx, st, "edge_runs", launch_edge_runs(m2, g.ws, g.plane, g.h, g.w, K, sbits, cbits, d_edges, e_plane, epitch, al,
-                                                           ctx->d_flags + 16, (u32 *)ctx->ws[6], 2 * persist_blocks(ctx, ctx->e3s_per_sm), st));
+    if (ctx->edge_join) {                               // the side stream has cleared the output planes
+        OMNI_CUDA(cudaStreamWaitEvent(st, ctx->edge_join, 0));
+        ctx->edge_join = nullptr;
+    }
+    if (sparse) {
+        if (!runs_done)
+            OMNI_LAUNCH(ctx, st, "edge_runs", launch_edge_runs(m2, g.ws, g.plane, g.h, g.w, K, sbits, cbits, d_edges, e_plane, epitch, al,
+                                                               ctx->d_flags + 16, (u32 *)ctx->ws[6], 2 * persist_blocks(ctx, ctx->e3s_per_sm), st));
         OMNI_LAUNCH(ctx, st, "edges3_bits", launch_edges3_sparse(m2, g.ws, g.plane, g.h, g.w, K, low, high, persist_blocks(ctx, ctx->e3s_per_sm),
                                                                  sbits, cbits, d_edges, e_plane, epitch, al, ctx->d_flags + 4,
                                                                  (u32 *)ctx->ws[5] + HYST_WL_OFFSET, HY_WL_CAP, ctx->d_flags + 16,
@@ -1250,11 +1474,14 @@ int fast_edges(omni_ctx *ctx, const u8 *d_masks, int K, int h, int w, size_t m_p
     if (ctx->h_flags[8]) return OMNI_ERR_UNSUPPORTED;     // not a {0,255} mask
     int kind = morph03_kind(prm);
     const u32 *m2 = bpp[0];
+    MorphRuns R{};
+    bool sparse = false;
+    FK_TRY(edge_pass_begin(ctx, g, K, bpp[2], bpp[3], d_edges, e_plane, epitch, st, &R, &sparse, false));
     if (kind > 0) {
-        OMNI_LAUNCH(ctx, st, "morph_bits", launch_morph(false, kind, bpp[0], bpp[1], g, K, nullptr, 0, 0, st));
+        OMNI_LAUNCH(ctx, st, "morph_bits", launch_morph(false, kind, bpp[0], bpp[1], g, K, nullptr, 0, 0, st, 0, -1, sparse ? &R : nullptr));
         m2 = bpp[1];
     }
-    return edges_from_bits(ctx, m2, bpp[2], bpp[3], g, K, low, high, d_edges, e_plane, epitch, st);
+    return edges_from_bits(ctx, m2, bpp[2], bpp[3], g, K, low, high, d_edges, e_plane, epitch, st, sparse, sparse && kind > 0);
 }
 
 int fast_color_edge(omni_ctx *ctx, const u8 *d_bgr, int h, int w, size_t pitch, const AssignParams &P,
@@ -1268,11 +1495,15 @@ int fast_color_edge(omni_ctx *ctx, const u8 *d_bgr, int h, int w, size_t pitch, 
     BitGeom g = make_geom(h, w);
     u32 *bpp[4];
     FK_TRY(bit_planes(ctx, g, P.K, 4, bpp));
+    // first of all: fork the side stream that clears the edge planes, so that it runs under the assignment kernel
+    MorphRuns R{};
+    bool sparse = false;
+    FK_TRY(edge_pass_begin(ctx, g, P.K, bpp[2], bpp[3], d_edges, e_plane, epitch, st, &R, &sparse, true));
     OMNI_CUDA(cudaMemsetAsync(bpp[0], 0, g.plane * (size_t)P.K * sizeof(u32), st));      // match_any stores only non-empty words
     FK_TRY(launch_assign_lab(ctx, d_bgr, h, w, pitch, P, d_labels, lpitch, bpp[0], g.ws, g.plane, st));
     int kind = morph03_kind(prm);
-    OMNI_LAUNCH(ctx, st, "morph_bits", launch_morph(true, kind, bpp[0], bpp[1], g, P.K, d_masks, m_plane, mpitch, st));
-    return edges_from_bits(ctx, bpp[1], bpp[2], bpp[3], g, P.K, low, high, d_edges, e_plane, epitch, st);
+    OMNI_LAUNCH(ctx, st, "morph_bits", launch_morph(true, kind, bpp[0], bpp[1], g, P.K, d_masks, m_plane, mpitch, st, 0, -1, sparse ? &R : nullptr));
+    return edges_from_bits(ctx, bpp[1], bpp[2], bpp[3], g, P.K, low, high, d_edges, e_plane, epitch, st, sparse, sparse);
 }
 
 
@@ -1284,14 +1515,12 @@ int fast_color_edge(omni_ctx *ctx, const u8 *d_bgr, int h, int w, size_t pitch, 
 //                    after the last band: edge kernel + hysteresis on the whole image
 //   copy-out stream: mask planes of band b as soon as morph(b) is done; labels; edge planes at the end   (D2H)
 // ------------------------------------------------------------------------------------------------
-#define HP_MAX_BANDS 8
-
 static int pipe_init(omni_ctx *ctx)
 {
     if (ctx->pipe_ready) return OMNI_OK;
     OMNI_CUDA(cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking));
     OMNI_CUDA(cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking));
-    for (int i = 0; i < 2 * HP_MAX_BANDS + 4; i++) OMNI_CUDA(cudaEventCreateWithFlags(&ctx->pipe_ev[i], cudaEventDisableTiming));
+    for (int i = 0; i < 2 * HP_MAX_BANDS + 6; i++) OMNI_CUDA(cudaEventCreateWithFlags(&ctx->pipe_ev[i], cudaEventDisableTiming));
     ctx->pipe_ready = 1;
     return OMNI_OK;
 }
@@ -1301,7 +1530,7 @@ void fast_ctx_release(omni_ctx *ctx)
     if (!ctx || !ctx->pipe_ready) return;
     cudaStreamDestroy(ctx->s_in);
     cudaStreamDestroy(ctx->s_out);
-    for (int i = 0; i < 2 * HP_MAX_BANDS + 4; i++) cudaEventDestroy(ctx->pipe_ev[i]);
+    for (int i = 0; i < 2 * HP_MAX_BANDS + 6; i++) cudaEventDestroy(ctx->pipe_ev[i]);
     ctx->pipe_ready = 0;
 }
 
@@ -1324,7 +1553,7 @@ int fast_host_color_edge(omni_ctx *ctx, const u8 *h_bgr, int h, int w, size_t pi
     // bands: multiples of the morphology strip height, at least 256 rows each
     int nb = HP_MAX_BANDS;
     while (nb > 1 && (h + nb - 1) / nb < 256) nb--;
-    int rows_per = ((h + nb - 1) / nb + MORPH_TR - 1) / MORPH_TR * MORPH_TR;
+    int rows_per = ((h + nb - 1) / nb + MORPH_TR_BIG - 1) / MORPH_TR_BIG * MORPH_TR_BIG;
     nb = (h + rows_per - 1) / rows_per;
     const int kind = morph03_kind(prm);
     // everything queued on the side streams must wait for what the caller queued before on the ctx stream -- nothing:
@@ -1339,9 +1568,12 @@ int fast_host_color_edge(omni_ctx *ctx, const u8 *h_bgr, int h, int w, size_t pi
         OMNI_CUDA(cudaEventRecord(evH[b], si));
     }
     OMNI_CUDA(cudaMemsetAsync(bpp[0], 0, g.plane * (size_t)K * sizeof(u32), sc));
+    MorphRuns R{};
+    bool sparse = false;
+    FK_TRY(edge_pass_begin(ctx, g, K, bpp[2], bpp[3], d_edges, eplane, ep, sc, &R, &sparse, true));
     auto morph_band = [&](int b) -> int {
         int y0 = b * rows_per, y1 = min(h, y0 + rows_per);
-        OMNI_LAUNCH(ctx, sc, "morph_bits", launch_morph(true, kind, bpp[0], bpp[1], g, K, d_masks, mplane, mp, sc, y0, y1));
+        OMNI_LAUNCH(ctx, sc, "morph_bits", launch_morph(true, kind, bpp[0], bpp[1], g, K, d_masks, mplane, mp, sc, y0, y1, sparse ? &R : nullptr));
         OMNI_CUDA(cudaEventRecord(evM[b], sc));
         OMNI_CUDA(cudaStreamWaitEvent(so, evM[b], 0));
         const bool contiguous = (h_mpitch == mp);
@@ -1368,7 +1600,7 @@ int fast_host_color_edge(omni_ctx *ctx, const u8 *h_bgr, int h, int w, size_t pi
         OMNI_CUDA(cudaStreamWaitEvent(so, evX[1], 0));
         OMNI_CUDA(cudaMemcpy2DAsync(h_labels, lpitch, d_labels, lp, (size_t)w, h, cudaMemcpyDeviceToHost, so));
     }
-    FK_TRY(edges_from_bits(ctx, bpp[1], bpp[2], bpp[3], g, K, low, high, d_edges, eplane, ep, sc));
+    FK_TRY(edges_from_bits(ctx, bpp[1], bpp[2], bpp[3], g, K, low, high, d_edges, eplane, ep, sc, sparse, sparse));
     OMNI_CUDA(cudaEventRecord(evX[2], sc));
     OMNI_CUDA(cudaStreamWaitEvent(so, evX[2], 0));
     for (int k = 0; k < K; k++) {
@@ -1456,21 +1688,34 @@ __device__ __forceinline__ void thin_substep(const u32 *__restrict__ src, u32 *_
         const int y0 = strip * TH_ROWS, y1 = min(h, y0 + TH_ROWS);
         const u32 *S = src + (size_t)k * plane;
         u32 *D = dst + (size_t)k * plane;
-        // a row as (left, own, right) words; the neighbours' words come from the neighbouring lanes
-        auto fetch = [&](const int y, u32 &l, u32 &m, u32 &r) {
-            const bool in = y >= 0 && y < h;
-            m = (in && active) ? __ldcg(S + (size_t)y * ws + c) : 0u;
+        // a row as (left, own, right) words; the neighbours' words come from the neighbouring lanes.  The loads run two
+        // rows ahead of the row being decided (L2 latency), the shuffles one row ahead.
+        struct Raw { u32 m, e; };                                           // own word; lanes 0 / 31: the word beyond the warp
+        auto ld = [&](const int y) {
+            Raw r = {0u, 0u};
+            if (y >= 0 && y < h) {
+                if (active) r.m = __ldcg(S + (size_t)y * ws + c);
+                if (lane == 0 && c > 0 && c - 1 < ww) r.e = __ldcg(S + (size_t)y * ws + c - 1);
+                if (lane == 31 && c + 1 < ww) r.e = __ldcg(S + (size_t)y * ws + c + 1);
+            }
+            return r;
+        };
+        auto mk = [&](const Raw raw, u32 &l, u32 &m, u32 &r) {
+            m = raw.m;
             l = __shfl_up_sync(0xffffffffu, m, 1);
             r = __shfl_down_sync(0xffffffffu, m, 1);
-            if (lane == 0) l = (in && c > 0 && c - 1 < ww) ? __ldcg(S + (size_t)y * ws + c - 1) : 0u;
-            if (lane == 31) r = (in && c + 1 < ww) ? __ldcg(S + (size_t)y * ws + c + 1) : 0u;
+            if (lane == 0) l = raw.e;
+            if (lane == 31) r = raw.e;
         };
         u32 ul, um, ur, ml, mm, mr, dl, dm, dr;
-        fetch(y0 - 1, ul, um, ur);
-        fetch(y0, ml, mm, mr);
+        mk(ld(y0 - 1), ul, um, ur);
+        mk(ld(y0), ml, mm, mr);
+        Raw nxt = ld(y0 + 1);
         int cnt = 0;
         for (int y = y0; y < y1; y++) {
-            fetch(y + 1, dl, dm, dr);
+            const Raw nn = ld(y + 2);
+            mk(nxt, dl, dm, dr);
+            nxt = nn;
             u32 del = 0u;
             if (mm) del = thin_delete_mask<STEP>(ul, um, ur, ml, mm, mr, dl, dm, dr);
             if (active) D[(size_t)y * ws + c] = mm & ~del;

@@ -37,6 +37,9 @@ int fast_color_edge(omni_ctx *ctx, const u8 *d_bgr, int h, int w, size_t pitch, 
 // Dense variant: every word of every plane.  Sparse variant: fk_edge_runs lists the runs of tiles that can hold an
 // edge pixel (and zero-fills the rest), the edge kernel walks only those.
 #define ET_MAXT 4                         // longest run, in tiles
+#define ET_R 8                            // tile rows
+struct E3RunOff { unsigned v[ET_MAXT]; };  // start of the list of runs of length nt = i + 1 inside the item buffer
+int edges3_pick_maxt(int h, int w, int K, int resident_warps);
 size_t edges3_run_words(int h, int w, int K, unsigned off[ET_MAXT]);
 bool edges3_sparse_ok(int h, int w, int K);
 int edges3_sparse_blocks_per_sm();
