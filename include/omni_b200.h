@@ -104,6 +104,17 @@ int omni_layer_masks(omni_ctx *ctx, const uint8_t *d_labels, int h, int w, size_
                      int open_iters, int close_iters,
                      uint8_t *d_masks, size_t plane_stride, size_t mpitch, void *stream);
 
+/* 02_color_extract.py:82-109, the legacy swatch mode (`extraction_mode == "swatch"`; unreachable through
+ * config.json because config.py:124-125 drops the key, kept for callers that build a Config by hand).
+ * h_colors: K x 3 int32 exactly as `cfg.colors` holds them (each component in [0,255]); per name the swatch is
+ * tried reversed (RGB -> BGR) and as-is with cv2.inRange(img, c - tol, c + tol) (bounds clipped to [0,255]), the
+ * candidate with more non-zeros wins (ties: the reversed one), then RECT-3 open and close.  d_masks as in
+ * omni_layer_masks.  h_choice (optional, K int32): 0 = reversed, 1 = as-is.  Synchronises the stream (the choice
+ * needs the two counts).  Fast path only (no generic variant). */
+int omni_swatch_masks(omni_ctx *ctx, const uint8_t *d_bgr, int h, int w, size_t pitch,
+                      const int32_t *h_colors, int K, int tol,
+                      uint8_t *d_masks, size_t plane_stride, size_t mpitch, int32_t *h_choice, void *stream);
+
 /* ---- stage 03: 03_edge_detect.py:23-34 per layer ------------------------------------------- */
 /* K independent planes: ELLIPSE(morph_k) open/close -> GaussianBlur(ksize, sigma 0) -> Canny(low,
  * high) (aperture 3, L1, 8-connected hysteresis).  Output {0,255}.  In and out may not alias.

@@ -626,6 +626,19 @@ extern "C" int omni_host_edges(omni_ctx *ctx, const uint8_t *h_masks, int K, int
     return OMNI_OK;
 }
 
+extern "C" int omni_swatch_masks(omni_ctx *ctx, const uint8_t *d_bgr, int h, int w, size_t pitch,
+                                 const int32_t *h_colors, int K, int tol,
+                                 uint8_t *d_masks, size_t plane_stride, size_t mpitch, int32_t *h_choice, void *stream)
+{
+    OMNI_TRY(set_device(ctx));
+    OMNI_REQUIRE(d_bgr && d_masks && h_colors && K >= 1 && K <= OMNI_MAX_K && h > 0 && w > 0, "omni_swatch_masks: bad arguments");
+    OMNI_REQUIRE(pitch >= (size_t)w * 3 && mpitch >= (size_t)w, "omni_swatch_masks: pitch smaller than a row");
+    OMNI_REQUIRE(tol >= 0 && tol <= 255, "omni_swatch_masks: color_tolerance %d outside [0,255]", tol);
+    for (int i = 0; i < 3 * K; i++)
+        OMNI_REQUIRE(h_colors[i] >= 0 && h_colors[i] <= 255, "omni_swatch_masks: swatch component %d outside [0,255]", h_colors[i]);
+    return fast_swatch_masks(ctx, d_bgr, h, w, pitch, h_colors, K, tol, d_masks, plane_stride, mpitch, h_choice, (cudaStream_t)stream);
+}
+
 // ---- stage 04: thinning ------------------------------------------------------------------------------------
 extern "C" int omni_thin_zhangsuen(omni_ctx *ctx, const uint8_t *d_in, int K, int h, int w, size_t in_plane_stride, size_t in_pitch,
                                    int max_iter, uint8_t *d_out, size_t out_plane_stride, size_t out_pitch,

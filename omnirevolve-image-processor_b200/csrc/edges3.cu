@@ -22,6 +22,9 @@
 #include <cuda_fp16.h>
 
 #define E3V_WARPS 2
+#ifndef E3_NMS_UNROLL
+#define E3_NMS_UNROLL 2                   // candidates per lane and NMS round (independent dependency chains)
+#endif
 #define E3V_LSTRIDE 40                    // u16 per lane region (80 bytes: conflict-free uint4 stores)
 
 // Per-warp shared memory.  Every lane stores ITS OWN window of a row (no cross-lane exchange is needed to
@@ -238,8 +241,8 @@ __global__ void __launch_bounds__(E3V_WARPS * 32) fk_edges3_simd(const __grid_co
         if (do_nms) {
             const u16 *mu = S.m[(rnr + 5) % 3], *mc = S.m[(rnr + 6) % 3], *md = S.m[(rnr + 7) % 3];
             const u16 *dxr = S.dx[rnr & 1], *dyr = S.dy[rnr & 1];
-            // two candidates per lane and round (independent dependency chains); a lane whose second index falls off the
-            // list repeats the last entry -- the result bits are OR-ed in, so a repeat is harmless
+            // E3_NMS_UNROLL candidates per lane and round (independent dependency chains); a lane whose later indices fall off
+            // the list repeats the last entry -- the result bits are OR-ed in, so a repeat is harmless
             auto nms_one = [&](const int item, int &o, u32 &bit, bool &ok, bool &strong) {
                 o = item >> 5;
                 const int e = item & 31;
@@ -259,21 +262,20 @@ __global__ void __launch_bounds__(E3V_WARPS * 32) fk_edges3_simd(const __grid_co
                 strong = m0 > high_bits;
                 bit = 1u << e;
             };
-            for (int i = lane; i < total; i += 64) {
-                const int item0 = S.list[i], item1 = S.list[min(i + 32, total - 1)];
-                int o0, o1;
-                u32 b0, b1;
-                bool ok0, ok1, st0, st1;
-                nms_one(item0, o0, b0, ok0, st0);
-                nms_one(item1, o1, b1, ok1, st1);
-                if (ok0) {
-                    atomicOr(&S.cw[o0], b0);
-                    if (st0) atomicOr(&S.sw[o0], b0);
-                }
-                if (ok1) {
-                    atomicOr(&S.cw[o1], b1);
-                    if (st1) atomicOr(&S.sw[o1], b1);
-                }
+            for (int i = lane; i < total; i += 32 * E3_NMS_UNROLL) {
+                int item[E3_NMS_UNROLL], o[E3_NMS_UNROLL];
+                u32 bt[E3_NMS_UNROLL];
+                bool ok[E3_NMS_UNROLL], st[E3_NMS_UNROLL];
+#pragma unroll
+                for (int q = 0; q < E3_NMS_UNROLL; q++) item[q] = S.list[min(i + 32 * q, total - 1)];
+#pragma unroll
+                for (int q = 0; q < E3_NMS_UNROLL; q++) nms_one(item[q], o[q], bt[q], ok[q], st[q]);
+#pragma unroll
+                for (int q = 0; q < E3_NMS_UNROLL; q++)
+                    if (ok[q]) {
+                        atomicOr(&S.cw[o[q]], bt[q]);
+                        if (st[q]) atomicOr(&S.sw[o[q]], bt[q]);
+                    }
             }
         }
         __syncwarp();

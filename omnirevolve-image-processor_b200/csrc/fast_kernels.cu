@@ -816,8 +816,11 @@ struct MorphRuns {
 // CODE: up to 8 steps, 4 bits each.  TAP: after this many steps the image is the stage-02 mask; it is
 // written as BYTES to `masks` (TAP = -1: nothing).  The final image is written as bits to `out_bits`
 // (may be NULL).
+#ifndef MORPH_MINB
+#define MORPH_MINB 1
+#endif
 template <u32 CODE, int TAP, bool RUNS, int TR>
-__global__ void __launch_bounds__(128) fk_morph(const u32 *__restrict__ in_bits, u32 *__restrict__ out_bits, int ws, size_t plane, int h,
+__global__ void __launch_bounds__(128, MORPH_MINB) fk_morph(const u32 *__restrict__ in_bits, u32 *__restrict__ out_bits, int ws, size_t plane, int h,
                                                 int w, u8 *__restrict__ masks, size_t mstride, size_t mpitch, int aligned16,
                                                 int y_lo, int y_hi /* rows [y_lo, y_hi) are produced; input rows around them must exist */,
                                                 const __grid_constant__ MorphRuns R)
@@ -1577,11 +1580,12 @@ int fast_host_color_edge(omni_ctx *ctx, const u8 *h_bgr, int h, int w, size_t pi
         OMNI_CUDA(cudaEventRecord(evM[b], sc));
         OMNI_CUDA(cudaStreamWaitEvent(so, evM[b], 0));
         const bool contiguous = (h_mpitch == mp);
-        for (int k = 0; k < K; k++) {
-            if (contiguous)
-                OMNI_CUDA(cudaMemcpyAsync(h_masks + (size_t)k * h_mplane + (size_t)y0 * h_mpitch, d_masks + (size_t)k * mplane + (size_t)y0 * mp,
-                                          (size_t)(y1 - y0 - 1) * mp + w, cudaMemcpyDeviceToHost, so));
-            else
+        if (contiguous) {
+            // the band of all K planes in ONE strided copy: "row" = a plane's band (contiguous rows), "pitch" = the plane stride
+            OMNI_CUDA(cudaMemcpy2DAsync(h_masks + (size_t)y0 * h_mpitch, h_mplane, d_masks + (size_t)y0 * mp, mplane,
+                                        (size_t)(y1 - y0 - 1) * mp + w, K, cudaMemcpyDeviceToHost, so));
+        } else {
+            for (int k = 0; k < K; k++)
                 OMNI_CUDA(cudaMemcpy2DAsync(h_masks + (size_t)k * h_mplane + (size_t)y0 * h_mpitch, h_mpitch,
                                             d_masks + (size_t)k * mplane + (size_t)y0 * mp, mp, (size_t)w, y1 - y0, cudaMemcpyDeviceToHost, so));
         }
@@ -1603,11 +1607,10 @@ int fast_host_color_edge(omni_ctx *ctx, const u8 *h_bgr, int h, int w, size_t pi
     FK_TRY(edges_from_bits(ctx, bpp[1], bpp[2], bpp[3], g, K, low, high, d_edges, eplane, ep, sc, sparse, sparse));
     OMNI_CUDA(cudaEventRecord(evX[2], sc));
     OMNI_CUDA(cudaStreamWaitEvent(so, evX[2], 0));
-    for (int k = 0; k < K; k++) {
-        if (h_epitch == ep)
-            OMNI_CUDA(cudaMemcpyAsync(h_edges + (size_t)k * h_eplane, d_edges + (size_t)k * eplane, (size_t)(h - 1) * ep + w,
-                                      cudaMemcpyDeviceToHost, so));
-        else
+    if (h_epitch == ep) {
+        OMNI_CUDA(cudaMemcpy2DAsync(h_edges, h_eplane, d_edges, eplane, (size_t)(h - 1) * ep + w, K, cudaMemcpyDeviceToHost, so));
+    } else {
+        for (int k = 0; k < K; k++)
             OMNI_CUDA(cudaMemcpy2DAsync(h_edges + (size_t)k * h_eplane, h_epitch, d_edges + (size_t)k * eplane, ep, (size_t)w, h,
                                         cudaMemcpyDeviceToHost, so));
     }
@@ -1671,9 +1674,16 @@ __device__ __forceinline__ u32 thin_delete_mask(u32 ul, u32 um, u32 ur, u32 ml, 
     return mm & a_ok & b_ok & c_ok;
 }
 
+// Unit skipping (exact).  Sub-steps are numbered t = 2 * iteration + (STEP - 1); every unit (16 rows x 1024 pixels) records
+// in ucur whether it deleted anything in sub-step t.  What a unit sees at t differs from what it saw at t - 2 (the same kind
+// of sub-step, where it deleted nothing more) only if it or one of its 8 neighbour units deleted something at t - 2 or
+// t - 1 (up1 / up2): otherwise the unit is skipped.  A unit that deletes at t always runs t + 1 (its own flag), which
+// rewrites the other plane set; so before every sub-step each unit's words are current in the set that is read, and a
+// skipped unit holds the same words in both sets.
 template <int STEP>
 __device__ __forceinline__ void thin_substep(const u32 *__restrict__ src, u32 *__restrict__ dst, int ws, size_t plane, int h, int ww, int K,
-                                             int *removed_it /* + k * max_iter */, int max_iter, volatile int *chg)
+                                             int *removed_it /* + k * max_iter */, int max_iter, volatile int *chg,
+                                             const u8 *up1, const u8 *up2, u8 *ucur, u8 *unext)
 {
     const int lane = threadIdx.x & 31;
     const int wcols = (ww + 31) / 32, strips = (h + TH_ROWS - 1) / TH_ROWS;
@@ -1683,6 +1693,16 @@ __device__ __forceinline__ void thin_substep(const u32 *__restrict__ src, u32 *_
         const int wx = (int)(u % wcols);
         const long long r0 = u / wcols;
         const int strip = (int)(r0 % strips), k = (int)(r0 / strips);
+        if (lane == 0) unext[u] = 0;                                        // the buffer sub-step t + 1 will set
+        if (up1) {
+            // lanes 0..8 / 9..17 look at the 3x3 unit neighbourhood in the flags of t - 1 / t - 2
+            int f = 0;
+            if (lane < 18) {
+                const int q = lane % 9, sx = wx + q % 3 - 1, sy = strip + q / 3 - 1;
+                if (sx >= 0 && sx < wcols && sy >= 0 && sy < strips) f = __ldcg((lane < 9 ? up1 : up2) + ((size_t)k * strips + sy) * wcols + sx);
+            }
+            if (!__any_sync(0xffffffffu, f != 0)) continue;
+        }
         const int c = wx * 32 + lane;
         const bool active = c < ww;
         const int y0 = strip * TH_ROWS, y1 = min(h, y0 + TH_ROWS);
@@ -1724,21 +1744,25 @@ __device__ __forceinline__ void thin_substep(const u32 *__restrict__ src, u32 *_
         }
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, d);
-        if (lane == 0 && cnt) { atomicAdd(removed_it + (size_t)k * max_iter, cnt); *chg = 1; }
+        if (lane == 0 && cnt) { atomicAdd(removed_it + (size_t)k * max_iter, cnt); *chg = 1; ucur[u] = 1; }
     }
 }
 
 __global__ void __launch_bounds__(256) fk_thin(u32 *__restrict__ A, u32 *__restrict__ B, int ws, size_t plane, int h, int w, int K, int max_iter,
-                                               int *__restrict__ removed, int *flags /* [0] iterations run, [1..3] rotating changed flags */)
+                                               int *__restrict__ removed, int *flags /* [0] iterations run, [1..3] rotating changed flags */,
+                                               u8 *__restrict__ unit_flags /* 4 x units, zeroed */, size_t units)
 {
     cg::grid_group grid = cg::this_grid();
     const int ww = (w + 31) >> 5;
     for (int it = 0; it < max_iter; it++) {
         volatile int *chg = flags + 1 + (it % 3);
-        thin_substep<1>(A, B, ws, plane, h, ww, K, removed + it, max_iter, chg);
+        // unit flags: four buffers rotate over the sub-steps t (written at t, read at t + 1 and t + 2, cleared at t + 3)
+        const int t1 = 2 * it, t2 = 2 * it + 1;
+        auto ub = [&](int t) { return unit_flags + (size_t)(t & 3) * units; };
+        thin_substep<1>(A, B, ws, plane, h, ww, K, removed + it, max_iter, chg, it > 0 ? ub(t1 - 1) : nullptr, ub(t1 - 2), ub(t1), ub(t1 + 1));
         __threadfence();
         grid.sync();
-        thin_substep<2>(B, A, ws, plane, h, ww, K, removed + it, max_iter, chg);
+        thin_substep<2>(B, A, ws, plane, h, ww, K, removed + it, max_iter, chg, it > 0 ? ub(t2 - 1) : nullptr, ub(t2 - 2), ub(t2), ub(t2 + 1));
         __threadfence();
         grid.sync();
         const int c = *chg;
@@ -1758,9 +1782,11 @@ int fast_thin(omni_ctx *ctx, const u8 *d_in, int K, int h, int w, size_t in_plan
     int al = ((uintptr_t)d_out % 16 == 0) && (out_plane % 16 == 0) && (out_pitch % 16 == 0);
     if (max_iter < 0) max_iter = 0;
     const size_t n_rem = (size_t)K * (max_iter > 0 ? max_iter : 1);
-    FK_TRY(omni_ws_reserve(ctx, 6, n_rem * sizeof(int)));
+    size_t units = (size_t)K * ((h + TH_ROWS - 1) / TH_ROWS) * ((g.ww + 31) / 32);
+    FK_TRY(omni_ws_reserve(ctx, 6, n_rem * sizeof(int) + 4 * units));
     int *d_removed = (int *)ctx->ws[6];
-    OMNI_CUDA(cudaMemsetAsync(d_removed, 0, n_rem * sizeof(int), st));
+    u8 *d_unit = (u8 *)(d_removed + n_rem);
+    OMNI_CUDA(cudaMemsetAsync(d_removed, 0, n_rem * sizeof(int) + 4 * units, st));
     OMNI_CUDA(cudaMemsetAsync(ctx->d_flags, 0, 8 * sizeof(int), st));
     OMNI_CUDA(cudaMemsetAsync(ctx->d_flags + 8, 0, sizeof(int), st));
     {
@@ -1776,13 +1802,12 @@ int fast_thin(omni_ctx *ctx, const u8 *d_in, int K, int h, int w, size_t in_plan
             ctx->thin_blocks = per_sm * (ctx->sm_count > 0 ? ctx->sm_count : 1);
         }
         // no more CTAs than warp units (8 warps per CTA): barriers get cheaper on small inputs
-        const long long units = (long long)K * ((h + TH_ROWS - 1) / TH_ROWS) * ((g.ww + 31) / 32);
-        int blocks = (int)std::min<long long>(ctx->thin_blocks, (units + 7) / 8);
+        int blocks = (int)std::min<long long>(ctx->thin_blocks, ((long long)units + 7) / 8);
         if (blocks < 1) blocks = 1;
         int ws = g.ws;
         size_t plane = g.plane;
         int *flags = ctx->d_flags;
-        void *args[] = {&bpp[0], &bpp[1], &ws, &plane, &h, &w, &K, &max_iter, &d_removed, &flags};
+        void *args[] = {&bpp[0], &bpp[1], &ws, &plane, &h, &w, &K, &max_iter, &d_removed, &flags, &d_unit, &units};
         OMNI_LAUNCH(ctx, st, "thin_zhangsuen", cudaLaunchCooperativeKernel((const void *)fk_thin, dim3(blocks), dim3(256), args, 0, st));
     }
     {
@@ -1802,5 +1827,79 @@ int fast_thin(omni_ctx *ctx, const u8 *d_in, int K, int h, int w, size_t in_plan
                 for (int i = 0; i < max_iter; i++) h_removed[(size_t)k * max_iter + i] = i < it ? rem[(size_t)k * max_iter + i] : 0;
         }
     }
+    return OMNI_OK;
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// stage 02, legacy swatch mode (02_color_extract.py:82-109).  Per name the swatch is tried as RGB
+// (reversed into BGR) and as-is: cv2.inRange with the clipped +-tol box, the candidate with more non-zeros wins
+// (>= favours the reversed one), RECT-3 open/close.  One pass over the image fills both candidate bit-plane sets
+// and their non-zero counts; the chosen planes go through the RECT open/close morphology kernel -> mask bytes.
+// ------------------------------------------------------------------------------------------------
+struct SwatchBoxes { u8 lo[2][OMNI_MAX_K][3], hi[2][OMNI_MAX_K][3]; int K; };
+
+__global__ void __launch_bounds__(256) fk_inrange_bits(const u8 *__restrict__ px, int h, int w, size_t pitch, const __grid_constant__ SwatchBoxes B,
+                                                       u32 *__restrict__ bits0, u32 *__restrict__ bits1, int ws, size_t plane,
+                                                       unsigned long long *__restrict__ counts /* [2][OMNI_MAX_K] */)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long total = (long long)h * ws;
+    unsigned long long cnt0 = 0, cnt1 = 0;                     // lane p: non-zeros of plane p of set 0 / 1
+    for (long long u = (long long)blockIdx.x * 8 + warp; u < total; u += (long long)gridDim.x * 8) {
+        const int y = (int)(u / ws), c = (int)(u - (long long)y * ws);
+        const int x = c * 32 + lane;
+        int v0 = -1, v1 = -1, v2 = -1;                         // outside the image: in no box
+        if (x < w) {
+            const u8 *p = px + (size_t)y * pitch + 3 * (size_t)x;
+            v0 = p[0]; v1 = p[1]; v2 = p[2];
+        }
+        for (int k = 0; k < B.K; k++) {
+#pragma unroll
+            for (int s = 0; s < 2; s++) {
+                const bool in = v0 >= B.lo[s][k][0] && v0 <= B.hi[s][k][0] && v1 >= B.lo[s][k][1] && v1 <= B.hi[s][k][1] &&
+                                v2 >= B.lo[s][k][2] && v2 <= B.hi[s][k][2];
+                const u32 word = __ballot_sync(0xffffffffu, in);
+                if (lane == 0) (s ? bits1 : bits0)[(size_t)k * plane + (size_t)y * ws + c] = word;
+                if (lane == k) { if (s) cnt1 += __popc(word); else cnt0 += __popc(word); }
+            }
+        }
+    }
+    if (lane < B.K) {
+        if (cnt0) atomicAdd(counts + lane, cnt0);
+        if (cnt1) atomicAdd(counts + OMNI_MAX_K + lane, cnt1);
+    }
+}
+
+int fast_swatch_masks(omni_ctx *ctx, const u8 *d_bgr, int h, int w, size_t pitch, const int32_t *h_colors, int K, int tol,
+                      u8 *d_masks, size_t plane_stride, size_t mpitch, int32_t *h_choice, cudaStream_t st)
+{
+    BitGeom g = make_geom(h, w);
+    u32 *bpp[3];
+    FK_TRY(bit_planes(ctx, g, K, 3, bpp));
+    SwatchBoxes B;
+    memset(&B, 0, sizeof(B));
+    B.K = K;
+    for (int i = 0; i < K; i++)
+        for (int d = 0; d < 3; d++) {
+            const int c1 = h_colors[3 * i + 2 - d], c2 = h_colors[3 * i + d];      // reversed (RGB -> BGR) / as-is
+            B.lo[0][i][d] = (u8)std::max(0, c1 - tol); B.hi[0][i][d] = (u8)std::min(255, c1 + tol);
+            B.lo[1][i][d] = (u8)std::max(0, c2 - tol); B.hi[1][i][d] = (u8)std::min(255, c2 + tol);
+        }
+    OMNI_CUDA(cudaMemsetAsync(ctx->d_counts, 0, 2 * OMNI_MAX_K * sizeof(unsigned long long), st));
+    {
+        KScope ks(ctx, "inrange_bits", st);
+        fk_inrange_bits<<<persist_blocks(ctx, 8), 256, 0, st>>>(d_bgr, h, w, pitch, B, bpp[0], bpp[1], g.ws, g.plane, ctx->d_counts);
+        OMNI_CUDA(cudaGetLastError());
+    }
+    OMNI_CUDA(cudaMemcpyAsync(ctx->h_counts, ctx->d_counts, 2 * OMNI_MAX_K * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    OMNI_CUDA(cudaStreamSynchronize(st));
+    for (int i = 0; i < K; i++) {
+        const int pick = ctx->h_counts[i] >= ctx->h_counts[OMNI_MAX_K + i] ? 0 : 1;               // nz1 >= nz2 -> m1 (02:100-101)
+        if (h_choice) h_choice[i] = pick;
+        OMNI_CUDA(cudaMemcpyAsync(bpp[2] + (size_t)i * g.plane, bpp[pick] + (size_t)i * g.plane, g.plane * sizeof(u32),
+                                  cudaMemcpyDeviceToDevice, st));
+    }
+    OMNI_LAUNCH(ctx, st, "morph_bits", launch_morph(true, 0, bpp[2], nullptr, g, K, d_masks, plane_stride, mpitch, st));
     return OMNI_OK;
 }

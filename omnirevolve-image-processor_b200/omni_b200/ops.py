@@ -144,6 +144,21 @@ class Engine:
                                             out.data_ptr(), out.stride(0), out.stride(1), self._stream()))
         return out
 
+    def swatch_masks(self, bgr: torch.Tensor, colors, tol: int = 30, out: torch.Tensor | None = None, with_choice: bool = False):
+        """02_color_extract.py:82-109 (swatch mode): K masks [K,H,W] u8 {0,255}; colors: K x 3 as in cfg.colors."""
+        _check_img(bgr, 3)
+        col = np.ascontiguousarray(np.asarray(colors, dtype=np.int32).reshape(-1, 3))
+        K = col.shape[0]
+        h, w = bgr.shape[:2]
+        if out is None:
+            out = torch.empty((K, h, w), dtype=torch.uint8, device=bgr.device)
+        _check_planes(out)
+        choice = np.zeros(K, np.int32)
+        i32p = C.POINTER(C.c_int32)
+        capi.check(self._L.omni_swatch_masks(self._h, bgr.data_ptr(), h, w, bgr.stride(0), col.ctypes.data_as(i32p), K, int(tol),
+                                             out.data_ptr(), out.stride(0), out.stride(1), choice.ctypes.data_as(i32p), self._stream()))
+        return (out, choice) if with_choice else out
+
     # ---- stage 03 ------------------------------------------------------------------------------
     def edges(self, masks: torch.Tensor, ec: EdgeConfig, out: torch.Tensor | None = None) -> torch.Tensor:
         """03_edge_detect.py:23-34 on K mask planes at once.  [K,H,W] u8 {0,255}."""

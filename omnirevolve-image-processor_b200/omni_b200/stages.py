@@ -126,9 +126,26 @@ def _lab_to_bgr(lab3) -> tuple:
 _CACHE: dict = {}          # (output_dir) -> fused results, so stage 03 in the same process skips recomputation
 
 
+def _swatch_extract(cfg, img, names) -> None:
+    """02_color_extract.py:82-109: legacy swatch mode (only reachable with a hand-built Config, config.py drops the key)."""
+    tol = int(getattr(cfg, "color_tolerance", 30))
+    colors = list(getattr(cfg, "colors", []))
+    if not colors or len(colors) < len(names):
+        raise RuntimeError("swatch mode: 'colors' must have \u2265 len(color_names) entries.")
+    import torch
+    cols = [[int(v) for v in colors[i]] for i in range(len(names))]
+    masks = get_engine().swatch_masks(torch.from_numpy(np.ascontiguousarray(img)).cuda(), cols, tol).cpu().numpy()
+    for i, name in enumerate(names):
+        os.makedirs(os.path.join(cfg.output_dir, name), exist_ok=True)
+        cv2.imwrite(os.path.join(cfg.output_dir, name, "mask.png"), masks[i])
+        print(f"Extracted (swatch): {name} | nz={int(np.count_nonzero(masks[i]))}")
+    print("Color extraction: done.")
+
+
 def color_extract_main(cfg) -> dict:
-    """02_color_extract.py:66-175 (k-means mode, the only mode reachable through config.json).  The fused
-    GPU call also produces the stage-03 edge planes; they are cached for detect_all_edges() when both
+    """02_color_extract.py:66-175.  k-means mode is the only one reachable through config.json; the swatch branch
+    (:82-109) is honoured when the Config object carries extraction_mode == "swatch".  The fused GPU call of the
+    k-means mode also produces the stage-03 edge planes; they are cached for detect_all_edges() when both
     stages run in one process, and recomputed from mask.png when stage 03 runs on its own."""
     os.makedirs(cfg.output_dir, exist_ok=True)
     path = os.path.join(cfg.output_dir, "resized.png")
@@ -137,6 +154,9 @@ def color_extract_main(cfg) -> dict:
         raise RuntimeError(f"Cannot read resized image: {path}")
     img = _ensure_bgr(img)
     names = list(cfg.color_names)
+    if str(getattr(cfg, "extraction_mode", "kmeans")).lower() == "swatch":
+        _swatch_extract(cfg, img, names)
+        return {}
     K = max(2, len(names))
     centers = kmeans_lab_centers(img, K)
     order, lut = darkness_lut(centers)

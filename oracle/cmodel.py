@@ -35,6 +35,8 @@ def lib():
         L.orc_edge_chain.restype = C.c_int
         L.orc_thin_zhangsuen.argtypes = [u8p, C.c_int, C.c_int, u8p, C.c_int, i32p]
         L.orc_thin_zhangsuen.restype = C.c_int
+        L.orc_swatch_masks.argtypes = [u8p, C.c_int, C.c_int, i32p, C.c_int, C.c_int, u8p, i32p]
+        L.orc_swatch_masks.restype = None
         _lib = L
     return _lib
 
@@ -157,3 +159,14 @@ def thin_zhangsuen(img, max_iter=120, with_log=False):
     removed = np.zeros(max(1, max_iter), np.int32)
     it = lib().orc_thin_zhangsuen(_p(img), img.shape[0], img.shape[1], _p(out), max_iter, _p(removed, C.c_int32))
     return (out, removed[:it].copy()) if with_log else out
+
+
+def swatch_masks(img_bgr, colors, tol=30, with_choice=False):
+    """02_color_extract.py:82-109 swatch branch: K masks (inRange of the better of RGB-reversed / as-is, RECT-3 open/close)."""
+    img = _u8(img_bgr)
+    col = np.ascontiguousarray(np.asarray(colors, np.int32).reshape(-1, 3))
+    K = col.shape[0]
+    out = np.empty((K,) + img.shape[:2], np.uint8)
+    choice = np.zeros(K, np.int32)
+    lib().orc_swatch_masks(_p(img), img.shape[0], img.shape[1], _p(col, C.c_int32), K, int(tol), _p(out), _p(choice, C.c_int32))
+    return (out, choice) if with_choice else out

@@ -434,3 +434,43 @@ ORC_API int orc_thin_zhangsuen(const uint8_t *in, int h, int w, uint8_t *out, in
     free(roi); free(del);
     return it;
 }
+
+
+/* ------------------------------------------------------------------------------------------ */
+/* 02_color_extract.py:82-109  legacy swatch extraction                       */
+/* ------------------------------------------------------------------------------------------ */
+/* Per name i: the swatch colours[i] is tried as RGB (-> BGR reversed) and as-is; cv2.inRange(img, c - tol, c + tol)
+ * with the bounds clipped to [0,255]; the candidate with more non-zeros wins (>= favours the reversed one, 02:100-101);
+ * RECT-3 open, then close.  img: h x w x 3 (BGR in memory); colors: K x 3 as written in config.json; masks: K planes;
+ * choice (optional): 0 = reversed (bgr1), 1 = as-is (bgr2). */
+ORC_API void orc_swatch_masks(const uint8_t *img, int h, int w, const int *colors, int K, int tol, uint8_t *masks, int *choice)
+{
+    size_t n = (size_t)h * w;
+    uint8_t se[9];
+    orc_structuring_element(0, 3, se);
+    uint8_t *m1 = (uint8_t *)malloc(n ? n : 1), *m2 = (uint8_t *)malloc(n ? n : 1);
+    for (int i = 0; i < K; i++) {
+        int c1[3] = {colors[3 * i + 2], colors[3 * i + 1], colors[3 * i]}, c2[3] = {colors[3 * i], colors[3 * i + 1], colors[3 * i + 2]};
+        int lo1[3], hi1[3], lo2[3], hi2[3];
+        for (int d = 0; d < 3; d++) {
+            lo1[d] = c1[d] - tol < 0 ? 0 : c1[d] - tol; hi1[d] = c1[d] + tol > 255 ? 255 : c1[d] + tol;
+            lo2[d] = c2[d] - tol < 0 ? 0 : c2[d] - tol; hi2[d] = c2[d] + tol > 255 ? 255 : c2[d] + tol;
+            /* np.array(..., np.uint8) of a value outside [0,255] cannot occur: max(0, .) / min(255, .) were applied first,
+             * but a swatch component > 255 + tol or < -tol would wrap there; such configs are rejected by the GPU entry point */
+        }
+        size_t nz1 = 0, nz2 = 0;
+        for (size_t p = 0; p < n; p++) {
+            const uint8_t *q = img + 3 * p;
+            int a = q[0] >= lo1[0] && q[0] <= hi1[0] && q[1] >= lo1[1] && q[1] <= hi1[1] && q[2] >= lo1[2] && q[2] <= hi1[2];
+            int b = q[0] >= lo2[0] && q[0] <= hi2[0] && q[1] >= lo2[1] && q[1] <= hi2[1] && q[2] >= lo2[2] && q[2] <= hi2[2];
+            m1[p] = a ? 255 : 0; m2[p] = b ? 255 : 0;
+            nz1 += a; nz2 += b;
+        }
+        uint8_t *out = masks + (size_t)i * n;
+        memcpy(out, nz1 >= nz2 ? m1 : m2, n);
+        if (choice) choice[i] = nz1 >= nz2 ? 0 : 1;
+        orc_morph_openclose(out, h, w, se, 3, 0, 1);
+        orc_morph_openclose(out, h, w, se, 3, 1, 1);
+    }
+    free(m1); free(m2);
+}

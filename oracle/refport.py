@@ -109,6 +109,24 @@ def color_extract(img_bgr: np.ndarray, K: int, centers: np.ndarray | None = None
     return centers[order], lut[labels], layer_masks(lut[labels], K)
 
 
+def swatch_masks(img_bgr: np.ndarray, colors, tol: int = 30) -> np.ndarray:
+    """02:82-109 (swatch mode) without files: per swatch the better of inRange(RGB->BGR) / inRange(as-is), RECT-3 open/close."""
+    se = cv2.getStructuringElement(cv2.MORPH_RECT, (3, 3))
+    out = []
+    for rgb in colors:
+        rgb = tuple(int(v) for v in rgb)
+        cands = []
+        for c in ((rgb[2], rgb[1], rgb[0]), rgb):
+            lower = np.array([max(0, c[0] - tol), max(0, c[1] - tol), max(0, c[2] - tol)], np.uint8)
+            upper = np.array([min(255, c[0] + tol), min(255, c[1] + tol), min(255, c[2] + tol)], np.uint8)
+            cands.append(cv2.inRange(img_bgr, lower, upper))
+        m = cands[0] if int(np.count_nonzero(cands[0])) >= int(np.count_nonzero(cands[1])) else cands[1]
+        m = cv2.morphologyEx(m, cv2.MORPH_OPEN, se, iterations=1)
+        m = cv2.morphologyEx(m, cv2.MORPH_CLOSE, se, iterations=1)
+        out.append(m)
+    return np.stack(out)
+
+
 # ---- 03_edge_detect.py:9-34 --------------------------------------------------------------------
 def ensure_odd(n) -> int:
     n = max(3, int(n))

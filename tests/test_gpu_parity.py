@@ -456,3 +456,46 @@ def test_thinning_function_mirror(eng, capsys):
     log = capsys.readouterr().out
     assert "[layer_x] Thinning ROI" in log and "Thin 01: removed=" in log and "Thinning done" in log
     assert np.array_equal(contours.thinning_zhangsuen(np.zeros((5, 5), np.uint8), "e"), np.zeros((5, 5), np.uint8))
+
+
+# ---- stage 02 swatch mode -------------------------------------------------------------------------
+def test_swatch_masks_golden(eng):
+    z = np.load(f"{GOLDEN}/swatch.npz")
+    for tol in (30, 60, 8):
+        got = host(eng.swatch_masks(dev(z["img"]), z["colors"], tol))
+        assert np.array_equal(got, z[f"masks_tol{tol}"]), tol
+
+
+@pytest.mark.parametrize("hw", [(1, 1), (7, 45), (130, 517), (512, 768)])
+def test_swatch_masks_vs_oracle(eng, hw):
+    cm = _cm()
+    img = synth(hw[0], hw[1], 17, cell=8) if min(hw) >= 8 else uniform_img(hw[0], hw[1], 3)
+    px = img.reshape(-1, 3)
+    cols = [px[0][::-1].tolist(), px[len(px) // 2].tolist(), [0, 0, 0], [255, 255, 255], [128, 10, 240], px[-1].tolist()]
+    for tol in (0, 30, 90, 255):
+        want, wc = cm.swatch_masks(img, cols, tol, with_choice=True)
+        got, gc = eng.swatch_masks(dev(img), cols, tol, with_choice=True)
+        assert np.array_equal(host(got), want), tol
+        assert np.array_equal(gc, wc), tol
+    with pytest.raises(Exception):
+        eng.swatch_masks(dev(img), [[300, 0, 0]], 30)
+
+
+def test_swatch_stage_function(eng, tmp_path):
+    """color_extract_main with a hand-built Config (extraction_mode='swatch'): files and log lines of 02:82-109."""
+    import cv2
+    from omni_b200 import stages, config as ocfg
+    z = np.load(f"{GOLDEN}/swatch.npz")
+    cfg = ocfg.Config()
+    cfg.output_dir = str(tmp_path)
+    cfg.color_names = ["layer_a", "layer_b", "layer_c", "layer_d"]
+    cfg.colors = z["colors"].tolist()
+    cfg.extraction_mode = "swatch"
+    cfg.color_tolerance = 60
+    cv2.imwrite(str(tmp_path / "resized.png"), z["img"])
+    stages.color_extract_main(cfg)
+    for i, n in enumerate(cfg.color_names):
+        assert np.array_equal(cv2.imread(str(tmp_path / n / "mask.png"), cv2.IMREAD_GRAYSCALE), z["masks_tol60"][i]), n
+    cfg.colors = cfg.colors[:2]
+    with pytest.raises(RuntimeError):
+        stages.color_extract_main(cfg)

@@ -98,3 +98,14 @@ def test_thinning_iteration_cap():
     cut = cm.thin_zhangsuen(img, max_iter=3)
     assert len(log) > 4 and log[-1] == 0 and (cut > 0).sum() > (full > 0).sum()
     assert np.array_equal(cut, rp.thinning_zhangsuen(img, max_iter=3))
+
+
+def test_swatch_golden():
+    """02_color_extract.py:82-109 (swatch mode): C model and cv2 replay vs masks frozen from the
+    unmodified reference branch (tools/make_golden_swatch.py)."""
+    z = np.load(f"{GOLDEN}/swatch.npz")
+    for tol in (30, 60, 8):
+        want = z[f"masks_tol{tol}"]
+        assert np.array_equal(cm.swatch_masks(z["img"], z["colors"], tol), want), tol
+        assert np.array_equal(rp.swatch_masks(z["img"], z["colors"], tol), want), tol
+    assert z["masks_tol60"].any()
