@@ -134,6 +134,7 @@ cudaError_t fast_resize_2x(const u8 *src, size_t spitch, u8 *dst, int dh, int dw
 // A thread owns one destination column of the tile: its horizontal taps (shared-memory byte offsets + weights) sit in
 // registers for all its destination rows, and the horizontal sum of a source row is reused when the next destination
 // row shares that source row (the fractional rows do).
+template <int MT>                         // taps per destination pixel and axis held in registers (>= floor(scale) + 2)
 __global__ void __launch_bounds__(RF_THREADS) fk_resize_frac(const u8 *__restrict__ src, int sh, int sw, size_t spitch, u8 *__restrict__ dst,
                                                              int dh, int dw, size_t dpitch, const ResizeTabDev t, int spitch_s, int vec_ok)
 {
@@ -185,10 +186,10 @@ __global__ void __launch_bounds__(RF_THREADS) fk_resize_frac(const u8 *__restric
     const int x = x0 + lx;
     if (x >= x1) return;
     const int xb = t.xofs[x], nt = t.xofs[x + 1] - xb;
-    int off[RF_MAXTAPS];
-    float wgt[RF_MAXTAPS];
+    int off[MT];
+    float wgt[MT];
 #pragma unroll
-    for (int q = 0; q < RF_MAXTAPS; q++) {
+    for (int q = 0; q < MT; q++) {
         off[q] = q < nt ? 3 * t.xsi[xb + q] - b0 : 0;
         wgt[q] = q < nt ? t.xal[xb + q] : 0.f;
     }
@@ -205,7 +206,7 @@ __global__ void __launch_bounds__(RF_THREADS) fk_resize_frac(const u8 *__restric
                 const u8 *r = s_src + (size_t)(sr - ys0) * spitch_s;
                 h0 = h1 = h2 = 0.f;
 #pragma unroll
-                for (int q = 0; q < RF_MAXTAPS; q++)
+                for (int q = 0; q < MT; q++)
                     if (q < nt) {                                              // same order as OpenCV: k ascending, 0 + p*a first
                         const u8 *p = r + off[q];
                         h0 = __fadd_rn(h0, __fmul_rn((float)p[0], wgt[q]));
@@ -240,16 +241,19 @@ cudaError_t fast_resize_frac(const u8 *src, int sh, int sw, size_t spitch, u8 *d
     const int rows = (int)(scy * RF_TY) + 3;
     const size_t smem = (size_t)rows * spitch_s;
     if (smem > 200 * 1024) return cudaErrorNotSupported;
-    static bool attr_set[64] = {false};
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (dev < 64 && !attr_set[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(fk_resize_frac, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        if (e != cudaSuccess) return e;
-        attr_set[dev] = true;
-    }
+    const int need = (int)floor(scx) + 2;
     dim3 grid((dw + RF_TX - 1) / RF_TX, (dh + RF_TY - 1) / RF_TY);
-    fk_resize_frac<<<grid, RF_THREADS, smem, st>>>(src, sh, sw, spitch, dst, dh, dw, dpitch, *tab, spitch_s, vec_ok);
+#define RF_LAUNCH(MT)                                                                                                             \
+    do {                                                                                                                          \
+        cudaError_t e = cudaFuncSetAttribute(fk_resize_frac<MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);        \
+        if (e != cudaSuccess) return e;                                                                                           \
+        fk_resize_frac<MT><<<grid, RF_THREADS, smem, st>>>(src, sh, sw, spitch, dst, dh, dw, dpitch, *tab, spitch_s, vec_ok);     \
+    } while (0)
+    if (need <= 3) RF_LAUNCH(3);
+    else if (need <= 4) RF_LAUNCH(4);
+    else if (need <= 6) RF_LAUNCH(6);
+    else RF_LAUNCH(RF_MAXTAPS);
+#undef RF_LAUNCH
     return cudaGetLastError();
 }
 

@@ -344,6 +344,42 @@ def test_full_size_config2(eng):
     assert torch.equal(eng.edges(m2, omni_b200.EdgeConfig()), edges)
 
 
+@pytest.mark.parametrize("shape", [(8192, 8192, 16, 1, 64), (1080, 1920, 8, 0, 32), (2000, 2000, 4, 2, 32)],
+                         ids=["config3_8192_k16", "config4_1080p_k8", "default_2000_k4"])
+def test_full_size_families_agree(eng, shape):
+    """BASELINE configs 3 and 4 (and the default max_dimension size) at FULL size: the two fast kernel families behind
+    the ABI -- sparse tile runs + RGB cells (default) and dense edges + Lab cells -- must give identical bytes; the oracle
+    pins one layer (its CPU chain needs ~1 s per 64 Mpx layer)."""
+    import omni_b200
+    cm, rp = _cm(), _rp()
+    h, w, K, seed, cell = shape
+    img = synth(h, w, seed, cell)
+    ctr = rp.kmeans_lab_centers(img, K)
+    _o, lut = rp.darkness_order(ctr)
+    lut = lut.astype(np.uint8)
+    d = dev(img)
+    ec = omni_b200.EdgeConfig()
+    try:
+        eng.set_fast_path(1)
+        l1, m1, e1 = eng.color_edge(d, ctr, lut, ec, want_labels=True)
+        eng.set_fast_path(2)
+        l2, m2, e2 = eng.color_edge(d, ctr, lut, ec, want_labels=True)
+    finally:
+        eng.set_fast_path(1)
+    assert torch.equal(l1, l2) and torch.equal(m1, m2) and torch.equal(e1, e2)
+    # size-independent property: the labels partition the image
+    assert int(torch.bincount(l1.flatten().int(), minlength=K).sum()) == h * w
+    k = K // 2
+    want_mask = rp.layer_masks((host(l1) == k).astype(np.uint8), 2)[1]
+    assert np.array_equal(host(m1[k]), want_mask)
+    assert np.array_equal(host(e1[k]), rp.edge_layer(want_mask))
+    # stage 04 hand-off at full size: skeleton is a subset of the edges and idempotent
+    sk = eng.thin_zhangsuen(e1)
+    assert bool(((sk > 0) <= (e1 > 0)).all())
+    assert torch.equal(eng.thin_zhangsuen(sk), sk)
+    assert np.array_equal(host(sk[k]), cm.thin_zhangsuen(host(e1[k])))
+
+
 def test_no_cpu_fallback_error_paths(eng):
     import omni_b200
     with pytest.raises(omni_b200.OmniError):
