@@ -135,6 +135,14 @@ int omni_color_edge(omni_ctx *ctx, const uint8_t *d_bgr, int h, int w, size_t pi
                     uint8_t *d_labels, size_t lpitch,
                     uint8_t *d_masks, size_t m_plane_stride, size_t mpitch,
                     uint8_t *d_edges, size_t e_plane_stride, size_t epitch, void *stream);
+/* The same for n_frames equally sized frames that share ONE centre set (video frames; BASELINE config 4), frame f at
+ * d_bgr + f*frame_stride.  Plane f*K + k of d_masks / d_edges is layer k of frame f (i.e. [n][K][H][W] when
+ * contiguous).  Results are identical to n_frames calls of omni_color_edge; the layers of up to OMNI_MAX_K / K frames
+ * go through each morphology / edge / hysteresis launch together, which is what fills the GPU on small frames. */
+int omni_color_edge_batch(omni_ctx *ctx, const uint8_t *d_bgr, int n_frames, size_t frame_stride, int h, int w, size_t pitch,
+                          const float *h_centers, int K, const uint8_t *h_lut, const omni_edge_params *prm,
+                          uint8_t *d_masks, size_t m_plane_stride, size_t mpitch,
+                          uint8_t *d_edges, size_t e_plane_stride, size_t epitch, void *stream);
 /* Host-buffer form: H2D of the image, kernels, D2H of labels (optional), masks and edges.
  * h_counts (optional, 3*K int64): per plane [pixels labelled p, mask non-zeros, edge non-zeros] --
  * the numbers 02:168 and 03:38 print and palette_by_name.json records. */

@@ -534,6 +534,40 @@ extern "C" int omni_color_edge(omni_ctx *ctx, const uint8_t *d_bgr, int h, int w
     return edges_dispatch(ctx, d_masks, K, h, w, m_plane_stride, mpitch, prm, bp, low, high, d_edges, e_plane_stride, epitch, st);
 }
 
+extern "C" int omni_color_edge_batch(omni_ctx *ctx, const uint8_t *d_bgr, int n_frames, size_t frame_stride, int h, int w, size_t pitch,
+                                     const float *h_centers, int K, const uint8_t *h_lut, const omni_edge_params *prm,
+                                     uint8_t *d_masks, size_t m_plane_stride, size_t mpitch,
+                                     uint8_t *d_edges, size_t e_plane_stride, size_t epitch, void *stream)
+{
+    OMNI_TRY(set_device(ctx));
+    OMNI_REQUIRE(d_bgr && d_masks && d_edges && h_centers && n_frames >= 1, "omni_color_edge_batch: bad arguments");
+    OMNI_REQUIRE(h > 0 && w > 0 && pitch >= (size_t)w * 3 && mpitch >= (size_t)w && epitch >= (size_t)w, "omni_color_edge_batch: bad geometry");
+    OMNI_REQUIRE(K >= 1 && K <= OMNI_MAX_K, "K=%d outside [1,%d]", K, OMNI_MAX_K);
+    BlurParams bp; int low, high;
+    OMNI_TRY(check_edge_params(prm, &bp, &low, &high));
+    AssignParams P;
+    OMNI_TRY(fill_assign(&P, h_centers, nullptr, K, h_lut));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int group = OMNI_MAX_K / K;                      // frames whose layers fit the plane dimension of one pass
+    for (int f0 = 0; f0 < n_frames; ) {
+        const int nf = (n_frames - f0) < group ? (n_frames - f0) : group;
+        const uint8_t *src = d_bgr + (size_t)f0 * frame_stride;
+        uint8_t *dm = d_masks + (size_t)f0 * K * m_plane_stride, *de = d_edges + (size_t)f0 * K * e_plane_stride;
+        int rc = OMNI_ERR_UNSUPPORTED;
+        if (ctx->fast && fast_edges_supported(prm) && nf > 1)
+            rc = fast_color_edge_batch(ctx, src, nf, frame_stride, h, w, pitch, P, prm, low, high, dm, m_plane_stride, mpitch,
+                                       de, e_plane_stride, epitch, st);
+        if (rc == OMNI_ERR_UNSUPPORTED) {                  // outside the fast path (or a single frame): frame by frame
+            for (int f = 0; f < nf; f++)
+                OMNI_TRY(omni_color_edge(ctx, src + (size_t)f * frame_stride, h, w, pitch, h_centers, K, h_lut, prm, nullptr, 0,
+                                         dm + (size_t)f * K * m_plane_stride, m_plane_stride, mpitch,
+                                         de + (size_t)f * K * e_plane_stride, e_plane_stride, epitch, stream));
+        } else if (rc != OMNI_OK) return rc;
+        f0 += nf;
+    }
+    return OMNI_OK;
+}
+
 // ---- counts / composite -----------------------------------------------------------------------------------
 extern "C" int omni_count_nonzero(omni_ctx *ctx, const uint8_t *d_planes, int K, int h, int w, size_t plane_stride, size_t pitch,
                                   int64_t *h_counts, void *stream)

@@ -426,7 +426,9 @@ __global__ void __launch_bounds__(RA_THREADS, 1) fk_assign_rgbcell(const u8 *__r
                                                                    const __grid_constant__ AssignParams P, const uint4 *__restrict__ rtab,
                                                                    const u32 *__restrict__ cells,
                                                                    u8 *__restrict__ labels, size_t lpitch,
-                                                                   u32 *__restrict__ bits, int ws, size_t plane)
+                                                                   u32 *__restrict__ bits, int ws, size_t plane,
+                                                                   int nf, size_t frame_stride /* a batch: nf frames of h rows; frame f
+                                                                   writes the K planes starting at plane f * K (labels: rows f * h ..) */)
 {
     extern __shared__ __align__(16) u8 smem[];
     const u32 *s_nib = reinterpret_cast<const u32 *>(smem);
@@ -447,17 +449,18 @@ __global__ void __launch_bounds__(RA_THREADS, 1) fk_assign_rgbcell(const u8 *__r
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int chunks = (w + 255) >> 8, K = P.K;
-    const int total = h * chunks, stride = gridDim.x * RA_WARPS;     // h * chunks < 2^30 (checked by the host)
-    const bool vec_ok = (((uintptr_t)px | pitch) & 15) == 0;
+    const int total = nf * h * chunks, stride = gridDim.x * RA_WARPS;     // nf * h * chunks < 2^30 (checked by the host)
+    const bool vec_ok = (((uintptr_t)px | pitch | frame_stride) & 15) == 0;
     u8 *spx = smem + RA_OFF_WARP + warp * RA_WARP_BYTES;              // per warp: the 256 pixels of the current chunk
     u8 *sq = spx + 768, *slab = sq + 256;                             //           queued pixel indices, their labels
     const u32 lt = (1u << lane) - 1u;
     uint4 pf0 = make_uint4(0, 0, 0, 0), pf1 = pf0;
     auto prefetch = [&](int u) {
         if (u < total) {
-            const int y = u / chunks, c = u - y * chunks;
+            const int yy = u / chunks, c = u - yy * chunks;
+            const int f = yy / h, y = yy - f * h;
             if (vec_ok && c * 256 + 256 <= w) {
-                const uint4 *src = reinterpret_cast<const uint4 *>(px + (size_t)y * pitch + (size_t)c * 768);
+                const uint4 *src = reinterpret_cast<const uint4 *>(px + (size_t)f * frame_stride + (size_t)y * pitch + (size_t)c * 768);
                 pf0 = __ldg(src + lane);
                 if (lane < 16) pf1 = __ldg(src + 32 + lane);
             }
@@ -466,7 +469,8 @@ __global__ void __launch_bounds__(RA_THREADS, 1) fk_assign_rgbcell(const u8 *__r
     int u = blockIdx.x * RA_WARPS + warp;
     prefetch(u);
     for (; u < total; u += stride) {
-        const int y = u / chunks, c = u - y * chunks;
+        const int yy = u / chunks, c = u - yy * chunks;
+        const int f = yy / h, y = yy - f * h;
         const int x0 = c * 256 + lane;
         const bool full = vec_ok && c * 256 + 256 <= w;
         __syncwarp();                                          // the previous chunk has been consumed
@@ -474,7 +478,7 @@ __global__ void __launch_bounds__(RA_THREADS, 1) fk_assign_rgbcell(const u8 *__r
             reinterpret_cast<uint4 *>(spx)[lane] = pf0;
             if (lane < 16) reinterpret_cast<uint4 *>(spx)[32 + lane] = pf1;
         } else {
-            const u8 *row = px + (size_t)y * pitch + (size_t)c * 768;
+            const u8 *row = px + (size_t)f * frame_stride + (size_t)y * pitch + (size_t)c * 768;
             const int nb = 3 * min(256, w - c * 256);
             for (int i = lane; i < nb; i += 32) spx[i] = row[i];
         }
@@ -530,13 +534,13 @@ __global__ void __launch_bounds__(RA_THREADS, 1) fk_assign_rgbcell(const u8 *__r
             if ((und >> g) & 1u) lab[g] = slab[32 * g + lane];
         // ---- phase 3: outputs ----
         if (labels) {
-            u8 *lrow = labels + (size_t)y * lpitch;
+            u8 *lrow = labels + (size_t)yy * lpitch;
 #pragma unroll
             for (int g = 0; g < 8; g++)
                 if (x0 + 32 * g < w) lrow[x0 + 32 * g] = (u8)lab[g];
         }
         if (bits) {
-            u32 *brow = bits + (size_t)y * ws + c * 8;
+            u32 *brow = bits + (size_t)f * K * plane + (size_t)y * ws + c * 8;
 #pragma unroll
             for (int g = 0; g < 8; g++) {
                 const u32 same = __match_any_sync(0xffffffffu, lab[g]);
@@ -1266,21 +1270,30 @@ static int assign_cells(omni_ctx *ctx, const AssignParams &P, u32 **cells, u8 **
 
 // Lab-centre assignment of rows [0, h) at px: labels and/or one-hot bit-plane words (either may be NULL)
 static int launch_assign_lab(omni_ctx *ctx, const u8 *px, int h, int w, size_t pitch, const AssignParams &P, u8 *labels, size_t lpitch,
-                             u32 *bits, int ws, size_t plane, cudaStream_t st, bool scoped = true)
+                             u32 *bits, int ws, size_t plane, cudaStream_t st, bool scoped = true, int nf = 1, size_t frame_stride = 0)
 {
+    // the RGB-cell kernel counts chunks in 32 bits and takes a whole batch; the Lab-cell kernel takes one frame per launch
+    const bool use_rgb = ctx->assign_rgbcell && P.K <= RC_MAX_K && (long long)nf * h * ((w + 255) >> 8) < (1ll << 30);
+    if (!use_rgb && nf > 1) {
+        for (int f = 0; f < nf; f++)
+            FK_TRY(launch_assign_lab(ctx, px + (size_t)f * frame_stride, h, w, pitch, P, labels ? labels + (size_t)f * h * lpitch : nullptr,
+                                     lpitch, bits ? bits + (size_t)f * P.K * plane : nullptr, ws, plane, st, scoped, 1, 0));
+        return OMNI_OK;
+    }
     u32 *cells = nullptr;
     u8 *rcells = nullptr;
     FK_TRY(assign_cells(ctx, P, &cells, &rcells, st));
     KScope ks(scoped ? ctx : nullptr, "assign_bits", st);
-    if (ctx->assign_rgbcell && P.K <= RC_MAX_K && (long long)h * ((w + 255) >> 8) < (1ll << 30)) {   // the kernel counts chunks in 32 bits
+    if (use_rgb) {
         if (!ctx->occ_assign_rgb) {
             OMNI_CUDA(cudaFuncSetAttribute(fk_assign_rgbcell, cudaFuncAttributeMaxDynamicSharedMemorySize, RA_SMEM));
             ctx->occ_assign_rgb = 1;
         }
         // one CTA per SM (its tables fill most of the shared memory); no more CTAs than chunks of 32 warps
-        const long long chunks = (long long)h * ((w + 255) >> 8);
+        const long long chunks = (long long)nf * h * ((w + 255) >> 8);
         const int grid = (int)std::max<long long>(1, std::min<long long>(persist_blocks(ctx, 1), (chunks + RA_WARPS - 1) / RA_WARPS));
-        fk_assign_rgbcell<<<grid, RA_THREADS, RA_SMEM, st>>>(px, h, w, pitch, P, (const uint4 *)rcells, cells, labels, lpitch, bits, ws, plane);
+        fk_assign_rgbcell<<<grid, RA_THREADS, RA_SMEM, st>>>(px, h, w, pitch, P, (const uint4 *)rcells, cells, labels, lpitch, bits, ws, plane,
+                                                             nf, frame_stride);
     } else {
         const int grid = resident_grid(ctx, fk_assign_bits<1>, 256, &ctx->occ_assign_lab);
         fk_assign_bits<1><<<grid, 256, 0, st>>>(px, h, w, pitch, P, cells, labels, lpitch, bits, ws, plane);
@@ -1513,6 +1526,31 @@ int fast_color_edge(omni_ctx *ctx, const u8 *d_bgr, int h, int w, size_t pitch, 
     return edges_from_bits(ctx, bpp[1], bpp[2], bpp[3], g, P.K, low, high, d_edges, e_plane, epitch, st, sparse, sparse);
 }
 
+
+// A batch of n equally sized frames that share one centre set (BASELINE config 4: video frames).  After the colour
+// assignment nothing couples the K layers of a frame, so the n * K layers of the batch are simply n * K planes of one
+// geometry: one morphology launch, one edge launch and one hysteresis launch serve the whole batch (a 1080p frame alone
+// cannot fill the machine).  Plane f * K + k of the mask / edge tensors belongs to layer k of frame f.  n * K <= OMNI_MAX_K.
+int fast_color_edge_batch(omni_ctx *ctx, const u8 *d_bgr, int n, size_t frame_stride, int h, int w, size_t pitch, const AssignParams &P,
+                          const omni_edge_params *prm, int low, int high, u8 *d_masks, size_t m_plane, size_t mpitch,
+                          u8 *d_edges, size_t e_plane, size_t epitch, cudaStream_t st)
+{
+    if (low < 0) return OMNI_ERR_UNSUPPORTED;
+    const int KT = n * P.K;
+    if (KT > OMNI_MAX_K) return OMNI_ERR_UNSUPPORTED;
+    OMNI_CUDA(fast_tables());
+    BitGeom g = make_geom(h, w);
+    u32 *bpp[4];
+    FK_TRY(bit_planes(ctx, g, KT, 4, bpp));
+    MorphRuns R{};
+    bool sparse = false;
+    FK_TRY(edge_pass_begin(ctx, g, KT, bpp[2], bpp[3], d_edges, e_plane, epitch, st, &R, &sparse, true));
+    OMNI_CUDA(cudaMemsetAsync(bpp[0], 0, g.plane * (size_t)KT * sizeof(u32), st));
+    FK_TRY(launch_assign_lab(ctx, d_bgr, h, w, pitch, P, nullptr, 0, bpp[0], g.ws, g.plane, st, true, n, frame_stride));
+    int kind = morph03_kind(prm);
+    OMNI_LAUNCH(ctx, st, "morph_bits", launch_morph(true, kind, bpp[0], bpp[1], g, KT, d_masks, m_plane, mpitch, st, 0, -1, sparse ? &R : nullptr));
+    return edges_from_bits(ctx, bpp[1], bpp[2], bpp[3], g, KT, low, high, d_edges, e_plane, epitch, st, sparse, sparse);
+}
 
 // ------------------------------------------------------------------------------------------------
 // Host-buffer fused call, pipelined over row bands (omni_host_color_edge when the fast path applies).

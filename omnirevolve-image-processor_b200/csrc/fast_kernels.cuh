@@ -68,3 +68,8 @@ int fast_thin(omni_ctx *ctx, const u8 *d_in, int K, int h, int w, size_t in_plan
 // stage 02 swatch mode (02_color_extract.py:82-109); h_colors: K x 3 ints as written in config.json, each in [0,255]
 int fast_swatch_masks(omni_ctx *ctx, const u8 *d_bgr, int h, int w, size_t pitch, const int32_t *h_colors, int K, int tol,
                       u8 *d_masks, size_t plane_stride, size_t mpitch, int32_t *h_choice, cudaStream_t st);
+
+// n frames sharing one centre set; their n * K layers are processed as n * K planes (n * K <= OMNI_MAX_K)
+int fast_color_edge_batch(omni_ctx *ctx, const u8 *d_bgr, int n, size_t frame_stride, int h, int w, size_t pitch, const AssignParams &P,
+                          const omni_edge_params *prm, int low, int high, u8 *d_masks, size_t m_plane, size_t mpitch,
+                          u8 *d_edges, size_t e_plane, size_t epitch, cudaStream_t st);

@@ -60,3 +60,20 @@ class FrameBatcher:
         r = self.eng.host_color_edge(frame, self.centers, self.lut, self.ec, want_labels=False,
                                      masks=self.masks, edges=self.edges, want_counts=True)
         return r["counts"]
+
+
+def frame_groups(n_frames: int, K: int, max_planes: int = 32) -> list:
+    """Split a rank's frames into groups whose n * K layers fit the plane dimension of one omni_color_edge_batch pass."""
+    per = max(1, max_planes // max(1, K))
+    return [range(lo, min(n_frames, lo + per)) for lo in range(0, n_frames, per)]
+
+
+class DeviceFrameBatcher:
+    """Device-resident frames of one rank through omni_color_edge_batch, a group of frames per call (their n * K layers are
+    the plane dimension of one morphology / edge / hysteresis launch).  Returns (masks, edges) tensors [n,K,H,W]."""
+
+    def __init__(self, engine, centers, lut, edge_cfg):
+        self.eng, self.centers, self.lut, self.ec = engine, np.asarray(centers, np.float32), lut, edge_cfg
+
+    def __call__(self, frames, masks=None, edges=None):
+        return self.eng.color_edge_batch(frames, self.centers, self.lut, self.ec, masks=masks, edges=edges)

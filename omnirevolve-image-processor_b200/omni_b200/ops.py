@@ -205,6 +205,29 @@ class Engine:
                                               out.ctypes.data_as(C.POINTER(C.c_int64)), self._stream()))
         return out
 
+    def color_edge_batch(self, frames: torch.Tensor, centers, lut, ec: EdgeConfig,
+                         masks: torch.Tensor | None = None, edges: torch.Tensor | None = None):
+        """n frames [n,H,W,3] sharing one centre set -> (masks[n,K,H,W], edges[n,K,H,W]); identical to n color_edge calls."""
+        if frames.dim() != 4 or frames.shape[3] != 3 or frames.dtype != torch.uint8 or not frames.is_cuda or frames.stride(3) != 1 \
+                or frames.stride(2) != 3:
+            raise ValueError("frames must be a CUDA uint8 tensor [n,H,W,3] with packed pixels")
+        ctr = np.ascontiguousarray(centers, dtype=np.float32).reshape(-1, 3)
+        K = ctr.shape[0]
+        lut_a = None if lut is None else np.ascontiguousarray(lut, dtype=np.uint8)
+        n, h, w = frames.shape[:3]
+        if masks is None:
+            masks = torch.empty((n, K, h, w), dtype=torch.uint8, device=frames.device)
+        if edges is None:
+            edges = torch.empty((n, K, h, w), dtype=torch.uint8, device=frames.device)
+        for t in (masks, edges):
+            if t.shape != (n, K, h, w) or t.dtype != torch.uint8 or not t.is_cuda or t.stride(3) != 1 or t.stride(0) != K * t.stride(1):
+                raise ValueError("masks/edges must be CUDA uint8 [n,K,H,W] with frame stride = K * plane stride")
+        p = ec.to_c()
+        capi.check(self._L.omni_color_edge_batch(
+            self._h, frames.data_ptr(), n, frames.stride(0), h, w, frames.stride(1), _f32p(ctr), K, _u8p(lut_a), C.byref(p),
+            masks.data_ptr(), masks.stride(1), masks.stride(2), edges.data_ptr(), edges.stride(1), edges.stride(2), self._stream()))
+        return masks, edges
+
     def edges_composite(self, edges: torch.Tensor, colors_bgr) -> torch.Tensor:
         """03_edge_detect.py:93-106 paint on a white canvas.  HxWx3 u8."""
         _check_planes(edges)

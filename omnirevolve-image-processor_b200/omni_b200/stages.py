@@ -166,9 +166,11 @@ def color_extract_main(cfg) -> dict:
     names_sorted = sorted(names, key=_darkness_rank)
     mapping = list(zip(names_sorted, range(len(names_sorted))))
     palette = {}
-    for name, k in mapping:
+    for name, _k in mapping:
         os.makedirs(os.path.join(cfg.output_dir, name), exist_ok=True)
-        cv2.imwrite(os.path.join(cfg.output_dir, name, "mask.png"), r["masks"][k])
+    with _io_pool(cfg, len(mapping)) as pool:                      # K PNG encodes in parallel (cv2 releases the GIL)
+        list(pool.map(lambda nk: cv2.imwrite(os.path.join(cfg.output_dir, nk[0], "mask.png"), r["masks"][nk[1]]), mapping))
+    for name, k in mapping:
         lab = centers_sorted[k]
         palette[name] = {
             "mode": "kmeans", "cluster_index": int(k), "cluster_lab": [int(lab[0]), int(lab[1]), int(lab[2])],
@@ -214,20 +216,33 @@ def process_color(color_name: str, cfg):
     return color_name, out_path
 
 
+def _io_pool(cfg, n_items: int):
+    from concurrent.futures import ThreadPoolExecutor
+    try:
+        workers = int(getattr(cfg, "n_cores", 0) or 0)
+    except (TypeError, ValueError):
+        workers = 0
+    return ThreadPoolExecutor(max_workers=max(1, min(n_items, workers if workers > 0 else (os.cpu_count() or 1))))
+
+
 def detect_all_edges(cfg) -> list:
     """03_edge_detect.py:42-48.  The reference fans layers out over a process pool; here all layers of
     equal size go through ONE batched GPU call (layers are the plane dimension of omni_edges)."""
     names = list(cfg.color_names)
-    masks = [_read_mask(n, cfg) for n in names]
+    # PNG decode / encode is what is left of this stage's wall time: spread it over threads the way the reference spreads
+    # layers over cfg.n_cores processes (cv2 releases the GIL); errors surface in layer order like in a serial loop
+    with _io_pool(cfg, len(names)) as pool:
+        masks = list(pool.map(lambda n: _read_mask(n, cfg), names))
     results = []
     shapes = {m.shape for m in masks}
     if len(shapes) == 1 and masks:
         edges = get_engine().host_edges(np.stack(masks), EdgeConfig.from_cfg(cfg))
     else:                                   # hand-edited masks of different sizes: one call per layer
         edges = [get_engine().host_edges(m[None], EdgeConfig.from_cfg(cfg))[0] for m in masks]
-    for n, e in zip(names, edges):
-        out_path = os.path.join(cfg.output_dir, n, "edges.png")
-        cv2.imwrite(out_path, e)
+    paths = [os.path.join(cfg.output_dir, n, "edges.png") for n in names]
+    with _io_pool(cfg, len(names)) as pool:
+        list(pool.map(lambda pe: cv2.imwrite(pe[0], pe[1]), zip(paths, edges)))
+    for n, e, out_path in zip(names, edges, paths):
         print(f"Edges extracted: {n} | nz={int(np.count_nonzero(e))}")
         results.append((n, out_path))
     return results

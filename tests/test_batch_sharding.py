@@ -22,6 +22,13 @@ def test_shard_range_partitions(n, world):
     assert seen == list(range(n))                 # contiguous, ordered, no overlap, complete
 
 
+def test_frame_groups():
+    assert [list(g) for g in batch.frame_groups(10, 8)] == [[0, 1, 2, 3], [4, 5, 6, 7], [8, 9]]
+    assert [list(g) for g in batch.frame_groups(3, 16)] == [[0, 1], [2]]
+    assert [list(g) for g in batch.frame_groups(2, 32)] == [[0], [1]]
+    assert batch.frame_groups(0, 8) == []
+
+
 def test_gather_single_process():
     local = batch.run_shard([np.full((2, 2), i) for i in range(3)], range(3), lambda f: np.full((4, 3), int(f[0, 0])))
     out = batch.gather_counts(local, 3, 4)

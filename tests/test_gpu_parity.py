@@ -535,3 +535,27 @@ def test_swatch_stage_function(eng, tmp_path):
     cfg.colors = cfg.colors[:2]
     with pytest.raises(RuntimeError):
         stages.color_extract_main(cfg)
+
+
+
+# ---- frame batches (BASELINE config 4) ------------------------------------------------------------------------------
+@pytest.mark.parametrize("n,K,hw", [(1, 4, (90, 130)), (4, 8, (135, 240)), (5, 8, (64, 100)), (3, 16, (70, 97)), (2, 32, (40, 64))])
+def test_color_edge_batch_equals_per_frame(eng_mode, n, K, hw):
+    """omni_color_edge_batch == n calls of omni_color_edge (incl. n*K > 32: several passes), and one frame vs the oracle."""
+    import omni_b200
+    rp = _rp()
+    frames = np.stack([synth(hw[0], hw[1], 50 + f, cell=16) for f in range(n)])
+    ctr = rp.kmeans_lab_centers(frames[0], K)
+    _o, lut = rp.darkness_order(ctr)
+    lut = lut.astype(np.uint8)
+    ec = omni_b200.EdgeConfig()
+    d = dev(frames)
+    masks = torch.full((n, K) + hw, 9, dtype=torch.uint8, device="cuda")
+    edges = torch.full((n, K) + hw, 9, dtype=torch.uint8, device="cuda")
+    eng_mode.color_edge_batch(d, ctr, lut, ec, masks=masks, edges=edges)
+    for f in range(n):
+        _l, m, e = eng_mode.color_edge(d[f], ctr, lut, ec)
+        assert torch.equal(masks[f], m) and torch.equal(edges[f], e), f
+    _cs, _ls, want = rp.color_extract(frames[-1], K, ctr)
+    assert np.array_equal(host(masks[-1]), want)
+    assert np.array_equal(host(edges[-1]), rp.edges_all(want))
