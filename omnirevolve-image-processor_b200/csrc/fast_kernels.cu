@@ -410,6 +410,12 @@ __global__ void __launch_bounds__(256) fk_build_rgbcells(const __grid_constant__
     mb[gi] = (u8)multi;
 }
 
+// Zero fill riding on the assignment kernel: the edge pass needs its output planes cleared (dead tiles are never
+// written, see edges3.cu); the assignment kernel is bound by instruction issue and leaves HBM idle, so every warp clears a
+// slice of those planes with a few 16-byte stores per chunk of pixels instead of a separate memset competing with it.
+struct ZeroJob { uint4 *p[2]; unsigned long long n16[2]; unsigned per[2]; };   // two regions, sizes in 16-byte units (0: nothing
+                                                                                 // to do); per = units per chunk of pixels (launcher)
+
 #define RA_THREADS 1024
 #define RA_WARPS (RA_THREADS / 32)
 // dynamic shared memory: [label nibbles | flags | cbrt | gamma | centres | lut | per warp: pixels 768, queue 256, labels 256]
@@ -428,7 +434,8 @@ __global__ void __launch_bounds__(RA_THREADS, 1) fk_assign_rgbcell(const u8 *__r
                                                                    u8 *__restrict__ labels, size_t lpitch,
                                                                    u32 *__restrict__ bits, int ws, size_t plane,
                                                                    int nf, size_t frame_stride /* a batch: nf frames of h rows; frame f
-                                                                   writes the K planes starting at plane f * K (labels: rows f * h ..) */)
+                                                                   writes the K planes starting at plane f * K (labels: rows f * h ..) */,
+                                                                   const __grid_constant__ ZeroJob Z)
 {
     extern __shared__ __align__(16) u8 smem[];
     const u32 *s_nib = reinterpret_cast<const u32 *>(smem);
@@ -458,7 +465,7 @@ __global__ void __launch_bounds__(RA_THREADS, 1) fk_assign_rgbcell(const u8 *__r
     auto prefetch = [&](int u) {
         if (u < total) {
             const int yy = u / chunks, c = u - yy * chunks;
-            const int f = yy / h, y = yy - f * h;
+            const int f = nf > 1 ? yy / h : 0, y = yy - f * h;     // one frame: no division
             if (vec_ok && c * 256 + 256 <= w) {
                 const uint4 *src = reinterpret_cast<const uint4 *>(px + (size_t)f * frame_stride + (size_t)y * pitch + (size_t)c * 768);
                 pf0 = __ldg(src + lane);
@@ -470,7 +477,7 @@ __global__ void __launch_bounds__(RA_THREADS, 1) fk_assign_rgbcell(const u8 *__r
     prefetch(u);
     for (; u < total; u += stride) {
         const int yy = u / chunks, c = u - yy * chunks;
-        const int f = yy / h, y = yy - f * h;
+        const int f = nf > 1 ? yy / h : 0, y = yy - f * h;     // one frame: no division
         const int x0 = c * 256 + lane;
         const bool full = vec_ok && c * 256 + 256 <= w;
         __syncwarp();                                          // the previous chunk has been consumed
@@ -483,6 +490,13 @@ __global__ void __launch_bounds__(RA_THREADS, 1) fk_assign_rgbcell(const u8 *__r
             for (int i = lane; i < nb; i += 32) spx[i] = row[i];
         }
         prefetch(u + stride);
+#pragma unroll
+        for (int z = 0; z < 2; z++) {                          // this chunk's slice of the zero-fill regions
+            if (Z.n16[z]) {
+                const unsigned long long lo = (unsigned long long)Z.per[z] * (unsigned)u, hi = min(Z.n16[z], lo + Z.per[z]);
+                for (unsigned long long i = lo + lane; i < hi; i += 32) Z.p[z][i] = make_uint4(0u, 0u, 0u, 0u);
+            }
+        }
         __syncwarp();
         // ---- phase 1: table lookup in shared memory; pixels of cells with several candidates are queued ----
         int lab[8];
@@ -1268,9 +1282,16 @@ static int assign_cells(omni_ctx *ctx, const AssignParams &P, u32 **cells, u8 **
     return OMNI_OK;
 }
 
+// will launch_assign_lab use the kernel that can carry a ZeroJob?
+static bool assign_takes_zero_job(omni_ctx *ctx, const AssignParams &P, int nf, int h, int w)
+{
+    return ctx->assign_rgbcell && P.K <= RC_MAX_K && (long long)nf * h * ((w + 255) >> 8) < (1ll << 30);
+}
+
 // Lab-centre assignment of rows [0, h) at px: labels and/or one-hot bit-plane words (either may be NULL)
 static int launch_assign_lab(omni_ctx *ctx, const u8 *px, int h, int w, size_t pitch, const AssignParams &P, u8 *labels, size_t lpitch,
-                             u32 *bits, int ws, size_t plane, cudaStream_t st, bool scoped = true, int nf = 1, size_t frame_stride = 0)
+                             u32 *bits, int ws, size_t plane, cudaStream_t st, bool scoped = true, int nf = 1, size_t frame_stride = 0,
+                             const ZeroJob *zero = nullptr /* only honoured by the RGB-cell kernel: check assign_takes_zero_job() */)
 {
     // the RGB-cell kernel counts chunks in 32 bits and takes a whole batch; the Lab-cell kernel takes one frame per launch
     const bool use_rgb = ctx->assign_rgbcell && P.K <= RC_MAX_K && (long long)nf * h * ((w + 255) >> 8) < (1ll << 30);
@@ -1292,8 +1313,11 @@ static int launch_assign_lab(omni_ctx *ctx, const u8 *px, int h, int w, size_t p
         // one CTA per SM (its tables fill most of the shared memory); no more CTAs than chunks of 32 warps
         const long long chunks = (long long)nf * h * ((w + 255) >> 8);
         const int grid = (int)std::max<long long>(1, std::min<long long>(persist_blocks(ctx, 1), (chunks + RA_WARPS - 1) / RA_WARPS));
+        ZeroJob Z{};
+        if (zero) Z = *zero;
+        for (int z = 0; z < 2; z++) Z.per[z] = (unsigned)((Z.n16[z] + (unsigned long long)chunks - 1) / (unsigned long long)chunks);
         fk_assign_rgbcell<<<grid, RA_THREADS, RA_SMEM, st>>>(px, h, w, pitch, P, (const uint4 *)rcells, cells, labels, lpitch, bits, ws, plane,
-                                                             nf, frame_stride);
+                                                             nf, frame_stride, Z);
     } else {
         const int grid = resident_grid(ctx, fk_assign_bits<1>, 256, &ctx->occ_assign_lab);
         fk_assign_bits<1><<<grid, 256, 0, st>>>(px, h, w, pitch, P, cells, labels, lpitch, bits, ws, plane);
@@ -1412,7 +1436,7 @@ static int run_hysteresis(omni_ctx *ctx, u32 *ebits, const u32 *cbits, const Bit
 // counts per length, [20] next warp item -- and, when the sparse edge kernel will run, fills the MorphRuns block that lets
 // the morphology kernel produce the run lists (returns false: dense edge kernel, nothing to prepare).
 static int edge_pass_begin(omni_ctx *ctx, const BitGeom &g, int K, u32 *sbits, u32 *cbits, u8 *d_edges, size_t e_plane, size_t epitch,
-                           cudaStream_t st, MorphRuns *R, bool *sparse, bool side_fill)
+                           cudaStream_t st, MorphRuns *R, bool *sparse, bool side_fill, ZeroJob *zjob = nullptr)
 {
     FK_TRY(omni_ws_reserve(ctx, 5, WS5_BYTES));
     OMNI_CUDA(cudaMemsetAsync(ctx->d_flags, 0, 24 * sizeof(int), st));
@@ -1426,6 +1450,13 @@ static int edge_pass_begin(omni_ctx *ctx, const BitGeom &g, int K, u32 *sbits, u
     R->run_counts = ctx->d_flags + 16; R->run_items = (u32 *)ctx->ws[6];
     R->maxt = edges3_pick_maxt(g.h, g.w, K, 2 * persist_blocks(ctx, ctx->e3s_per_sm));
     R->zero_fill = side_fill ? 0 : 1;
+    if (side_fill && zjob && epitch == (size_t)g.w && e_plane == epitch * (size_t)g.h && (uintptr_t)d_edges % 16 == 0 &&
+        (e_plane * (size_t)K) % 16 == 0 && cbits == sbits + ((g.plane * (size_t)K * sizeof(u32) + 255) & ~(size_t)255) / sizeof(u32)) {
+        // contiguous planes: the assignment kernel clears them on the way (ZeroJob)
+        zjob->p[0] = (uint4 *)d_edges; zjob->n16[0] = e_plane * (size_t)K / 16;
+        zjob->p[1] = (uint4 *)sbits;   zjob->n16[1] = (size_t)((u8 *)cbits - (u8 *)sbits + g.plane * (size_t)K * sizeof(u32)) / 16;
+        return OMNI_OK;
+    }
     if (side_fill) {
         // The zeros of the dead tiles (most of the 2K bytes per pixel the edge pass writes) do not depend on anything: clear
         // the edge byte planes and the candidate / strong bit-planes on a side stream while the colour assignment and the
@@ -1518,9 +1549,11 @@ int fast_color_edge(omni_ctx *ctx, const u8 *d_bgr, int h, int w, size_t pitch, 
     // first of all: fork the side stream that clears the edge planes, so that it runs under the assignment kernel
     MorphRuns R{};
     bool sparse = false;
-    FK_TRY(edge_pass_begin(ctx, g, P.K, bpp[2], bpp[3], d_edges, e_plane, epitch, st, &R, &sparse, true));
+    ZeroJob Z{};
+    const bool zj = assign_takes_zero_job(ctx, P, 1, h, w);
+    FK_TRY(edge_pass_begin(ctx, g, P.K, bpp[2], bpp[3], d_edges, e_plane, epitch, st, &R, &sparse, true, zj ? &Z : nullptr));
     OMNI_CUDA(cudaMemsetAsync(bpp[0], 0, g.plane * (size_t)P.K * sizeof(u32), st));      // match_any stores only non-empty words
-    FK_TRY(launch_assign_lab(ctx, d_bgr, h, w, pitch, P, d_labels, lpitch, bpp[0], g.ws, g.plane, st));
+    FK_TRY(launch_assign_lab(ctx, d_bgr, h, w, pitch, P, d_labels, lpitch, bpp[0], g.ws, g.plane, st, true, 1, 0, &Z));
     int kind = morph03_kind(prm);
     OMNI_LAUNCH(ctx, st, "morph_bits", launch_morph(true, kind, bpp[0], bpp[1], g, P.K, d_masks, m_plane, mpitch, st, 0, -1, sparse ? &R : nullptr));
     return edges_from_bits(ctx, bpp[1], bpp[2], bpp[3], g, P.K, low, high, d_edges, e_plane, epitch, st, sparse, sparse);
@@ -1544,9 +1577,11 @@ int fast_color_edge_batch(omni_ctx *ctx, const u8 *d_bgr, int n, size_t frame_st
     FK_TRY(bit_planes(ctx, g, KT, 4, bpp));
     MorphRuns R{};
     bool sparse = false;
-    FK_TRY(edge_pass_begin(ctx, g, KT, bpp[2], bpp[3], d_edges, e_plane, epitch, st, &R, &sparse, true));
+    ZeroJob Z{};
+    const bool zj = assign_takes_zero_job(ctx, P, n, h, w);
+    FK_TRY(edge_pass_begin(ctx, g, KT, bpp[2], bpp[3], d_edges, e_plane, epitch, st, &R, &sparse, true, zj ? &Z : nullptr));
     OMNI_CUDA(cudaMemsetAsync(bpp[0], 0, g.plane * (size_t)KT * sizeof(u32), st));
-    FK_TRY(launch_assign_lab(ctx, d_bgr, h, w, pitch, P, nullptr, 0, bpp[0], g.ws, g.plane, st, true, n, frame_stride));
+    FK_TRY(launch_assign_lab(ctx, d_bgr, h, w, pitch, P, nullptr, 0, bpp[0], g.ws, g.plane, st, true, n, frame_stride, &Z));
     int kind = morph03_kind(prm);
     OMNI_LAUNCH(ctx, st, "morph_bits", launch_morph(true, kind, bpp[0], bpp[1], g, KT, d_masks, m_plane, mpitch, st, 0, -1, sparse ? &R : nullptr));
     return edges_from_bits(ctx, bpp[1], bpp[2], bpp[3], g, KT, low, high, d_edges, e_plane, epitch, st, sparse, sparse);

@@ -10,10 +10,24 @@ import ctypes as C
 import threading
 from dataclasses import dataclass
 
+import sys
+
 import numpy as np
-import torch
 
 from . import capi
+
+
+class _LazyTorch:
+    """`torch` is imported on first use: the host-buffer operators (what the drop-in stage scripts call) need only
+    ctypes + NumPy, and a stage process should not pay the ~2 s torch import the reference's 0.5 s stages never had."""
+
+    def __getattr__(self, name):
+        import torch as _t
+        globals()["torch"] = _t
+        return getattr(_t, name)
+
+
+torch = _LazyTorch()
 
 
 @dataclass
@@ -72,9 +86,11 @@ class Engine:
 
     def __init__(self, device: int | None = None):
         L = capi.lib()
-        if not torch.cuda.is_available():
+        if L.omni_device_count() <= 0:
             raise capi.OmniError(-2, "no CUDA device visible; libomni_b200 has no CPU fallback")
-        self.device = torch.cuda.current_device() if device is None else int(device)
+        if device is None:                  # torch's current device when torch is in use, else device 0
+            device = sys.modules["torch"].cuda.current_device() if "torch" in sys.modules else 0
+        self.device = int(device)
         h = C.c_void_p()
         capi.check(L.omni_ctx_create(self.device, C.byref(h)))
         self._h, self._L = h, L
@@ -363,7 +379,8 @@ _engines = threading.local()
 
 def get_engine(device: int | None = None) -> Engine:
     """Per-thread, per-device Engine cache."""
-    dev = torch.cuda.current_device() if (device is None and torch.cuda.is_available()) else (device or 0)
+    dev = (sys.modules["torch"].cuda.current_device() if (device is None and "torch" in sys.modules
+                                                           and sys.modules["torch"].cuda.is_available()) else (device or 0))
     cache = getattr(_engines, "cache", None)
     if cache is None:
         cache = _engines.cache = {}

@@ -65,3 +65,15 @@ def test_product_never_imports_oracle():
                 txt = open(os.path.join(d, f), errors="replace").read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M), os.path.join(d, f)
                 assert "liboracle" not in txt, os.path.join(d, f)
+
+
+def test_host_path_does_not_import_torch():
+    """The stage scripts' host-buffer operators need ctypes + NumPy only: importing the package (and the stage mirrors)
+    must not pull in torch -- a stage process should not pay an import the reference's stages never had."""
+    import subprocess
+    import sys
+    pkg = os.path.join(ROOT, "omnirevolve-image-processor_b200")
+    code = ("import sys; sys.path.insert(0, %r); import omni_b200; from omni_b200 import stages, contours, batch; "
+            "assert 'torch' not in sys.modules, 'torch imported eagerly'; print('LAZY_OK')" % pkg)
+    r = subprocess.run([sys.executable, "-c", code], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=120)
+    assert r.returncode == 0 and "LAZY_OK" in r.stdout, r.stdout[-1500:]
