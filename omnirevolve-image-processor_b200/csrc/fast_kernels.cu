@@ -491,10 +491,12 @@ __global__ void __launch_bounds__(RA_THREADS, 1) fk_assign_rgbcell(const u8 *__r
         }
         prefetch(u + stride);
 #pragma unroll
-        for (int z = 0; z < 2; z++) {                          // this chunk's slice of the zero-fill regions
+        for (int z = 0; z < 2; z++) {                          // this chunk's slice of the zero-fill regions (per: multiple of 32)
             if (Z.n16[z]) {
-                const unsigned long long lo = (unsigned long long)Z.per[z] * (unsigned)u, hi = min(Z.n16[z], lo + Z.per[z]);
-                for (unsigned long long i = lo + lane; i < hi; i += 32) Z.p[z][i] = make_uint4(0u, 0u, 0u, 0u);
+                unsigned long long idx = (unsigned long long)Z.per[z] * (unsigned)u + lane;
+                uint4 *q = Z.p[z] + idx;
+                for (unsigned it = Z.per[z] >> 5; it > 0; it--, idx += 32, q += 32)
+                    if (idx < Z.n16[z]) *q = make_uint4(0u, 0u, 0u, 0u);
             }
         }
         __syncwarp();
@@ -1315,7 +1317,8 @@ static int launch_assign_lab(omni_ctx *ctx, const u8 *px, int h, int w, size_t p
         const int grid = (int)std::max<long long>(1, std::min<long long>(persist_blocks(ctx, 1), (chunks + RA_WARPS - 1) / RA_WARPS));
         ZeroJob Z{};
         if (zero) Z = *zero;
-        for (int z = 0; z < 2; z++) Z.per[z] = (unsigned)((Z.n16[z] + (unsigned long long)chunks - 1) / (unsigned long long)chunks);
+        for (int z = 0; z < 2; z++)                         // units per chunk, rounded up to one store per lane
+            Z.per[z] = (unsigned)(((Z.n16[z] + (unsigned long long)chunks - 1) / (unsigned long long)chunks + 31) & ~31ull);
         fk_assign_rgbcell<<<grid, RA_THREADS, RA_SMEM, st>>>(px, h, w, pitch, P, (const uint4 *)rcells, cells, labels, lpitch, bits, ws, plane,
                                                              nf, frame_stride, Z);
     } else {
