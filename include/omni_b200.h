@@ -178,6 +178,16 @@ int omni_host_thin_zhangsuen(omni_ctx *ctx, const uint8_t *h_in, int K, int h, i
                              int max_iter, uint8_t *h_out, size_t out_plane_stride, size_t out_pitch,
                              int32_t *h_removed, int32_t *h_iters);
 
+/* 04_find_contours.py:121-125 for all components at once: d_deg = cv2.filter2D(S, CV_8U, ones(3,3) minus the centre,
+ * borderType=BORDER_CONSTANT) with S = (skeleton > 0), i.e. the number of set 8-neighbours of every pixel; d_nodes: 1 on
+ * skeleton pixels with exactly one neighbour (`endpoints`, :124), 2 on skeleton pixels with three or more (`junctions`,
+ * :125), 0 elsewhere.  The reference recomputes both per connected component on the whole image (its O(components x
+ * pixels) term); a pixel's neighbours lie in its own component, so `deg[comp_mask == 1]` of the reference equals this
+ * map there.  Either output may be NULL.  In and out may not alias. */
+int omni_skeleton_degree(omni_ctx *ctx, const uint8_t *d_skel, int K, int h, int w, size_t s_plane_stride, size_t spitch,
+                         uint8_t *d_deg, size_t d_plane_stride, size_t dpitch,
+                         uint8_t *d_nodes, size_t n_plane_stride, size_t npitch, void *stream);
+
 /* Diagnostics of the last omni_edges / omni_color_edge call on this ctx: number of global
  * hysteresis passes that were needed (>= 1). */
 int omni_last_hysteresis_passes(omni_ctx *ctx);

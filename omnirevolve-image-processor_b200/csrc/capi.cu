@@ -703,6 +703,20 @@ extern "C" int omni_host_thin_zhangsuen(omni_ctx *ctx, const uint8_t *h_in, int 
     return OMNI_OK;
 }
 
+extern "C" int omni_skeleton_degree(omni_ctx *ctx, const uint8_t *d_skel, int K, int h, int w, size_t s_plane_stride, size_t spitch,
+                                    uint8_t *d_deg, size_t d_plane_stride, size_t dpitch,
+                                    uint8_t *d_nodes, size_t n_plane_stride, size_t npitch, void *stream)
+{
+    OMNI_TRY(set_device(ctx));
+    OMNI_REQUIRE(d_skel && (d_deg || d_nodes) && K >= 1 && K <= OMNI_MAX_K && h > 0 && w > 0, "omni_skeleton_degree: bad arguments");
+    OMNI_REQUIRE(spitch >= (size_t)w && (!d_deg || dpitch >= (size_t)w) && (!d_nodes || npitch >= (size_t)w),
+                 "omni_skeleton_degree: pitch smaller than a row");
+    OMNI_LAUNCH(ctx, (cudaStream_t)stream, "skeleton_degree",
+                g_skeleton_degree(d_skel, s_plane_stride, spitch, K, h, w, d_deg, d_plane_stride, dpitch, d_nodes, n_plane_stride, npitch,
+                                  (cudaStream_t)stream));
+    return OMNI_OK;
+}
+
 extern "C" int omni_host_color_edge(omni_ctx *ctx, const uint8_t *h_bgr, int h, int w, size_t pitch,
                                     const float *h_centers, int K, const uint8_t *h_lut, const omni_edge_params *prm,
                                     uint8_t *h_labels, size_t lpitch,

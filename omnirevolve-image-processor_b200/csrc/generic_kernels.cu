@@ -460,6 +460,44 @@ cudaError_t g_composite(const u8 *edges, size_t plane, size_t pitch, int K, int 
     return cudaGetLastError();
 }
 
+// 04_find_contours.py:121-130: deg = cv2.filter2D(S, CV_8U, ones(3,3) - centre, BORDER_CONSTANT) with S = (skeleton > 0):
+// the number of set 8-neighbours of EVERY pixel (outside the image counts 0); nodes: 1 where an S pixel has deg == 1
+// (endpoint, :124), 2 where it has deg >= 3 (junction, :125), else 0.  The reference evaluates this per connected component on the
+// component's mask; a pixel's neighbours belong to its own component, so on component pixels the global map is the same.
+__global__ void k_skeleton_degree(const u8 *__restrict__ skel, size_t s_plane, size_t spitch, int h, int w, u8 *__restrict__ deg,
+                                  size_t d_plane, size_t dpitch, u8 *__restrict__ nodes, size_t n_plane, size_t npitch)
+{
+    int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y, k = blockIdx.z;
+    if (x >= w || y >= h) return;
+    const u8 *S = skel + (size_t)k * s_plane;
+    int n = 0;
+#pragma unroll
+    for (int dy = -1; dy <= 1; dy++) {
+        const int yy = y + dy;
+        if (yy < 0 || yy >= h) continue;
+        const u8 *row = S + (size_t)yy * spitch;
+#pragma unroll
+        for (int dx = -1; dx <= 1; dx++) {
+            const int xx = x + dx;
+            if ((dx | dy) == 0 || xx < 0 || xx >= w) continue;
+            n += __ldg(row + xx) != 0;
+        }
+    }
+    if (deg) deg[(size_t)k * d_plane + (size_t)y * dpitch + x] = (u8)n;
+    if (nodes) {
+        const bool on = S[(size_t)y * spitch + x] != 0;
+        nodes[(size_t)k * n_plane + (size_t)y * npitch + x] = (u8)(on ? (n == 1 ? 1 : (n >= 3 ? 2 : 0)) : 0);
+    }
+}
+
+cudaError_t g_skeleton_degree(const u8 *skel, size_t s_plane, size_t spitch, int K, int h, int w, u8 *deg, size_t d_plane, size_t dpitch,
+                              u8 *nodes, size_t n_plane, size_t npitch, cudaStream_t st)
+{
+    dim3 b(64, 4), g((w + 63) / 64, (h + 3) / 4, K);
+    k_skeleton_degree<<<g, b, 0, st>>>(skel, s_plane, spitch, h, w, deg, d_plane, dpitch, nodes, n_plane, npitch);
+    return cudaGetLastError();
+}
+
 cudaError_t g_copy2d_planes(const u8 *src, size_t s_plane, size_t spitch, u8 *dst, size_t d_plane, size_t dpitch,
                             int K, int h, int w, cudaStream_t st)
 {

@@ -131,6 +131,8 @@ cudaError_t g_count_labels(const u8 *labels, size_t pitch, int h, int w, int K, 
                            cudaStream_t st);
 cudaError_t g_composite(const u8 *edges, size_t plane, size_t pitch, int K, int h, int w, const u8 *colors_bgr,
                         u8 *canvas, size_t cpitch, cudaStream_t st);
+cudaError_t g_skeleton_degree(const u8 *skel, size_t s_plane, size_t spitch, int K, int h, int w, u8 *deg, size_t d_plane, size_t dpitch,
+                              u8 *nodes, size_t n_plane, size_t npitch, cudaStream_t st);
 cudaError_t g_copy2d_planes(const u8 *src, size_t s_plane, size_t spitch, u8 *dst, size_t d_plane, size_t dpitch,
                             int K, int h, int w, cudaStream_t st);
 

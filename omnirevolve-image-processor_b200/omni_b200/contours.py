@@ -50,3 +50,15 @@ def thinning_zhangsuen(bin_0_255: np.ndarray, layer: str) -> np.ndarray:
         print(f"[{layer}] Thin {it:02d}: removed={r:6d} | total={total_removed:7d} ({pct:5.1f}%) | {dt / max(1, n_it):.2f}s", flush=True)
     print(f"[{layer}] Thinning done in {dt:.2f}s, fg_now={total0 - total_removed} px", flush=True)
     return out[0].astype(bin_0_255.dtype, copy=False)
+
+
+def skeleton_degree(skel_0_255: np.ndarray):
+    """04_find_contours.py:117-125 for ALL components at once: (deg, endpoints, junctions) of the skeleton -- what
+    trace_centerlines recomputes per component with a full-image filter2D.  On the pixels of a component the maps equal the
+    reference's per-component ones (a pixel's 8-neighbours belong to its own component), so inside the component loop
+    `deg`, `endpoints`, `junctions` can be replaced by `deg_all`, `ep_all & (comp_mask == 1)`, `jn_all & (comp_mask == 1)`."""
+    import torch
+    sk = torch.from_numpy(np.ascontiguousarray(skel_0_255, dtype=np.uint8)[None]).cuda()
+    deg, nodes = get_engine().skeleton_degree(sk)
+    nodes = nodes[0].cpu().numpy()
+    return deg[0].cpu().numpy(), nodes == 1, nodes == 2

@@ -275,6 +275,18 @@ class Engine:
             removed.ctypes.data_as(i32p) if with_log else None, iters.ctypes.data_as(i32p) if with_log else None, self._stream()))
         return (out, removed[:, :max_iter], iters) if with_log else out
 
+    def skeleton_degree(self, skel: torch.Tensor):
+        """04_find_contours.py:121-125 on K skeleton planes: (deg[K,H,W] = set 8-neighbours per pixel, nodes[K,H,W] with
+        1 = endpoint, 2 = junction)."""
+        _check_planes(skel)
+        K, h, w = skel.shape
+        deg = torch.empty((K, h, w), dtype=torch.uint8, device=skel.device)
+        nodes = torch.empty((K, h, w), dtype=torch.uint8, device=skel.device)
+        capi.check(self._L.omni_skeleton_degree(self._h, skel.data_ptr(), K, h, w, skel.stride(0), skel.stride(1),
+                                                deg.data_ptr(), deg.stride(0), deg.stride(1),
+                                                nodes.data_ptr(), nodes.stride(0), nodes.stride(1), self._stream()))
+        return deg, nodes
+
     def host_thin_zhangsuen(self, planes: np.ndarray, max_iter: int = 120):
         """Host-buffer form: NumPy [K,H,W] u8 in, (skeletons, removed[K,max_iter], iters[K]) out."""
         planes = np.ascontiguousarray(planes, dtype=np.uint8)

@@ -207,3 +207,32 @@ def thinning_zhangsuen(bin_0_255: np.ndarray, max_iter: int = 120) -> np.ndarray
                 roi[dele] = 0
                 changed = True
     return (roi * 255).astype(np.uint8)
+
+
+def skeleton_degree(skel_0_255: np.ndarray):
+    """04_find_contours.py:117-125 for the whole skeleton at once: (deg, endpoints, junctions) with the reference's own
+    calls (filter2D with the 3x3 ring kernel, BORDER_CONSTANT)."""
+    S = (skel_0_255 > 0).astype(np.uint8)
+    kernel = np.ones((3, 3), np.uint8)
+    kernel[1, 1] = 0
+    deg = cv2.filter2D(S, cv2.CV_8U, kernel, borderType=cv2.BORDER_CONSTANT)
+    return deg, (S == 1) & (deg == 1), (S == 1) & (deg >= 3)
+
+
+def skeleton_degree_per_component(skel_0_255: np.ndarray):
+    """The reference's actual loop (04:113-125): per connected component, deg / endpoints / junctions on the component mask;
+    returns the union over components (what the global map must reproduce on skeleton pixels)."""
+    S = (skel_0_255 > 0).astype(np.uint8)
+    num, labels = cv2.connectedComponents(S, connectivity=8)
+    kernel = np.ones((3, 3), np.uint8)
+    kernel[1, 1] = 0
+    deg_on = np.zeros(S.shape, np.uint8)
+    endpoints = np.zeros(S.shape, bool)
+    junctions = np.zeros(S.shape, bool)
+    for comp_id in range(1, num):
+        comp_mask = (labels == comp_id).astype(np.uint8)
+        deg = cv2.filter2D(comp_mask, cv2.CV_8U, kernel, borderType=cv2.BORDER_CONSTANT)
+        deg_on[comp_mask == 1] = deg[comp_mask == 1]
+        endpoints |= (comp_mask == 1) & (deg == 1)
+        junctions |= (comp_mask == 1) & (deg >= 3)
+    return deg_on, endpoints, junctions

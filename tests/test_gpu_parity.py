@@ -559,3 +559,19 @@ def test_color_edge_batch_equals_per_frame(eng_mode, n, K, hw):
     _cs, _ls, want = rp.color_extract(frames[-1], K, ctr)
     assert np.array_equal(host(masks[-1]), want)
     assert np.array_equal(host(edges[-1]), rp.edges_all(want))
+
+
+@pytest.mark.parametrize("hw", [(1, 1), (3, 40), (64, 64), (211, 333)])
+def test_skeleton_degree(eng, hw):
+    """04_find_contours.py:121-125 (degree / endpoint / junction maps) vs the reference's filter2D call on the whole skeleton."""
+    rp, cm = _rp(), _cm()
+    h, w = hw
+    rng = np.random.default_rng(h + w)
+    planes = np.stack([cm.thin_zhangsuen(blob_mask(h, w, 5, 0.5, k=5)) if min(h, w) > 12 else (rng.random((h, w)) < 0.5).astype(np.uint8) * 255,
+                       (rng.random((h, w)) < 0.3).astype(np.uint8) * 7, np.full((h, w), 255, np.uint8)])
+    deg, nodes = eng.skeleton_degree(dev(planes))
+    deg, nodes = host(deg), host(nodes)
+    for k in range(planes.shape[0]):
+        wd, ep, jn = rp.skeleton_degree(planes[k])
+        assert np.array_equal(deg[k], wd), k
+        assert np.array_equal(nodes[k] == 1, ep) and np.array_equal(nodes[k] == 2, jn), k

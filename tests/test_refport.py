@@ -70,3 +70,16 @@ def test_edge_layer_and_resize(tmp_path):
             e = cv2.imread(str(tmp_path / n / "edges.png"), cv2.IMREAD_GRAYSCALE)
             assert np.array_equal(e, rp.edge_layer(m, lo, hi, ks))
         assert ed._ensure_odd(ks) == rp.ensure_odd(ks)
+
+
+def test_skeleton_degree_global_equals_per_component():
+    """The one-shot degree map equals the reference's per-component maps on skeleton pixels (04:113-125)."""
+    from helpers import blob_mask
+    from oracle import cmodel as cm
+    for seed in (1, 2):
+        sk = cm.thin_zhangsuen(blob_mask(90, 140, seed, 0.45, k=5))
+        deg, ep, jn = rp.skeleton_degree(sk)
+        deg_c, ep_c, jn_c = rp.skeleton_degree_per_component(sk)
+        on = sk > 0
+        assert np.array_equal(deg[on], deg_c[on]) and np.array_equal(ep, ep_c) and np.array_equal(jn, jn_c)
+        assert ep.any() or jn.any()
