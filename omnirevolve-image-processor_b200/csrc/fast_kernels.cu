@@ -1633,11 +1633,22 @@ int fast_host_color_edge(omni_ctx *ctx, const u8 *h_bgr, int h, int w, size_t pi
     FK_TRY(bit_planes(ctx, g, K, 4, bpp));
     cudaStream_t sc = ctx->stream, si = ctx->s_in, so = ctx->s_out;
     cudaEvent_t *evH = ctx->pipe_ev, *evM = ctx->pipe_ev + HP_MAX_BANDS, *evX = ctx->pipe_ev + 2 * HP_MAX_BANDS;
-    // bands: multiples of the morphology strip height, at least 256 rows each
-    int nb = HP_MAX_BANDS;
-    while (nb > 1 && (h + nb - 1) / nb < 256) nb--;
-    int rows_per = ((h + nb - 1) / nb + MORPH_TR_BIG - 1) / MORPH_TR_BIG * MORPH_TR_BIG;
-    nb = (h + rows_per - 1) / rows_per;
+    // bands: multiples of the morphology strip height.  Tall images start with short bands (128, 128, 256, 512 rows) so that the
+    // first masks leave for the host while most of the image is still arriving; the rest is split evenly.
+    int ys[HP_MAX_BANDS + 1];
+    int nb = 0;
+    ys[0] = 0;
+    if (h >= 2048) {
+        const int lead[4] = {128, 128, 256, 512};
+        for (int i = 0; i < 4; i++) { ys[nb + 1] = ys[nb] + lead[i]; nb++; }
+    }
+    {
+        const int left = h - ys[nb], slots = HP_MAX_BANDS - nb;
+        int n_even = slots;
+        while (n_even > 1 && (left + n_even - 1) / n_even < 256) n_even--;
+        const int per = ((left + n_even - 1) / n_even + MORPH_TR_BIG - 1) / MORPH_TR_BIG * MORPH_TR_BIG;
+        while (ys[nb] < h) { ys[nb + 1] = min(h, ys[nb] + per); nb++; }
+    }
     const int kind = morph03_kind(prm);
     // everything queued on the side streams must wait for what the caller queued before on the ctx stream -- nothing:
     // omni_host_* calls own ctx->stream; a start event orders the side streams after earlier work of this ctx
@@ -1645,7 +1656,7 @@ int fast_host_color_edge(omni_ctx *ctx, const u8 *h_bgr, int h, int w, size_t pi
     OMNI_CUDA(cudaStreamWaitEvent(si, evX[0], 0));
     OMNI_CUDA(cudaStreamWaitEvent(so, evX[0], 0));
     for (int b = 0; b < nb; b++) {
-        int y0 = b * rows_per, rows = min(rows_per, h - y0);
+        int y0 = ys[b], rows = ys[b + 1] - y0;
         OMNI_CUDA(cudaMemcpy2DAsync(d_img + (size_t)y0 * ip, ip, h_bgr + (size_t)y0 * pitch, pitch, (size_t)w * 3, rows,
                                     cudaMemcpyHostToDevice, si));
         OMNI_CUDA(cudaEventRecord(evH[b], si));
@@ -1655,7 +1666,7 @@ int fast_host_color_edge(omni_ctx *ctx, const u8 *h_bgr, int h, int w, size_t pi
     bool sparse = false;
     FK_TRY(edge_pass_begin(ctx, g, K, bpp[2], bpp[3], d_edges, eplane, ep, sc, &R, &sparse, true));
     auto morph_band = [&](int b) -> int {
-        int y0 = b * rows_per, y1 = min(h, y0 + rows_per);
+        int y0 = ys[b], y1 = ys[b + 1];
         OMNI_LAUNCH(ctx, sc, "morph_bits", launch_morph(true, kind, bpp[0], bpp[1], g, K, d_masks, mplane, mp, sc, y0, y1, sparse ? &R : nullptr));
         OMNI_CUDA(cudaEventRecord(evM[b], sc));
         OMNI_CUDA(cudaStreamWaitEvent(so, evM[b], 0));
@@ -1672,7 +1683,7 @@ int fast_host_color_edge(omni_ctx *ctx, const u8 *h_bgr, int h, int w, size_t pi
         return OMNI_OK;
     };
     for (int b = 0; b < nb; b++) {
-        int y0 = b * rows_per, rows = min(rows_per, h - y0);
+        int y0 = ys[b], rows = ys[b + 1] - y0;
         OMNI_CUDA(cudaStreamWaitEvent(sc, evH[b], 0));
         FK_TRY(launch_assign_lab(ctx, d_img + (size_t)y0 * ip, rows, w, ip, P, want_labels ? d_labels + (size_t)y0 * lp : nullptr, lp,
                                  bpp[0] + (size_t)y0 * g.ws, g.ws, g.plane, sc));

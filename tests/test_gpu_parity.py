@@ -575,3 +575,22 @@ def test_skeleton_degree(eng, hw):
         wd, ep, jn = rp.skeleton_degree(planes[k])
         assert np.array_equal(deg[k], wd), k
         assert np.array_equal(nodes[k] == 1, ep) and np.array_equal(nodes[k] == 2, jn), k
+
+
+@pytest.mark.parametrize("hw,K", [((2200, 300), 4), ((2048, 96), 8), ((4100, 64), 3), ((300, 500), 5)])
+def test_host_color_edge_bands(eng_mode, hw, K):
+    """The band-pipelined host-buffer call (short lead bands on tall images) == the device-resident call, incl. counts."""
+    import omni_b200
+    rp = _rp()
+    img = synth(hw[0], hw[1], 7, cell=16)
+    ctr = rp.kmeans_lab_centers(img, K)
+    _o, lut = rp.darkness_order(ctr)
+    lut = lut.astype(np.uint8)
+    ec = omni_b200.EdgeConfig()
+    r = eng_mode.host_color_edge(img, ctr, lut, ec, want_labels=True, want_counts=True)
+    labels, masks, edges = eng_mode.color_edge(dev(img), ctr, lut, ec, want_labels=True)
+    assert np.array_equal(r["labels"], host(labels))
+    assert np.array_equal(r["masks"], host(masks))
+    assert np.array_equal(r["edges"], host(edges))
+    assert np.array_equal(r["counts"][:, 1], (host(masks) > 0).reshape(K, -1).sum(1))
+    assert np.array_equal(r["counts"][:, 2], (host(edges) > 0).reshape(K, -1).sum(1))
