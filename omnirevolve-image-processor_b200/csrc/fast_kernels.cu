@@ -788,6 +788,9 @@ __host__ __device__ constexpr bool op_is_erode(int op) { return op == ST_ER || o
 
 #define MORPH_TR 32          // rows per strip (default)
 #define MORPH_TR_BIG 64      // ... when the grid is large enough: 16+TR rows are processed for TR produced
+#ifndef MORPH_BIG_MIN_WARPS
+#define MORPH_BIG_MIN_WARPS 2048
+#endif
 
 // Output-of-range fix-up for a value that the step with opcode `next` will consume: columns outside the
 // image and rows outside the image must read as that step's identity element.
@@ -997,7 +1000,7 @@ static cudaError_t launch_morph(bool with02, int morph03, const u32 *in_bits, u3
     if (y_hi <= y_lo) return cudaSuccess;
     // taller strips (less halo work) once there are plenty of warps: 128-thread CTAs, 4 warps each
     const long long warps_big = (long long)((g.ww + 127) / 128) * 4 * ((y_hi - y_lo + MORPH_TR_BIG - 1) / MORPH_TR_BIG) * K;
-    const bool big = warps_big >= 8192 && (y_lo % MORPH_TR_BIG) == 0;
+    const bool big = warps_big >= MORPH_BIG_MIN_WARPS && (y_lo % MORPH_TR_BIG) == 0;
     const int tr = big ? MORPH_TR_BIG : MORPH_TR;
     dim3 b(128), grid((g.ww + 127) / 128, (y_hi - y_lo + tr - 1) / tr, K);
     int al = masks && ((uintptr_t)masks % 16 == 0) && (mstride % 16 == 0) && (mpitch % 16 == 0);
