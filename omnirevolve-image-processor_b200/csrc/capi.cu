@@ -68,6 +68,7 @@ extern "C" int omni_ctx_destroy(omni_ctx *c)
     for (int i = 0; i < OMNI_WS_SLOTS; i++) if (c->ws[i]) cudaFree(c->ws[i]);
     for (auto &kv : c->resize_tabs) if (kv.second.d_blob) cudaFree(kv.second.d_blob);
     if (c->d_flags) cudaFree(c->d_flags);
+    if (c->d_rgb_boxes) cudaFree(c->d_rgb_boxes);
     if (c->d_counts) cudaFree(c->d_counts);
     if (c->h_flags) cudaFreeHost(c->h_flags);
     if (c->h_counts) cudaFreeHost(c->h_counts);

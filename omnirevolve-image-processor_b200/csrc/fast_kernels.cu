@@ -338,11 +338,10 @@ __device__ __forceinline__ void lab_noclamp(const u16 *gam, const u16 *cbrt, int
 
 // ---- RGB-cell variant (the default for Lab centres) -------------------------------------------------------
 // The same exact pruning, one level earlier: the RGB cube is cut into 64^3 cells of 4x4x4 colours and every cell gets
-// the set of centres that can be nearest for SOME colour of the cell.  OpenCV's integer Lab pipeline is monotone where
-// it matters: gamma[] and cbrt[] are non-decreasing tables and X, Y, Z are sums with positive coefficients, so over a
-// cell fX, fY, fZ lie between their values at the cell's low and high corner; L rises with fY, a with fX - fY, b with
-// fY - fZ, which bounds the cell's image by a Lab box (tight in L, conservative in a and b).  The box goes through
-// the dmin / dmax test of fk_build_cells.  ~79 % (K=8) / ~69 % (K=16) of the pixels of the benchmark images fall
+// the set of centres that can be nearest for SOME colour of the cell.  The cell's image in Lab space is bounded by the
+// exact box of its 64 colours (fk_rgb_boxes: cv2's integer Lab of every colour, min / max per channel; the boxes depend
+// only on the colour space, so they are computed once per context, 1.5 MB).  The box goes through
+// the dmin / dmax test of fk_build_cells.  ~88 % (K=8) / ~82 % (K=16) of the pixels of the benchmark images fall
 // into a cell with ONE candidate: their label is a table lookup, no Lab conversion at all.  The others (flagged
 // in a second, one-bit table) are compacted over the warp (shared-memory queue) and take the Lab-cell path of
 // fk_assign_bits: Lab conversion, candidate set of their Lab cell, the reference's float32 evaluation.
@@ -352,32 +351,38 @@ __device__ __forceinline__ void lab_noclamp(const u16 *gam, const u16 *cbrt, int
 #define RC_NIB_BYTES (RC_COUNT / 2)
 #define RC_MB_BYTES (RC_COUNT / 8)
 #define RC_MAX_K 16
-__device__ __forceinline__ void lab_f(const u16 *gam, const u16 *cbrt, int B8, int G8, int R8, int &fX, int &fY, int &fZ)
+// exact Lab bounding box of every RGB cell: boxes[6 * cell + (0..2)] = min L, a, b; [3..5] = max (centre-independent)
+__global__ void __launch_bounds__(256) fk_rgb_boxes(u8 *__restrict__ boxes)
 {
-    const int B = gam[B8], G = gam[G8], R = gam[R8];
-    fX = cbrt[(R * 1777 + G * 1541 + B * 778 + 2048) >> 12];
-    fY = cbrt[(R * 871 + G * 2929 + B * 296 + 2048) >> 12];
-    fZ = cbrt[(R * 73 + G * 448 + B * 3575 + 2048) >> 12];
+    const int ci = blockIdx.x * blockDim.x + threadIdx.x;               // cell = (B >> 2, G >> 2, R >> 2), B slowest
+    if (ci >= RC_COUNT) return;
+    const int b0 = (ci >> (2 * 6)) << RC_SHIFT, g0 = ((ci >> 6) & (RC_N - 1)) << RC_SHIFT, r0 = (ci & (RC_N - 1)) << RC_SHIFT;
+    int lo[3] = {255, 255, 255}, hi[3] = {0, 0, 0};
+    for (int db = 0; db < (1 << RC_SHIFT); db++)
+        for (int dg = 0; dg < (1 << RC_SHIFT); dg++)
+            for (int dr = 0; dr < (1 << RC_SHIFT); dr++) {
+                int v[3];
+                lab_noclamp(f_lab_tab, f_lab_tab + 256, b0 + db, g0 + dg, r0 + dr, v[0], v[1], v[2]);
+#pragma unroll
+                for (int d = 0; d < 3; d++) { lo[d] = min(lo[d], v[d]); hi[d] = max(hi[d], v[d]); }
+            }
+#pragma unroll
+    for (int d = 0; d < 3; d++) { boxes[6 * ci + d] = (u8)lo[d]; boxes[6 * ci + 3 + d] = (u8)hi[d]; }
 }
 
 // one thread = 8 cells consecutive in R: one u32 of label nibbles + one byte of "several candidates" flags
-__global__ void __launch_bounds__(256) fk_build_rgbcells(const __grid_constant__ AssignParams P, u32 *__restrict__ nib, u8 *__restrict__ mb)
+__global__ void __launch_bounds__(256) fk_build_rgbcells(const __grid_constant__ AssignParams P, const u8 *__restrict__ boxes,
+                                                         u32 *__restrict__ nib, u8 *__restrict__ mb)
 {
-    const int gi = blockIdx.x * blockDim.x + threadIdx.x;               // cell index / 8; cell = (B >> 2, G >> 2, R >> 2), B slowest
+    const int gi = blockIdx.x * blockDim.x + threadIdx.x;               // cell index / 8
     if (gi >= RC_COUNT / 8) return;
     const int K = P.K;
     u32 nibbles = 0u, multi = 0u;
     for (int q = 0; q < 8; q++) {
         const int ci = gi * 8 + q;
-        const int b0 = (ci >> (2 * 6)) << RC_SHIFT, g0 = ((ci >> 6) & (RC_N - 1)) << RC_SHIFT, r0 = (ci & (RC_N - 1)) << RC_SHIFT;
-        const int span = (1 << RC_SHIFT) - 1;
-        int xl, yl, zl, xh, yh, zh;
-        lab_f(f_lab_tab, f_lab_tab + 256, b0, g0, r0, xl, yl, zl);
-        lab_f(f_lab_tab, f_lab_tab + 256, b0 + span, g0 + span, r0 + span, xh, yh, zh);
-        const float lo[3] = {(float)((296 * yl - 1336934 + 16384) >> 15), (float)((500 * (xl - yh) + 128 * 32768 + 16384) >> 15),
-                             (float)((200 * (yl - zh) + 128 * 32768 + 16384) >> 15)};
-        const float hi[3] = {(float)((296 * yh - 1336934 + 16384) >> 15), (float)((500 * (xh - yl) + 128 * 32768 + 16384) >> 15),
-                             (float)((200 * (yh - zl) + 128 * 32768 + 16384) >> 15)};
+        float lo[3], hi[3];
+#pragma unroll
+        for (int d = 0; d < 3; d++) { lo[d] = (float)boxes[6 * ci + d]; hi[d] = (float)boxes[6 * ci + 3 + d]; }
         float U = 3.0e38f;
         bool sane = true;
         for (int k = 0; k < K; k++) {
@@ -1280,8 +1285,14 @@ static int assign_cells(omni_ctx *ctx, const AssignParams &P, u32 **cells, u8 **
         OMNI_CUDA(cudaGetLastError());
     }
     if (variant == 2) {
+        if (!ctx->d_rgb_boxes) {                           // centre-independent: once per context
+            OMNI_CUDA(cudaMalloc(&ctx->d_rgb_boxes, (size_t)RC_COUNT * 6));
+            KScope ks(ctx, "rgb_boxes", st);
+            fk_rgb_boxes<<<RC_COUNT / 256, 256, 0, st>>>(ctx->d_rgb_boxes);
+            OMNI_CUDA(cudaGetLastError());
+        }
         KScope ks(ctx, "build_rgbcells", st);
-        fk_build_rgbcells<<<RC_COUNT / 8 / 256, 256, 0, st>>>(P, (u32 *)*rcells, *rcells + RC_NIB_BYTES);
+        fk_build_rgbcells<<<RC_COUNT / 8 / 256, 256, 0, st>>>(P, ctx->d_rgb_boxes, (u32 *)*rcells, *rcells + RC_NIB_BYTES);
         OMNI_CUDA(cudaGetLastError());
     }
     return OMNI_OK;

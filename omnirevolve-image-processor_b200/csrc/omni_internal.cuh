@@ -93,7 +93,8 @@ struct omni_ctx {
     int cells_valid = 0, cells_K = 0;
     void *cells_stream = nullptr;
     float cells_c[OMNI_MAX_K * 3];
-    u8 cells_lut[OMNI_MAX_K] = {};             // co-resident CTAs of the cooperative hysteresis kernel (0 = not queried yet)
+    u8 cells_lut[OMNI_MAX_K] = {};
+    u8 *d_rgb_boxes = nullptr;                 // exact Lab box of every 4x4x4 RGB cell (centre-independent, built on first use)             // co-resident CTAs of the cooperative hysteresis kernel (0 = not queried yet)
 };
 
 // Brackets one kernel launch: counts it and, when profiling is on, records a CUDA event pair on the
