@@ -467,9 +467,10 @@ __global__ void __launch_bounds__(RA_THREADS, 1) fk_assign_rgbcell(const u8 *__r
     u8 *sq = spx + 768, *slab = sq + 256;                             //           queued pixel indices, their labels
     const u32 lt = (1u << lane) - 1u;
     uint4 pf0 = make_uint4(0, 0, 0, 0), pf1 = pf0;
-    auto prefetch = [&](int u) {
+    // chunk u = (row yy of the batch, chunk c of the row); the pair is advanced without divisions
+    const int dyy = stride / chunks, dc = stride - dyy * chunks;
+    auto prefetch = [&](int u, int yy, int c) {
         if (u < total) {
-            const int yy = u / chunks, c = u - yy * chunks;
             const int f = nf > 1 ? yy / h : 0, y = yy - f * h;     // one frame: no division
             if (vec_ok && c * 256 + 256 <= w) {
                 const uint4 *src = reinterpret_cast<const uint4 *>(px + (size_t)f * frame_stride + (size_t)y * pitch + (size_t)c * 768);
@@ -479,9 +480,12 @@ __global__ void __launch_bounds__(RA_THREADS, 1) fk_assign_rgbcell(const u8 *__r
         }
     };
     int u = blockIdx.x * RA_WARPS + warp;
-    prefetch(u);
+    int yy_n = u / chunks, c_n = u - yy_n * chunks;                // the chunk the prefetch registers hold
+    prefetch(u, yy_n, c_n);
     for (; u < total; u += stride) {
-        const int yy = u / chunks, c = u - yy * chunks;
+        const int yy = yy_n, c = c_n;
+        yy_n += dyy; c_n += dc;
+        if (c_n >= chunks) { c_n -= chunks; yy_n++; }
         const int f = nf > 1 ? yy / h : 0, y = yy - f * h;     // one frame: no division
         const int x0 = c * 256 + lane;
         const bool full = vec_ok && c * 256 + 256 <= w;
@@ -494,7 +498,7 @@ __global__ void __launch_bounds__(RA_THREADS, 1) fk_assign_rgbcell(const u8 *__r
             const int nb = 3 * min(256, w - c * 256);
             for (int i = lane; i < nb; i += 32) spx[i] = row[i];
         }
-        prefetch(u + stride);
+        prefetch(u + stride, yy_n, c_n);
 #pragma unroll
         for (int z = 0; z < 2; z++) {                          // this chunk's slice of the zero-fill regions (per: multiple of 32)
             if (Z.n16[z]) {
@@ -561,11 +565,13 @@ __global__ void __launch_bounds__(RA_THREADS, 1) fk_assign_rgbcell(const u8 *__r
                 if (x0 + 32 * g < w) lrow[x0 + 32 * g] = (u8)lab[g];
         }
         if (bits) {
-            u32 *brow = bits + (size_t)f * K * plane + (size_t)y * ws + c * 8;
+            // 32-bit word offsets (the host checks nf * K * plane < 2^31).  A valid pixel (label < K) implies its word exists.
+            u32 *brow = bits + ((u32)(f * K) * (u32)plane + (u32)y * (u32)ws + (u32)c * 8u);
+            const u32 plane32 = (u32)plane;
 #pragma unroll
             for (int g = 0; g < 8; g++) {
                 const u32 same = __match_any_sync(0xffffffffu, lab[g]);
-                if (lab[g] < K && lane == __ffs(same) - 1 && c * 8 + g < ws) brow[(size_t)lab[g] * plane + g] = same;
+                if (lab[g] < K && (same & lt) == 0u) brow[(u32)lab[g] * plane32 + g] = same;      // the lowest lane of each label stores
             }
         }
     }
@@ -1301,7 +1307,9 @@ static int assign_cells(omni_ctx *ctx, const AssignParams &P, u32 **cells, u8 **
 // will launch_assign_lab use the kernel that can carry a ZeroJob?
 static bool assign_takes_zero_job(omni_ctx *ctx, const AssignParams &P, int nf, int h, int w)
 {
-    return ctx->assign_rgbcell && P.K <= RC_MAX_K && (long long)nf * h * ((w + 255) >> 8) < (1ll << 30);
+    const unsigned long long plane = (unsigned long long)(((((w + 31) >> 5) + 3) & ~3)) * h;
+    return ctx->assign_rgbcell && P.K <= RC_MAX_K && (long long)nf * h * ((w + 255) >> 8) < (1ll << 30) &&
+           (unsigned long long)nf * P.K * plane < (1ull << 31);
 }
 
 // Lab-centre assignment of rows [0, h) at px: labels and/or one-hot bit-plane words (either may be NULL)
@@ -1310,7 +1318,8 @@ static int launch_assign_lab(omni_ctx *ctx, const u8 *px, int h, int w, size_t p
                              const ZeroJob *zero = nullptr /* only honoured by the RGB-cell kernel: check assign_takes_zero_job() */)
 {
     // the RGB-cell kernel counts chunks in 32 bits and takes a whole batch; the Lab-cell kernel takes one frame per launch
-    const bool use_rgb = ctx->assign_rgbcell && P.K <= RC_MAX_K && (long long)nf * h * ((w + 255) >> 8) < (1ll << 30);
+    const bool use_rgb = ctx->assign_rgbcell && P.K <= RC_MAX_K && (long long)nf * h * ((w + 255) >> 8) < (1ll << 30) &&
+                         (unsigned long long)nf * P.K * plane < (1ull << 31);        // 32-bit word offsets inside the kernel
     if (!use_rgb && nf > 1) {
         for (int f = 0; f < nf; f++)
             FK_TRY(launch_assign_lab(ctx, px + (size_t)f * frame_stride, h, w, pitch, P, labels ? labels + (size_t)f * h * lpitch : nullptr,
