@@ -18,6 +18,7 @@
 #include "omni_tables.inc"
 
 #include <algorithm>
+#include <type_traits>
 #include <cooperative_groups.h>
 #include <math.h>
 #include <stdlib.h>
@@ -805,15 +806,17 @@ __host__ __device__ constexpr bool op_is_erode(int op) { return op == ST_ER || o
 
 // Output-of-range fix-up for a value that the step with opcode `next` will consume: columns outside the
 // image and rows outside the image must read as that step's identity element.
-template <int NEXT>
+// ROWFIX = false: every row the strip touches lies inside the image (all but the first and last strips of a plane), so only
+// the columns need the fix-up -- the row tests were a third of the kernel's instructions.
+template <int NEXT, bool ROWFIX>
 __device__ __forceinline__ W64 oob_fix(W64 v, W64 colvalid, bool row_inside)
 {
     if (NEXT == ST_NONE) { v.lo &= colvalid.lo; v.hi &= colvalid.hi; return v; }
     if (op_is_erode(NEXT)) {
-        if (!row_inside) { v.lo = v.hi = 0xffffffffu; return v; }
+        if (ROWFIX && !row_inside) { v.lo = v.hi = 0xffffffffu; return v; }
         v.lo |= ~colvalid.lo; v.hi |= ~colvalid.hi;
     } else {
-        if (!row_inside) { v.lo = v.hi = 0u; return v; }
+        if (ROWFIX && !row_inside) { v.lo = v.hi = 0u; return v; }
         v.lo &= colvalid.lo; v.hi &= colvalid.hi;
     }
     return v;
@@ -822,7 +825,7 @@ __device__ __forceinline__ W64 oob_fix(W64 v, W64 colvalid, bool row_inside)
 template <u32 CODE, int S>
 struct MorphChain {
     // applies steps S.. of CODE to `cur` (= image_S row `t - S`), updating the rolling rows
-    template <int TAP>
+    template <int TAP, bool ROWFIX>
     static __device__ __forceinline__ void run(W64 cur, W64 (&p1)[8], W64 (&p2)[8], int t, int h, W64 colvalid, W64 &tap_out, W64 &fin)
     {
         constexpr int N = code_len(CODE);
@@ -833,8 +836,8 @@ struct MorphChain {
             W64 out = morph_step<OP>(p2[S], p1[S], cur);
             p2[S] = p1[S]; p1[S] = cur;
             const int r = t - S - 1;                       // row of image_{S+1} just produced
-            out = oob_fix<NEXT>(out, colvalid, r >= 0 && r < h);
-            MorphChain<CODE, S + 1>::template run<TAP>(out, p1, p2, t, h, colvalid, tap_out, fin);
+            out = oob_fix<NEXT, ROWFIX>(out, colvalid, !ROWFIX || (r >= 0 && r < h));
+            MorphChain<CODE, S + 1>::template run<TAP, ROWFIX>(out, p1, p2, t, h, colvalid, tap_out, fin);
         } else {
             fin = cur;
         }
@@ -898,6 +901,8 @@ __global__ void __launch_bounds__(128, MORPH_MINB) fk_morph(const u32 *__restric
         }
     };
     u32 live1 = 0u, live0 = 0u;                            // per tile of the strip: "has a 1" / "has a 0" in the grown tile
+    auto rows = [&](auto rowfix_tag) {
+    constexpr bool ROWFIX = decltype(rowfix_tag)::value;
     fetch(y0 - N - EXT);
     for (int t = y0 - N - EXT; t < y1 + N + EXT; t++) {
         W64 cur;
@@ -905,10 +910,10 @@ __global__ void __launch_bounds__(128, MORPH_MINB) fk_morph(const u32 *__restric
         cur.lo = (nl >> 16) | (no << 16);
         cur.hi = (no >> 16) | (nr << 16);
         fetch(t + 1);
-        cur = oob_fix<OP0>(cur, colvalid, inside);
+        cur = oob_fix<OP0, ROWFIX>(cur, colvalid, !ROWFIX || inside);
         W64 tap, fin;
         tap.lo = tap.hi = fin.lo = fin.hi = 0u;
-        MorphChain<CODE, 0>::template run<TAP>(cur, p1, p2, t, h, colvalid, tap, fin);
+        MorphChain<CODE, 0>::template run<TAP, ROWFIX>(cur, p1, p2, t, h, colvalid, tap, fin);
         if (TAP >= 0) {
             const int r = t - TAP;
             if (r >= y0 && r < y1 && active) {
@@ -924,7 +929,7 @@ __global__ void __launch_bounds__(128, MORPH_MINB) fk_morph(const u32 *__restric
             }
         }
         if (RUNS) {
-            if (r >= y0 - 2 && r < y1 + 2 && r >= 0 && r < h) {
+            if (r >= y0 - 2 && r < y1 + 2 && (!ROWFIX || (r >= 0 && r < h))) {
                 // window bits 14..49 = pixels 32c-2 .. 32c+33; fin is already 0 outside the image
                 const u32 m_lo = 0xFFFFC000u & colvalid.lo, m_hi = 0x0003FFFFu & colvalid.hi;
                 const bool h1 = ((fin.lo & m_lo) | (fin.hi & m_hi)) != 0u, h0 = ((~fin.lo & m_lo) | (~fin.hi & m_hi)) != 0u;
@@ -938,6 +943,10 @@ __global__ void __launch_bounds__(128, MORPH_MINB) fk_morph(const u32 *__restric
             }
         }
     }
+    };
+    // every row of every image in the chain that this strip touches: [y0 - 2N - EXT, y1 + N + EXT)
+    if (y0 - 2 * N - EXT >= 0 && y1 + N + EXT <= h) rows(std::false_type{});
+    else rows(std::true_type{});
     if (RUNS) {
         const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
         const u32 live = active ? (live1 & live0) : 0u;
