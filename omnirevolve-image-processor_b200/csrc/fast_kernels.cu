@@ -148,31 +148,29 @@ __global__ void __launch_bounds__(RF_THREADS) fk_resize_frac(const u8 *__restric
     const int nbytes = 3 * (xs1 + 1) - b0;
     const int nrows = ys1 - ys0 + 1;
     if (vec_ok) {
-        // 16-byte vectors, four independent loads in flight per thread (the staging is latency-bound otherwise)
-        const int nv = (nbytes + 15) >> 4, total = nrows * nv;
-        for (int i0 = threadIdx.x; i0 < total; i0 += 4 * RF_THREADS) {
-            uint4 val[4];
-            bool vec[4];
+        // 16-byte vectors; 64 threads per source row, four rows per pass and three passes in flight (no divisions, and the
+        // staging is latency-bound otherwise)
+        const int nv = (nbytes + 15) >> 4;
+        const int lr = threadIdx.x >> 6, v0 = threadIdx.x & 63;
+        for (int vb = v0; vb < nv; vb += 64) {
+            const bool vec = b0 + 16 * vb + 16 <= 3 * sw;                      // never read past the row's pixels
+            for (int r0 = lr; r0 < nrows; r0 += 12) {
+                uint4 val[3];
 #pragma unroll
-            for (int q = 0; q < 4; q++) {
-                const int i = i0 + q * RF_THREADS;
-                vec[q] = false;
-                if (i < total) {
-                    const int r = i / nv, v = i - r * nv;
-                    vec[q] = b0 + 16 * v + 16 <= 3 * sw;
-                    if (vec[q]) val[q] = __ldg(reinterpret_cast<const uint4 *>(src + (size_t)(ys0 + r) * spitch + b0 + 16 * v));
+                for (int q = 0; q < 3; q++) {
+                    const int r = r0 + 4 * q;
+                    if (r < nrows && vec) val[q] = __ldg(reinterpret_cast<const uint4 *>(src + (size_t)(ys0 + r) * spitch + b0 + 16 * vb));
                 }
-            }
 #pragma unroll
-            for (int q = 0; q < 4; q++) {
-                const int i = i0 + q * RF_THREADS;
-                if (i < total) {
-                    const int r = i / nv, v = i - r * nv;
-                    u8 *d = s_src + (size_t)r * spitch_s + 16 * v;
-                    if (vec[q]) *reinterpret_cast<uint4 *>(d) = val[q];
-                    else {                                                     // never read past the row's pixels
-                        const u8 *g = src + (size_t)(ys0 + r) * spitch + b0 + 16 * v;
-                        for (int e = 0; b0 + 16 * v + e < 3 * sw; e++) d[e] = g[e];
+                for (int q = 0; q < 3; q++) {
+                    const int r = r0 + 4 * q;
+                    if (r < nrows) {
+                        u8 *d = s_src + (size_t)r * spitch_s + 16 * vb;
+                        if (vec) *reinterpret_cast<uint4 *>(d) = val[q];
+                        else {
+                            const u8 *g = src + (size_t)(ys0 + r) * spitch + b0 + 16 * vb;
+                            for (int e = 0; b0 + 16 * vb + e < 3 * sw; e++) d[e] = g[e];
+                        }
                     }
                 }
             }
