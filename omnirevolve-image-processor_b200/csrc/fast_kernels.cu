@@ -797,7 +797,9 @@ __host__ __device__ constexpr int code_len(u32 code) { int n = 0; while (n < 8 &
 __host__ __device__ constexpr bool op_is_erode(int op) { return op == ST_ER || op == ST_EC; }
 
 #define MORPH_TR 32          // rows per strip (default)
-#define MORPH_TR_BIG 64      // ... when the grid is large enough: 16+TR rows are processed for TR produced
+#ifndef MORPH_TR_BIG
+#define MORPH_TR_BIG 48      // ... when the grid is large enough: 16+TR rows are processed for TR produced (A/B: 48 beats 32 and 64)
+#endif
 #ifndef MORPH_BIG_MIN_WARPS
 #define MORPH_BIG_MIN_WARPS 2048
 #endif
