@@ -594,3 +594,46 @@ def test_host_color_edge_bands(eng_mode, hw, K):
     assert np.array_equal(r["edges"], host(edges))
     assert np.array_equal(r["counts"][:, 1], (host(masks) > 0).reshape(K, -1).sum(1))
     assert np.array_equal(r["counts"][:, 2], (host(edges) > 0).reshape(K, -1).sum(1))
+
+
+@pytest.mark.parametrize("seed", list(range(24)))
+def test_fuzz_fused_vs_oracle(eng, seed):
+    """Randomised shapes / centres / thresholds through the fused call (sparse tile runs, RGB cells, zero fill, run lists
+    from the morphology kernel) against the C oracle: odd sizes, adversarial centres (duplicates, half-integers, far away),
+    float thresholds, every stage-03 morphology setting of the fast path."""
+    import omni_b200
+    cm = _cm()
+    rng = np.random.default_rng(1000 + seed)
+    h, w = int(rng.integers(1, 260)), int(rng.integers(1, 700))
+    K = int(rng.integers(2, 17))
+    kind = seed % 4
+    if kind == 0:
+        img = uniform_img(h, w, seed)
+    elif kind == 1:
+        img = synth(max(h, 8), max(w, 8), seed, cell=8)[:h, :w]
+    elif kind == 2:                                       # few flat regions: many uniform tiles, long straight boundaries
+        img = np.zeros((h, w, 3), np.uint8)
+        img[:, : w // 2] = rng.integers(0, 256, 3)
+        img[h // 3:, w // 3:] = rng.integers(0, 256, 3)
+        img[:, -1:] = rng.integers(0, 256, 3)
+    else:
+        img = np.clip(synth(max(h, 8), max(w, 8), seed, cell=4)[:h, :w].astype(np.int16) + rng.integers(-40, 41, (h, w, 3)), 0, 255).astype(np.uint8)
+    img = np.ascontiguousarray(img)
+    ctr = (rng.random((K, 3)) * np.array([255, 190, 190]) + np.array([0, 30, 30])).astype(np.float32)
+    if seed % 3 == 0:
+        ctr = np.round(ctr * 2) / 2                       # half-integer centres: exact ties between centres are possible
+    if seed % 5 == 0 and K > 2:
+        ctr[1] = ctr[0]                                   # duplicated centre: first minimum must win
+    if seed % 7 == 0:
+        ctr[-1] = [400.0, -50.0, 300.0]                   # a centre no colour is close to
+    lut = rng.permutation(K).astype(np.uint8)
+    low, high = float(rng.uniform(0, 120)), float(rng.uniform(20, 400))
+    mk = [3, 3, 1, 3][seed % 4]
+    oi, ci = [(1, 1), (1, 0), (1, 1), (0, 1)][(seed // 4) % 4]
+    ec = omni_b200.EdgeConfig(low=low, high=high, ksize=3, morph_k=mk, open_iters=oi, close_iters=ci)
+    labels, masks, edges = eng.color_edge(dev(img), ctr, lut, ec, want_labels=True)
+    raw = cm.assign_f32(cm.bgr2lab(img), ctr)
+    assert np.array_equal(host(labels), lut[raw])
+    wm = cm.layer_masks(raw, K, lut)
+    assert np.array_equal(host(masks), wm)
+    assert np.array_equal(host(edges), _edge_want(wm, ksize=3, low=low, high=high, morph_k=mk, open_iters=oi, close_iters=ci))
