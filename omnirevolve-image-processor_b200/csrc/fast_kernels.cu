@@ -566,11 +566,12 @@ __global__ void __launch_bounds__(RA_THREADS, 1) fk_assign_rgbcell(const u8 *__r
         if (bits) {
             // 32-bit word offsets (the host checks nf * K * plane < 2^31).  A valid pixel (label < K) implies its word exists.
             u32 *brow = bits + ((u32)(f * K) * (u32)plane + (u32)y * (u32)ws + (u32)c * 8u);
-            const u32 plane32 = (u32)plane;
+            const u32 plane_bytes = (u32)plane * 4u;               // one multiply-add (32 x 32 + 64) gives the plane's row
 #pragma unroll
             for (int g = 0; g < 8; g++) {
                 const u32 same = __match_any_sync(0xffffffffu, lab[g]);
-                if (lab[g] < K && (same & lt) == 0u) brow[(u32)lab[g] * plane32 + g] = same;      // the lowest lane of each label stores
+                if (lab[g] < K && (same & lt) == 0u)                  // the lowest lane of each label stores its word
+                    reinterpret_cast<u32 *>(reinterpret_cast<char *>(brow) + (unsigned long long)(u32)lab[g] * plane_bytes)[g] = same;
             }
         }
     }
@@ -1318,7 +1319,7 @@ static bool assign_takes_zero_job(omni_ctx *ctx, const AssignParams &P, int nf, 
 {
     const unsigned long long plane = (unsigned long long)(((((w + 31) >> 5) + 3) & ~3)) * h;
     return ctx->assign_rgbcell && P.K <= RC_MAX_K && (long long)nf * h * ((w + 255) >> 8) < (1ll << 30) &&
-           (unsigned long long)nf * P.K * plane < (1ull << 31);
+           (unsigned long long)nf * P.K * plane < (1ull << 30);
 }
 
 // Lab-centre assignment of rows [0, h) at px: labels and/or one-hot bit-plane words (either may be NULL)
@@ -1328,7 +1329,7 @@ static int launch_assign_lab(omni_ctx *ctx, const u8 *px, int h, int w, size_t p
 {
     // the RGB-cell kernel counts chunks in 32 bits and takes a whole batch; the Lab-cell kernel takes one frame per launch
     const bool use_rgb = ctx->assign_rgbcell && P.K <= RC_MAX_K && (long long)nf * h * ((w + 255) >> 8) < (1ll << 30) &&
-                         (unsigned long long)nf * P.K * plane < (1ull << 31);        // 32-bit word offsets inside the kernel
+                         (unsigned long long)nf * P.K * plane < (1ull << 30);        // 32-bit word / byte offsets inside the kernel
     if (!use_rgb && nf > 1) {
         for (int f = 0; f < nf; f++)
             FK_TRY(launch_assign_lab(ctx, px + (size_t)f * frame_stride, h, w, pitch, P, labels ? labels + (size_t)f * h * lpitch : nullptr,
