@@ -798,27 +798,27 @@ __host__ __device__ constexpr int code_len(u32 code) { int n = 0; while (n < 8 &
 __host__ __device__ constexpr bool op_is_erode(int op) { return op == ST_ER || op == ST_EC; }
 
 #define MORPH_TR 32          // rows per strip (default)
-#ifndef MORPH_TR_BIG
-#define MORPH_TR_BIG 48      // ... when the grid is large enough: 16+TR rows are processed for TR produced (A/B: 48 beats 32 and 64)
-#endif
-#ifndef MORPH_BIG_MIN_WARPS
-#define MORPH_BIG_MIN_WARPS 2048
-#endif
+#define MORPH_TR_MID 48      // ... from 2048 warps on (A/B at 4096^2: 48 beats 32 and 64): TR + 16 (+4) rows are processed for TR produced
+#define MORPH_TR_BIG 64      // ... from 8192 warps on (8192^2, K=16: less halo work wins once there are plenty of warps)
+#define MORPH_MID_MIN_WARPS 2048
+#define MORPH_BIG_MIN_WARPS 8192
 
 // Output-of-range fix-up for a value that the step with opcode `next` will consume: columns outside the
 // image and rows outside the image must read as that step's identity element.
 // ROWFIX = false: every row the strip touches lies inside the image (all but the first and last strips of a plane), so only
 // the columns need the fix-up -- the row tests were a third of the kernel's instructions.
-template <int NEXT, bool ROWFIX>
+// COLFIX = false: every window pixel of every lane of the warp lies inside the image (warps away from the left / right
+// border), so the columns need no fix-up either.
+template <int NEXT, bool ROWFIX, bool COLFIX>
 __device__ __forceinline__ W64 oob_fix(W64 v, W64 colvalid, bool row_inside)
 {
-    if (NEXT == ST_NONE) { v.lo &= colvalid.lo; v.hi &= colvalid.hi; return v; }
+    if (NEXT == ST_NONE) { if (COLFIX) { v.lo &= colvalid.lo; v.hi &= colvalid.hi; } return v; }
     if (op_is_erode(NEXT)) {
         if (ROWFIX && !row_inside) { v.lo = v.hi = 0xffffffffu; return v; }
-        v.lo |= ~colvalid.lo; v.hi |= ~colvalid.hi;
+        if (COLFIX) { v.lo |= ~colvalid.lo; v.hi |= ~colvalid.hi; }
     } else {
         if (ROWFIX && !row_inside) { v.lo = v.hi = 0u; return v; }
-        v.lo &= colvalid.lo; v.hi &= colvalid.hi;
+        if (COLFIX) { v.lo &= colvalid.lo; v.hi &= colvalid.hi; }
     }
     return v;
 }
@@ -826,7 +826,7 @@ __device__ __forceinline__ W64 oob_fix(W64 v, W64 colvalid, bool row_inside)
 template <u32 CODE, int S>
 struct MorphChain {
     // applies steps S.. of CODE to `cur` (= image_S row `t - S`), updating the rolling rows
-    template <int TAP, bool ROWFIX>
+    template <int TAP, bool ROWFIX, bool COLFIX>
     static __device__ __forceinline__ void run(W64 cur, W64 (&p1)[8], W64 (&p2)[8], int t, int h, W64 colvalid, W64 &tap_out, W64 &fin)
     {
         constexpr int N = code_len(CODE);
@@ -837,8 +837,8 @@ struct MorphChain {
             W64 out = morph_step<OP>(p2[S], p1[S], cur);
             p2[S] = p1[S]; p1[S] = cur;
             const int r = t - S - 1;                       // row of image_{S+1} just produced
-            out = oob_fix<NEXT, ROWFIX>(out, colvalid, !ROWFIX || (r >= 0 && r < h));
-            MorphChain<CODE, S + 1>::template run<TAP, ROWFIX>(out, p1, p2, t, h, colvalid, tap_out, fin);
+            out = oob_fix<NEXT, ROWFIX, COLFIX>(out, colvalid, !ROWFIX || (r >= 0 && r < h));
+            MorphChain<CODE, S + 1>::template run<TAP, ROWFIX, COLFIX>(out, p1, p2, t, h, colvalid, tap_out, fin);
         } else {
             fin = cur;
         }
@@ -902,8 +902,8 @@ __global__ void __launch_bounds__(128, MORPH_MINB) fk_morph(const u32 *__restric
         }
     };
     u32 live1 = 0u, live0 = 0u;                            // per tile of the strip: "has a 1" / "has a 0" in the grown tile
-    auto rows = [&](auto rowfix_tag) {
-    constexpr bool ROWFIX = decltype(rowfix_tag)::value;
+    auto rows = [&](auto rowfix_tag, auto colfix_tag) {
+    constexpr bool ROWFIX = decltype(rowfix_tag)::value, COLFIX = decltype(colfix_tag)::value;
     fetch(y0 - N - EXT);
     for (int t = y0 - N - EXT; t < y1 + N + EXT; t++) {
         W64 cur;
@@ -911,10 +911,10 @@ __global__ void __launch_bounds__(128, MORPH_MINB) fk_morph(const u32 *__restric
         cur.lo = (nl >> 16) | (no << 16);
         cur.hi = (no >> 16) | (nr << 16);
         fetch(t + 1);
-        cur = oob_fix<OP0, ROWFIX>(cur, colvalid, !ROWFIX || inside);
+        cur = oob_fix<OP0, ROWFIX, COLFIX>(cur, colvalid, !ROWFIX || inside);
         W64 tap, fin;
         tap.lo = tap.hi = fin.lo = fin.hi = 0u;
-        MorphChain<CODE, 0>::template run<TAP, ROWFIX>(cur, p1, p2, t, h, colvalid, tap, fin);
+        MorphChain<CODE, 0>::template run<TAP, ROWFIX, COLFIX>(cur, p1, p2, t, h, colvalid, tap, fin);
         if (TAP >= 0) {
             const int r = t - TAP;
             if (r >= y0 && r < y1 && active) {
@@ -946,8 +946,11 @@ __global__ void __launch_bounds__(128, MORPH_MINB) fk_morph(const u32 *__restric
     }
     };
     // every row of every image in the chain that this strip touches: [y0 - 2N - EXT, y1 + N + EXT)
-    if (y0 - 2 * N - EXT >= 0 && y1 + N + EXT <= h) rows(std::false_type{});
-    else rows(std::true_type{});
+    const bool rowfix = !(y0 - 2 * N - EXT >= 0 && y1 + N + EXT <= h);                          // uniform per CTA
+    // uniform per warp (lanes right of the image have left already when there is no list flush to attend)
+    const bool colfix = __any_sync(__activemask(), (colvalid.lo & colvalid.hi) != 0xffffffffu);
+    if (rowfix) { if (colfix) rows(std::true_type{}, std::true_type{}); else rows(std::true_type{}, std::false_type{}); }
+    else { if (colfix) rows(std::false_type{}, std::true_type{}); else rows(std::false_type{}, std::false_type{}); }
     if (RUNS) {
         const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
         const u32 live = active ? (live1 & live0) : 0u;
@@ -1020,18 +1023,24 @@ static cudaError_t launch_morph(bool with02, int morph03, const u32 *in_bits, u3
     if (y_hi < 0) y_hi = g.h;
     if (y_hi <= y_lo) return cudaSuccess;
     // taller strips (less halo work) once there are plenty of warps: 128-thread CTAs, 4 warps each
-    const long long warps_big = (long long)((g.ww + 127) / 128) * 4 * ((y_hi - y_lo + MORPH_TR_BIG - 1) / MORPH_TR_BIG) * K;
-    const bool big = warps_big >= MORPH_BIG_MIN_WARPS && (y_lo % MORPH_TR_BIG) == 0;
-    const int tr = big ? MORPH_TR_BIG : MORPH_TR;
+    auto warps_at = [&](int tr) { return (long long)((g.ww + 127) / 128) * 4 * ((y_hi - y_lo + tr - 1) / tr) * K; };
+    int tr = MORPH_TR;
+    if (warps_at(MORPH_TR_BIG) >= MORPH_BIG_MIN_WARPS && (y_lo % MORPH_TR_BIG) == 0) tr = MORPH_TR_BIG;
+    else if (warps_at(MORPH_TR_MID) >= MORPH_MID_MIN_WARPS && (y_lo % MORPH_TR_MID) == 0) tr = MORPH_TR_MID;
     dim3 b(128), grid((g.ww + 127) / 128, (y_hi - y_lo + tr - 1) / tr, K);
     int al = masks && ((uintptr_t)masks % 16 == 0) && (mstride % 16 == 0) && (mpitch % 16 == 0);
     MorphRuns R{};
     if (runs) R = *runs;
 #define LM2(CODE, TAP, RUNS, TR) fk_morph<CODE, TAP, RUNS, TR><<<grid, b, 0, st>>>(in_bits, out_bits, g.ws, g.plane, g.h, g.w, masks, mstride, mpitch, al, y_lo, y_hi, R)
+#define LM3(CODE, TAP, RUNS)                                                          \
+    do {                                                                               \
+        if (tr == MORPH_TR_BIG) LM2(CODE, TAP, RUNS, MORPH_TR_BIG);                    \
+        else if (tr == MORPH_TR_MID) LM2(CODE, TAP, RUNS, MORPH_TR_MID);               \
+        else LM2(CODE, TAP, RUNS, MORPH_TR);                                           \
+    } while (0)
 #define LM(CODE, TAP)                                                                  \
     do {                                                                               \
-        if (runs) { if (big) LM2(CODE, TAP, true, MORPH_TR_BIG); else LM2(CODE, TAP, true, MORPH_TR); }   \
-        else { if (big) LM2(CODE, TAP, false, MORPH_TR_BIG); else LM2(CODE, TAP, false, MORPH_TR); }      \
+        if (runs) LM3(CODE, TAP, true); else LM3(CODE, TAP, false);                    \
     } while (0)
     if (with02) {
         switch (morph03) {
@@ -1049,6 +1058,7 @@ static cudaError_t launch_morph(bool with02, int morph03, const u32 *in_bits, u3
         }
     }
 #undef LM
+#undef LM3
 #undef LM2
     return cudaGetLastError();
 }
