@@ -408,7 +408,10 @@ __global__ void __launch_bounds__(256) fk_build_rgbcells(const __grid_constant__
         }
         const bool single = sane && mask != 0u && (mask & (mask - 1u)) == 0u;
         if (single) nibbles |= (u32)(P.lut[__ffs(mask) - 1] & 15u) << (4 * q);
-        else multi |= 1u << q;
+        else {
+            multi |= 1u << q;
+            if (K < 16) nibbles |= 15u << (4 * q);               // K <= 15: the label table itself says "several candidates"
+        }
     }
     nib[gi] = nibbles;
     mb[gi] = (u8)multi;
@@ -432,6 +435,7 @@ struct ZeroJob { uint4 *p[2]; unsigned long long n16[2]; unsigned per[2]; };   /
 #define RA_WARP_BYTES (768 + 256 + 256)
 #define RA_SMEM (RA_OFF_WARP + RA_WARPS * RA_WARP_BYTES)
 
+template <bool SEP_MULTI>                  // K == 16: the "several candidates" flag needs its own bit table; K <= 15: nibble 15
 __global__ void __launch_bounds__(RA_THREADS, 1) fk_assign_rgbcell(const u8 *__restrict__ px, int h, int w, size_t pitch,
                                                                    const __grid_constant__ AssignParams P, const uint4 *__restrict__ rtab,
                                                                    const u32 *__restrict__ cells,
@@ -448,7 +452,8 @@ __global__ void __launch_bounds__(RA_THREADS, 1) fk_assign_rgbcell(const u8 *__r
     u16 *s_gam = reinterpret_cast<u16 *>(smem + RA_OFF_GAM);
     float4 *s_ctr = reinterpret_cast<float4 *>(smem + RA_OFF_CTR);
     u8 *s_lut = smem + RA_OFF_LUT;
-    for (int i = threadIdx.x; i < (RC_NIB_BYTES + RC_MB_BYTES) / 16; i += RA_THREADS) reinterpret_cast<uint4 *>(smem)[i] = __ldg(rtab + i);
+    for (int i = threadIdx.x; i < (RC_NIB_BYTES + (SEP_MULTI ? RC_MB_BYTES : 0)) / 16; i += RA_THREADS)
+        reinterpret_cast<uint4 *>(smem)[i] = __ldg(rtab + i);
     for (int i = threadIdx.x; i < 2048; i += RA_THREADS) {
         s_cbrt[i] = f_lab_tab[256 + i];
         if (i < 256) s_gam[i] = f_lab_tab[i];
@@ -522,7 +527,7 @@ __global__ void __launch_bounds__(RA_THREADS, 1) fk_assign_rgbcell(const u8 *__r
                 const u32 v0 = p[0], v1 = p[1], v2 = p[2];
                 const u32 ci = ((v0 >> RC_SHIFT) << 12) | ((v1 >> RC_SHIFT) << 6) | (v2 >> RC_SHIFT);
                 lab[g] = (s_nib[ci >> 3] >> ((ci & 7u) * 4u)) & 15u;
-                multi = (s_mb[ci >> 5] >> (ci & 31u)) & 1u;
+                multi = SEP_MULTI ? ((s_mb[ci >> 5] >> (ci & 31u)) & 1u) != 0u : lab[g] == 15;
             }
             const u32 bal = __ballot_sync(0xffffffffu, multi);
             if (multi) {
@@ -1290,11 +1295,19 @@ static int bit_planes(omni_ctx *ctx, const BitGeom &g, int K, int n, u32 **out /
     return OMNI_OK;
 }
 
+// the RGB-cell tables hold output labels in 4 bits (15 = "several candidates" when K <= 15): every label must be < K
+static bool lut_below_k(const AssignParams &P)
+{
+    for (int k = 0; k < P.K; k++)
+        if (P.lut[k] >= P.K) return false;
+    return true;
+}
+
 // candidate-cell tables for the centres of this call (workspace slot 5), built on the device
 static int assign_cells(omni_ctx *ctx, const AssignParams &P, u32 **cells, u8 **rcells, cudaStream_t st)
 {
     FK_TRY(omni_ws_reserve(ctx, 5, WS5_BYTES));
-    const int variant = (ctx->assign_rgbcell && P.K <= RC_MAX_K) ? 2 : 1;
+    const int variant = (ctx->assign_rgbcell && P.K <= RC_MAX_K && lut_below_k(P)) ? 2 : 1;
     *cells = (u32 *)ctx->ws[5];
     *rcells = (u8 *)((u32 *)ctx->ws[5] + RGBCELL_OFFSET);
     // same centres (and label map) as the previous call on this ctx (a batch of frames): the tables in the workspace are
@@ -1328,7 +1341,7 @@ static int assign_cells(omni_ctx *ctx, const AssignParams &P, u32 **cells, u8 **
 static bool assign_takes_zero_job(omni_ctx *ctx, const AssignParams &P, int nf, int h, int w)
 {
     const unsigned long long plane = (unsigned long long)(((((w + 31) >> 5) + 3) & ~3)) * h;
-    return ctx->assign_rgbcell && P.K <= RC_MAX_K && (long long)nf * h * ((w + 255) >> 8) < (1ll << 30) &&
+    return ctx->assign_rgbcell && P.K <= RC_MAX_K && lut_below_k(P) && (long long)nf * h * ((w + 255) >> 8) < (1ll << 30) &&
            (unsigned long long)nf * P.K * plane < (1ull << 30);
 }
 
@@ -1338,7 +1351,7 @@ static int launch_assign_lab(omni_ctx *ctx, const u8 *px, int h, int w, size_t p
                              const ZeroJob *zero = nullptr /* only honoured by the RGB-cell kernel: check assign_takes_zero_job() */)
 {
     // the RGB-cell kernel counts chunks in 32 bits and takes a whole batch; the Lab-cell kernel takes one frame per launch
-    const bool use_rgb = ctx->assign_rgbcell && P.K <= RC_MAX_K && (long long)nf * h * ((w + 255) >> 8) < (1ll << 30) &&
+    const bool use_rgb = ctx->assign_rgbcell && P.K <= RC_MAX_K && lut_below_k(P) && (long long)nf * h * ((w + 255) >> 8) < (1ll << 30) &&
                          (unsigned long long)nf * P.K * plane < (1ull << 30);        // 32-bit word / byte offsets inside the kernel
     if (!use_rgb && nf > 1) {
         for (int f = 0; f < nf; f++)
@@ -1352,7 +1365,8 @@ static int launch_assign_lab(omni_ctx *ctx, const u8 *px, int h, int w, size_t p
     KScope ks(scoped ? ctx : nullptr, "assign_bits", st);
     if (use_rgb) {
         if (!ctx->occ_assign_rgb) {
-            OMNI_CUDA(cudaFuncSetAttribute(fk_assign_rgbcell, cudaFuncAttributeMaxDynamicSharedMemorySize, RA_SMEM));
+            OMNI_CUDA(cudaFuncSetAttribute(fk_assign_rgbcell<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, RA_SMEM));
+            OMNI_CUDA(cudaFuncSetAttribute(fk_assign_rgbcell<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, RA_SMEM));
             ctx->occ_assign_rgb = 1;
         }
         // one CTA per SM (its tables fill most of the shared memory); no more CTAs than chunks of 32 warps
@@ -1362,8 +1376,12 @@ static int launch_assign_lab(omni_ctx *ctx, const u8 *px, int h, int w, size_t p
         if (zero) Z = *zero;
         for (int z = 0; z < 2; z++)                         // units per chunk, rounded up to one store per lane
             Z.per[z] = (unsigned)(((Z.n16[z] + (unsigned long long)chunks - 1) / (unsigned long long)chunks + 31) & ~31ull);
-        fk_assign_rgbcell<<<grid, RA_THREADS, RA_SMEM, st>>>(px, h, w, pitch, P, (const uint4 *)rcells, cells, labels, lpitch, bits, ws, plane,
-                                                             nf, frame_stride, Z);
+        if (P.K >= 16)
+            fk_assign_rgbcell<true><<<grid, RA_THREADS, RA_SMEM, st>>>(px, h, w, pitch, P, (const uint4 *)rcells, cells, labels, lpitch, bits, ws,
+                                                                       plane, nf, frame_stride, Z);
+        else
+            fk_assign_rgbcell<false><<<grid, RA_THREADS, RA_SMEM, st>>>(px, h, w, pitch, P, (const uint4 *)rcells, cells, labels, lpitch, bits, ws,
+                                                                        plane, nf, frame_stride, Z);
     } else {
         const int grid = resident_grid(ctx, fk_assign_bits<1>, 256, &ctx->occ_assign_lab);
         fk_assign_bits<1><<<grid, 256, 0, st>>>(px, h, w, pitch, P, cells, labels, lpitch, bits, ws, plane);

@@ -637,3 +637,14 @@ def test_fuzz_fused_vs_oracle(eng, seed):
     wm = cm.layer_masks(raw, K, lut)
     assert np.array_equal(host(masks), wm)
     assert np.array_equal(host(edges), _edge_want(wm, ksize=3, low=low, high=high, morph_k=mk, open_iters=oi, close_iters=ci))
+
+
+def test_assign_lut_outside_k(eng):
+    """A label map with values >= K (allowed by the ABI, < 32): the RGB-cell tables cannot hold them -> Lab-cell kernel; same labels."""
+    cm = _cm()
+    img = synth(120, 333, 4, cell=16)
+    K = 5
+    ctr = _rp().kmeans_lab_centers(img, K)
+    lut = np.array([20, 3, 31, 0, 15], np.uint8)
+    got = host(eng.assign_lab(dev(img), ctr, lut))
+    assert np.array_equal(got, lut[cm.assign_f32(cm.bgr2lab(img), ctr)])
