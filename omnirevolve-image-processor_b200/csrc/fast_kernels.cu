@@ -1115,16 +1115,22 @@ __global__ void __launch_bounds__(HY_THREADS) fk_hysteresis(u32 *__restrict__ eb
                 const int k = (int)(o / plane), rem = (int)(o - (size_t)k * plane);
                 const int y = rem / ws, c = rem - y * ws;
                 u32 *E = ebits + (size_t)k * plane + (size_t)y * ws;
-                const u32 cv = __ldg(cbits + o), ev = __ldcg(E + c);
+                // every load of the item is issued at once (one L2 round trip instead of three dependent ones)
+                const u32 cv = __ldg(cbits + o);
+                u32 m3[3], l3[3], r3[3];
+#pragma unroll
+                for (int dy = -1; dy <= 1; dy++) {
+                    const bool in = y + dy >= 0 && y + dy < h;
+                    const u32 *Er = E + (ptrdiff_t)dy * ws;
+                    m3[dy + 1] = in ? __ldcg(Er + c) : 0u;
+                    l3[dy + 1] = (in && c > 0) ? __ldcg(Er + c - 1) : 0u;
+                    r3[dy + 1] = (in && c + 1 < wwl) ? __ldcg(Er + c + 1) : 0u;
+                }
+                const u32 ev = m3[1];
                 if ((cv & ~ev) == 0u) continue;
                 u32 d = 0u;
 #pragma unroll
-                for (int dy = -1; dy <= 1; dy++) {
-                    if (y + dy < 0 || y + dy >= h) continue;
-                    const u32 *Er = E + (ptrdiff_t)dy * ws;
-                    u32 m = __ldcg(Er + c), l = c > 0 ? __ldcg(Er + c - 1) : 0u, r = c + 1 < wwl ? __ldcg(Er + c + 1) : 0u;
-                    d |= m | (m << 1) | (m >> 1) | (l >> 31) | (r << 31);
-                }
+                for (int q = 0; q < 3; q++) d |= m3[q] | (m3[q] << 1) | (m3[q] >> 1) | (l3[q] >> 31) | (r3[q] << 31);
                 u32 nv = ev | (cv & d);
                 for (;;) {
                     u32 t = nv | (cv & ((nv << 1) | (nv >> 1)));
