@@ -82,3 +82,47 @@ def test_assign_labels_dropin():
     z = np.load(f"{GOLDEN}/functions.npz")
     for K in (2, 4, 8, 16):
         assert np.array_equal(process_colors_gpu.assign_labels(z["al_img"], z[f"al_pal{K}"]), z[f"al_lab{K}"])
+
+
+def test_stage04_shim_swaps_only_the_thinning(tmp_path):
+    """The stage-04 shim loads `04_find_contours_ref.py` (the reference's renamed file -- here a stand-in with the same
+    surface), replaces `thinning_zhangsuen` by the GPU mirror and runs the original `vectorize_all`."""
+    import shutil
+    import subprocess
+    import sys
+    import cv2
+    import numpy as np
+    from helpers import blob_mask
+    from oracle import cmodel as cm
+    src = os.path.join(ROOT, "omnirevolve-image-processor_b200", "image_processor")
+    for f in ("04_find_contours.py", "_omni_path.py"):
+        shutil.copy(os.path.join(src, f), tmp_path / f)
+    (tmp_path / "04_find_contours_ref.py").write_text(
+        "import os, cv2, numpy as np\n"
+        "def load_config():\n"
+        "    class C: pass\n"
+        "    c = C(); c.output_dir = os.environ['OUT_DIR']; c.color_names = ['layer_a', 'layer_b']; return c\n"
+        "def thinning_zhangsuen(img, layer):\n"
+        "    raise RuntimeError('the CPU thinning must have been replaced')\n"
+        "def trace_centerlines(skel, layer):\n"
+        "    return [skel]\n"
+        "def vectorize_layer(name, cfg):\n"
+        "    e = cv2.imread(os.path.join(cfg.output_dir, name, 'edges.png'), cv2.IMREAD_GRAYSCALE)\n"
+        "    sk = thinning_zhangsuen(e, layer=name)\n"
+        "    np.save(os.path.join(cfg.output_dir, name, 'skel.npy'), trace_centerlines(sk, name)[0]); return name, []\n"
+        "def vectorize_all(cfg):\n"
+        "    return dict(vectorize_layer(n, cfg) for n in cfg.color_names)\n")
+    out = tmp_path / "out"
+    want = {}
+    for i, n in enumerate(("layer_a", "layer_b")):
+        os.makedirs(out / n)
+        e = cv2.Canny(cv2.GaussianBlur(blob_mask(120, 160, 30 + i, 0.4, k=7), (3, 3), 0), 50, 150)
+        cv2.imwrite(str(out / n / "edges.png"), e)
+        want[n] = cm.thin_zhangsuen(e)
+    env = dict(os.environ, OUT_DIR=str(out), OMNI_B200_HOME=os.path.join(ROOT, "omnirevolve-image-processor_b200"))
+    r = subprocess.run([sys.executable, str(tmp_path / "04_find_contours.py")], env=env, stdout=subprocess.PIPE,
+                       stderr=subprocess.STDOUT, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:]
+    assert "[layer_a] Thinning ROI" in r.stdout and "Thinning done" in r.stdout
+    for n in want:
+        assert np.array_equal(np.load(out / n / "skel.npy"), want[n]), n

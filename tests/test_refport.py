@@ -83,3 +83,41 @@ def test_skeleton_degree_global_equals_per_component():
         on = sk > 0
         assert np.array_equal(deg[on], deg_c[on]) and np.array_equal(ep, ep_c) and np.array_equal(jn, jn_c)
         assert ep.any() or jn.any()
+
+
+def test_stage04_swap_point_with_real_reference(tmp_path):
+    """The stage-04 shim (image_processor/04_find_contours.py) replaces ONE module global of the reference's stage 04.
+    With the real reference file: the names the shim relies on exist, `vectorize_layer` resolves `thinning_zhangsuen`
+    through the module globals, and a skeleton that equals the reference's (here from the pinned C oracle -- the GPU
+    kernel is checked against the same oracle) yields the reference's contours.pkl byte for byte."""
+    import contextlib
+    import io
+    import pickle
+    from oracle import cmodel as cm
+    from helpers import blob_mask
+    ref = _load("04_find_contours.py", "ref_fc_swap")
+    for name in ("thinning_zhangsuen", "trace_centerlines", "vectorize_layer", "vectorize_all", "load_config"):
+        assert callable(getattr(ref, name)), name
+
+    class Cfg:
+        pass
+    cfg = Cfg()
+    cfg.output_dir = str(tmp_path)
+    cfg.color_names = ["layer_a"]
+    os.makedirs(tmp_path / "layer_a")
+    edges = cv2.Canny(cv2.GaussianBlur(blob_mask(60, 80, 3, 0.4, k=7), (3, 3), 0), 50, 150)
+    cv2.imwrite(str(tmp_path / "layer_a" / "edges.png"), edges)
+    with contextlib.redirect_stdout(io.StringIO()):
+        ref.vectorize_all(cfg)
+    want = pickle.load(open(tmp_path / "layer_a" / "contours.pkl", "rb"))
+    calls = []
+
+    def swapped(bin_0_255, layer):
+        calls.append(layer)
+        return cm.thin_zhangsuen(bin_0_255)
+    ref.thinning_zhangsuen = swapped
+    with contextlib.redirect_stdout(io.StringIO()):
+        ref.vectorize_all(cfg)
+    got = pickle.load(open(tmp_path / "layer_a" / "contours.pkl", "rb"))
+    assert calls == ["layer_a"]
+    assert len(got) == len(want) and all(np.array_equal(a, b) for a, b in zip(got, want))
