@@ -239,15 +239,17 @@ __global__ void __launch_bounds__(E3V_WARPS * 32) fk_edges3_simd(const __grid_co
         }
         __syncwarp();
         if (do_nms) {
-            const u16 *mu = S.m[(rnr + 5) % 3], *mc = S.m[(rnr + 6) % 3], *md = S.m[(rnr + 7) % 3];
+            // the three magnitude rows live in one array: neighbour = centre row + a (uniform) row offset + a column offset
+            const u16 *mc = S.m[(rnr + 6) % 3];
+            const int dU = (((rnr + 5) % 3) - ((rnr + 6) % 3)) * (32 * E3V_LSTRIDE), dD = (((rnr + 7) % 3) - ((rnr + 6) % 3)) * (32 * E3V_LSTRIDE);
             const u16 *dxr = S.dx[rnr & 1], *dyr = S.dy[rnr & 1];
             // E3_NMS_UNROLL candidates per lane and round (independent dependency chains); a lane whose later indices fall off
             // the list repeats the last entry -- the result bits are OR-ed in, so a repeat is harmless
             auto nms_one = [&](const int item, int &o, u32 &bit, bool &ok, bool &strong) {
                 o = item >> 5;
                 const int e = item & 31;
-                const int bi = o * E3V_LSTRIDE + e;
-                const int m0 = mc[bi + 2];
+                const u16 *pc = mc + (o * E3V_LSTRIDE + e + 2);
+                const int m0 = pc[0];
                 // cv2.Canny's direction test  |dy| * 2^15 < |dx| * TG22  /  > |dx| * (TG22 + 2^16), TG22 = 13573, in float32:
                 // |dx|, |dy| <= 1020 are integers, so |dx| * 13573 < 2^24 and (|dy| - 2|dx|) * 2^15 are exact
                 const u32 dxb = dxr[item], dyb = dyr[item];
@@ -255,9 +257,8 @@ __global__ void __launch_bounds__(E3V_WARPS * 32) fk_edges3_simd(const __grid_co
                 const float tg = __fmul_rn(ax, 13573.f);
                 const bool hz = __fmul_rn(ay, 32768.f) < tg, vt = __fmul_rn(__fsub_rn(ay, __fadd_rn(ax, ax)), 32768.f) > tg;
                 const int s = ((dxb ^ dyb) & 0x8000u) ? -1 : 1;             // fp16 differences are never -0
-                const int off = hz ? 1 : (vt ? 0 : s);                    // a = (row above|same)[x - off], b = (row below|same)[x + off]
-                const u16 *ra = hz ? mc : mu, *rb = hz ? mc : md;
-                const int a = ra[bi + 2 - off], b = rb[bi + 2 + off];
+                const int t = vt ? 0 : s;                                   // a = (row above | same)[x - off], b = (row below | same)[x + off]
+                const int a = pc[hz ? -1 : dU - t], b = pc[hz ? 1 : dD + t];
                 ok = m0 > a && (m0 > b || ((hz || vt) && m0 == b));
                 strong = m0 > high_bits;
                 bit = 1u << e;
