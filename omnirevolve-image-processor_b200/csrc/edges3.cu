@@ -7,10 +7,15 @@
 // columns (1024 pixels).  Everything dense is SIMD-in-register:
 //   bits --6-bit LUT--> horizontal (1,2,1) sums, 4 px per 32-bit word (bytes)
 //        --rolling rows--> v = (1,2,1)x(1,2,1) bit sum in [0,16]     B = 16 v - (v > 8)   (exact 8.8 blur)
-//        --unpack--> 2 px per word (16-bit lanes): vertical Sobel parts, dx, dy, |dx|+|dy|  (VIADD/VIMNMX.16x2)
+//        --unpack--> 2 px per word (fp16x2 lanes, exact: all values are integers <= 2040): vertical Sobel parts, dx, dy,
+//                    |dx|+|dy|  (HADD2 / HFMA2)
 //        --sign bits--> 32-bit "m > low" mask per lane-row.
-// Only the ~7 % of pixels with m > low go through the 32-bit direction test + neighbour compare; their
-// m / dx / dy come from a per-warp shared-memory row ring.
+// Only the ~7 % of pixels with m > low go through the direction test (float32, exact) + neighbour compare; their
+// m / dx / dy come from a per-warp shared-memory row ring; candidates are compacted over the warp.
+//
+// Two variants of one kernel: DENSE walks every word of every plane; SPARSE (the default) walks only the runs of tiles
+// that can hold an edge pixel -- the lists come from the morphology kernel (fast_kernels.cu, MorphRuns) or from
+// fk_edge_runs below, the zeros of all other tiles from the zero fill that rides on the assignment kernel.
 //
 // Borders.  Blur uses REFLECT_101 on the mask, Sobel uses REPLICATE on the blurred image, m = 0 outside.  Both
 // are obtained by patching only the BITS that enter the pipeline: with bit(-1) := bit(1) (REFLECT_101) and

@@ -7,11 +7,16 @@
 // 16.8 MB -- they live in the 126 MB L2 between the kernels, so HBM sees only the image read (3 B/px) and
 // the mask / edge byte planes written once each (2K B/px): the algorithmic N*(3+2K) bytes.
 //
-//   fk_assign_bits    image -> [labels] + raw one-hot bit-planes P0           (02:35-36,53-55,121-127,150)
+//   fk_assign_rgbcell image -> [labels] + raw one-hot bit-planes P0           (02:35-36,53-55,121-127,150)
+//                     (RGB-cell tables in shared memory; fk_assign_bits = the Lab-cell generation, K > 16 / palette mode);
+//                     its warps also clear the edge planes for the dead tiles of the edge pass (ZeroJob)
 //   fk_morph<CODE>    P0 -> RECT-3 open/close -> mask BYTES (mask.png content) (02:151-154)
 //                        -> ELLIPSE-3 open/close -> bit-planes M2              (03:23-30)
-//   fk_edges3         M2 -> blur-3 -> Sobel -> NMS -> strong/candidate bit-planes S, C   (03:33-34)
-//   fk_hysteresis     cooperative: E = S; E |= C & dilate8(E) to the global fixed point; E -> edge BYTES
+//                        + run lists of the live tiles for the sparse edge kernel (MorphRuns)
+//   fk_edges3_simd    M2 -> blur-3 -> Sobel -> NMS -> strong/candidate bit-planes S, C + edge BYTES (edges3.cu; 03:33-34)
+//   fk_hysteresis     E = S; E |= C & dilate8(E) to the global fixed point, promoted pixels patched into the edge bytes
+//   also here: fractional / 2:1 resize (01), swatch mode (02:82-109), Zhang-Suen thinning (04:35-99), frame batches and
+//   the band-pipelined host-buffer call
 //
 // Reference call sites are relative to /root/reference/image_processor/.  Arithmetic: SURVEY.md App. A.
 #include "fast_kernels.cuh"
