@@ -1802,7 +1802,6 @@ int fast_host_color_edge(omni_ctx *ctx, const u8 *h_bgr, int h, int w, size_t pi
 // all planes until the last one converges (or to max_iter) gives every plane the reference's result;
 // removed[k * max_iter + i] = pixels deleted from plane k in iteration i + 1 (the number the reference logs).
 // ------------------------------------------------------------------------------------------------
-#define TH_ROWS 16
 
 __device__ __forceinline__ u32 th_xor3(u32 a, u32 b, u32 c) { return a ^ b ^ c; }
 __device__ __forceinline__ u32 th_maj(u32 a, u32 b, u32 c) { return (a & b) | (c & (a | b)); }
@@ -1846,7 +1845,7 @@ __device__ __forceinline__ u32 thin_delete_mask(u32 ul, u32 um, u32 ur, u32 ml, 
 template <int STEP>
 __device__ __forceinline__ void thin_substep(const u32 *__restrict__ src, u32 *__restrict__ dst, int ws, size_t plane, int h, int ww, int K,
                                              int *removed_it /* + k * max_iter */, int max_iter, volatile int *chg,
-                                             const u8 *up1, const u8 *up2, u8 *ucur, u8 *unext)
+                                             const u8 *up1, const u8 *up2, u8 *ucur, u8 *unext, const int TH_ROWS /* rows per unit */)
 {
     const int lane = threadIdx.x & 31;
     const int wcols = (ww + 31) / 32, strips = (h + TH_ROWS - 1) / TH_ROWS;
@@ -1913,7 +1912,7 @@ __device__ __forceinline__ void thin_substep(const u32 *__restrict__ src, u32 *_
 
 __global__ void __launch_bounds__(256) fk_thin(u32 *__restrict__ A, u32 *__restrict__ B, int ws, size_t plane, int h, int w, int K, int max_iter,
                                                int *__restrict__ removed, int *flags /* [0] iterations run, [1..3] rotating changed flags */,
-                                               u8 *__restrict__ unit_flags /* 4 x units, zeroed */, size_t units)
+                                               u8 *__restrict__ unit_flags /* 4 x units, zeroed */, size_t units, int unit_rows)
 {
     cg::grid_group grid = cg::this_grid();
     const int ww = (w + 31) >> 5;
@@ -1922,10 +1921,10 @@ __global__ void __launch_bounds__(256) fk_thin(u32 *__restrict__ A, u32 *__restr
         // unit flags: four buffers rotate over the sub-steps t (written at t, read at t + 1 and t + 2, cleared at t + 3)
         const int t1 = 2 * it, t2 = 2 * it + 1;
         auto ub = [&](int t) { return unit_flags + (size_t)(t & 3) * units; };
-        thin_substep<1>(A, B, ws, plane, h, ww, K, removed + it, max_iter, chg, it > 0 ? ub(t1 - 1) : nullptr, ub(t1 - 2), ub(t1), ub(t1 + 1));
+        thin_substep<1>(A, B, ws, plane, h, ww, K, removed + it, max_iter, chg, it > 0 ? ub(t1 - 1) : nullptr, ub(t1 - 2), ub(t1), ub(t1 + 1), unit_rows);
         __threadfence();
         grid.sync();
-        thin_substep<2>(B, A, ws, plane, h, ww, K, removed + it, max_iter, chg, it > 0 ? ub(t2 - 1) : nullptr, ub(t2 - 2), ub(t2), ub(t2 + 1));
+        thin_substep<2>(B, A, ws, plane, h, ww, K, removed + it, max_iter, chg, it > 0 ? ub(t2 - 1) : nullptr, ub(t2 - 2), ub(t2), ub(t2 + 1), unit_rows);
         __threadfence();
         grid.sync();
         const int c = *chg;
@@ -1945,7 +1944,25 @@ int fast_thin(omni_ctx *ctx, const u8 *d_in, int K, int h, int w, size_t in_plan
     int al = ((uintptr_t)d_out % 16 == 0) && (out_plane % 16 == 0) && (out_pitch % 16 == 0);
     if (max_iter < 0) max_iter = 0;
     const size_t n_rem = (size_t)K * (max_iter > 0 ? max_iter : 1);
-    size_t units = (size_t)K * ((h + TH_ROWS - 1) / TH_ROWS) * ((g.ww + 31) / 32);
+    if (ctx->thin_blocks == 0) {
+        int per_sm = 0;
+        OMNI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fk_thin, 256, 0));
+        if (per_sm < 1) { omni_set_error("thinning kernel cannot be made resident"); return OMNI_ERR_CUDA; }
+        ctx->thin_blocks = per_sm * (ctx->sm_count > 0 ? ctx->sm_count : 1);
+    }
+    // rows per unit (a warp walks a unit's rows + 2 halo rows in sequence): the height that minimises the longest chain of a
+    // full sweep, ceil(units / resident warps) * (rows + 2)
+    int unit_rows = 16;
+    {
+        const long long warps = (long long)ctx->thin_blocks * 8, cols = (g.ww + 31) / 32;
+        long long best = -1;
+        for (int tr = 6; tr <= 32; tr++) {
+            const long long u = (long long)K * ((h + tr - 1) / tr) * cols;
+            const long long cost = ((u + warps - 1) / warps) * (tr + 2);
+            if (best < 0 || cost < best) { best = cost; unit_rows = tr; }
+        }
+    }
+    size_t units = (size_t)K * ((h + unit_rows - 1) / unit_rows) * ((g.ww + 31) / 32);
     FK_TRY(omni_ws_reserve(ctx, 6, n_rem * sizeof(int) + 4 * units));
     int *d_removed = (int *)ctx->ws[6];
     u8 *d_unit = (u8 *)(d_removed + n_rem);
@@ -1958,19 +1975,13 @@ int fast_thin(omni_ctx *ctx, const u8 *d_in, int K, int h, int w, size_t in_plan
         OMNI_CUDA(cudaGetLastError());
     }
     if (max_iter > 0) {
-        if (ctx->thin_blocks == 0) {
-            int per_sm = 0;
-            OMNI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fk_thin, 256, 0));
-            if (per_sm < 1) { omni_set_error("thinning kernel cannot be made resident"); return OMNI_ERR_CUDA; }
-            ctx->thin_blocks = per_sm * (ctx->sm_count > 0 ? ctx->sm_count : 1);
-        }
         // no more CTAs than warp units (8 warps per CTA): barriers get cheaper on small inputs
         int blocks = (int)std::min<long long>(ctx->thin_blocks, ((long long)units + 7) / 8);
         if (blocks < 1) blocks = 1;
         int ws = g.ws;
         size_t plane = g.plane;
         int *flags = ctx->d_flags;
-        void *args[] = {&bpp[0], &bpp[1], &ws, &plane, &h, &w, &K, &max_iter, &d_removed, &flags, &d_unit, &units};
+        void *args[] = {&bpp[0], &bpp[1], &ws, &plane, &h, &w, &K, &max_iter, &d_removed, &flags, &d_unit, &units, &unit_rows};
         OMNI_LAUNCH(ctx, st, "thin_zhangsuen", cudaLaunchCooperativeKernel((const void *)fk_thin, dim3(blocks), dim3(256), args, 0, st));
     }
     {
