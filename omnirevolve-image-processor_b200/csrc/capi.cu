@@ -105,12 +105,15 @@ extern "C" int omni_last_hysteresis_passes(omni_ctx *ctx)
 {
     if (!ctx) return 0;
     if (ctx->last_hyst_passes < 0) {              // the bit-plane kernel leaves its round count in d_flags[0]
-        int v = 0;
-        if (cudaSetDevice(ctx->device) != cudaSuccess || cudaMemcpy(&v, ctx->d_flags, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) {
+        // read on the stream the kernel ran on, then wait for it (the legacy stream does not order against non-blocking streams)
+        cudaStream_t st = ctx->last_hyst_stream;
+        if (cudaSetDevice(ctx->device) != cudaSuccess ||
+            cudaMemcpyAsync(ctx->h_flags + 9, ctx->d_flags, sizeof(int), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+            cudaStreamSynchronize(st) != cudaSuccess) {
             cudaGetLastError();
             return 0;
         }
-        ctx->last_hyst_passes = v;
+        ctx->last_hyst_passes = ctx->h_flags[9];
     }
     return ctx->last_hyst_passes;
 }
@@ -631,8 +634,14 @@ extern "C" int omni_host_assign_rgb_i16wrap(omni_ctx *ctx, const uint8_t *h_rgb,
 static int copy_planes_d2h(u8 *h_dst, size_t h_plane, size_t hpitch, const u8 *d_src, size_t d_plane, size_t dpitch,
                            int K, int h, int w, cudaStream_t st)
 {
-    if (hpitch == dpitch && h_plane == d_plane) {       // one contiguous copy
+    // one contiguous copy only when the host rows are gap-free: with hpitch > w the bytes between the rows belong to the
+    // caller (a view into a wider array) and must not be touched
+    if (hpitch == (size_t)w && dpitch == hpitch && h_plane == d_plane) {
         OMNI_CUDA(cudaMemcpyAsync(h_dst, d_src, d_plane * (size_t)(K - 1) + dpitch * (size_t)(h - 1) + w, cudaMemcpyDeviceToHost, st));
+        return OMNI_OK;
+    }
+    if (hpitch == (size_t)w && dpitch == hpitch) {      // gap-free planes, different plane strides: one 2-D copy (row = plane)
+        OMNI_CUDA(cudaMemcpy2DAsync(h_dst, h_plane, d_src, d_plane, (size_t)w * h, K, cudaMemcpyDeviceToHost, st));
         return OMNI_OK;
     }
     for (int k = 0; k < K; k++)

@@ -21,6 +21,7 @@
 // Reference call sites are relative to /root/reference/image_processor/.  Arithmetic: SURVEY.md App. A.
 #include "fast_kernels.cuh"
 #include "omni_tables.inc"
+#include "fast_device.cuh"
 
 #include <algorithm>
 #include <type_traits>
@@ -35,23 +36,6 @@ namespace cg = cooperative_groups;
 // ------------------------------------------------------------------------------------------------
 // shared helpers
 // ------------------------------------------------------------------------------------------------
-struct BitGeom {
-    int h, w;
-    int ww;            // words per row that hold pixels
-    int ws;            // row stride in words (multiple of 4)
-    size_t plane;      // words per plane
-};
-
-static BitGeom make_geom(int h, int w)
-{
-    BitGeom g;
-    g.h = h; g.w = w;
-    g.ww = (w + 31) >> 5;
-    g.ws = (g.ww + 3) & ~3;
-    g.plane = (size_t)g.ws * h;
-    return g;
-}
-
 __device__ u16 f_lab_tab[256 + 2048];          // gamma[256] | cbrt[2041]
 static bool f_tab_ready[64] = {false};
 
@@ -277,18 +261,6 @@ cudaError_t fast_resize_frac(const u8 *src, int sh, int sw, size_t spitch, u8 *d
 // __match_any_sync on the labels of a 32-pixel group: the mask a lane gets back IS the word of its label's
 // plane; the lowest lane of each label stores it (the planes are zeroed beforehand).
 // ------------------------------------------------------------------------------------------------
-#define CELL_SHIFT 3
-#define CELL_N (256 >> CELL_SHIFT)                 // 32 cells per axis
-#define CELL_COUNT (CELL_N * CELL_N * CELL_N)
-// RGB cells (fk_build_rgbcells): 4x4x4 colours each, 64 per axis
-#define RC_SHIFT 2
-#define RC_N (256 >> RC_SHIFT)
-#define RC_COUNT (RC_N * RC_N * RC_N)
-// workspace slot 5: [Lab candidate-cell table (u32) | hysteresis worklist | RGB cell tables: label nibbles, flags]
-#define HYST_WL_OFFSET CELL_COUNT
-#define RGBCELL_OFFSET (CELL_COUNT + 8192)
-#define WS5_BYTES ((size_t)(CELL_COUNT + 8192) * sizeof(u32) + (size_t)RC_COUNT / 2 + (size_t)RC_COUNT / 8)
-
 __global__ void __launch_bounds__(256) fk_build_cells(const __grid_constant__ AssignParams P, u32 *__restrict__ cells)
 {
     // float32 is enough here: coordinates <= 255 and |centre| < 1e4 (checked), so dmin/dmax carry an absolute
@@ -326,20 +298,6 @@ __global__ void __launch_bounds__(256) fk_build_cells(const __grid_constant__ As
     cells[ci] = mask;
 }
 
-// cv2 BGR->Lab (8-bit) for one pixel, without the final saturate_cast: with OpenCV's tables L, a, b stay
-// inside [0,255] for every input (L 0..255, a 42..226, b 20..223 over all 2^24 colours -- the exhaustive GPU test
-// covers it), so the clamps of the generic kernel are no-ops here.
-__device__ __forceinline__ void lab_noclamp(const u16 *gam, const u16 *cbrt, int B8, int G8, int R8, int &L, int &a, int &b)
-{
-    const int B = gam[B8], G = gam[G8], R = gam[R8];
-    const int fX = cbrt[(R * 1777 + G * 1541 + B * 778 + 2048) >> 12];
-    const int fY = cbrt[(R * 871 + G * 2929 + B * 296 + 2048) >> 12];
-    const int fZ = cbrt[(R * 73 + G * 448 + B * 3575 + 2048) >> 12];
-    L = (296 * fY - 1336934 + 16384) >> 15;
-    a = (500 * (fX - fY) + 128 * 32768 + 16384) >> 15;
-    b = (200 * (fY - fZ) + 128 * 32768 + 16384) >> 15;
-}
-
 // ---- RGB-cell variant (the default for Lab centres) -------------------------------------------------------
 // The same exact pruning, one level earlier: the RGB cube is cut into 64^3 cells of 4x4x4 colours and every cell gets
 // the set of centres that can be nearest for SOME colour of the cell.  The cell's image in Lab space is bounded by the
@@ -352,9 +310,6 @@ __device__ __forceinline__ void lab_noclamp(const u16 *gam, const u16 *cbrt, int
 // The tables are 4 bits (label, K <= 16) + 1 bit (several candidates) per cell = 160 KB and live in SHARED memory: one
 // 1024-thread CTA per SM copies them in once and then streams pixels (random lookups from global memory were bound
 // by L1 sector traffic: the +-12 noise of neighbouring pixels scatters a warp's 32 lookups over ~20 sectors).
-#define RC_NIB_BYTES (RC_COUNT / 2)
-#define RC_MB_BYTES (RC_COUNT / 8)
-#define RC_MAX_K 16
 // exact Lab bounding box of every RGB cell: boxes[6 * cell + (0..2)] = min L, a, b; [3..5] = max (centre-independent)
 __global__ void __launch_bounds__(256) fk_rgb_boxes(u8 *__restrict__ boxes)
 {
@@ -421,12 +376,6 @@ __global__ void __launch_bounds__(256) fk_build_rgbcells(const __grid_constant__
     nib[gi] = nibbles;
     mb[gi] = (u8)multi;
 }
-
-// Zero fill riding on the assignment kernel: the edge pass needs its output planes cleared (dead tiles are never
-// written, see edges3.cu); the assignment kernel is bound by instruction issue and leaves HBM idle, so every warp clears a
-// slice of those planes with a few 16-byte stores per chunk of pixels instead of a separate memset competing with it.
-struct ZeroJob { uint4 *p[2]; unsigned long long n16[2]; unsigned per[2]; };   // two regions, sizes in 16-byte units (0: nothing
-                                                                                 // to do); per = units per chunk of pixels (launcher)
 
 #define RA_THREADS 1024
 #define RA_WARPS (RA_THREADS / 32)
@@ -785,86 +734,10 @@ __global__ void __launch_bounds__(256) fk_expand_bits(const u32 *__restrict__ bi
 // the chain are software-pipelined down the rows (step s lags the input by s rows), state in registers.
 // Pixels outside the image are "ignored" by OpenCV: erode sees 1s, dilate sees 0s -- applied per step.
 // ------------------------------------------------------------------------------------------------
-enum { ST_NONE = 0, ST_ER = 1, ST_DR = 2, ST_EC = 3, ST_DC = 4 };   // erode/dilate x RECT/CROSS
-
-struct W64 { u32 lo, hi; };
-__device__ __forceinline__ W64 w_shl(W64 a) { W64 r; r.lo = a.lo << 1; r.hi = __funnelshift_l(a.lo, a.hi, 1); return r; }
-__device__ __forceinline__ W64 w_shr(W64 a) { W64 r; r.lo = __funnelshift_r(a.lo, a.hi, 1); r.hi = a.hi >> 1; return r; }
-__device__ __forceinline__ W64 w_and3(W64 a, W64 b, W64 c) { W64 r; r.lo = a.lo & b.lo & c.lo; r.hi = a.hi & b.hi & c.hi; return r; }
-__device__ __forceinline__ W64 w_or3(W64 a, W64 b, W64 c) { W64 r; r.lo = a.lo | b.lo | c.lo; r.hi = a.hi | b.hi | c.hi; return r; }
-
-template <int OP>
-__device__ __forceinline__ W64 morph_step(W64 u, W64 m, W64 d)
-{
-    if (OP == ST_ER) { W64 v = w_and3(u, m, d); return w_and3(v, w_shl(v), w_shr(v)); }
-    if (OP == ST_DR) { W64 v = w_or3(u, m, d); return w_or3(v, w_shl(v), w_shr(v)); }
-    if (OP == ST_EC) { W64 v = w_and3(m, w_shl(m), w_shr(m)); return w_and3(v, u, d); }
-    if (OP == ST_DC) { W64 v = w_or3(m, w_shl(m), w_shr(m)); return w_or3(v, u, d); }
-    return m;
-}
-
-__host__ __device__ constexpr int code_op(u32 code, int i) { return (int)((code >> (4 * i)) & 15u); }
-__host__ __device__ constexpr int code_len(u32 code) { int n = 0; while (n < 8 && code_op(code, n) != ST_NONE) n++; return n; }
-__host__ __device__ constexpr bool op_is_erode(int op) { return op == ST_ER || op == ST_EC; }
-
-#define MORPH_TR 32          // rows per strip (default)
-#define MORPH_TR_MID 48      // ... from 2048 warps on (A/B at 4096^2: 48 beats 32 and 64): TR + 16 (+4) rows are processed for TR produced
-#define MORPH_TR_BIG 64      // ... from 8192 warps on (8192^2, K=16: less halo work wins once there are plenty of warps)
-#define MORPH_MID_MIN_WARPS 2048
-#define MORPH_BIG_MIN_WARPS 8192
-
-// Output-of-range fix-up for a value that the step with opcode `next` will consume: columns outside the
-// image and rows outside the image must read as that step's identity element.
-// ROWFIX = false: every row the strip touches lies inside the image (all but the first and last strips of a plane), so only
-// the columns need the fix-up -- the row tests were a third of the kernel's instructions.
-// COLFIX = false: every window pixel of every lane of the warp lies inside the image (warps away from the left / right
-// border), so the columns need no fix-up either.
-template <int NEXT, bool ROWFIX, bool COLFIX>
-__device__ __forceinline__ W64 oob_fix(W64 v, W64 colvalid, bool row_inside)
-{
-    if (NEXT == ST_NONE) { if (COLFIX) { v.lo &= colvalid.lo; v.hi &= colvalid.hi; } return v; }
-    if (op_is_erode(NEXT)) {
-        if (ROWFIX && !row_inside) { v.lo = v.hi = 0xffffffffu; return v; }
-        if (COLFIX) { v.lo |= ~colvalid.lo; v.hi |= ~colvalid.hi; }
-    } else {
-        if (ROWFIX && !row_inside) { v.lo = v.hi = 0u; return v; }
-        if (COLFIX) { v.lo &= colvalid.lo; v.hi &= colvalid.hi; }
-    }
-    return v;
-}
-
-template <u32 CODE, int S>
-struct MorphChain {
-    // applies steps S.. of CODE to `cur` (= image_S row `t - S`), updating the rolling rows
-    template <int TAP, bool ROWFIX, bool COLFIX>
-    static __device__ __forceinline__ void run(W64 cur, W64 (&p1)[8], W64 (&p2)[8], int t, int h, W64 colvalid, W64 &tap_out, W64 &fin)
-    {
-        constexpr int N = code_len(CODE);
-        if (S == TAP) tap_out = cur;
-        if constexpr (S < N) {
-            constexpr int OP = code_op(CODE, S);
-            constexpr int NEXT = (S + 1 < N) ? code_op(CODE, S + 1) : ST_NONE;
-            W64 out = morph_step<OP>(p2[S], p1[S], cur);
-            p2[S] = p1[S]; p1[S] = cur;
-            const int r = t - S - 1;                       // row of image_{S+1} just produced
-            out = oob_fix<NEXT, ROWFIX, COLFIX>(out, colvalid, !ROWFIX || (r >= 0 && r < h));
-            MorphChain<CODE, S + 1>::template run<TAP, ROWFIX, COLFIX>(out, p1, p2, t, h, colvalid, tap_out, fin);
-        } else {
-            fin = cur;
-        }
-    }
-};
-
 // Run lists of the sparse edge kernel, produced by the morphology kernel itself (RUNS = true): the final image rows
 // pass through this lane's registers with 8 valid halo pixels per side, which is all fk_edge_runs (edges3.cu) needs
 // to classify the lane's MORPH_TR / ET_R tiles -- see the comment there for the rule and the list layout.  The strip is
 // extended by 2 final rows at each end for the tiles' 2-row halo.
-struct MorphRuns {
-    u32 *sbits, *cbits; u8 *edges; size_t estride, epitch; int aligned16;
-    int *run_counts; u32 *run_items; E3RunOff off; int maxt;
-    int zero_fill;                    // 1: the kernel writes the zeros of the dead tiles; 0: the planes were cleared beforehand
-};
-
 // CODE: up to 8 steps, 4 bits each.  TAP: after this many steps the image is the stage-02 mask; it is
 // written as BYTES to `masks` (TAP = -1: nothing).  The final image is written as bits to `out_bits`
 // (may be NULL).
@@ -1012,18 +885,6 @@ __global__ void __launch_bounds__(128, MORPH_MINB) fk_morph(const u32 *__restric
         }
     }
 }
-
-constexpr u32 mk_code(int a, int b = 0, int c = 0, int d = 0, int e = 0, int f = 0, int g = 0, int hh = 0)
-{
-    return (u32)a | ((u32)b << 4) | ((u32)c << 8) | ((u32)d << 12) | ((u32)e << 16) | ((u32)f << 20) | ((u32)g << 24) | ((u32)hh << 28);
-}
-constexpr u32 CODE_R_OC = mk_code(ST_ER, ST_DR, ST_DR, ST_ER);                       // 02: RECT open, close
-constexpr u32 CODE_C_O = mk_code(ST_EC, ST_DC);                                     // 03: cross open
-constexpr u32 CODE_C_C = mk_code(ST_DC, ST_EC);                                     // 03: cross close
-constexpr u32 CODE_C_OC = mk_code(ST_EC, ST_DC, ST_DC, ST_EC);                      // 03: cross open, close
-constexpr u32 CODE_F_O = mk_code(ST_ER, ST_DR, ST_DR, ST_ER, ST_EC, ST_DC);
-constexpr u32 CODE_F_C = mk_code(ST_ER, ST_DR, ST_DR, ST_ER, ST_DC, ST_EC);
-constexpr u32 CODE_F_OC = mk_code(ST_ER, ST_DR, ST_DR, ST_ER, ST_EC, ST_DC, ST_DC, ST_EC);
 
 // morph03: 0 none, 1 open, 2 close, 3 open+close.  with02: prepend the RECT open/close and emit mask bytes.
 // runs != NULL: also classify the tiles of the final image for the sparse edge kernel (MorphRuns).
@@ -1504,6 +1365,7 @@ static int run_hysteresis(omni_ctx *ctx, u32 *ebits, const u32 *cbits, const Bit
     OMNI_LAUNCH(ctx, st, "hysteresis_bits", cudaLaunchCooperativeKernel((const void *)fk_hysteresis, dim3(ctx->hyst_blocks), dim3(HY_THREADS),
                                                                         args, 0, st));
     ctx->last_hyst_passes = -1;           // lives in d_flags[0]; fetched lazily by omni_last_hysteresis_passes
+    ctx->last_hyst_stream = st;
     return OMNI_OK;
 }
 
@@ -1742,7 +1604,7 @@ int fast_host_color_edge(omni_ctx *ctx, const u8 *h_bgr, int h, int w, size_t pi
         OMNI_LAUNCH(ctx, sc, "morph_bits", launch_morph(true, kind, bpp[0], bpp[1], g, K, d_masks, mplane, mp, sc, y0, y1, sparse ? &R : nullptr));
         OMNI_CUDA(cudaEventRecord(evM[b], sc));
         OMNI_CUDA(cudaStreamWaitEvent(so, evM[b], 0));
-        const bool contiguous = (h_mpitch == mp);
+        const bool contiguous = (h_mpitch == mp && mp == (size_t)w);      // gap-free rows on both sides only
         if (contiguous) {
             // the band of all K planes in ONE strided copy: "row" = a plane's band (contiguous rows), "pitch" = the plane stride
             OMNI_CUDA(cudaMemcpy2DAsync(h_masks + (size_t)y0 * h_mpitch, h_mplane, d_masks + (size_t)y0 * mp, mplane,
@@ -1770,7 +1632,7 @@ int fast_host_color_edge(omni_ctx *ctx, const u8 *h_bgr, int h, int w, size_t pi
     FK_TRY(edges_from_bits(ctx, bpp[1], bpp[2], bpp[3], g, K, low, high, d_edges, eplane, ep, sc, sparse, sparse));
     OMNI_CUDA(cudaEventRecord(evX[2], sc));
     OMNI_CUDA(cudaStreamWaitEvent(so, evX[2], 0));
-    if (h_epitch == ep) {
+    if (h_epitch == ep && ep == (size_t)w) {            // gap-free rows: a plane is one contiguous run
         OMNI_CUDA(cudaMemcpy2DAsync(h_edges, h_eplane, d_edges, eplane, (size_t)(h - 1) * ep + w, K, cudaMemcpyDeviceToHost, so));
     } else {
         for (int k = 0; k < K; k++)
@@ -1967,7 +1829,8 @@ int fast_thin(omni_ctx *ctx, const u8 *d_in, int K, int h, int w, size_t in_plan
     int *d_removed = (int *)ctx->ws[6];
     u8 *d_unit = (u8 *)(d_removed + n_rem);
     OMNI_CUDA(cudaMemsetAsync(d_removed, 0, n_rem * sizeof(int) + 4 * units, st));
-    OMNI_CUDA(cudaMemsetAsync(ctx->d_flags, 0, 8 * sizeof(int), st));
+    // the thinning kernel has its own flag block (d_flags[32..39]): d_flags[0] keeps the pass count of the last hysteresis
+    OMNI_CUDA(cudaMemsetAsync(ctx->d_flags + 32, 0, 8 * sizeof(int), st));
     OMNI_CUDA(cudaMemsetAsync(ctx->d_flags + 8, 0, sizeof(int), st));
     {
         KScope ks(ctx, "bytes_to_bits", st);
@@ -1980,7 +1843,7 @@ int fast_thin(omni_ctx *ctx, const u8 *d_in, int K, int h, int w, size_t in_plan
         if (blocks < 1) blocks = 1;
         int ws = g.ws;
         size_t plane = g.plane;
-        int *flags = ctx->d_flags;
+        int *flags = ctx->d_flags + 32;
         void *args[] = {&bpp[0], &bpp[1], &ws, &plane, &h, &w, &K, &max_iter, &d_removed, &flags, &d_unit, &units, &unit_rows};
         OMNI_LAUNCH(ctx, st, "thin_zhangsuen", cudaLaunchCooperativeKernel((const void *)fk_thin, dim3(blocks), dim3(256), args, 0, st));
     }

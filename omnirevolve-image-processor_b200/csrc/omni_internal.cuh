@@ -71,6 +71,7 @@ struct omni_ctx {
     cudaStream_t stream = nullptr;   // own stream for the omni_host_* entry points
     std::map<std::tuple<int, int, int, int>, ResizeTab> resize_tabs;
     int last_hyst_passes = 0;
+    cudaStream_t last_hyst_stream = nullptr;   // the stream the pass count in d_flags[0] is ordered on
     // launch accounting / per-kernel CUDA-event timing (omni_profile_*)
     long long launches = 0;
     int prof_on = 0;
