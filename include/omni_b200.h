@@ -62,10 +62,16 @@ int omni_version(void);
 const char *omni_last_error_string(void);
 int omni_device_count(void);
 /* Which implementation serves the calls: 0 = generic kernels only, 1 = fast bit-plane kernels where
- * the parameters allow (default; the edge kernel walks only the tile runs that can hold an edge),
- * 2 = as 1 with the dense edge kernel (every tile).  All three give identical bytes.  For tests and
- * A/B measurements. */
+ * the parameters allow (default: the fused colour+edge calls run the sparse generation -- label-domain
+ * open, morphology and edges only where a plane has pixels), 2 = dense generation with the dense edge
+ * kernel and the Lab-cell assignment, 3 = dense generation as shipped in round 1 (RGB-cell assignment,
+ * morphology over every word, edge kernel over the live tile runs).  All give identical bytes.  For
+ * tests and A/B measurements. */
 int omni_set_fast_path(omni_ctx *ctx, int enable);
+/* The candidate-centre tables of the colour assignment are rebuilt only when the centres change
+ * (default, enable != 0: frames of a video share one centre set).  enable == 0 rebuilds them on every
+ * call -- what a stream of single images with their own k-means centres pays. */
+int omni_set_table_cache(omni_ctx *ctx, int enable);
 int omni_ctx_create(int device, omni_ctx **out);
 int omni_ctx_destroy(omni_ctx *ctx);
 /* Pinned host memory for the omni_host_* entry points (pageable memory works, but is slower). */

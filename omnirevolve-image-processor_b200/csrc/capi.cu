@@ -49,6 +49,8 @@ extern "C" int omni_ctx_create(int device, omni_ctx **out)
         c->edge_sparse = (ev && ev[0] == '1') ? 0 : 1;
         ev = getenv("OMNI_B200_ASSIGN_LABCELL");
         c->assign_rgbcell = (ev && ev[0] == '1') ? 0 : 1;
+        ev = getenv("OMNI_B200_DENSE_PIPELINE");
+        c->pipeline = (ev && ev[0] == '1') ? 0 : 1;
     }
     OMNI_CUDA(cudaMalloc(&c->d_flags, 64 * sizeof(int)));
     OMNI_CUDA(cudaMemset(c->d_flags, 0, 64 * sizeof(int)));
@@ -84,7 +86,18 @@ extern "C" int omni_set_fast_path(omni_ctx *ctx, int enable)
 {
     OMNI_REQUIRE(ctx != nullptr, "omni_set_fast_path: ctx is NULL");
     ctx->fast = enable ? 1 : 0;
-    if (enable) ctx->edge_sparse = ctx->assign_rgbcell = (enable == 2) ? 0 : 1;
+    if (enable) {
+        ctx->edge_sparse = ctx->assign_rgbcell = (enable == 2) ? 0 : 1;
+        ctx->pipeline = (enable == 1) ? 1 : 0;
+    }
+    return OMNI_OK;
+}
+
+extern "C" int omni_set_table_cache(omni_ctx *ctx, int enable)
+{
+    OMNI_REQUIRE(ctx != nullptr, "omni_set_table_cache: ctx is NULL");
+    ctx->table_cache = enable ? 1 : 0;
+    if (!enable) ctx->cells_valid = ctx->cells3_valid = 0;
     return OMNI_OK;
 }
 
@@ -255,8 +268,9 @@ const ResizeTab *omni_get_resize_tab(omni_ctx *ctx, int sh, int sw, int dh, int 
     size_t o_ya = o; memcpy(&blob[o], ya.data(), ya.size() * 4); o += ya.size();
     ResizeTab t;
     if (cudaMalloc(&t.d_blob, blob.size() * 4) != cudaSuccess) { cudaGetLastError(); return nullptr; }
-    // synchronous copy from pageable memory: tables are built once per geometry and cached
-    if (cudaMemcpy(t.d_blob, blob.data(), blob.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess) {
+    // synchronous copy from pageable memory (tables are built once per geometry and cached); the device-wide wait makes the
+    // bytes visible to `st` whatever its flags (the legacy stream does not order against non-blocking streams)
+    if (cudaMemcpy(t.d_blob, blob.data(), blob.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess) {
         cudaGetLastError(); cudaFree(t.d_blob); return nullptr;
     }
     (void)st;

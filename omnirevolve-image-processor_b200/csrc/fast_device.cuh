@@ -1,7 +1,10 @@
 // fast_device.cuh -- device code and small host helpers shared by the bit-plane translation units (fast_kernels.cu: the
-// dense generation; sparse_pipe.cu: the sparse generation of the fused colour+edge path).  Not part of the public ABI.
+// dense generation; label_pipe.cu: the sparse generation of the fused colour+edge path).  Not part of the public ABI.
 #pragma once
 #include "fast_kernels.cuh"
+#include <type_traits>
+
+#define HY_WL_CAP 8192                 // words holding weak candidates (hysteresis worklist); more than this -> full sweeps
 
 struct BitGeom {
     int h, w;
@@ -150,3 +153,33 @@ constexpr u32 CODE_F_O = mk_code(ST_ER, ST_DR, ST_DR, ST_ER, ST_EC, ST_DC);
 constexpr u32 CODE_F_C = mk_code(ST_ER, ST_DR, ST_DR, ST_ER, ST_DC, ST_EC);
 constexpr u32 CODE_F_OC = mk_code(ST_ER, ST_DR, ST_DR, ST_ER, ST_EC, ST_DC, ST_DC, ST_EC);
 
+
+// ---- helpers defined in fast_kernels.cu, shared with label_pipe.cu ---------------------------------------
+cudaError_t fast_tables();
+const u16 *fast_lab_table();                            // device address of the Lab tables (after fast_tables())
+int persist_blocks(omni_ctx *ctx, int per_sm);
+bool lut_below_k(const AssignParams &P);
+int fast_rgb_boxes(omni_ctx *ctx, cudaStream_t st);     // ctx->d_rgb_boxes, built on first use
+cudaError_t launch_build_cells(const AssignParams &P, u32 *cells, cudaStream_t st);
+int run_hysteresis(omni_ctx *ctx, u32 *ebits, const u32 *cbits, const BitGeom &g, int K, u8 *d_edges, size_t e_plane, size_t epitch,
+                   cudaStream_t st);
+int edge_pass_begin(omni_ctx *ctx, const BitGeom &g, int K, u32 *sbits, u32 *cbits, u8 *d_edges, size_t e_plane, size_t epitch,
+                    cudaStream_t st, MorphRuns *R, bool *sparse, bool side_fill, ZeroJob *zjob = nullptr);
+int morph03_kind(const omni_edge_params *p);
+
+// shared-memory layout of the table-driven assignment kernels (fk_assign_rgbcell, fk_assign_slices)
+#define RA_THREADS 1024
+#define RA_WARPS (RA_THREADS / 32)
+#define RA_OFF_MB RC_NIB_BYTES
+#define RA_OFF_CBRT (RA_OFF_MB + RC_MB_BYTES)
+#define RA_OFF_GAM (RA_OFF_CBRT + 2048 * 2)
+#define RA_OFF_CTR (RA_OFF_GAM + 256 * 2)
+#define RA_OFF_LUT (RA_OFF_CTR + OMNI_MAX_K * 16)
+#define RA_OFF_WARP (RA_OFF_LUT + 64)
+#define RA_WARP_BYTES (768 + 256 + 256)
+#define RA_SMEM (RA_OFF_WARP + RA_WARPS * RA_WARP_BYTES)
+
+// sparse generation of the fused colour+edge call (label_pipe.cu); OMNI_ERR_UNSUPPORTED: use the dense generation
+int sparse_color_edge(omni_ctx *ctx, const u8 *d_bgr, int nf, size_t frame_stride, int h, int w, size_t pitch, const AssignParams &P,
+                      const omni_edge_params *prm, int low, int high, u8 *d_labels, size_t lpitch,
+                      u8 *d_masks, size_t m_plane, size_t mpitch, u8 *d_edges, size_t e_plane, size_t epitch, cudaStream_t st);

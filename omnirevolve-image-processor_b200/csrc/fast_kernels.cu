@@ -39,7 +39,7 @@ namespace cg = cooperative_groups;
 __device__ u16 f_lab_tab[256 + 2048];          // gamma[256] | cbrt[2041]
 static bool f_tab_ready[64] = {false};
 
-static cudaError_t fast_tables()
+cudaError_t fast_tables()
 {
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
@@ -48,6 +48,10 @@ static cudaError_t fast_tables()
     e = cudaMemcpyToSymbol(f_lab_tab, OMNI_LAB_GAMMA, sizeof(OMNI_LAB_GAMMA), 0);
     if (e != cudaSuccess) return e;
     e = cudaMemcpyToSymbol(f_lab_tab, OMNI_LAB_CBRT, sizeof(OMNI_LAB_CBRT), 256 * sizeof(u16));
+    if (e != cudaSuccess) return e;
+    // one-time upload from pageable memory through the legacy stream: callers launch on non-blocking streams, which the
+    // legacy stream does not order against -- wait for the copy to land before anything can read the tables
+    e = cudaDeviceSynchronize();
     if (e != cudaSuccess) return e;
     if (dev < 64) f_tab_ready[dev] = true;
     return cudaSuccess;
@@ -377,18 +381,6 @@ __global__ void __launch_bounds__(256) fk_build_rgbcells(const __grid_constant__
     mb[gi] = (u8)multi;
 }
 
-#define RA_THREADS 1024
-#define RA_WARPS (RA_THREADS / 32)
-// dynamic shared memory: [label nibbles | flags | cbrt | gamma | centres | lut | per warp: pixels 768, queue 256, labels 256]
-#define RA_OFF_MB RC_NIB_BYTES
-#define RA_OFF_CBRT (RA_OFF_MB + RC_MB_BYTES)
-#define RA_OFF_GAM (RA_OFF_CBRT + 2048 * 2)
-#define RA_OFF_CTR (RA_OFF_GAM + 256 * 2)
-#define RA_OFF_LUT (RA_OFF_CTR + OMNI_MAX_K * 16)
-#define RA_OFF_WARP (RA_OFF_LUT + 64)
-#define RA_WARP_BYTES (768 + 256 + 256)
-#define RA_SMEM (RA_OFF_WARP + RA_WARPS * RA_WARP_BYTES)
-
 template <bool SEP_MULTI>                  // K == 16: the "several candidates" flag needs its own bit table; K <= 15: nibble 15
 __global__ void __launch_bounds__(RA_THREADS, 1) fk_assign_rgbcell(const u8 *__restrict__ px, int h, int w, size_t pitch,
                                                                    const __grid_constant__ AssignParams P, const uint4 *__restrict__ rtab,
@@ -638,6 +630,29 @@ __global__ void __launch_bounds__(256) fk_assign_bits(const u8 *__restrict__ px,
             }
         }
     }
+}
+
+const u16 *fast_lab_table()
+{
+    void *p = nullptr;
+    if (cudaGetSymbolAddress(&p, f_lab_tab) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return (const u16 *)p;
+}
+
+cudaError_t launch_build_cells(const AssignParams &P, u32 *cells, cudaStream_t st)
+{
+    fk_build_cells<<<CELL_COUNT / 256, 256, 0, st>>>(P, cells);
+    return cudaGetLastError();
+}
+
+int fast_rgb_boxes(omni_ctx *ctx, cudaStream_t st)
+{
+    if (ctx->d_rgb_boxes) return OMNI_OK;              // centre-independent: once per context
+    OMNI_CUDA(cudaMalloc(&ctx->d_rgb_boxes, (size_t)RC_COUNT * 6));
+    KScope ks(ctx, "rgb_boxes", st);
+    fk_rgb_boxes<<<RC_COUNT / 256, 256, 0, st>>>(ctx->d_rgb_boxes);
+    OMNI_CUDA(cudaGetLastError());
+    return OMNI_OK;
 }
 
 // labels u8 -> one-hot bit-planes (omni_layer_masks entry)
@@ -950,7 +965,6 @@ static cudaError_t launch_morph(bool with02, int morph03, const u32 *in_bits, u3
 #define HB_TW 32                      // tile words (1024 pixels)
 #define HY_WORD_ROUNDS 4
 #define HY_THREADS 1024                // one CTA resolves the whole worklist in the common case: make it a big one
-#define HY_WL_CAP 8192                 // words holding weak candidates; more than this -> full sweeps
 
 __device__ __forceinline__ void hy_patch_bytes(u8 *row, u32 promoted)
 {
@@ -1141,7 +1155,7 @@ __global__ void __launch_bounds__(HY_THREADS) fk_hysteresis(u32 *__restrict__ eb
 // ------------------------------------------------------------------------------------------------
 #define HP_MAX_BANDS 8
 static int pipe_init(omni_ctx *ctx);
-static int persist_blocks(omni_ctx *ctx, int per_sm) { return (ctx->sm_count > 0 ? ctx->sm_count : 148) * per_sm; }
+int persist_blocks(omni_ctx *ctx, int per_sm) { return (ctx->sm_count > 0 ? ctx->sm_count : 148) * per_sm; }
 
 // persistent grid of a kernel = SM count x the number of its CTAs that are resident per SM (queried once)
 template <typename Kern>
@@ -1168,7 +1182,7 @@ static int bit_planes(omni_ctx *ctx, const BitGeom &g, int K, int n, u32 **out /
 }
 
 // the RGB-cell tables hold output labels in 4 bits (15 = "several candidates" when K <= 15): every label must be < K
-static bool lut_below_k(const AssignParams &P)
+bool lut_below_k(const AssignParams &P)
 {
     for (int k = 0; k < P.K; k++)
         if (P.lut[k] >= P.K) return false;
@@ -1184,7 +1198,7 @@ static int assign_cells(omni_ctx *ctx, const AssignParams &P, u32 **cells, u8 **
     *rcells = (u8 *)((u32 *)ctx->ws[5] + RGBCELL_OFFSET);
     // same centres (and label map) as the previous call on this ctx (a batch of frames): the tables in the workspace are
     // still valid (calls on one ctx are serialised and go to one stream at a time, see omni_b200.h)
-    if (ctx->cells_valid == variant && ctx->cells_stream == (void *)st && ctx->cells_K == P.K &&
+    if (ctx->table_cache && ctx->cells_valid == variant && ctx->cells_stream == (void *)st && ctx->cells_K == P.K &&
         memcmp(ctx->cells_c, P.c, sizeof(float) * 3 * P.K) == 0 && memcmp(ctx->cells_lut, P.lut, P.K) == 0)
         return OMNI_OK;
     memcpy(ctx->cells_c, P.c, sizeof(float) * 3 * P.K);
@@ -1196,12 +1210,7 @@ static int assign_cells(omni_ctx *ctx, const AssignParams &P, u32 **cells, u8 **
         OMNI_CUDA(cudaGetLastError());
     }
     if (variant == 2) {
-        if (!ctx->d_rgb_boxes) {                           // centre-independent: once per context
-            OMNI_CUDA(cudaMalloc(&ctx->d_rgb_boxes, (size_t)RC_COUNT * 6));
-            KScope ks(ctx, "rgb_boxes", st);
-            fk_rgb_boxes<<<RC_COUNT / 256, 256, 0, st>>>(ctx->d_rgb_boxes);
-            OMNI_CUDA(cudaGetLastError());
-        }
+        FK_TRY(fast_rgb_boxes(ctx, st));
         KScope ks(ctx, "build_rgbcells", st);
         fk_build_rgbcells<<<RC_COUNT / 8 / 256, 256, 0, st>>>(P, ctx->d_rgb_boxes, (u32 *)*rcells, *rcells + RC_NIB_BYTES);
         OMNI_CUDA(cudaGetLastError());
@@ -1304,7 +1313,7 @@ int fast_layer_masks(omni_ctx *ctx, const u8 *d_labels, int h, int w, size_t lpi
 }
 
 // which stage-03 morphology the parameters ask for: 0 none, 1 open, 2 close, 3 both; -1 = not on the fast path
-static int morph03_kind(const omni_edge_params *p)
+int morph03_kind(const omni_edge_params *p)
 {
     int oi = p->open_iters > 0 ? p->open_iters : 0, ci = p->close_iters > 0 ? p->close_iters : 0;
     if (p->morph_k == 1) return 0;                    // 1x1 element: identity
@@ -1348,7 +1357,7 @@ int fast_morph03_bytes(omni_ctx *ctx, const u8 *d_masks, int K, int h, int w, si
     return OMNI_OK;
 }
 
-static int run_hysteresis(omni_ctx *ctx, u32 *ebits, const u32 *cbits, const BitGeom &g, int K, u8 *d_edges,
+int run_hysteresis(omni_ctx *ctx, u32 *ebits, const u32 *cbits, const BitGeom &g, int K, u8 *d_edges,
                           size_t e_plane, size_t epitch, cudaStream_t st)
 {
     if (ctx->hyst_blocks == 0) {
@@ -1372,8 +1381,8 @@ static int run_hysteresis(omni_ctx *ctx, u32 *ebits, const u32 *cbits, const Bit
 // Zeroes the device flags of an edge pass -- d_flags: [0] rounds, [1..3] changed flags, [4] weak-word count, [16..19] run
 // counts per length, [20] next warp item -- and, when the sparse edge kernel will run, fills the MorphRuns block that lets
 // the morphology kernel produce the run lists (returns false: dense edge kernel, nothing to prepare).
-static int edge_pass_begin(omni_ctx *ctx, const BitGeom &g, int K, u32 *sbits, u32 *cbits, u8 *d_edges, size_t e_plane, size_t epitch,
-                           cudaStream_t st, MorphRuns *R, bool *sparse, bool side_fill, ZeroJob *zjob = nullptr)
+int edge_pass_begin(omni_ctx *ctx, const BitGeom &g, int K, u32 *sbits, u32 *cbits, u8 *d_edges, size_t e_plane, size_t epitch,
+                           cudaStream_t st, MorphRuns *R, bool *sparse, bool side_fill, ZeroJob *zjob)
 {
     FK_TRY(omni_ws_reserve(ctx, 5, WS5_BYTES));
     OMNI_CUDA(cudaMemsetAsync(ctx->d_flags, 0, 24 * sizeof(int), st));
@@ -1479,6 +1488,11 @@ int fast_color_edge(omni_ctx *ctx, const u8 *d_bgr, int h, int w, size_t pitch, 
 {
     (void)bp;
     if (low < 0) return OMNI_ERR_UNSUPPORTED;
+    if (ctx->pipeline == 1) {                          // sparse generation (label_pipe.cu) where it applies
+        const int rc = sparse_color_edge(ctx, d_bgr, 1, 0, h, w, pitch, P, prm, low, high, d_labels, lpitch, d_masks, m_plane, mpitch,
+                                         d_edges, e_plane, epitch, st);
+        if (rc != OMNI_ERR_UNSUPPORTED) return rc;
+    }
     OMNI_CUDA(fast_tables());
     BitGeom g = make_geom(h, w);
     u32 *bpp[4];
@@ -1508,6 +1522,11 @@ int fast_color_edge_batch(omni_ctx *ctx, const u8 *d_bgr, int n, size_t frame_st
     if (low < 0) return OMNI_ERR_UNSUPPORTED;
     const int KT = n * P.K;
     if (KT > OMNI_MAX_K) return OMNI_ERR_UNSUPPORTED;
+    if (ctx->pipeline == 1) {
+        const int rc = sparse_color_edge(ctx, d_bgr, n, frame_stride, h, w, pitch, P, prm, low, high, nullptr, 0, d_masks, m_plane, mpitch,
+                                         d_edges, e_plane, epitch, st);
+        if (rc != OMNI_ERR_UNSUPPORTED) return rc;
+    }
     OMNI_CUDA(fast_tables());
     BitGeom g = make_geom(h, w);
     u32 *bpp[4];

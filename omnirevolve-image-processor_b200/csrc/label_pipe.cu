@@ -1,0 +1,668 @@
+// label_pipe.cu -- the label-domain generation of the fused colour+edge call (omni_color_edge / omni_color_edge_batch).
+//
+// The first generation (fast_kernels.cu) writes K one-hot bit-planes and pushes every one of them through the 8-step
+// morphology chain on 64-bit windows.  Here:
+//
+//   fk_assign_slices   image -> label BIT-SLICES (4 planes: bit b of the 4-bit label of every pixel) [+ u8 labels]
+//                      (02_color_extract.py:35-36,53-55,121-127; the same exact table-driven assignment as fk_assign_rgbcell, but a
+//                      lane owns 8 consecutive pixels -- three 8-byte shared-memory loads instead of 24 byte loads -- and there are
+//                      no per-plane stores and no __match_any: 4 slice words per 32 pixels come out of a 4x4 byte transpose)
+//   fk_label_open      RECT-3 OPEN of all K one-hot planes at once, in the label domain (02:152):
+//                        erode_k  = [label == k] & U        U  = "the 3x3 neighbourhood (inside the image) has one label"
+//                        open_k   = [label == k] & Od       Od = dilate3(U)     (a pixel next to a uniform pixel q has q's label)
+//                      so the first two steps of the chain cost ONE plane (Od) instead of K
+//   fk_morph_lab       per plane k: open_k = Od & [label == k] from the slices on the fly, then the remaining steps (02:153 RECT-3
+//                      close -> mask BYTES; 03:23-30 ELLIPSE-3 open/close -> bit-plane M2) on 32-bit words: lanes are adjacent word
+//                      columns, the neighbour bits of a step come from two warp shuffles (ALU pipe: 2 LOP3 + 2 SHF per step and
+//                      32 pixels instead of 4 + 4 on a 64-bit window); 30 owned columns + a halo lane on each side per warp.
+//                      Classifies its tiles for the sparse edge kernel (edges3.cu) like fk_morph does.
+//   fk_edges3_simd<sparse> + fk_hysteresis as before.
+//
+// Reference call sites are relative to /root/reference/image_processor/.  Bit-exactness against the oracle is checked by the same
+// GPU tests as the first generation (tests/test_gpu_parity.py runs every family).
+#include "fast_device.cuh"
+
+#include <algorithm>
+#include <string.h>
+
+#define LP_ZBUF 8192                      // zeroed shared-memory block behind the tables of fk_assign_slices (bulk-store source)
+#define SP_TRY(expr) do { int rc__ = (expr); if (rc__ != OMNI_OK) return rc__; } while (0)
+
+
+// ------------------------------------------------------------------------------------------------
+// RGB-cell tables in the index layout of fk_assign_slices: cell = (B >> 2) | (G >> 2) << 6 | (R >> 2) << 12; the label nibble of
+// cell i lives in byte (i & 0x1FFFF), high nibble when i >= 2^17; K == 16 has a separate "several candidates" bit per cell.
+// The pruning rule is fk_build_rgbcells' (fast_kernels.cu): exact Lab box of the cell, dmin <= min dmax + 2.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) fk_build_rgbcells3(const __grid_constant__ AssignParams P, const u8 *__restrict__ boxes,
+                                                          u8 *__restrict__ nb, u32 *__restrict__ mb)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;                // < 2^17
+    const int K = P.K;
+    u32 byte = 0u;
+    bool multi[2];
+#pragma unroll
+    for (int hs = 0; hs < 2; hs++) {
+        const int idx = i + (hs << 17);
+        const int ci = ((idx & 63) << 12) | (((idx >> 6) & 63) << 6) | (idx >> 12);     // box index: B slowest (fk_rgb_boxes)
+        float lo[3], hi[3];
+#pragma unroll
+        for (int d = 0; d < 3; d++) { lo[d] = (float)boxes[6 * ci + d]; hi[d] = (float)boxes[6 * ci + 3 + d]; }
+        float U = 3.0e38f;
+        bool sane = true;
+        for (int k = 0; k < K; k++) {
+            float dmax = 0.f;
+#pragma unroll
+            for (int d = 0; d < 3; d++) {
+                float c = P.c[3 * k + d];
+                sane = sane && (fabsf(c) < 1.0e4f);                 // also false for NaN
+                float m = fmaxf(fabsf(lo[d] - c), fabsf(hi[d] - c));
+                dmax += m * m;
+            }
+            U = fminf(U, dmax);
+        }
+        u32 mask = 0u;
+        for (int k = 0; k < K; k++) {
+            float dmin = 0.f;
+#pragma unroll
+            for (int d = 0; d < 3; d++) {
+                float c = P.c[3 * k + d];
+                float n = fminf(fmaxf(c, lo[d]), hi[d]);
+                dmin += (n - c) * (n - c);
+            }
+            if (dmin <= U + 2.0f) mask |= 1u << k;
+        }
+        const bool single = sane && mask != 0u && (mask & (mask - 1u)) == 0u;
+        multi[hs] = !single;
+        const u32 nib = single ? (u32)(P.lut[__ffs(mask) - 1] & 15u) : (K < 16 ? 15u : 0u);
+        byte |= nib << (4 * hs);
+    }
+    nb[i] = (u8)byte;
+    const u32 b0 = __ballot_sync(0xffffffffu, multi[0]), b1 = __ballot_sync(0xffffffffu, multi[1]);
+    if ((threadIdx.x & 31) == 0) { mb[i >> 5] = b0; mb[(i + (1 << 17)) >> 5] = b1; }
+}
+
+// ------------------------------------------------------------------------------------------------
+// fk_assign_slices: one 1024-thread CTA per SM holds the tables in shared memory (as fk_assign_rgbcell); a warp takes 256 pixels
+// of a row, a lane 8 consecutive ones (24 bytes = three 8-byte shared-memory loads).  Pixels whose RGB cell has several candidate
+// centres are compacted over the warp and get the Lab conversion + the reference's float32 argmin over the Lab cell's candidates.
+// Output: per 32 pixels one word in each of the 4 label bit-slices (a 4x4 byte transpose over 4 lanes), optionally u8 labels.
+// ------------------------------------------------------------------------------------------------
+template <bool SEP_MULTI>
+__global__ void __launch_bounds__(RA_THREADS, 1) fk_assign_slices(const u8 *__restrict__ px, int h, int w, size_t pitch,
+                                                                  const __grid_constant__ AssignParams P, const uint4 *__restrict__ rtab,
+                                                                  const u32 *__restrict__ cells, const u16 *__restrict__ labtab,
+                                                                  u8 *__restrict__ labels, size_t lpitch, u32 *__restrict__ slices,
+                                                                  int ws, int nf, size_t frame_stride,
+                                                                  const __grid_constant__ ZeroJob Z)
+{
+    extern __shared__ __align__(16) u8 smem[];
+    const u8 *s_nb = smem;
+    const u32 *s_mb = reinterpret_cast<const u32 *>(smem + RA_OFF_MB);
+    u16 *s_cbrt = reinterpret_cast<u16 *>(smem + RA_OFF_CBRT);
+    u16 *s_gam = reinterpret_cast<u16 *>(smem + RA_OFF_GAM);
+    float4 *s_ctr = reinterpret_cast<float4 *>(smem + RA_OFF_CTR);
+    u8 *s_lut = smem + RA_OFF_LUT;
+    for (int i = threadIdx.x; i < (RC_NIB_BYTES + (SEP_MULTI ? RC_MB_BYTES : 0)) / 16; i += RA_THREADS)
+        reinterpret_cast<uint4 *>(smem)[i] = __ldg(rtab + i);
+    for (int i = threadIdx.x; i < 2048; i += RA_THREADS) {
+        s_cbrt[i] = labtab[256 + i];
+        if (i < 256) s_gam[i] = labtab[i];
+    }
+    if (threadIdx.x < OMNI_MAX_K) {
+        s_lut[threadIdx.x] = P.lut[threadIdx.x];
+        s_ctr[threadIdx.x] = make_float4(P.c[3 * threadIdx.x], P.c[3 * threadIdx.x + 1], P.c[3 * threadIdx.x + 2], 0.f);
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int chunks = (w + 255) >> 8;
+    const int total = nf * h * chunks, stride = gridDim.x * RA_WARPS;     // nf * h * chunks < 2^30 (checked by the host)
+    const bool vec_ok = (((uintptr_t)px | pitch | frame_stride) & 15) == 0;
+    const bool lab_vec = labels && ((((uintptr_t)labels | lpitch) & 7) == 0);
+    u8 *spx = smem + RA_OFF_WARP + warp * RA_WARP_BYTES;              // per warp: the 256 pixels of the current chunk
+    u8 *sq = spx + 768, *slab = sq + 256;                             //           queued pixel indices, their labels
+    const u32 sel1 = (lane & 1) ? 0x3715u : 0x6240u, sel2 = (lane & 2) ? 0x3276u : 0x5410u;
+    // zero source of the bulk stores (never written again): make the generic-proxy writes visible to the async proxy
+    const u32 zsrc = (u32)__cvta_generic_to_shared(smem + RA_SMEM);
+    for (int i = threadIdx.x; i < LP_ZBUF / 16; i += RA_THREADS) reinterpret_cast<uint4 *>(smem + RA_SMEM)[i] = make_uint4(0u, 0u, 0u, 0u);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    uint4 pf0 = make_uint4(0, 0, 0, 0), pf1 = pf0;
+    const int dyy = stride / chunks, dc = stride - dyy * chunks;
+    auto prefetch = [&](int u, int yy, int c) {
+        if (u < total) {
+            const int f = nf > 1 ? yy / h : 0, y = yy - f * h;
+            if (vec_ok && c * 256 + 256 <= w) {
+                const uint4 *src = reinterpret_cast<const uint4 *>(px + (size_t)f * frame_stride + (size_t)y * pitch + (size_t)c * 768);
+                pf0 = __ldg(src + lane);
+                if (lane < 16) pf1 = __ldg(src + 32 + lane);
+            }
+        }
+    };
+    int u = blockIdx.x * RA_WARPS + warp;
+    int yy_n = u / chunks, c_n = u - yy_n * chunks;
+    prefetch(u, yy_n, c_n);
+    for (; u < total; u += stride) {
+        const int yy = yy_n, c = c_n;
+        yy_n += dyy; c_n += dc;
+        if (c_n >= chunks) { c_n -= chunks; yy_n++; }
+        const int f = nf > 1 ? yy / h : 0, y = yy - f * h;
+        const bool full = vec_ok && c * 256 + 256 <= w;
+        __syncwarp();                                          // the previous chunk has been consumed
+        if (full) {
+            reinterpret_cast<uint4 *>(spx)[lane] = pf0;
+            if (lane < 16) reinterpret_cast<uint4 *>(spx)[32 + lane] = pf1;
+        } else {
+            const u8 *row = px + (size_t)f * frame_stride + (size_t)y * pitch + (size_t)c * 768;
+            const int nb = 3 * min(256, w - c * 256);
+            for (int i = lane; i < nb; i += 32) spx[i] = row[i];
+        }
+        prefetch(u + stride, yy_n, c_n);
+        // this chunk's slice of the zero-fill regions: bulk copies (TMA engine) from the zeroed shared-memory block, issued by one
+        // lane -- no LSU wavefronts, the stores drain while the warp works on its pixels
+        if (lane == 0) {
+#pragma unroll
+            for (int z = 0; z < 2; z++) {
+                if (Z.n16[z]) {
+                    unsigned long long idx = (unsigned long long)Z.per[z] * (unsigned)u;
+                    unsigned long long left = idx < Z.n16[z] ? min((unsigned long long)Z.per[z], Z.n16[z] - idx) * 16ull : 0ull;
+                    char *dst = reinterpret_cast<char *>(Z.p[z] + idx);
+                    while (left) {
+                        const u32 n = (u32)min(left, (unsigned long long)LP_ZBUF);
+                        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(zsrc), "r"(n) : "memory");
+                        dst += n; left -= n;
+                    }
+                }
+            }
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+        __syncwarp();
+        // ---- phase 1: the lane's 8 pixels: RGB-cell lookups ----
+        const uint2 *q2 = reinterpret_cast<const uint2 *>(spx + 24 * lane);
+        const uint2 qa = q2[0], qb = q2[1], qc = q2[2];
+        const u32 wv[6] = {qa.x, qa.y, qb.x, qb.y, qc.x, qc.y};
+        const int xbase = c * 256 + 8 * lane;
+        u32 nibw = 0u, mm = 0u;
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const int qi = (3 * j) >> 2, o = (3 * j) & 3;
+            u32 v;
+            if (o == 0) v = wv[qi];
+            else if (o == 1) v = wv[qi] >> 8;
+            else if (o == 2) v = __byte_perm(wv[qi], wv[(qi + 1) % 6], 0x4432);
+            else v = __byte_perm(wv[qi], wv[(qi + 1) % 6], 0x5543);
+            const u32 idx = ((v >> 2) & 0x3Fu) | ((v >> 4) & 0xFC0u) | ((v >> 6) & 0x3F000u);
+            u32 lab = ((u32)s_nb[idx & 0x1FFFFu] >> ((idx >> 15) & 4u)) & 15u;
+            bool multi = SEP_MULTI ? ((s_mb[idx >> 5] >> (idx & 31u)) & 1u) != 0u : lab == 15u;
+            if (!full && xbase + j >= w) { lab = 0u; multi = false; }
+            nibw |= lab << (4 * j);
+            mm |= (multi ? 1u : 0u) << j;
+        }
+        // ---- the undecided pixels, compacted over the warp ----
+        const int cnt = __popc(mm);
+        int x = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            int t = __shfl_up_sync(0xffffffffu, x, d);
+            if (lane >= d) x += t;
+        }
+        const int nq = __shfl_sync(0xffffffffu, x, 31);
+        if (nq) {
+            int pos = x - cnt;
+#pragma unroll
+            for (int j = 0; j < 8; j++)
+                if ((mm >> j) & 1u) sq[pos++] = (u8)(8 * lane + j);
+            __syncwarp();
+            // ---- phase 2: Lab conversion + the reference's float32 argmin over the Lab cell's candidates ----
+            for (int i = lane; i < nq; i += 32) {
+                const int pi = sq[i];
+                const u8 *p = spx + 3 * pi;
+                int L, a, b, best = 0;
+                lab_noclamp(s_gam, s_cbrt, p[0], p[1], p[2], L, a, b);
+                u32 mk = __ldg(cells + (((L >> CELL_SHIFT) * CELL_N + (a >> CELL_SHIFT)) * CELL_N + (b >> CELL_SHIFT)));
+                const float f0 = (float)L, f1 = (float)a, f2 = (float)b;
+                float bd = 3.0e38f;
+                do {
+                    const int k = __ffs(mk) - 1;
+                    mk &= mk - 1u;
+                    const float4 ck = s_ctr[k];
+                    float d0 = __fsub_rn(f0, ck.x), d1 = __fsub_rn(f1, ck.y), d2 = __fsub_rn(f2, ck.z);
+                    float d = __fadd_rn(__fadd_rn(__fmul_rn(d0, d0), __fmul_rn(d1, d1)), __fmul_rn(d2, d2));
+                    if (d < bd) { bd = d; best = k; }
+                } while (mk);
+                slab[pi] = s_lut[best];
+            }
+            __syncwarp();
+            if (mm) {
+                const uint2 lb = *reinterpret_cast<const uint2 *>(slab + 8 * lane);
+                u32 t0 = lb.x & 0x0F0F0F0Fu, t1 = lb.y & 0x0F0F0F0Fu;            // 8 label bytes -> 8 nibbles
+                t0 = (t0 | (t0 >> 4)) & 0x00FF00FFu; t0 = (t0 | (t0 >> 8)) & 0xFFFFu;
+                t1 = (t1 | (t1 >> 4)) & 0x00FF00FFu; t1 = (t1 | (t1 >> 8)) & 0xFFFFu;
+                const u32 fix = t0 | (t1 << 16);
+                u32 m = mm;                                                       // 8 flag bits -> nibble mask
+                m = (m | (m << 12)) & 0x000F000Fu; m = (m | (m << 6)) & 0x03030303u; m = (m | (m << 3)) & 0x11111111u;
+                m *= 15u;
+                nibw = (nibw & ~m) | (fix & m);
+            }
+        }
+        // ---- phase 3: outputs ----
+        if (labels) {
+            u32 b0 = nibw & 0xFFFFu, b1 = nibw >> 16;                             // 4 nibbles -> 4 bytes
+            b0 = (b0 | (b0 << 8)) & 0x00FF00FFu; b0 = (b0 | (b0 << 4)) & 0x0F0F0F0Fu;
+            b1 = (b1 | (b1 << 8)) & 0x00FF00FFu; b1 = (b1 | (b1 << 4)) & 0x0F0F0F0Fu;
+            u8 *lrow = labels + (size_t)yy * lpitch + xbase;
+            if (lab_vec && xbase + 8 <= w) *reinterpret_cast<uint2 *>(lrow) = make_uint2(b0, b1);
+            else
+                for (int j = 0; j < 8 && xbase + j < w; j++) lrow[j] = (u8)((nibw >> (4 * j)) & 15u);
+        }
+        {
+            u32 r[4];
+#pragma unroll
+            for (int b = 0; b < 4; b++) {
+                const u32 xb = (nibw >> b) & 0x11111111u;
+                const u32 x1 = (xb | (xb >> 3)) & 0x03030303u;
+                r[b] = x1 * 0x01041040u;                                           // byte 3 = bit b of the lane's 8 labels
+            }
+            const u32 pk = __byte_perm(__byte_perm(r[0], r[1], 0x7373), __byte_perm(r[2], r[3], 0x7373), 0x5410);
+            // 4x4 byte transpose over the lanes of a quad: lane (quad q, r) ends with the 32-pixel word of slice r
+            u32 t = __shfl_xor_sync(0xffffffffu, pk, 1);
+            const u32 v1 = __byte_perm(pk, t, sel1);
+            t = __shfl_xor_sync(0xffffffffu, v1, 2);
+            const u32 word = __byte_perm(v1, t, sel2);
+            // interleaved layout: the 4 slice words of a word column are adjacent (uint4 per column): the warp writes 128 B
+            if (c * 8 + (lane >> 2) < ws) slices[(((size_t)f * h + y) * ws + (size_t)c * 8) * 4 + lane] = word;
+        }
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");     // the zero block must outlive its readers
+}
+
+// ------------------------------------------------------------------------------------------------
+// fk_label_open: Od = dilate3(U), one bit-plane per frame.  A lane owns a word column and walks down a strip; a warp covers 30
+// owned columns + a halo lane on each side (the dilation needs U of the neighbouring words).  Per label row r:
+//   dh(r) = "differs from the left or right neighbour",  dv(r) = "differs from the pixel above"      (bit-slice XORs)
+//   U(r-1) = ~(dh(r-2) | dh(r-1) | dh(r) | dv(r-1) | dv(r))         (neighbours outside the image are ignored, as cv2.erode does)
+//   Od(r-2) = hU(r-3) | hU(r-2) | hU(r-1),  hU = U | U << 1 | U >> 1                                    (cv2.dilate: outside = 0)
+// ------------------------------------------------------------------------------------------------
+#define LO_WARPS 4
+#define LP_COLS 30                        // owned word columns per warp (fk_label_open, fk_morph_lab)
+#define LO_ROWS 16                        // rows per strip
+
+__global__ void __launch_bounds__(LO_WARPS * 32) fk_label_open(const uint4 *__restrict__ slices, int ws, size_t plane, int h, int w, int nf,
+                                                               u32 *__restrict__ od_out, int strips, int wcols)
+{
+    const int lane = threadIdx.x & 31;
+    const long long gw = (long long)blockIdx.x * LO_WARPS + (threadIdx.x >> 5);
+    const long long per_f = (long long)strips * wcols;
+    if (gw >= per_f * nf) return;
+    const int f = (int)(gw / per_f);
+    const int rem = (int)(gw - (long long)f * per_f);
+    const int strip = rem / wcols, wx = rem - strip * wcols;
+    const int ww = (w + 31) >> 5;
+    const int c = wx * LP_COLS - 1 + lane;
+    const bool inimg = c >= 0 && c < ww;
+    const bool owned = inimg && lane >= 1 && lane <= LP_COLS;
+    const u32 cm = inimg ? range_mask(32 * c, w) : 0u;
+    const u32 lfix = (c == 0) ? 1u : 0u;                                   // pixel 0 has no left neighbour
+    const u32 rfix = (c == ww - 1) ? (1u << ((w - 1) & 31)) : 0u;          // pixel w-1 has no right neighbour
+    const uint4 *sl = slices + (size_t)f * plane;           // uint4 per word column: the 4 slice words
+    u32 *od = od_out + (size_t)f * plane;
+    const int ys = strip * LO_ROWS, ye = min(h, ys + LO_ROWS);
+    u32 sp[4] = {0u, 0u, 0u, 0u}, dh1 = 0u, dh2 = 0u, dv1 = 0u, hu2 = 0u, hu3 = 0u;
+    u32 ns[4], ne[4];                                                      // slices of the next row (loaded one row ahead)
+    auto fetch = [&](const int r) {
+        const bool rin = r >= 0 && r < h;
+        uint4 v = make_uint4(0u, 0u, 0u, 0u), ev = v;
+        if (rin) {
+            const uint4 *row = sl + (size_t)r * ws;
+            if (inimg) v = __ldg(row + c);
+            if (lane == 0 && c - 1 >= 0 && c - 1 < ww) ev = __ldg(row + c - 1);
+            if (lane == 31 && c + 1 >= 0 && c + 1 < ww) ev = __ldg(row + c + 1);
+        }
+        ns[0] = v.x; ns[1] = v.y; ns[2] = v.z; ns[3] = v.w;
+        ne[0] = ev.x; ne[1] = ev.y; ne[2] = ev.z; ne[3] = ev.w;
+    };
+    fetch(ys - 2);
+    for (int r = ys - 2; r < ye + 2; r++) {
+        u32 s[4], e[4];
+#pragma unroll
+        for (int b = 0; b < 4; b++) { s[b] = ns[b]; e[b] = ne[b]; }
+        fetch(r + 1);
+        const bool rin = r >= 0 && r < h;
+        u32 dl = 0u, dr = 0u, dv = 0u;
+#pragma unroll
+        for (int b = 0; b < 4; b++) {
+            const u32 m = s[b];
+            u32 l = __shfl_up_sync(0xffffffffu, m, 1), rr = __shfl_down_sync(0xffffffffu, m, 1);
+            if (lane == 0) l = e[b];
+            if (lane == 31) rr = e[b];
+            dl |= m ^ __funnelshift_l(l, m, 1);
+            dr |= m ^ __funnelshift_r(m, rr, 1);
+            dv |= m ^ sp[b];
+            sp[b] = m;
+        }
+        dl &= ~lfix; dr &= ~rfix;
+        const u32 dh0 = rin ? (dl | dr) : 0u;
+        const u32 dv0 = (rin && r > 0) ? dv : 0u;
+        const bool yin = r - 1 >= 0 && r - 1 < h;
+        const u32 U = yin ? (~(dh2 | dh1 | dh0 | dv1 | dv0) & cm) : 0u;
+        const u32 l = __shfl_up_sync(0xffffffffu, U, 1), rr = __shfl_down_sync(0xffffffffu, U, 1);
+        const u32 hu1 = U | __funnelshift_l(l, U, 1) | __funnelshift_r(U, rr, 1);
+        const int z = r - 2;
+        if (owned && z >= ys && z < ye) od[(size_t)z * ws + c] = (hu3 | hu2 | hu1) & cm;
+        hu3 = hu2; hu2 = hu1; dh2 = dh1; dh1 = dh0; dv1 = dv0;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// fk_morph_lab: the chain after the label-domain open for plane blockIdx.z, on 32-bit words with shuffled neighbour bits.
+// Structure and outputs are fk_morph's (fast_kernels.cu): a strip of TR rows per warp, steps lagging each other by one row in
+// registers, mask bytes tapped after the RECT close, final bit-plane M2 + run lists / dead-tile zeros for the sparse edge kernel.
+// A halo lane's word is wrong in one more outer bit per step, never in the bit its owned neighbour reads.
+// ------------------------------------------------------------------------------------------------
+template <int OP>
+__device__ __forceinline__ u32 step32(const u32 u, const u32 m, const u32 d)
+{
+    if (OP == ST_ER || OP == ST_DR) {
+        const u32 v = OP == ST_ER ? (u & m & d) : (u | m | d);
+        const u32 l = __shfl_up_sync(0xffffffffu, v, 1), r = __shfl_down_sync(0xffffffffu, v, 1);
+        const u32 sl = __funnelshift_l(l, v, 1), sr = __funnelshift_r(v, r, 1);
+        return OP == ST_ER ? (v & sl & sr) : (v | sl | sr);
+    }
+    if (OP == ST_EC || OP == ST_DC) {
+        const u32 l = __shfl_up_sync(0xffffffffu, m, 1), r = __shfl_down_sync(0xffffffffu, m, 1);
+        const u32 sl = __funnelshift_l(l, m, 1), sr = __funnelshift_r(m, r, 1);
+        return OP == ST_EC ? ((m & sl & sr) & u & d) : ((m | sl | sr) | u | d);
+    }
+    return m;
+}
+
+template <int NEXT, bool ROWFIX, bool COLFIX>
+__device__ __forceinline__ u32 oob_fix32(u32 v, const u32 colvalid, const bool row_inside)
+{
+    if (NEXT == ST_NONE) return COLFIX ? (v & colvalid) : v;
+    if (op_is_erode(NEXT)) {
+        if (ROWFIX && !row_inside) return 0xffffffffu;
+        return COLFIX ? (v | ~colvalid) : v;
+    }
+    if (ROWFIX && !row_inside) return 0u;
+    return COLFIX ? (v & colvalid) : v;
+}
+
+template <u32 CODE, int S>
+struct MorphChain32 {
+    template <int TAP, bool ROWFIX, bool COLFIX>
+    static __device__ __forceinline__ void run(u32 cur, u32 (&p1)[8], u32 (&p2)[8], int t, int h, u32 colvalid, u32 &tap_out, u32 &fin)
+    {
+        constexpr int N = code_len(CODE);
+        if (S == TAP) tap_out = cur;
+        if constexpr (S < N) {
+            constexpr int OP = code_op(CODE, S);
+            constexpr int NEXT = (S + 1 < N) ? code_op(CODE, S + 1) : ST_NONE;
+            u32 out = step32<OP>(p2[S], p1[S], cur);
+            p2[S] = p1[S]; p1[S] = cur;
+            const int r = t - S - 1;
+            out = oob_fix32<NEXT, ROWFIX, COLFIX>(out, colvalid, !ROWFIX || (r >= 0 && r < h));
+            MorphChain32<CODE, S + 1>::template run<TAP, ROWFIX, COLFIX>(out, p1, p2, t, h, colvalid, tap_out, fin);
+        } else {
+            fin = cur;
+        }
+    }
+};
+
+template <u32 CODE, int TAP, int TR>
+__global__ void __launch_bounds__(128) fk_morph_lab(const uint4 *__restrict__ slices, const u32 *__restrict__ od, u32 *__restrict__ out_bits, int ws,
+                                                    size_t plane, int h, int w, int K, u8 *__restrict__ masks, size_t mstride, size_t mpitch,
+                                                    int aligned16, int wcols, const __grid_constant__ MorphRuns R)
+{
+    constexpr int N = code_len(CODE);
+    constexpr int EXT = 2;
+    constexpr int TILES = TR / ET_R;
+    __shared__ uint2 s_lut8[256];
+    __shared__ u32 s_item[4][TILES][32];
+    expand_lut_init(s_lut8, threadIdx.x, blockDim.x);
+    __syncthreads();
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int wx = blockIdx.x * 4 + wid;
+    if (wx >= wcols) return;                                  // whole warps only: the list flush below is warp-wide
+    const int ww = (w + 31) >> 5;
+    const int c = wx * LP_COLS - 1 + lane;
+    const bool inimg = c >= 0 && c < ww;
+    const bool owned = inimg && lane >= 1 && lane <= LP_COLS;
+    const int p = blockIdx.z, f = p / K, k = p - f * K;
+    const int y0 = blockIdx.y * TR, y1 = min(h, y0 + TR);
+    const int t_first = y0 - N - EXT;
+    // running pointers of the row being fetched (t + 1), the tapped row (t - TAP) and the final row (t - N); they may point
+    // outside the planes while the row is outside [0, h): never dereferenced then
+    const uint4 *sl = slices + (ptrdiff_t)f * (ptrdiff_t)plane + (ptrdiff_t)t_first * ws + c;
+    const u32 *odp = od + (ptrdiff_t)f * (ptrdiff_t)plane + (ptrdiff_t)t_first * ws + c;
+    u8 *mrow = masks + (size_t)p * mstride + (ptrdiff_t)(t_first - TAP) * (ptrdiff_t)mpitch;
+    u32 *frow = out_bits + (ptrdiff_t)p * (ptrdiff_t)plane + (ptrdiff_t)(t_first - N) * ws + c;
+    const u32 n0 = (k & 1) ? 0u : 0xffffffffu, n1 = (k & 2) ? 0u : 0xffffffffu, n2 = (k & 4) ? 0u : 0xffffffffu,
+              n3 = (k & 8) ? 0u : 0xffffffffu;
+    const u32 colvalid = inimg ? range_mask(32 * c, w) : 0u;
+    // pixels 32c-2, 32c-1 (top bits of the left lane's word) and 32c+32, 32c+33 (low bits of the right lane's) inside the image?
+    const u32 lv = (c >= 1 && c <= ww) ? 0xC0000000u : 0u;
+    const u32 rv = (c + 1 >= 0) ? (range_mask(32 * c + 32, w) & 3u) : 0u;
+    constexpr int OP0 = code_op(CODE, 0);
+    u32 p1[8], p2[8];
+#pragma unroll
+    for (int s = 0; s < 8; s++) p1[s] = p2[s] = 0u;
+    // the slice words and Od of the next row are loaded one row ahead and stay RAW in registers until they are needed (combining
+    // them at once would wait for the loads right there)
+    uint4 nsl = make_uint4(0u, 0u, 0u, 0u);
+    u32 nod = 0u;
+    auto fetch = [&](const int t) {
+        nod = 0u;
+        if (t >= 0 && t < h && inimg) { nod = __ldg(odp); nsl = __ldg(sl); }
+        odp += ws; sl += ws;
+    };
+    u32 live1 = 0u, live0 = 0u;
+    auto rows = [&](auto rowfix_tag, auto colfix_tag) {
+        constexpr bool ROWFIX = decltype(rowfix_tag)::value, COLFIX = decltype(colfix_tag)::value;
+        fetch(t_first);
+        for (int t = t_first; t < y1 + N + EXT; t++) {
+            u32 cur = nod & (nsl.x ^ n0) & (nsl.y ^ n1) & (nsl.z ^ n2) & (nsl.w ^ n3);          // open_k = Od & [label == k]
+            const bool inside = t >= 0 && t < h;
+            fetch(t + 1);
+            cur = oob_fix32<OP0, ROWFIX, COLFIX>(cur, colvalid, !ROWFIX || inside);
+            u32 tap = 0u, fin = 0u;
+            MorphChain32<CODE, 0>::template run<TAP, ROWFIX, COLFIX>(cur, p1, p2, t, h, colvalid, tap, fin);
+            {
+                const int r = t - TAP;
+                if (r >= y0 && r < y1 && owned) store_word_bytes_lut(mrow, 32 * c, w, tap, aligned16 != 0, s_lut8);
+                mrow += mpitch;
+            }
+            const int r = t - N;
+            if (r >= y0 && r < y1 && owned) *frow = fin & colvalid;
+            frow += ws;
+            if (r >= y0 - 2 && r < y1 + 2 && (!ROWFIX || (r >= 0 && r < h))) {       // warp-uniform
+                const u32 l = __shfl_up_sync(0xffffffffu, fin, 1), rr = __shfl_down_sync(0xffffffffu, fin, 1);
+                const bool h1 = ((fin & colvalid) | (l & lv) | (rr & rv)) != 0u, h0 = ((~fin & colvalid) | (~l & lv) | (~rr & rv)) != 0u;
+                const int q = r - y0, sub = q & 7;
+                u32 m = 1u << ((q >> 3) + 1);                           // tile q / 8 (floor), biased by one
+                if (sub < 2) m |= m >> 1;                                // also the 2-row halo of the tile above
+                if (sub >= 6) m |= m << 1;                               // ... of the tile below
+                m = (m >> 1) & ((1u << TILES) - 1u);
+                if (h1) live1 |= m;
+                if (h0) live0 |= m;
+            }
+        }
+    };
+    const bool rowfix = !(y0 - N - EXT >= 0 && y1 + N + EXT <= h);                                  // uniform per CTA
+    const bool colfix = __any_sync(0xffffffffu, colvalid != 0xffffffffu);                          // uniform per warp
+    if (rowfix) { if (colfix) rows(std::true_type{}, std::true_type{}); else rows(std::true_type{}, std::false_type{}); }
+    else { if (colfix) rows(std::false_type{}, std::true_type{}); else rows(std::false_type{}, std::false_type{}); }
+    // ---- run lists of the sparse edge kernel (see fk_morph / fk_edge_runs for the rule and the list layout) ----
+    const u32 live = owned ? (live1 & live0) : 0u;
+    int n_items = 0, run = 0, run_j0 = 0;
+    u32 lens = 0u;
+    auto emit = [&]() {
+        lens |= (u32)run << (3 * n_items);
+        s_item[wid][n_items++][lane] = ((u32)p << 27) | ((u32)run_j0 << 13) | (u32)c;
+        run = 0;
+    };
+#pragma unroll
+    for (int tl = 0; tl < TILES; tl++) {
+        const int ty0 = y0 + tl * ET_R;
+        if (ty0 >= y1) break;
+        if ((live >> tl) & 1u) {
+            if (run == 0) run_j0 = ty0 / ET_R;
+            if (++run == R.maxt) emit();
+        } else {
+            if (run) emit();
+            if (owned && R.zero_fill) {
+                const int ty1 = min(y1, ty0 + ET_R);
+                for (int y = ty0; y < ty1; y++) {
+                    const size_t o = (size_t)p * plane + (size_t)y * ws + c;
+                    R.cbits[o] = 0u; R.sbits[o] = 0u;
+                    store_word_bytes(R.edges + (size_t)p * R.estride + (size_t)y * R.epitch, 32 * c, w, 0u, R.aligned16 != 0);
+                }
+            }
+        }
+    }
+    if (run) emit();
+#pragma unroll
+    for (int nt = 1; nt <= ET_MAXT; nt++) {
+        int mine = 0;
+        for (int i = 0; i < n_items; i++) mine += ((lens >> (3 * i)) & 7u) == (u32)nt;
+        int x = mine;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            int y = __shfl_up_sync(0xffffffffu, x, d);
+            if (lane >= d) x += y;
+        }
+        const int total = __shfl_sync(0xffffffffu, x, 31);
+        if (total == 0) continue;
+        int base = 0;
+        if (lane == 31) base = atomicAdd(R.run_counts + nt - 1, total);
+        base = __shfl_sync(0xffffffffu, base, 31);
+        int pos = base + x - mine;
+        for (int i = 0; i < n_items; i++)
+            if (((lens >> (3 * i)) & 7u) == (u32)nt) R.run_items[R.off.v[nt - 1] + pos++] = s_item[wid][i][lane];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+// workspace slot 5 tail (after the tables of the first generation): [Lab cells (u32) | label nibbles | several-candidates bits]
+#define WS5_LABEL_BYTES ((size_t)CELL_COUNT * sizeof(u32) + RC_NIB_BYTES + RC_MB_BYTES)
+
+static int label_tables(omni_ctx *ctx, const AssignParams &P, u32 **cells, u8 **rtab, cudaStream_t st)
+{
+    SP_TRY(omni_ws_reserve(ctx, 5, WS5_BYTES + WS5_LABEL_BYTES));
+    *cells = (u32 *)((u8 *)ctx->ws[5] + WS5_BYTES);
+    *rtab = (u8 *)(*cells + CELL_COUNT);
+    if (ctx->table_cache && ctx->cells3_valid && ctx->cells3_ws == ctx->ws[5] && ctx->cells3_stream == (void *)st && ctx->cells3_K == P.K &&
+        memcmp(ctx->cells3_c, P.c, sizeof(float) * 3 * P.K) == 0 && memcmp(ctx->cells3_lut, P.lut, P.K) == 0)
+        return OMNI_OK;
+    memcpy(ctx->cells3_c, P.c, sizeof(float) * 3 * P.K);
+    memcpy(ctx->cells3_lut, P.lut, P.K);
+    ctx->cells3_K = P.K; ctx->cells3_stream = (void *)st; ctx->cells3_valid = 1; ctx->cells3_ws = ctx->ws[5];
+    OMNI_LAUNCH(ctx, st, "build_cells", launch_build_cells(P, *cells, st));
+    SP_TRY(fast_rgb_boxes(ctx, st));
+    KScope ks(ctx, "build_rgbcells", st);
+    fk_build_rgbcells3<<<(1 << 17) / 256, 256, 0, st>>>(P, ctx->d_rgb_boxes, *rtab, (u32 *)(*rtab + RC_NIB_BYTES));
+    OMNI_CUDA(cudaGetLastError());
+    return OMNI_OK;
+}
+
+constexpr u32 CODE_L_N = mk_code(ST_DR, ST_ER);                                         // RECT close only (stage-03 morphology off)
+constexpr u32 CODE_L_O = mk_code(ST_DR, ST_ER, ST_EC, ST_DC);
+constexpr u32 CODE_L_C = mk_code(ST_DR, ST_ER, ST_DC, ST_EC);
+constexpr u32 CODE_L_OC = mk_code(ST_DR, ST_ER, ST_EC, ST_DC, ST_DC, ST_EC);
+
+static cudaError_t launch_morph_lab(int kind, const uint4 *slices, const u32 *od, u32 *m2, const BitGeom &g, int K, int KT, u8 *masks,
+                                    size_t mstride, size_t mpitch, const MorphRuns &R, cudaStream_t st)
+{
+    const int wcols = (g.ww + LP_COLS - 1) / LP_COLS;
+    const int al = ((uintptr_t)masks % 16 == 0) && (mstride % 16 == 0) && (mpitch % 16 == 0);
+    // taller strips (less halo work) once there are plenty of warps
+    const long long warps64 = (long long)wcols * ((g.h + 63) / 64) * KT;
+    const int tr = warps64 >= 4096 ? 64 : 32;
+    dim3 b(128), grid((wcols + 3) / 4, (g.h + tr - 1) / tr, KT);
+#define LL2(CODE, TRV) fk_morph_lab<CODE, 2, TRV><<<grid, b, 0, st>>>(slices, od, m2, g.ws, g.plane, g.h, g.w, K, masks, mstride, mpitch, al, wcols, R)
+#define LL(CODE) do { if (tr == 64) LL2(CODE, 64); else LL2(CODE, 32); } while (0)
+    switch (kind) {
+    case 0: LL(CODE_L_N); break;
+    case 1: LL(CODE_L_O); break;
+    case 2: LL(CODE_L_C); break;
+    default: LL(CODE_L_OC); break;
+    }
+#undef LL
+#undef LL2
+    return cudaGetLastError();
+}
+
+int sparse_color_edge(omni_ctx *ctx, const u8 *d_bgr, int nf, size_t frame_stride, int h, int w, size_t pitch, const AssignParams &P,
+                      const omni_edge_params *prm, int low, int high, u8 *d_labels, size_t lpitch,
+                      u8 *d_masks, size_t m_plane, size_t mpitch, u8 *d_edges, size_t e_plane, size_t epitch, cudaStream_t st)
+{
+    const int K = P.K, KT = nf * K;
+    const int kind = morph03_kind(prm);
+    if (low < 0 || kind < 0 || prm->ksize != 3) return OMNI_ERR_UNSUPPORTED;
+    if (K > RC_MAX_K || KT > OMNI_MAX_K || !lut_below_k(P) || !edges3_sparse_ok(h, w, KT)) return OMNI_ERR_UNSUPPORTED;
+    const BitGeom g = make_geom(h, w);
+    if ((long long)nf * h * ((w + 255) >> 8) >= (1ll << 30)) return OMNI_ERR_UNSUPPORTED;
+    OMNI_CUDA(fast_tables());
+    // ---- workspace (slot 4): [label slices 4 nf | Od nf | M2 KT | S KT | C KT], the S and C sets laid out as edge_pass_begin expects
+    const size_t pbytes = g.plane * sizeof(u32);
+    auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    const size_t o_sl = 0, o_od = al(o_sl + pbytes * 4 * nf), o_m2 = al(o_od + pbytes * nf), o_s = al(o_m2 + pbytes * KT),
+                 o_c = o_s + al(pbytes * KT), bits_total = al(o_c + pbytes * KT);
+    SP_TRY(omni_ws_reserve(ctx, 4, bits_total));
+    u8 *b4 = (u8 *)ctx->ws[4];
+    u32 *slices = (u32 *)(b4 + o_sl), *od = (u32 *)(b4 + o_od), *M2 = (u32 *)(b4 + o_m2), *sbits = (u32 *)(b4 + o_s), *cbits = (u32 *)(b4 + o_c);
+    // the zeros of the dead edge tiles ride on the assignment kernel (ZeroJob) or, for strided planes, on a side stream
+    MorphRuns R{};
+    bool sparse = false;
+    ZeroJob Z{};
+    SP_TRY(edge_pass_begin(ctx, g, KT, sbits, cbits, d_edges, e_plane, epitch, st, &R, &sparse, true, &Z));
+    if (!sparse) return OMNI_ERR_UNSUPPORTED;
+    u32 *cells = nullptr;
+    u8 *rtab = nullptr;
+    SP_TRY(label_tables(ctx, P, &cells, &rtab, st));
+    const u16 *labtab = fast_lab_table();
+    if (!labtab) { omni_set_error("Lab tables not available"); return OMNI_ERR_CUDA; }
+    // ---- 1. assignment -> label bit-slices ----
+    {
+        if (!ctx->occ_assign_sl) {
+            OMNI_CUDA(cudaFuncSetAttribute(fk_assign_slices<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, RA_SMEM + LP_ZBUF));
+            OMNI_CUDA(cudaFuncSetAttribute(fk_assign_slices<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, RA_SMEM + LP_ZBUF));
+            ctx->occ_assign_sl = 1;
+        }
+        const long long chunks = (long long)nf * h * ((w + 255) >> 8);
+        const int grid = (int)std::max<long long>(1, std::min<long long>(persist_blocks(ctx, 1), (chunks + RA_WARPS - 1) / RA_WARPS));
+        for (int z = 0; z < 2; z++)                         // units per chunk, rounded up to one store per lane
+            Z.per[z] = (unsigned)(((Z.n16[z] + (unsigned long long)chunks - 1) / (unsigned long long)chunks + 31) & ~31ull);
+        KScope ks(ctx, "assign_bits", st);
+        if (K >= 16)
+            fk_assign_slices<true><<<grid, RA_THREADS, RA_SMEM + LP_ZBUF, st>>>(d_bgr, h, w, pitch, P, (const uint4 *)rtab, cells, labtab, d_labels, lpitch,
+                                                                      slices, g.ws, nf, frame_stride, Z);
+        else
+            fk_assign_slices<false><<<grid, RA_THREADS, RA_SMEM + LP_ZBUF, st>>>(d_bgr, h, w, pitch, P, (const uint4 *)rtab, cells, labtab, d_labels, lpitch,
+                                                                       slices, g.ws, nf, frame_stride, Z);
+        OMNI_CUDA(cudaGetLastError());
+    }
+    // ---- 2. label-domain open: Od ----
+    {
+        const int wcols = (g.ww + LP_COLS - 1) / LP_COLS, strips = (h + LO_ROWS - 1) / LO_ROWS;
+        const long long warps = (long long)nf * strips * wcols;
+        KScope ks(ctx, "label_open", st);
+        fk_label_open<<<(unsigned)((warps + LO_WARPS - 1) / LO_WARPS), LO_WARPS * 32, 0, st>>>((const uint4 *)slices, g.ws, g.plane, h, w, nf, od, strips, wcols);
+        OMNI_CUDA(cudaGetLastError());
+    }
+    // ---- 3. the rest of the morphology chain per plane, run lists for the edge kernel ----
+    OMNI_LAUNCH(ctx, st, "morph_bits", launch_morph_lab(kind, (const uint4 *)slices, od, M2, g, K, KT, d_masks, m_plane, mpitch, R, st));
+    // ---- 4. edges on the live tile runs, hysteresis ----
+    if (ctx->edge_join) {                               // the side stream has cleared the output planes
+        OMNI_CUDA(cudaStreamWaitEvent(st, ctx->edge_join, 0));
+        ctx->edge_join = nullptr;
+    }
+    const int al16 = ((uintptr_t)d_edges % 16 == 0) && (e_plane % 16 == 0) && (epitch % 16 == 0);
+    OMNI_LAUNCH(ctx, st, "edges3_bits", launch_edges3_sparse(M2, g.ws, g.plane, h, w, KT, low, high, persist_blocks(ctx, ctx->e3s_per_sm),
+                                                             sbits, cbits, d_edges, e_plane, epitch, al16, ctx->d_flags + 4,
+                                                             (u32 *)ctx->ws[5] + HYST_WL_OFFSET, HY_WL_CAP, ctx->d_flags + 16,
+                                                             ctx->d_flags + 20, (const u32 *)ctx->ws[6], st));
+    return run_hysteresis(ctx, sbits, cbits, g, KT, d_edges, e_plane, epitch, st);
+}

@@ -95,6 +95,14 @@ struct omni_ctx {
     void *cells_stream = nullptr;
     float cells_c[OMNI_MAX_K * 3];
     u8 cells_lut[OMNI_MAX_K] = {};
+    // the same for the tables of the sparse generation (label_pipe.cu; tail of ws[5])
+    int cells3_valid = 0, cells3_K = 0;
+    void *cells3_stream = nullptr, *cells3_ws = nullptr;
+    float cells3_c[OMNI_MAX_K * 3];
+    u8 cells3_lut[OMNI_MAX_K] = {};
+    int table_cache = 1;                       // 0: rebuild the candidate tables on every call (omni_set_table_cache)
+    int occ_assign_sl = 0;
+    int pipeline = 1;                          // fused colour+edge call: 1 = sparse generation (label_pipe.cu), 0 = dense generation
     u8 *d_rgb_boxes = nullptr;                 // exact Lab box of every 4x4x4 RGB cell (centre-independent, built on first use)             // co-resident CTAs of the cooperative hysteresis kernel (0 = not queried yet)
 };
 

@@ -21,6 +21,7 @@ EXPORTS = [
     "omni_edges", "omni_host_edges", "omni_color_edge", "omni_host_color_edge", "omni_count_nonzero",
     "omni_edges_composite", "omni_last_hysteresis_passes", "omni_launch_count", "omni_profile_enable",
     "omni_profile_summary", "omni_thin_zhangsuen", "omni_host_thin_zhangsuen", "omni_swatch_masks", "omni_color_edge_batch", "omni_skeleton_degree",
+    "omni_set_table_cache",
 ]
 
 
@@ -56,6 +57,7 @@ def lib():
         "omni_last_error_string": ([], C.c_char_p),
         "omni_device_count": ([], i),
         "omni_set_fast_path": ([vp, i], i),
+        "omni_set_table_cache": ([vp, i], i),
         "omni_ctx_create": ([i, C.POINTER(vp)], i),
         "omni_ctx_destroy": ([vp], i),
         "omni_host_alloc": ([sz, C.POINTER(vp)], i),

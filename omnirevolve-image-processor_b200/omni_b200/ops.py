@@ -107,8 +107,13 @@ class Engine:
             pass
 
     def set_fast_path(self, enable):
-        """False/0: generic kernels; True/1: bit-plane fast path (default); 2: fast path with the dense edge kernel."""
+        """False/0: generic kernels; True/1: bit-plane fast path (default: sparse generation of the fused call);
+        2: dense generation with the dense edge kernel; 3: dense generation as shipped in round 1."""
         capi.check(self._L.omni_set_fast_path(self._h, int(enable)))
+
+    def set_table_cache(self, enable: bool):
+        """False: rebuild the candidate-centre tables on every call (single images with their own centres)."""
+        capi.check(self._L.omni_set_table_cache(self._h, 1 if enable else 0))
 
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)

@@ -20,7 +20,7 @@ def eng():
     e.close()
 
 
-@pytest.fixture(scope="module", params=[1, 2, 0], ids=["fast", "fast_dense_edges", "generic"])
+@pytest.fixture(scope="module", params=[1, 3, 2, 0], ids=["fast", "fast_dense_pipeline", "fast_dense_edges", "generic"])
 def eng_mode(request, eng):
     eng.set_fast_path(request.param)
     yield eng

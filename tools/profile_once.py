@@ -9,7 +9,7 @@ import numpy as np, torch, omni_b200          # noqa: E402
 from omni_b200.synth import synth              # noqa: E402
 from omni_b200 import stages                   # noqa: E402
 
-cfg = {"config2": (4096, 4096, 8, 0, 32), "config3": (8192, 8192, 16, 1, 64), "config4": (1080, 1920, 8, 0, 32)}[sys.argv[1] if len(sys.argv) > 1 else "config2"]
+cfg = {"config5": (4096, 4096, 16, 0, 32), "config2": (4096, 4096, 8, 0, 32), "config3": (8192, 8192, 16, 1, 64), "config4": (1080, 1920, 8, 0, 32)}[sys.argv[1] if len(sys.argv) > 1 else "config2"]
 h, w, K, seed, cell = cfg
 eng = omni_b200.Engine(0)
 img = synth(h, w, seed, cell)
