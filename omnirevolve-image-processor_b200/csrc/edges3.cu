@@ -129,6 +129,30 @@ __global__ void __launch_bounds__(E3V_WARPS * 32) fk_edges3_simd(const __grid_co
     };
     auto step = [&](const int tt, u32 (&hA)[10], u32 (&hB)[10], u32 (&hC)[10], u32 (&UA)[20], u32 (&UB)[20], u32 (&UC)[20]) {
         const int t = y0 + tt;
+        // ---- (0) candidate list of row t-3 (its candidate mask is known since the previous step): compacted over the warp.
+        // Branch-free and first in the step, so that the shuffle chain of the prefix sum and the list stores overlap with the
+        // dense arithmetic of (1)-(4) instead of standing alone in front of the NMS.
+        const int rn = t - 3, rnr = tt - 3;
+        const bool do_nms = rnr >= 0 && rnr < nrows;                        // warp-uniform
+        const bool mine = active && rn < y1;                                // this lane has a row to resolve
+        int total;
+        {
+            const u32 mk = (do_nms && mine) ? cand_prev : 0u;
+            const int cnt = __popc(mk);
+            int x = cnt;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                int y = __shfl_up_sync(0xffffffffu, x, d);
+                if (lane >= d) x += y;
+            }
+            total = __shfl_sync(0xffffffffu, x, 31);
+            int pos = x - cnt;
+            const u32 tag = (u32)lane << 5;
+#pragma unroll
+            for (int e = 0; e < 32; e++)                                    // flat and predicated: no find-first-set chain
+                if ((mk >> e) & 1u) S.list[pos++] = (u16)(tag | e);
+            S.cw[lane] = 0u; S.sw[lane] = 0u;
+        }
         // ---- (1) bit row t (prefetched one step ahead), 40-pixel window: index e <-> pixel 32c - 4 + e ---------------
         u32 lo = (pf_l >> 28) | (pf_o << 4), hi = (pf_o >> 28) | (pf_r << 4);
         if (is_lb) {                                   // pixels -1, -2 := pixels 1, 0
@@ -218,30 +242,7 @@ __global__ void __launch_bounds__(E3V_WARPS * 32) fk_edges3_simd(const __grid_co
                 *reinterpret_cast<uint2 *>(mreg + 32) = make_uint2(0u, 0u);
             }
         }
-        // ---- (5) NMS + thresholds for row t-3: candidates compacted over the warp, one per lane and round -----------
-        const int rn = t - 3, rnr = tt - 3;
-        const bool do_nms = rnr >= 0 && rnr < nrows;                        // warp-uniform
-        const bool mine = active && rn < y1;                                // this lane has a row to resolve
-        int total = 0;
-        if (do_nms) {
-            u32 mk = mine ? cand_prev : 0u;
-            const int cnt = __popc(mk);
-            int x = cnt;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                int y = __shfl_up_sync(0xffffffffu, x, d);
-                if (lane >= d) x += y;
-            }
-            total = __shfl_sync(0xffffffffu, x, 31);
-            int pos = x - cnt;
-            const u32 tag = (u32)lane << 5;
-            while (mk) {
-                const int e = __ffs(mk) - 1;
-                mk &= mk - 1u;
-                S.list[pos++] = (u16)(tag | e);
-            }
-            S.cw[lane] = 0u; S.sw[lane] = 0u;
-        }
+        // ---- (5) NMS + thresholds for row t-3: the candidates (compacted over the warp in (0)) are resolved one per lane and round --
         __syncwarp();
         if (do_nms) {
             // the three magnitude rows live in one array: neighbour = centre row + a (uniform) row offset + a column offset
@@ -308,6 +309,17 @@ __global__ void __launch_bounds__(E3V_WARPS * 32) fk_edges3_simd(const __grid_co
     for (int j = 0; j < 20; j++) UA[j] = UB[j] = UC[j] = 0u;
     const int tt_end = nrows + 2;
     load_row(y0 - 3);
+#ifndef E3_ROTATE_THREE
+    // one instance of the step (a third of the code: the three rotated copies do not fit the instruction caches); the rolling
+    // rows move by register copies instead
+    for (int tt = -3; tt <= tt_end; tt++) {
+        step(tt, hA, hB, hC, UA, UB, UC);
+#pragma unroll
+        for (int q = 0; q < 10; q++) { hA[q] = hB[q]; hB[q] = hC[q]; }
+#pragma unroll
+        for (int j = 0; j < 20; j++) { UA[j] = UB[j]; UB[j] = UC[j]; }
+    }
+#else
     for (int tt = -3; tt <= tt_end; tt += 3) {
         step(tt, hA, hB, hC, UA, UB, UC);
         if (tt + 1 > tt_end) break;
@@ -315,6 +327,7 @@ __global__ void __launch_bounds__(E3V_WARPS * 32) fk_edges3_simd(const __grid_co
         if (tt + 2 > tt_end) break;
         step(tt + 2, hC, hA, hB, UC, UA, UB);
     }
+#endif
     };  // process
 
     if (!SPARSE) {

@@ -163,14 +163,16 @@ __global__ void __launch_bounds__(RA_THREADS, 1) fk_assign_slices(const u8 *__re
         if (lane == 0) {
 #pragma unroll
             for (int z = 0; z < 2; z++) {
-                if (Z.n16[z]) {
-                    unsigned long long idx = (unsigned long long)Z.per[z] * (unsigned)u;
-                    unsigned long long left = idx < Z.n16[z] ? min((unsigned long long)Z.per[z], Z.n16[z] - idx) * 16ull : 0ull;
-                    char *dst = reinterpret_cast<char *>(Z.p[z] + idx);
-                    while (left) {
-                        const u32 n = (u32)min(left, (unsigned long long)LP_ZBUF);
-                        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(zsrc), "r"(n) : "memory");
-                        dst += n; left -= n;
+                if (Z.per[z]) {
+                    const unsigned long long idx = (unsigned long long)Z.per[z] * (unsigned)u;
+                    if (idx < Z.n16[z]) {
+                        u32 left = (u32)min((unsigned long long)Z.per[z], Z.n16[z] - idx) * 16u;      // per * 16 < 2^32 (launcher)
+                        char *dst = reinterpret_cast<char *>(Z.p[z] + idx);
+                        do {
+                            const u32 n = min(left, (u32)LP_ZBUF);
+                            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(zsrc), "r"(n) : "memory");
+                            dst += n; left -= n;
+                        } while (left);
                     }
                 }
             }
@@ -192,11 +194,20 @@ __global__ void __launch_bounds__(RA_THREADS, 1) fk_assign_slices(const u8 *__re
             else if (o == 2) v = __byte_perm(wv[qi], wv[(qi + 1) % 6], 0x4432);
             else v = __byte_perm(wv[qi], wv[(qi + 1) % 6], 0x5543);
             const u32 idx = ((v >> 2) & 0x3Fu) | ((v >> 4) & 0xFC0u) | ((v >> 6) & 0x3F000u);
-            u32 lab = ((u32)s_nb[idx & 0x1FFFFu] >> ((idx >> 15) & 4u)) & 15u;
-            bool multi = SEP_MULTI ? ((s_mb[idx >> 5] >> (idx & 31u)) & 1u) != 0u : lab == 15u;
-            if (!full && xbase + j >= w) { lab = 0u; multi = false; }
+            const u32 lab = ((u32)s_nb[idx & 0x1FFFFu] >> ((idx >> 15) & 4u)) & 15u;
             nibw |= lab << (4 * j);
-            mm |= (multi ? 1u : 0u) << j;
+            if (SEP_MULTI) mm |= ((s_mb[idx >> 5] >> (idx & 31u)) & 1u) << j;
+        }
+        if (!SEP_MULTI) {                                      // K <= 15: nibble 15 = "several candidates"; 8 nibbles -> 8 flag bits
+            u32 t = nibw & (nibw >> 1) & (nibw >> 2) & (nibw >> 3) & 0x11111111u;
+            t = (t | (t >> 3)) & 0x03030303u;
+            mm = (t * 0x01041040u) >> 24;
+        }
+        if (!full) {                                           // pixels right of the image: label 0, never queued
+            const int nv = max(0, min(8, w - xbase));
+            const u32 keep = nv >= 8 ? 0xffffffffu : ((1u << (4 * nv)) - 1u);
+            nibw &= keep;
+            mm &= (1u << nv) - 1u;
         }
         // ---- the undecided pixels, compacted over the warp ----
         const int cnt = __popc(mm);
@@ -285,7 +296,7 @@ __global__ void __launch_bounds__(RA_THREADS, 1) fk_assign_slices(const u8 *__re
 // ------------------------------------------------------------------------------------------------
 #define LO_WARPS 4
 #define LP_COLS 30                        // owned word columns per warp (fk_label_open, fk_morph_lab)
-#define LO_ROWS 16                        // rows per strip
+#define LO_ROWS 8                         // rows per strip (short strips: the kernel is latency-bound, it needs many warps)
 
 __global__ void __launch_bounds__(LO_WARPS * 32) fk_label_open(const uint4 *__restrict__ slices, int ws, size_t plane, int h, int w, int nf,
                                                                u32 *__restrict__ od_out, int strips, int wcols)
@@ -409,10 +420,17 @@ struct MorphChain32 {
     }
 };
 
+#ifndef ML_ORDER
+#define ML_ORDER 1
+#endif
+#ifndef ML_MINB
+#define ML_MINB 1
+#endif
 template <u32 CODE, int TAP, int TR>
-__global__ void __launch_bounds__(128) fk_morph_lab(const uint4 *__restrict__ slices, const u32 *__restrict__ od, u32 *__restrict__ out_bits, int ws,
+__global__ void __launch_bounds__(128, ML_MINB) fk_morph_lab(const uint4 *__restrict__ slices, const u32 *__restrict__ od, u32 *__restrict__ out_bits, int ws,
                                                     size_t plane, int h, int w, int K, u8 *__restrict__ masks, size_t mstride, size_t mpitch,
-                                                    int aligned16, int wcols, const __grid_constant__ MorphRuns R)
+                                                    int aligned16, int wcols, int strips, int n_planes, long long n_units,
+                                                    const __grid_constant__ MorphRuns R)
 {
     constexpr int N = code_len(CODE);
     constexpr int EXT = 2;
@@ -422,14 +440,22 @@ __global__ void __launch_bounds__(128) fk_morph_lab(const uint4 *__restrict__ sl
     expand_lut_init(s_lut8, threadIdx.x, blockDim.x);
     __syncthreads();
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int wx = blockIdx.x * 4 + wid;
-    if (wx >= wcols) return;                                  // whole warps only: the list flush below is warp-wide
+    // warp unit = (plane, strip, group of 30 word columns), columns fastest: every warp of every CTA has work
+    const long long unit = (long long)blockIdx.x * 4 + wid;
+    if (unit >= n_units) return;                              // whole warps only: the list flush below is warp-wide
+    const int wx = (int)(unit % wcols);
+    const long long u2 = unit / wcols;
+#if ML_ORDER == 1
+    const int p = (int)(u2 % n_planes), strip = (int)(u2 / n_planes);       // the planes of a strip run together: they share its label rows
+#else
+    const int strip = (int)(u2 % strips), p = (int)(u2 / strips);
+#endif
     const int ww = (w + 31) >> 5;
     const int c = wx * LP_COLS - 1 + lane;
     const bool inimg = c >= 0 && c < ww;
     const bool owned = inimg && lane >= 1 && lane <= LP_COLS;
-    const int p = blockIdx.z, f = p / K, k = p - f * K;
-    const int y0 = blockIdx.y * TR, y1 = min(h, y0 + TR);
+    const int f = p / K, k = p - f * K;
+    const int y0 = strip * TR, y1 = min(h, y0 + TR);
     const int t_first = y0 - N - EXT;
     // running pointers of the row being fetched (t + 1), the tapped row (t - TAP) and the final row (t - N); they may point
     // outside the planes while the row is outside [0, h): never dereferenced then
@@ -488,7 +514,7 @@ __global__ void __launch_bounds__(128) fk_morph_lab(const uint4 *__restrict__ sl
             }
         }
     };
-    const bool rowfix = !(y0 - N - EXT >= 0 && y1 + N + EXT <= h);                                  // uniform per CTA
+    const bool rowfix = !(y0 - N - EXT >= 0 && y1 + N + EXT <= h);                                  // uniform per warp
     const bool colfix = __any_sync(0xffffffffu, colvalid != 0xffffffffu);                          // uniform per warp
     if (rowfix) { if (colfix) rows(std::true_type{}, std::true_type{}); else rows(std::true_type{}, std::false_type{}); }
     else { if (colfix) rows(std::false_type{}, std::true_type{}); else rows(std::false_type{}, std::false_type{}); }
@@ -579,9 +605,15 @@ static cudaError_t launch_morph_lab(int kind, const uint4 *slices, const u32 *od
     const int al = ((uintptr_t)masks % 16 == 0) && (mstride % 16 == 0) && (mpitch % 16 == 0);
     // taller strips (less halo work) once there are plenty of warps
     const long long warps64 = (long long)wcols * ((g.h + 63) / 64) * KT;
+#ifdef ML_TR
+    const int tr = ML_TR;
+#else
     const int tr = warps64 >= 4096 ? 64 : 32;
-    dim3 b(128), grid((wcols + 3) / 4, (g.h + tr - 1) / tr, KT);
-#define LL2(CODE, TRV) fk_morph_lab<CODE, 2, TRV><<<grid, b, 0, st>>>(slices, od, m2, g.ws, g.plane, g.h, g.w, K, masks, mstride, mpitch, al, wcols, R)
+#endif
+    const int strips = (g.h + tr - 1) / tr;
+    const long long n_units = (long long)wcols * strips * KT;
+    dim3 b(128), grid((unsigned)((n_units + 3) / 4));
+#define LL2(CODE, TRV) fk_morph_lab<CODE, 2, TRV><<<grid, b, 0, st>>>(slices, od, m2, g.ws, g.plane, g.h, g.w, K, masks, mstride, mpitch, al, wcols, strips, KT, n_units, R)
 #define LL(CODE) do { if (tr == 64) LL2(CODE, 64); else LL2(CODE, 32); } while (0)
     switch (kind) {
     case 0: LL(CODE_L_N); break;

@@ -11,7 +11,7 @@ from oracle import cmodel as cm
 eng = omni_b200.Engine(0)
 mode = sys.argv[1] if len(sys.argv) > 1 else "small"
 cases = [(64, 96, 4, 0), (200, 333, 4, 1), (257, 1030, 8, 2), (512, 768, 16, 3), (33, 40, 2, 4), (1080, 1920, 8, 5), (8, 32, 3, 6), (7, 31, 5, 7),
-         (100, 2049, 7, 8)] if mode == "small" else [(4096, 4096, 16, 0), (4096, 4096, 8, 0), (2160, 3840, 12, 1)]
+         (100, 2049, 7, 8)] if mode == "small" else ([(4096, 4096, 16, 0), (4096, 4096, 8, 0)] if mode == "time" else [(4096, 4096, 16, 0), (4096, 4096, 8, 0), (2160, 3840, 12, 1)])
 bad = 0
 for (h, w, K, seed) in cases:
     img = synth(h, w, seed)
@@ -21,6 +21,8 @@ for (h, w, K, seed) in cases:
     d = torch.from_numpy(img).cuda()
     for ec in (omni_b200.EdgeConfig(), omni_b200.EdgeConfig(open_iters=0), omni_b200.EdgeConfig(close_iters=0), omni_b200.EdgeConfig(morph_k=1), omni_b200.EdgeConfig(low=100, high=200)):
         if mode != "small" and ec != omni_b200.EdgeConfig():
+            continue
+        if mode == "time":
             continue
         out = {}
         for m in (1, 3):
@@ -67,7 +69,7 @@ else:
         d = torch.from_numpy(img).cuda(); m = torch.empty((K, h, w), dtype=torch.uint8, device="cuda"); e = torch.empty_like(m)
         flush = torch.empty(384 << 20, dtype=torch.uint8, device="cuda")
         ec = omni_b200.EdgeConfig()
-        for mode_ in (1, 3):
+        for mode_ in ((1,) if os.environ.get("PROBE_ONLY1") else (1, 3)):
             eng.set_fast_path(mode_)
             for _ in range(3): eng.color_edge(d, ctr, lut, ec, masks=m, edges=e)
             ts = []
