@@ -159,6 +159,31 @@ int omni_host_color_edge(omni_ctx *ctx, const uint8_t *h_bgr, int h, int w, size
                          uint8_t *h_edges, size_t e_plane_stride, size_t epitch,
                          int64_t *h_counts);
 
+/* ---- packed outputs: 1 bit per pixel ------------------------------------------------------- */
+/* mask.png / edges.png hold only 0 and 255, so a layer is one BIT per pixel: the planes leave the GPU 8 x smaller (PCIe is what
+ * bounds the host-buffer calls), and the row format OMNI_BITS_MSB_FIRST is the scanline of a 1-bit greyscale PNG, which
+ * cv2.imread(..., IMREAD_GRAYSCALE) decodes to the same {0,255} array (stages 04-13 read identical pixels).
+ * Same computation as omni_color_edge[_batch]: n_frames frames sharing one centre set (n_frames * K <= OMNI_MAX_K), plane f * K + k =
+ * layer k of frame f; rows are `pitch` bytes apart (>= ceil(w / 8)), unused bits of the last byte are 0.
+ * prm == NULL: colour layers only (02_color_extract.py on its own; d_edge_bits unused).
+ * h_counts (optional, 3 * n_frames * K int64: per plane [pixels labelled, mask non-zeros, edge non-zeros]) makes the device form
+ * synchronise the stream. */
+#define OMNI_BITS_LSB_FIRST 0    /* pixel x = bit (x & 7) of byte x >> 3       (numpy.packbits(..., bitorder="little")) */
+#define OMNI_BITS_MSB_FIRST 1    /* pixel x = bit 7 - (x & 7) of byte x >> 3   (PNG bit depth 1, numpy.packbits default) */
+int omni_color_edge_packed(omni_ctx *ctx, const uint8_t *d_bgr, int n_frames, size_t frame_stride, int h, int w, size_t pitch,
+                           const float *h_centers, int K, const uint8_t *h_lut, const omni_edge_params *prm,
+                           uint8_t *d_mask_bits, size_t mb_plane_stride, size_t mb_pitch,
+                           uint8_t *d_edge_bits, size_t eb_plane_stride, size_t eb_pitch, int bit_order,
+                           int64_t *h_counts, void *stream);
+/* Host buffers (pinned for full speed); any number of frames: groups of OMNI_MAX_K / K frames go through the device with the H2D
+ * of the next group and the D2H of the previous one overlapping the kernels.  Planes must be back to back (plane stride =
+ * pitch * h).  Returns when all results are in the host buffers. */
+int omni_host_color_edge_packed(omni_ctx *ctx, const uint8_t *h_bgr, int n_frames, size_t frame_stride, int h, int w, size_t pitch,
+                                const float *h_centers, int K, const uint8_t *h_lut, const omni_edge_params *prm,
+                                uint8_t *h_mask_bits, size_t mb_plane_stride, size_t mb_pitch,
+                                uint8_t *h_edge_bits, size_t eb_plane_stride, size_t eb_pitch, int bit_order,
+                                int64_t *h_counts);
+
 /* Non-zero count of each of K planes (02:157, 03:38 `np.count_nonzero`); h_counts: K int64.
  * Synchronises the stream. */
 int omni_count_nonzero(omni_ctx *ctx, const uint8_t *d_planes, int K, int h, int w, size_t plane_stride, size_t pitch,

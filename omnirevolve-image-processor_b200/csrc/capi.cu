@@ -78,6 +78,11 @@ extern "C" int omni_ctx_destroy(omni_ctx *c)
     for (auto &r : c->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     for (auto e : c->ev_pool) cudaEventDestroy(e);
     fast_ctx_release(c);
+    if (c->pk_ready) {
+        cudaStreamDestroy(c->pk_in); cudaStreamDestroy(c->pk_out);
+        for (auto e : c->pk_ev) cudaEventDestroy(e);
+    }
+    if (c->pk_counts) cudaFreeHost(c->pk_counts);
     delete c;
     return OMNI_OK;
 }
@@ -586,6 +591,160 @@ extern "C" int omni_color_edge_batch(omni_ctx *ctx, const uint8_t *d_bgr, int n_
     return OMNI_OK;
 }
 
+static inline size_t pad16(size_t v) { return (v + 15) & ~(size_t)15; }
+
+// ---- packed (1 bit per pixel) outputs ------------------------------------------------------------------------
+// Device body shared by the three packed entry points: n frames at d_bgr -> packed planes (device, caller layout) + counts on
+// the device (ctx->d_counts: [pixels | mask non-zeros | edge non-zeros], OMNI_MAX_K each) when want_counts.
+static int packed_device(omni_ctx *ctx, const u8 *d_bgr, int nf, size_t frame_stride, int h, int w, size_t pitch, const float *h_centers,
+                         int K, const uint8_t *h_lut, const omni_edge_params *prm, u8 *d_mb, size_t mb_plane, size_t mb_pitch,
+                         u8 *d_eb, size_t eb_plane, size_t eb_pitch, int bit_order, bool want_counts, cudaStream_t st)
+{
+    OMNI_REQUIRE(bit_order == OMNI_BITS_LSB_FIRST || bit_order == OMNI_BITS_MSB_FIRST, "bit_order must be OMNI_BITS_LSB_FIRST or OMNI_BITS_MSB_FIRST");
+    OMNI_REQUIRE(nf >= 1 && nf * K <= OMNI_MAX_K, "n_frames * K = %d exceeds %d planes per call", nf * K, OMNI_MAX_K);
+    const size_t rb = ((size_t)w + 7) / 8;
+    OMNI_REQUIRE(mb_pitch >= rb && (!prm || eb_pitch >= rb), "packed row pitch smaller than ceil(w / 8) bytes");
+    BlurParams bp; int low = 0, high = 0;
+    if (prm) OMNI_TRY(check_edge_params(prm, &bp, &low, &high));
+    AssignParams P;
+    OMNI_TRY(fill_assign(&P, h_centers, nullptr, K, h_lut));
+    unsigned long long *dc = want_counts ? ctx->d_counts : nullptr;
+    int rc = OMNI_ERR_UNSUPPORTED;
+    if (ctx->fast && ctx->pipeline == 1)
+        rc = label_color_edge_packed(ctx, d_bgr, nf, frame_stride, h, w, pitch, P, prm, low, high, d_mb, mb_plane, mb_pitch, d_eb, eb_plane,
+                                     eb_pitch, bit_order == OMNI_BITS_MSB_FIRST, dc, st);
+    if (rc != OMNI_ERR_UNSUPPORTED) return rc;
+    // any other family: byte planes in workspace slot 3's tail, then packed
+    const size_t bp_pitch = ((size_t)w + 15) & ~(size_t)15, bplane = bp_pitch * h, lp = bp_pitch;
+    const int KT = nf * K;
+    OMNI_TRY(omni_ws_reserve(ctx, 2, lp * h + 2 * bplane * KT));
+    u8 *dl = (u8 *)ctx->ws[2], *dm = dl + lp * h, *de = dm + bplane * KT;
+    if (dc) OMNI_CUDA(cudaMemsetAsync(dc, 0, 3 * OMNI_MAX_K * sizeof(unsigned long long), st));
+    omni_edge_params none{1, 0, 0, 3, 50.0, 150.0};          // masks only: the edge planes of a cheap dummy pass are dropped
+    for (int f = 0; f < nf; f++) {
+        const u8 *img = d_bgr + (size_t)f * frame_stride;
+        if (prm) {
+            OMNI_TRY(omni_color_edge(ctx, img, h, w, pitch, h_centers, K, h_lut, prm, dl, lp, dm + (size_t)f * K * bplane, bplane, bp_pitch,
+                                     de + (size_t)f * K * bplane, bplane, bp_pitch, st));
+        } else {
+            (void)none;
+            OMNI_TRY(omni_assign_lab_f32(ctx, img, h, w, pitch, h_centers, K, h_lut, dl, lp, st));
+            OMNI_TRY(omni_layer_masks(ctx, dl, h, w, lp, K, 1, 1, dm + (size_t)f * K * bplane, bplane, bp_pitch, st));
+        }
+        if (dc) OMNI_LAUNCH(ctx, st, "count_labels", g_count_labels(dl, lp, h, w, K, dc + (size_t)f * K, st));
+    }
+    OMNI_LAUNCH(ctx, st, "pack_bytes", g_pack_bytes(dm, bplane, bp_pitch, KT, h, w, d_mb, mb_plane, mb_pitch, bit_order, dc ? dc + OMNI_MAX_K : nullptr, st));
+    if (prm)
+        OMNI_LAUNCH(ctx, st, "pack_bytes", g_pack_bytes(de, bplane, bp_pitch, KT, h, w, d_eb, eb_plane, eb_pitch, bit_order, dc ? dc + 2 * OMNI_MAX_K : nullptr, st));
+    return OMNI_OK;
+}
+
+static void fetch_counts(omni_ctx *ctx, int KT, int64_t *h_counts)
+{
+    for (int k = 0; k < KT; k++) {
+        h_counts[3 * k] = (int64_t)ctx->h_counts[k];
+        h_counts[3 * k + 1] = (int64_t)ctx->h_counts[OMNI_MAX_K + k];
+        h_counts[3 * k + 2] = (int64_t)ctx->h_counts[2 * OMNI_MAX_K + k];
+    }
+}
+
+extern "C" int omni_color_edge_packed(omni_ctx *ctx, const uint8_t *d_bgr, int n_frames, size_t frame_stride, int h, int w, size_t pitch,
+                                      const float *h_centers, int K, const uint8_t *h_lut, const omni_edge_params *prm,
+                                      uint8_t *d_mask_bits, size_t mb_plane_stride, size_t mb_pitch,
+                                      uint8_t *d_edge_bits, size_t eb_plane_stride, size_t eb_pitch, int bit_order,
+                                      int64_t *h_counts, void *stream)
+{
+    OMNI_TRY(set_device(ctx));
+    OMNI_REQUIRE(d_bgr && d_mask_bits && h_centers && (d_edge_bits || !prm), "omni_color_edge_packed: NULL pointer");
+    OMNI_REQUIRE(h > 0 && w > 0 && pitch >= (size_t)w * 3 && K >= 1 && K <= OMNI_MAX_K, "omni_color_edge_packed: bad geometry");
+    cudaStream_t st = (cudaStream_t)stream;
+    OMNI_TRY(packed_device(ctx, d_bgr, n_frames, frame_stride, h, w, pitch, h_centers, K, h_lut, prm, d_mask_bits, mb_plane_stride, mb_pitch,
+                           d_edge_bits, eb_plane_stride, eb_pitch, bit_order, h_counts != nullptr, st));
+    if (h_counts) {
+        OMNI_CUDA(cudaMemcpyAsync(ctx->h_counts, ctx->d_counts, 3 * OMNI_MAX_K * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+        OMNI_CUDA(cudaStreamSynchronize(st));
+        fetch_counts(ctx, n_frames * K, h_counts);
+    }
+    return OMNI_OK;
+}
+
+// Host buffers, n frames sharing one centre set, H2D / kernels / D2H of consecutive frame groups overlapped (two staging slots on
+// three streams).  Results are complete in the host buffers when the call returns.
+extern "C" int omni_host_color_edge_packed(omni_ctx *ctx, const uint8_t *h_bgr, int n_frames, size_t frame_stride, int h, int w, size_t pitch,
+                                           const float *h_centers, int K, const uint8_t *h_lut, const omni_edge_params *prm,
+                                           uint8_t *h_mask_bits, size_t mb_plane_stride, size_t mb_pitch,
+                                           uint8_t *h_edge_bits, size_t eb_plane_stride, size_t eb_pitch, int bit_order,
+                                           int64_t *h_counts)
+{
+    OMNI_TRY(set_device(ctx));
+    OMNI_REQUIRE(h_bgr && h_mask_bits && h_centers && (h_edge_bits || !prm) && n_frames >= 1, "omni_host_color_edge_packed: bad arguments");
+    OMNI_REQUIRE(h > 0 && w > 0 && pitch >= (size_t)w * 3 && K >= 1 && K <= OMNI_MAX_K, "omni_host_color_edge_packed: bad geometry");
+    const size_t rb = ((size_t)w + 7) / 8;
+    OMNI_REQUIRE(mb_pitch >= rb && (!prm || eb_pitch >= rb), "packed row pitch smaller than ceil(w / 8) bytes");
+    OMNI_REQUIRE(mb_plane_stride == mb_pitch * (size_t)h && (!prm || eb_plane_stride == eb_pitch * (size_t)h),
+                 "omni_host_color_edge_packed: planes must be back to back (plane stride = pitch * h)");
+    const int G = OMNI_MAX_K / K;                           // frames per device pass (their G * K layers are its planes)
+    const int n_groups = (n_frames + G - 1) / G;
+    if (!ctx->pk_ready) {
+        OMNI_CUDA(cudaStreamCreateWithFlags(&ctx->pk_in, cudaStreamNonBlocking));
+        OMNI_CUDA(cudaStreamCreateWithFlags(&ctx->pk_out, cudaStreamNonBlocking));
+        for (auto &e : ctx->pk_ev) OMNI_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        ctx->pk_ready = 1;
+    }
+    if (h_counts && ctx->pk_counts_cap < (size_t)n_groups) {        // pinned: one block of counts per group, read after the last copy
+        if (ctx->pk_counts) OMNI_CUDA(cudaFreeHost(ctx->pk_counts));
+        ctx->pk_counts = nullptr; ctx->pk_counts_cap = 0;
+        OMNI_CUDA(cudaHostAlloc(&ctx->pk_counts, (size_t)n_groups * 3 * OMNI_MAX_K * sizeof(unsigned long long), cudaHostAllocDefault));
+        ctx->pk_counts_cap = (size_t)n_groups;
+    }
+    const size_t ip = pad16((size_t)w * 3), img_bytes = pad16(ip * h), dp = pad16(rb), dplane = dp * h;
+    const size_t slot_in = img_bytes * G, slot_out = pad16(dplane * (size_t)G * K);
+    OMNI_TRY(omni_ws_reserve(ctx, 3, 2 * slot_in + 4 * slot_out));
+    u8 *base = (u8 *)ctx->ws[3];
+    cudaStream_t sc = ctx->stream, si = ctx->pk_in, so = ctx->pk_out;
+    // events: [0,1] H2D of slot done, [2,3] kernels of slot done (inputs free, outputs ready), [4,5] D2H of slot done
+    OMNI_CUDA(cudaEventRecord(ctx->pk_ev[6], sc));          // order the side streams after earlier work of this ctx
+    OMNI_CUDA(cudaStreamWaitEvent(si, ctx->pk_ev[6], 0));
+    OMNI_CUDA(cudaStreamWaitEvent(so, ctx->pk_ev[6], 0));
+    for (int gi = 0; gi < n_groups; gi++) {
+        const int s = gi & 1, f0 = gi * G, nf = (n_frames - f0) < G ? (n_frames - f0) : G;
+        u8 *d_in = base + (size_t)s * slot_in, *d_mb = base + 2 * slot_in + (size_t)(2 * s) * slot_out, *d_eb = d_mb + slot_out;
+        if (gi >= 2) OMNI_CUDA(cudaStreamWaitEvent(si, ctx->pk_ev[2 + s], 0));      // the kernels of group gi-2 have read this slot
+        for (int f = 0; f < nf; f++)
+            OMNI_CUDA(cudaMemcpy2DAsync(d_in + (size_t)f * img_bytes, ip, h_bgr + (size_t)(f0 + f) * frame_stride, pitch, (size_t)w * 3, h,
+                                        cudaMemcpyHostToDevice, si));
+        OMNI_CUDA(cudaEventRecord(ctx->pk_ev[s], si));
+        OMNI_CUDA(cudaStreamWaitEvent(sc, ctx->pk_ev[s], 0));
+        if (gi >= 2) OMNI_CUDA(cudaStreamWaitEvent(sc, ctx->pk_ev[4 + s], 0));      // the D2H of group gi-2 has drained this slot's outputs
+        OMNI_TRY(packed_device(ctx, d_in, nf, img_bytes, h, w, ip, h_centers, K, h_lut, prm, d_mb, dplane, dp, d_eb, dplane, dp, bit_order,
+                               h_counts != nullptr, sc));
+        if (h_counts)
+            OMNI_CUDA(cudaMemcpyAsync(ctx->pk_counts + (size_t)gi * 3 * OMNI_MAX_K, ctx->d_counts, 3 * OMNI_MAX_K * sizeof(unsigned long long),
+                                      cudaMemcpyDeviceToHost, sc));
+        OMNI_CUDA(cudaEventRecord(ctx->pk_ev[2 + s], sc));
+        OMNI_CUDA(cudaStreamWaitEvent(so, ctx->pk_ev[2 + s], 0));
+        // the nf * K planes of the group are back to back on both sides: one strided copy of h * nf * K rows
+        OMNI_CUDA(cudaMemcpy2DAsync(h_mask_bits + (size_t)f0 * K * mb_plane_stride, mb_pitch, d_mb, dp, rb, (size_t)h * nf * K,
+                                    cudaMemcpyDeviceToHost, so));
+        if (prm)
+            OMNI_CUDA(cudaMemcpy2DAsync(h_edge_bits + (size_t)f0 * K * eb_plane_stride, eb_pitch, d_eb, dp, rb, (size_t)h * nf * K,
+                                        cudaMemcpyDeviceToHost, so));
+        OMNI_CUDA(cudaEventRecord(ctx->pk_ev[4 + s], so));
+    }
+    OMNI_CUDA(cudaStreamSynchronize(so));
+    OMNI_CUDA(cudaStreamSynchronize(sc));
+    if (h_counts)
+        for (int gi = 0; gi < n_groups; gi++) {
+            const int f0 = gi * G, nf = (n_frames - f0) < G ? (n_frames - f0) : G;
+            const unsigned long long *pc = ctx->pk_counts + (size_t)gi * 3 * OMNI_MAX_K;
+            for (int k = 0; k < nf * K; k++) {
+                int64_t *o = h_counts + 3 * ((size_t)f0 * K + k);
+                o[0] = (int64_t)pc[k]; o[1] = (int64_t)pc[OMNI_MAX_K + k]; o[2] = (int64_t)pc[2 * OMNI_MAX_K + k];
+            }
+        }
+    return OMNI_OK;
+}
+
 // ---- counts / composite -----------------------------------------------------------------------------------
 extern "C" int omni_count_nonzero(omni_ctx *ctx, const uint8_t *d_planes, int K, int h, int w, size_t plane_stride, size_t pitch,
                                   int64_t *h_counts, void *stream)
@@ -613,7 +772,6 @@ extern "C" int omni_edges_composite(omni_ctx *ctx, const uint8_t *d_edges, int K
 
 // ---- host-buffer entry points -------------------------------------------------------------------------------
 // Staging layout in workspace slot 3: [image | labels | masks | edges], rows padded to 16 bytes.
-static inline size_t pad16(size_t v) { return (v + 15) & ~(size_t)15; }
 
 extern "C" int omni_host_resize_area_u8c3(omni_ctx *ctx, const uint8_t *h_src, int sh, int sw, size_t spitch,
                                           uint8_t *h_dst, int dh, int dw, size_t dpitch)

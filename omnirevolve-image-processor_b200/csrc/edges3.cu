@@ -297,7 +297,7 @@ __global__ void __launch_bounds__(E3V_WARPS * 32) fk_edges3_simd(const __grid_co
             }
             // edge bytes for E = S; the hysteresis kernel patches the (rare) promoted weak pixels afterwards
             // (arithmetic bit->byte expansion: a 2 KB table would cost the 6th resident CTA per SM)
-            store_word_bytes(edges + (size_t)k * estride + (size_t)rn * epitch, 32 * c, w, sw, aligned16 != 0);
+            if (edges) store_word_bytes(edges + (size_t)k * estride + (size_t)rn * epitch, 32 * c, w, sw, aligned16 != 0);     // NULL: bit-planes only
         }
         cand_prev = cand;
     };
@@ -453,7 +453,7 @@ __global__ void __launch_bounds__(ER_WARPS * 32) fk_edge_runs(const u32 *__restr
                 for (int y = j * ET_R; y < y1; y++) {
                     const size_t o = (size_t)k * plane + (size_t)y * ws + c;
                     cbits[o] = 0u; sbits[o] = 0u;
-                    store_word_bytes(edges + (size_t)k * estride + (size_t)y * epitch, 32 * c, w, 0u, aligned16 != 0);
+                    if (edges) store_word_bytes(edges + (size_t)k * estride + (size_t)y * epitch, 32 * c, w, 0u, aligned16 != 0);
                 }
             }
         }

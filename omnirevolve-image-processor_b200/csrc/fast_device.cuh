@@ -183,3 +183,4 @@ int morph03_kind(const omni_edge_params *p);
 int sparse_color_edge(omni_ctx *ctx, const u8 *d_bgr, int nf, size_t frame_stride, int h, int w, size_t pitch, const AssignParams &P,
                       const omni_edge_params *prm, int low, int high, u8 *d_labels, size_t lpitch,
                       u8 *d_masks, size_t m_plane, size_t mpitch, u8 *d_edges, size_t e_plane, size_t epitch, cudaStream_t st);
+

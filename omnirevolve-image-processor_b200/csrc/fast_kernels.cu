@@ -873,7 +873,7 @@ __global__ void __launch_bounds__(128, MORPH_MINB) fk_morph(const u32 *__restric
                     for (int y = ty0; y < ty1; y++) {
                         const size_t o = (size_t)k * plane + (size_t)y * ws + c;
                         R.cbits[o] = 0u; R.sbits[o] = 0u;
-                        store_word_bytes(R.edges + (size_t)k * R.estride + (size_t)y * R.epitch, 32 * c, w, 0u, R.aligned16 != 0);
+                        if (R.edges) store_word_bytes(R.edges + (size_t)k * R.estride + (size_t)y * R.epitch, 32 * c, w, 0u, R.aligned16 != 0);
                     }
                 }
             }
@@ -968,6 +968,7 @@ static cudaError_t launch_morph(bool with02, int morph03, const u32 *in_bits, u3
 
 __device__ __forceinline__ void hy_patch_bytes(u8 *row, u32 promoted)
 {
+    if (row == nullptr) return;                       // packed outputs: the bit-planes are the result
     while (promoted) {
         int e = __ffs(promoted) - 1;
         promoted &= promoted - 1u;
@@ -1020,7 +1021,7 @@ __global__ void __launch_bounds__(HY_THREADS) fk_hysteresis(u32 *__restrict__ eb
                 if (nv != ev) {
                     E[c] = nv;
                     changed = 1;
-                    hy_patch_bytes(edges + (size_t)k * estride + (size_t)y * epitch + 32 * c, nv & ~ev);
+                    hy_patch_bytes(edges ? edges + (size_t)k * estride + (size_t)y * epitch + 32 * c : nullptr, nv & ~ev);
                 }
             }
             rounds++;
@@ -1067,7 +1068,7 @@ __global__ void __launch_bounds__(HY_THREADS) fk_hysteresis(u32 *__restrict__ eb
                     if (nv != ev) {
                         E[c] = nv;
                         *chg = 1;
-                        hy_patch_bytes(edges + (size_t)k * estride + (size_t)y * epitch + 32 * c, nv & ~ev);
+                        hy_patch_bytes(edges ? edges + (size_t)k * estride + (size_t)y * epitch + 32 * c : nullptr, nv & ~ev);
                     }
                 }
             }
@@ -1132,7 +1133,7 @@ __global__ void __launch_bounds__(HY_THREADS) fk_hysteresis(u32 *__restrict__ eb
                             u32 nv = s_e[(ly + 1) * SW + lc + 1], old = __ldcg(E + (size_t)gy * ws + gc);
                             if (nv & ~old) {
                                 E[(size_t)gy * ws + gc] = nv | old;
-                                hy_patch_bytes(edges + (size_t)k * estride + (size_t)gy * epitch + 32 * gc, nv & ~old);
+                                hy_patch_bytes(edges ? edges + (size_t)k * estride + (size_t)gy * epitch + 32 * gc : nullptr, nv & ~old);
                             }
                         }
                     }

@@ -73,3 +73,8 @@ int fast_swatch_masks(omni_ctx *ctx, const u8 *d_bgr, int h, int w, size_t pitch
 int fast_color_edge_batch(omni_ctx *ctx, const u8 *d_bgr, int n, size_t frame_stride, int h, int w, size_t pitch, const AssignParams &P,
                           const omni_edge_params *prm, int low, int high, u8 *d_masks, size_t m_plane, size_t mpitch,
                           u8 *d_edges, size_t e_plane, size_t epitch, cudaStream_t st);
+
+// packed (1 bit per pixel) outputs of the fused call (label_pipe.cu); prm == NULL: colour layers only
+int label_color_edge_packed(omni_ctx *ctx, const u8 *d_bgr, int nf, size_t frame_stride, int h, int w, size_t pitch, const AssignParams &P,
+                            const omni_edge_params *prm, int low, int high, u8 *d_mask_bits, size_t mb_plane, size_t mb_pitch,
+                            u8 *d_edge_bits, size_t eb_plane, size_t eb_pitch, int msb_first, unsigned long long *d_counts, cudaStream_t st);

@@ -508,3 +508,33 @@ cudaError_t g_copy2d_planes(const u8 *src, size_t s_plane, size_t spitch, u8 *ds
     }
     return cudaSuccess;
 }
+
+// byte planes (non-zero = set) -> packed rows in the caller's layout, with optional per-plane non-zero counts (generic family of
+// the packed entry points: whatever the byte-plane kernels produced, 8 pixels per output byte)
+__global__ void __launch_bounds__(256) k_pack_bytes(const u8 *__restrict__ src, size_t s_plane, size_t spitch, int K, int h, int w,
+                                                    u8 *__restrict__ dst, size_t d_plane, size_t dpitch, int msb_first,
+                                                    unsigned long long *__restrict__ counts)
+{
+    const int rb = (w + 7) >> 3;
+    const long long total = (long long)K * h * rb;
+    for (long long u = (long long)blockIdx.x * blockDim.x + threadIdx.x; u < total; u += (long long)gridDim.x * blockDim.x) {
+        const int j = (int)(u % rb);
+        const long long r2 = u / rb;
+        const int y = (int)(r2 % h), k = (int)(r2 / h);
+        const u8 *row = src + (size_t)k * s_plane + (size_t)y * spitch + 8 * j;
+        unsigned v = 0;
+        for (int i = 0; i < 8 && 8 * j + i < w; i++)
+            if (row[i]) v |= msb_first ? (0x80u >> i) : (1u << i);
+        dst[(size_t)k * d_plane + (size_t)y * dpitch + j] = (u8)v;
+        if (counts && v) atomicAdd(counts + k, (unsigned long long)__popc(v));
+    }
+}
+
+cudaError_t g_pack_bytes(const u8 *src, size_t s_plane, size_t spitch, int K, int h, int w, u8 *dst, size_t d_plane, size_t dpitch,
+                         int msb_first, unsigned long long *counts, cudaStream_t st)
+{
+    const long long total = (long long)K * h * ((w + 7) >> 3);
+    const int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+    k_pack_bytes<<<blocks > 0 ? blocks : 1, 256, 0, st>>>(src, s_plane, spitch, K, h, w, dst, d_plane, dpitch, msb_first, counts);
+    return cudaGetLastError();
+}

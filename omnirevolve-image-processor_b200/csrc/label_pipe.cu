@@ -426,14 +426,16 @@ struct MorphChain32 {
 #ifndef ML_MINB
 #define ML_MINB 1
 #endif
-template <u32 CODE, int TAP, int TR>
+// RUNS = false: masks only (stage 02 on its own): no final bit-plane, no tile classification.  masks == NULL: no mask bytes
+// (packed outputs); tap_bits != NULL: the mask as a bit-plane.
+template <u32 CODE, int TAP, int TR, bool RUNS>
 __global__ void __launch_bounds__(128, ML_MINB) fk_morph_lab(const uint4 *__restrict__ slices, const u32 *__restrict__ od, u32 *__restrict__ out_bits, int ws,
                                                     size_t plane, int h, int w, int K, u8 *__restrict__ masks, size_t mstride, size_t mpitch,
-                                                    int aligned16, int wcols, int strips, int n_planes, long long n_units,
+                                                    int aligned16, u32 *__restrict__ tap_bits, int wcols, int strips, int n_planes, long long n_units,
                                                     const __grid_constant__ MorphRuns R)
 {
     constexpr int N = code_len(CODE);
-    constexpr int EXT = 2;
+    constexpr int EXT = RUNS ? 2 : 0;
     constexpr int TILES = TR / ET_R;
     __shared__ uint2 s_lut8[256];
     __shared__ u32 s_item[4][TILES][32];
@@ -462,6 +464,7 @@ __global__ void __launch_bounds__(128, ML_MINB) fk_morph_lab(const uint4 *__rest
     const uint4 *sl = slices + (ptrdiff_t)f * (ptrdiff_t)plane + (ptrdiff_t)t_first * ws + c;
     const u32 *odp = od + (ptrdiff_t)f * (ptrdiff_t)plane + (ptrdiff_t)t_first * ws + c;
     u8 *mrow = masks + (size_t)p * mstride + (ptrdiff_t)(t_first - TAP) * (ptrdiff_t)mpitch;
+    u32 *trow = tap_bits + (ptrdiff_t)p * (ptrdiff_t)plane + (ptrdiff_t)(t_first - TAP) * ws + c;
     u32 *frow = out_bits + (ptrdiff_t)p * (ptrdiff_t)plane + (ptrdiff_t)(t_first - N) * ws + c;
     const u32 n0 = (k & 1) ? 0u : 0xffffffffu, n1 = (k & 2) ? 0u : 0xffffffffu, n2 = (k & 4) ? 0u : 0xffffffffu,
               n3 = (k & 8) ? 0u : 0xffffffffu;
@@ -495,9 +498,13 @@ __global__ void __launch_bounds__(128, ML_MINB) fk_morph_lab(const uint4 *__rest
             MorphChain32<CODE, 0>::template run<TAP, ROWFIX, COLFIX>(cur, p1, p2, t, h, colvalid, tap, fin);
             {
                 const int r = t - TAP;
-                if (r >= y0 && r < y1 && owned) store_word_bytes_lut(mrow, 32 * c, w, tap, aligned16 != 0, s_lut8);
-                mrow += mpitch;
+                if (r >= y0 && r < y1 && owned) {
+                    if (masks) store_word_bytes_lut(mrow, 32 * c, w, tap, aligned16 != 0, s_lut8);
+                    if (tap_bits) *trow = tap & colvalid;
+                }
+                mrow += mpitch; trow += ws;
             }
+            if (!RUNS) continue;
             const int r = t - N;
             if (r >= y0 && r < y1 && owned) *frow = fin & colvalid;
             frow += ws;
@@ -518,6 +525,7 @@ __global__ void __launch_bounds__(128, ML_MINB) fk_morph_lab(const uint4 *__rest
     const bool colfix = __any_sync(0xffffffffu, colvalid != 0xffffffffu);                          // uniform per warp
     if (rowfix) { if (colfix) rows(std::true_type{}, std::true_type{}); else rows(std::true_type{}, std::false_type{}); }
     else { if (colfix) rows(std::false_type{}, std::true_type{}); else rows(std::false_type{}, std::false_type{}); }
+    if (!RUNS) return;
     // ---- run lists of the sparse edge kernel (see fk_morph / fk_edge_runs for the rule and the list layout) ----
     const u32 live = owned ? (live1 & live0) : 0u;
     int n_items = 0, run = 0, run_j0 = 0;
@@ -541,7 +549,7 @@ __global__ void __launch_bounds__(128, ML_MINB) fk_morph_lab(const uint4 *__rest
                 for (int y = ty0; y < ty1; y++) {
                     const size_t o = (size_t)p * plane + (size_t)y * ws + c;
                     R.cbits[o] = 0u; R.sbits[o] = 0u;
-                    store_word_bytes(R.edges + (size_t)p * R.estride + (size_t)y * R.epitch, 32 * c, w, 0u, R.aligned16 != 0);
+                    if (R.edges) store_word_bytes(R.edges + (size_t)p * R.estride + (size_t)y * R.epitch, 32 * c, w, 0u, R.aligned16 != 0);
                 }
             }
         }
@@ -598,11 +606,11 @@ constexpr u32 CODE_L_O = mk_code(ST_DR, ST_ER, ST_EC, ST_DC);
 constexpr u32 CODE_L_C = mk_code(ST_DR, ST_ER, ST_DC, ST_EC);
 constexpr u32 CODE_L_OC = mk_code(ST_DR, ST_ER, ST_EC, ST_DC, ST_DC, ST_EC);
 
-static cudaError_t launch_morph_lab(int kind, const uint4 *slices, const u32 *od, u32 *m2, const BitGeom &g, int K, int KT, u8 *masks,
-                                    size_t mstride, size_t mpitch, const MorphRuns &R, cudaStream_t st)
+static cudaError_t launch_morph_lab(int kind /* -1: masks only */, const uint4 *slices, const u32 *od, u32 *m2, const BitGeom &g, int K, int KT,
+                                    u8 *masks, size_t mstride, size_t mpitch, u32 *tap_bits, const MorphRuns &R, cudaStream_t st)
 {
     const int wcols = (g.ww + LP_COLS - 1) / LP_COLS;
-    const int al = ((uintptr_t)masks % 16 == 0) && (mstride % 16 == 0) && (mpitch % 16 == 0);
+    const int al = masks && ((uintptr_t)masks % 16 == 0) && (mstride % 16 == 0) && (mpitch % 16 == 0);
     // taller strips (less halo work) once there are plenty of warps
     const long long warps64 = (long long)wcols * ((g.h + 63) / 64) * KT;
 #ifdef ML_TR
@@ -613,44 +621,57 @@ static cudaError_t launch_morph_lab(int kind, const uint4 *slices, const u32 *od
     const int strips = (g.h + tr - 1) / tr;
     const long long n_units = (long long)wcols * strips * KT;
     dim3 b(128), grid((unsigned)((n_units + 3) / 4));
-#define LL2(CODE, TRV) fk_morph_lab<CODE, 2, TRV><<<grid, b, 0, st>>>(slices, od, m2, g.ws, g.plane, g.h, g.w, K, masks, mstride, mpitch, al, wcols, strips, KT, n_units, R)
-#define LL(CODE) do { if (tr == 64) LL2(CODE, 64); else LL2(CODE, 32); } while (0)
+#define LL2(CODE, TRV, RUNS) fk_morph_lab<CODE, 2, TRV, RUNS><<<grid, b, 0, st>>>(slices, od, m2, g.ws, g.plane, g.h, g.w, K, masks, mstride, mpitch, al, tap_bits, wcols, strips, KT, n_units, R)
+#define LL(CODE, RUNS) do { if (tr == 64) LL2(CODE, 64, RUNS); else LL2(CODE, 32, RUNS); } while (0)
     switch (kind) {
-    case 0: LL(CODE_L_N); break;
-    case 1: LL(CODE_L_O); break;
-    case 2: LL(CODE_L_C); break;
-    default: LL(CODE_L_OC); break;
+    case -1: LL(CODE_L_N, false); break;
+    case 0: LL(CODE_L_N, true); break;
+    case 1: LL(CODE_L_O, true); break;
+    case 2: LL(CODE_L_C, true); break;
+    default: LL(CODE_L_OC, true); break;
     }
 #undef LL
 #undef LL2
     return cudaGetLastError();
 }
 
-int sparse_color_edge(omni_ctx *ctx, const u8 *d_bgr, int nf, size_t frame_stride, int h, int w, size_t pitch, const AssignParams &P,
-                      const omni_edge_params *prm, int low, int high, u8 *d_labels, size_t lpitch,
-                      u8 *d_masks, size_t m_plane, size_t mpitch, u8 *d_edges, size_t e_plane, size_t epitch, cudaStream_t st)
+// Internal bit-planes of the last label-pipeline call on a ctx (valid until the next call): bit i of word c of row y = pixel 32c + i,
+// rows g.ws words apart, planes g.plane words apart.
+struct LabelPlanes { u32 *slices, *mask_bits, *edge_bits; };
+
+// prm == NULL: colour layers only (02_color_extract.py on its own: no stage-03 work).  d_masks / d_edges may be NULL (packed
+// outputs: the bit-planes in `out` are the result).
+static int label_pipeline(omni_ctx *ctx, const u8 *d_bgr, int nf, size_t frame_stride, int h, int w, size_t pitch, const AssignParams &P,
+                          const omni_edge_params *prm, int low, int high, u8 *d_labels, size_t lpitch,
+                          u8 *d_masks, size_t m_plane, size_t mpitch, u8 *d_edges, size_t e_plane, size_t epitch, bool want_mask_bits,
+                          cudaStream_t st, LabelPlanes *out)
 {
     const int K = P.K, KT = nf * K;
-    const int kind = morph03_kind(prm);
-    if (low < 0 || kind < 0 || prm->ksize != 3) return OMNI_ERR_UNSUPPORTED;
+    const int kind = prm ? morph03_kind(prm) : -1;
+    if (prm && (low < 0 || kind < 0 || prm->ksize != 3)) return OMNI_ERR_UNSUPPORTED;
     if (K > RC_MAX_K || KT > OMNI_MAX_K || !lut_below_k(P) || !edges3_sparse_ok(h, w, KT)) return OMNI_ERR_UNSUPPORTED;
     const BitGeom g = make_geom(h, w);
     if ((long long)nf * h * ((w + 255) >> 8) >= (1ll << 30)) return OMNI_ERR_UNSUPPORTED;
     OMNI_CUDA(fast_tables());
-    // ---- workspace (slot 4): [label slices 4 nf | Od nf | M2 KT | S KT | C KT], the S and C sets laid out as edge_pass_begin expects
+    // ---- workspace (slot 4): [label slices 4 nf | Od nf | M2 KT | S KT | C KT | mask bits KT]; S and C laid out as edge_pass_begin expects
     const size_t pbytes = g.plane * sizeof(u32);
     auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
     const size_t o_sl = 0, o_od = al(o_sl + pbytes * 4 * nf), o_m2 = al(o_od + pbytes * nf), o_s = al(o_m2 + pbytes * KT),
-                 o_c = o_s + al(pbytes * KT), bits_total = al(o_c + pbytes * KT);
+                 o_c = o_s + al(pbytes * KT), o_mb = al(o_c + pbytes * KT), bits_total = al(o_mb + (want_mask_bits ? pbytes * KT : 0));
     SP_TRY(omni_ws_reserve(ctx, 4, bits_total));
     u8 *b4 = (u8 *)ctx->ws[4];
     u32 *slices = (u32 *)(b4 + o_sl), *od = (u32 *)(b4 + o_od), *M2 = (u32 *)(b4 + o_m2), *sbits = (u32 *)(b4 + o_s), *cbits = (u32 *)(b4 + o_c);
-    // the zeros of the dead edge tiles ride on the assignment kernel (ZeroJob) or, for strided planes, on a side stream
+    u32 *mbits = want_mask_bits ? (u32 *)(b4 + o_mb) : nullptr;
+    if (out) { out->slices = slices; out->mask_bits = mbits; out->edge_bits = prm ? sbits : nullptr; }
+    // the zeros of the dead edge tiles: byte planes -> they ride on the assignment kernel (ZeroJob; strided planes: side stream);
+    // bit-planes only -> the morphology kernel clears the candidate / strong words of its dead tiles
     MorphRuns R{};
     bool sparse = false;
     ZeroJob Z{};
-    SP_TRY(edge_pass_begin(ctx, g, KT, sbits, cbits, d_edges, e_plane, epitch, st, &R, &sparse, true, &Z));
-    if (!sparse) return OMNI_ERR_UNSUPPORTED;
+    if (prm) {
+        SP_TRY(edge_pass_begin(ctx, g, KT, sbits, cbits, d_edges, e_plane, epitch, st, &R, &sparse, d_edges != nullptr, d_edges ? &Z : nullptr));
+        if (!sparse) return OMNI_ERR_UNSUPPORTED;
+    }
     u32 *cells = nullptr;
     u8 *rtab = nullptr;
     SP_TRY(label_tables(ctx, P, &cells, &rtab, st));
@@ -669,11 +690,11 @@ int sparse_color_edge(omni_ctx *ctx, const u8 *d_bgr, int nf, size_t frame_strid
             Z.per[z] = (unsigned)(((Z.n16[z] + (unsigned long long)chunks - 1) / (unsigned long long)chunks + 31) & ~31ull);
         KScope ks(ctx, "assign_bits", st);
         if (K >= 16)
-            fk_assign_slices<true><<<grid, RA_THREADS, RA_SMEM + LP_ZBUF, st>>>(d_bgr, h, w, pitch, P, (const uint4 *)rtab, cells, labtab, d_labels, lpitch,
-                                                                      slices, g.ws, nf, frame_stride, Z);
+            fk_assign_slices<true><<<grid, RA_THREADS, RA_SMEM + LP_ZBUF, st>>>(d_bgr, h, w, pitch, P, (const uint4 *)rtab, cells, labtab, d_labels,
+                                                                                lpitch, slices, g.ws, nf, frame_stride, Z);
         else
-            fk_assign_slices<false><<<grid, RA_THREADS, RA_SMEM + LP_ZBUF, st>>>(d_bgr, h, w, pitch, P, (const uint4 *)rtab, cells, labtab, d_labels, lpitch,
-                                                                       slices, g.ws, nf, frame_stride, Z);
+            fk_assign_slices<false><<<grid, RA_THREADS, RA_SMEM + LP_ZBUF, st>>>(d_bgr, h, w, pitch, P, (const uint4 *)rtab, cells, labtab, d_labels,
+                                                                                 lpitch, slices, g.ws, nf, frame_stride, Z);
         OMNI_CUDA(cudaGetLastError());
     }
     // ---- 2. label-domain open: Od ----
@@ -681,20 +702,156 @@ int sparse_color_edge(omni_ctx *ctx, const u8 *d_bgr, int nf, size_t frame_strid
         const int wcols = (g.ww + LP_COLS - 1) / LP_COLS, strips = (h + LO_ROWS - 1) / LO_ROWS;
         const long long warps = (long long)nf * strips * wcols;
         KScope ks(ctx, "label_open", st);
-        fk_label_open<<<(unsigned)((warps + LO_WARPS - 1) / LO_WARPS), LO_WARPS * 32, 0, st>>>((const uint4 *)slices, g.ws, g.plane, h, w, nf, od, strips, wcols);
+        fk_label_open<<<(unsigned)((warps + LO_WARPS - 1) / LO_WARPS), LO_WARPS * 32, 0, st>>>((const uint4 *)slices, g.ws, g.plane, h, w, nf, od, strips,
+                                                                                              wcols);
         OMNI_CUDA(cudaGetLastError());
     }
     // ---- 3. the rest of the morphology chain per plane, run lists for the edge kernel ----
-    OMNI_LAUNCH(ctx, st, "morph_bits", launch_morph_lab(kind, (const uint4 *)slices, od, M2, g, K, KT, d_masks, m_plane, mpitch, R, st));
+    OMNI_LAUNCH(ctx, st, "morph_bits", launch_morph_lab(kind, (const uint4 *)slices, od, M2, g, K, KT, d_masks, m_plane, mpitch, mbits, R, st));
+    if (!prm) return OMNI_OK;
     // ---- 4. edges on the live tile runs, hysteresis ----
     if (ctx->edge_join) {                               // the side stream has cleared the output planes
         OMNI_CUDA(cudaStreamWaitEvent(st, ctx->edge_join, 0));
         ctx->edge_join = nullptr;
     }
-    const int al16 = ((uintptr_t)d_edges % 16 == 0) && (e_plane % 16 == 0) && (epitch % 16 == 0);
+    const int al16 = d_edges && ((uintptr_t)d_edges % 16 == 0) && (e_plane % 16 == 0) && (epitch % 16 == 0);
     OMNI_LAUNCH(ctx, st, "edges3_bits", launch_edges3_sparse(M2, g.ws, g.plane, h, w, KT, low, high, persist_blocks(ctx, ctx->e3s_per_sm),
                                                              sbits, cbits, d_edges, e_plane, epitch, al16, ctx->d_flags + 4,
                                                              (u32 *)ctx->ws[5] + HYST_WL_OFFSET, HY_WL_CAP, ctx->d_flags + 16,
                                                              ctx->d_flags + 20, (const u32 *)ctx->ws[6], st));
     return run_hysteresis(ctx, sbits, cbits, g, KT, d_edges, e_plane, epitch, st);
+}
+
+int sparse_color_edge(omni_ctx *ctx, const u8 *d_bgr, int nf, size_t frame_stride, int h, int w, size_t pitch, const AssignParams &P,
+                      const omni_edge_params *prm, int low, int high, u8 *d_labels, size_t lpitch,
+                      u8 *d_masks, size_t m_plane, size_t mpitch, u8 *d_edges, size_t e_plane, size_t epitch, cudaStream_t st)
+{
+    return label_pipeline(ctx, d_bgr, nf, frame_stride, h, w, pitch, P, prm, low, high, d_labels, lpitch, d_masks, m_plane, mpitch, d_edges,
+                          e_plane, epitch, false, st, nullptr);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Packed outputs: the internal bit-planes re-laid for the caller (row pitch in bytes, LSB- or MSB-first bit order), per-plane
+// pixel counts.  One thread per 32-pixel word.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) fk_pack_planes(const u32 *__restrict__ src, int ws, size_t plane, int K, int h, int w,
+                                                      u8 *__restrict__ dst, size_t dplane, size_t dpitch, int msb_first,
+                                                      unsigned long long *__restrict__ counts)
+{
+    const int ww = (w + 31) >> 5, rb = (w + 7) >> 3;
+    const long long total = (long long)K * h * ww;
+    const int lane = threadIdx.x & 31;
+    for (long long base = ((long long)blockIdx.x * blockDim.x + threadIdx.x) - lane; base < total; base += (long long)gridDim.x * blockDim.x) {
+        const long long u = base + lane;
+        u32 word = 0u;
+        int k = 0;
+        if (u < total) {
+            const int c = (int)(u % ww);
+            const long long r2 = u / ww;
+            const int y = (int)(r2 % h);
+            k = (int)(r2 / h);
+            word = src[(size_t)k * plane + (size_t)y * ws + c] & range_mask(32 * c, w);
+            const u32 o = msb_first ? __byte_perm(__brev(word), 0u, 0x0123) : word;
+            u8 *row = dst + (size_t)k * dplane + (size_t)y * dpitch + 4 * c;
+            if (4 * c + 4 <= rb && (((uintptr_t)row) & 3) == 0) *reinterpret_cast<u32 *>(row) = o;
+            else
+                for (int i = 0; 4 * c + i < rb && i < 4; i++) row[i] = (u8)(o >> (8 * i));
+        }
+        if (counts) {
+            const int n = __popc(word);
+            if ((long long)h * ww < 32) {                        // tiny planes: a warp may touch many of them
+                if (n) atomicAdd(counts + k, (unsigned long long)n);
+            } else {                                             // a warp straddles at most two planes: one atomic per plane
+                const int k0 = __shfl_sync(0xffffffffu, k, 0);
+                int a = (k == k0) ? n : 0, b = (k == k0) ? 0 : n;
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, d); b += __shfl_xor_sync(0xffffffffu, b, d); }
+                if (lane == 0) {
+                    if (a) atomicAdd(counts + k0, (unsigned long long)a);
+                    if (b) atomicAdd(counts + k0 + 1, (unsigned long long)b);
+                }
+            }
+        }
+    }
+}
+
+// caller layout (pitch, bit order) -> internal bit-planes (padding words zero)
+__global__ void __launch_bounds__(256) fk_unpack_planes(const u8 *__restrict__ src, size_t splane, size_t spitch, int msb_first, int K, int h, int w,
+                                                        u32 *__restrict__ dst, int ws, size_t plane)
+{
+    const int rb = (w + 7) >> 3;
+    const long long total = (long long)K * h * ws;
+    for (long long u = (long long)blockIdx.x * blockDim.x + threadIdx.x; u < total; u += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(u % ws);
+        const long long r2 = u / ws;
+        const int y = (int)(r2 % h), k = (int)(r2 / h);
+        const u8 *row = src + (size_t)k * splane + (size_t)y * spitch + 4 * c;
+        u32 v = 0u;
+        for (int i = 0; i < 4 && 4 * c + i < rb; i++) v |= (u32)row[i] << (8 * i);
+        if (msb_first) v = __brev(__byte_perm(v, 0u, 0x0123));
+        dst[(size_t)k * plane + (size_t)y * ws + c] = v & range_mask(32 * c, w);
+    }
+}
+
+// pixels per label from the label bit-slices (one thread per word, K ballots)
+__global__ void __launch_bounds__(256) fk_count_labels_sl(const uint4 *__restrict__ slices, int ws, int h, int w, int K,
+                                                          unsigned long long *__restrict__ counts)
+{
+    const int ww = (w + 31) >> 5;
+    const long long total = (long long)h * ww;
+    const int lane = threadIdx.x & 31;
+    unsigned long long mine = 0;                             // lane k: pixels of label k seen by this warp
+    for (long long base = ((long long)blockIdx.x * blockDim.x + threadIdx.x) - lane; base < total; base += (long long)gridDim.x * blockDim.x) {
+        const long long u = base + lane;
+        uint4 s = make_uint4(0u, 0u, 0u, 0u);
+        u32 valid = 0u;
+        if (u < total) {
+            const int c = (int)(u % ww), y = (int)(u / ww);
+            s = __ldg(slices + (size_t)y * ws + c);
+            valid = range_mask(32 * c, w);
+        }
+        for (int k = 0; k < K; k++) {
+            const u32 m = valid & ((k & 1) ? s.x : ~s.x) & ((k & 2) ? s.y : ~s.y) & ((k & 4) ? s.z : ~s.z) & ((k & 8) ? s.w : ~s.w);
+            int n = __popc(m);
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) n += __shfl_xor_sync(0xffffffffu, n, d);
+            if (lane == k) mine += (unsigned long long)n;
+        }
+    }
+    if (lane < K && mine) atomicAdd(counts + lane, mine);
+}
+
+// Body of omni_color_edge_packed / omni_host_color_edge_packed* (capi.cu checks the arguments): nf frames sharing one centre set;
+// plane f * K + k of the outputs is layer k of frame f.  d_* outputs are DEVICE buffers in the caller's layout; d_counts (optional,
+// device, 3 * OMNI_MAX_K u64: [0..) pixels per label, [OMNI_MAX_K..) mask non-zeros, [2 OMNI_MAX_K..) edge non-zeros per plane,
+// cleared here).  OMNI_ERR_UNSUPPORTED: outside the label pipeline (K > 16, edge_kernel_size != 3, ...).
+int label_color_edge_packed(omni_ctx *ctx, const u8 *d_bgr, int nf, size_t frame_stride, int h, int w, size_t pitch, const AssignParams &P,
+                            const omni_edge_params *prm, int low, int high, u8 *d_mask_bits, size_t mb_plane, size_t mb_pitch,
+                            u8 *d_edge_bits, size_t eb_plane, size_t eb_pitch, int msb_first, unsigned long long *d_counts, cudaStream_t st)
+{
+    LabelPlanes L{};
+    SP_TRY(label_pipeline(ctx, d_bgr, nf, frame_stride, h, w, pitch, P, prm, low, high, nullptr, 0, nullptr, 0, 0, nullptr, 0, 0, true, st, &L));
+    const BitGeom g = make_geom(h, w);
+    const int K = P.K, KT = nf * K;
+    if (d_counts) OMNI_CUDA(cudaMemsetAsync(d_counts, 0, 3 * OMNI_MAX_K * sizeof(unsigned long long), st));
+    const int blocks = persist_blocks(ctx, 8);
+    {
+        KScope ks(ctx, "pack_planes", st);
+        fk_pack_planes<<<blocks, 256, 0, st>>>(L.mask_bits, g.ws, g.plane, KT, h, w, d_mask_bits, mb_plane, mb_pitch, msb_first,
+                                               d_counts ? d_counts + OMNI_MAX_K : nullptr);
+        OMNI_CUDA(cudaGetLastError());
+    }
+    if (prm) {
+        KScope ks(ctx, "pack_planes", st);
+        fk_pack_planes<<<blocks, 256, 0, st>>>(L.edge_bits, g.ws, g.plane, KT, h, w, d_edge_bits, eb_plane, eb_pitch, msb_first,
+                                               d_counts ? d_counts + 2 * OMNI_MAX_K : nullptr);
+        OMNI_CUDA(cudaGetLastError());
+    }
+    if (d_counts)
+        for (int f = 0; f < nf; f++) {
+            KScope ks(ctx, "count_labels", st);
+            fk_count_labels_sl<<<blocks, 256, 0, st>>>((const uint4 *)L.slices + (size_t)f * g.plane, g.ws, h, w, K, d_counts + (size_t)f * K);
+            OMNI_CUDA(cudaGetLastError());
+        }
+    return OMNI_OK;
 }

@@ -102,6 +102,12 @@ struct omni_ctx {
     u8 cells3_lut[OMNI_MAX_K] = {};
     int table_cache = 1;                       // 0: rebuild the candidate tables on every call (omni_set_table_cache)
     int occ_assign_sl = 0;
+    // streams / events / pinned counts of omni_host_color_edge_packed (two staging slots)
+    int pk_ready = 0;
+    cudaStream_t pk_in = nullptr, pk_out = nullptr;
+    cudaEvent_t pk_ev[7] = {};
+    unsigned long long *pk_counts = nullptr;
+    size_t pk_counts_cap = 0;                  // groups of 3 * OMNI_MAX_K counts
     int pipeline = 1;                          // fused colour+edge call: 1 = sparse generation (label_pipe.cu), 0 = dense generation
     u8 *d_rgb_boxes = nullptr;                 // exact Lab box of every 4x4x4 RGB cell (centre-independent, built on first use)             // co-resident CTAs of the cooperative hysteresis kernel (0 = not queried yet)
 };
@@ -143,6 +149,8 @@ cudaError_t g_composite(const u8 *edges, size_t plane, size_t pitch, int K, int 
                         u8 *canvas, size_t cpitch, cudaStream_t st);
 cudaError_t g_skeleton_degree(const u8 *skel, size_t s_plane, size_t spitch, int K, int h, int w, u8 *deg, size_t d_plane, size_t dpitch,
                               u8 *nodes, size_t n_plane, size_t npitch, cudaStream_t st);
+cudaError_t g_pack_bytes(const u8 *src, size_t s_plane, size_t spitch, int K, int h, int w, u8 *dst, size_t d_plane, size_t dpitch,
+                         int msb_first, unsigned long long *counts, cudaStream_t st);
 cudaError_t g_copy2d_planes(const u8 *src, size_t s_plane, size_t spitch, u8 *dst, size_t d_plane, size_t dpitch,
                             int K, int h, int w, cudaStream_t st);
 

@@ -217,6 +217,65 @@ class Engine:
             self._stream()))
         return labels, masks, edges
 
+    def color_edge_packed(self, frames: torch.Tensor, centers, lut, ec: "EdgeConfig | None", msb_first: bool = True,
+                          want_counts: bool = False):
+        """Packed form of color_edge / color_edge_batch: frames [H,W,3] or [n,H,W,3] (n * K <= 32) ->
+        (mask_bits, edge_bits | None[, counts]) as CUDA uint8 tensors [n*K, H, ceil(W/8)], one BIT per pixel (msb_first: the
+        scanline format of a 1-bit PNG = numpy.packbits default).  ec=None: colour layers only (stage 02 on its own)."""
+        if frames.dim() == 3:
+            frames = frames.unsqueeze(0)
+        if frames.dim() != 4 or frames.shape[3] != 3 or frames.dtype != torch.uint8 or not frames.is_cuda or frames.stride(3) != 1 \
+                or frames.stride(2) != 3:
+            raise ValueError("frames must be a CUDA uint8 tensor [n,H,W,3] (or [H,W,3]) with packed pixels")
+        ctr = np.ascontiguousarray(centers, dtype=np.float32).reshape(-1, 3)
+        K = ctr.shape[0]
+        lut_a = None if lut is None else np.ascontiguousarray(lut, dtype=np.uint8)
+        n, h, w = frames.shape[:3]
+        rb = (w + 7) // 8
+        mb = torch.empty((n * K, h, rb), dtype=torch.uint8, device=frames.device)
+        eb = torch.empty((n * K, h, rb), dtype=torch.uint8, device=frames.device) if ec is not None else None
+        counts = np.zeros((n * K, 3), np.int64) if want_counts else None
+        p = ec.to_c() if ec is not None else None
+        capi.check(self._L.omni_color_edge_packed(
+            self._h, frames.data_ptr(), n, frames.stride(0), h, w, frames.stride(1), _f32p(ctr), K, _u8p(lut_a),
+            C.byref(p) if p is not None else None, mb.data_ptr(), mb.stride(0), mb.stride(1),
+            eb.data_ptr() if eb is not None else None, eb.stride(0) if eb is not None else 0, eb.stride(1) if eb is not None else 0,
+            capi.BITS_MSB_FIRST if msb_first else capi.BITS_LSB_FIRST,
+            counts.ctypes.data_as(C.POINTER(C.c_int64)) if counts is not None else None, self._stream()))
+        return (mb, eb, counts) if want_counts else (mb, eb)
+
+    def host_color_edge_packed(self, frames: np.ndarray, centers, lut, ec: "EdgeConfig | None", msb_first: bool = True,
+                               mask_bits: np.ndarray | None = None, edge_bits: np.ndarray | None = None, want_counts: bool = True):
+        """Host frames [n,H,W,3] (or one [H,W,3]) sharing one centre set -> dict(mask_bits, edge_bits, counts): uint8 arrays
+        [n*K, H, ceil(W/8)], one bit per pixel.  Any n: frame groups are pipelined through the device (H2D / kernels / D2H overlap).
+        Pass pinned arrays (pinned_empty) for `frames`, `mask_bits`, `edge_bits` for full PCIe speed."""
+        fr = np.asarray(frames)
+        if fr.ndim == 3:
+            fr = fr[None]
+        if fr.dtype != np.uint8 or fr.ndim != 4 or fr.shape[3] != 3 or fr.strides[3] != 1 or fr.strides[2] != 3:
+            fr = np.ascontiguousarray(fr, dtype=np.uint8)
+        ctr = np.ascontiguousarray(centers, dtype=np.float32).reshape(-1, 3)
+        K = ctr.shape[0]
+        lut_a = None if lut is None else np.ascontiguousarray(lut, dtype=np.uint8)
+        n, h, w = fr.shape[:3]
+        rb = (w + 7) // 8
+        if mask_bits is None:
+            mask_bits = np.empty((n * K, h, rb), np.uint8)
+        if edge_bits is None and ec is not None:
+            edge_bits = np.empty((n * K, h, rb), np.uint8)
+        for a in (mask_bits, edge_bits):
+            if a is not None and (a.shape != (n * K, h, rb) or a.dtype != np.uint8 or not a.flags.c_contiguous):
+                raise ValueError("mask_bits / edge_bits must be C-contiguous uint8 [n*K, H, ceil(W/8)]")
+        counts = np.zeros((n * K, 3), np.int64) if want_counts else None
+        p = ec.to_c() if ec is not None else None
+        capi.check(self._L.omni_host_color_edge_packed(
+            self._h, fr.ctypes.data, n, fr.strides[0], h, w, fr.strides[1], _f32p(ctr), K, _u8p(lut_a),
+            C.byref(p) if p is not None else None, mask_bits.ctypes.data, mask_bits.strides[0], mask_bits.strides[1],
+            edge_bits.ctypes.data if edge_bits is not None else None, edge_bits.strides[0] if edge_bits is not None else 0,
+            edge_bits.strides[1] if edge_bits is not None else 0, capi.BITS_MSB_FIRST if msb_first else capi.BITS_LSB_FIRST,
+            counts.ctypes.data_as(C.POINTER(C.c_int64)) if counts is not None else None))
+        return {"mask_bits": mask_bits, "edge_bits": edge_bits, "counts": counts}
+
     def count_nonzero(self, planes: torch.Tensor) -> np.ndarray:
         """np.count_nonzero per plane (02:157, 03:38)."""
         _check_planes(planes)

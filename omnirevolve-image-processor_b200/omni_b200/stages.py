@@ -123,7 +123,18 @@ def _lab_to_bgr(lab3) -> tuple:
     return int(bgr[0]), int(bgr[1]), int(bgr[2])
 
 
-_CACHE: dict = {}          # (output_dir) -> fused results, so stage 03 in the same process skips recomputation
+def _write_layer_png(path: str, plane_u8=None, bits=None, w=None) -> None:
+    """mask.png / edges.png: a 1-bit greyscale PNG (decodes through cv2.imread to the same {0,255} pixels; see omni_b200/png1.py)
+    unless OMNI_B200_PNG_BITS=8.  Give either the u8 plane or its MSB-first packed rows."""
+    from . import png1
+    if png1.use_1bit():
+        if bits is None:
+            bits, w = np.packbits(plane_u8 > 0, axis=1), plane_u8.shape[1]
+        png1.write_png1(path, bits, w)
+    else:
+        if plane_u8 is None:
+            plane_u8 = png1.unpack_rows(bits, w)
+        cv2.imwrite(path, plane_u8)
 
 
 def _swatch_extract(cfg, img, names) -> None:
@@ -137,16 +148,15 @@ def _swatch_extract(cfg, img, names) -> None:
     masks = get_engine().swatch_masks(torch.from_numpy(np.ascontiguousarray(img)).cuda(), cols, tol).cpu().numpy()
     for i, name in enumerate(names):
         os.makedirs(os.path.join(cfg.output_dir, name), exist_ok=True)
-        cv2.imwrite(os.path.join(cfg.output_dir, name, "mask.png"), masks[i])
+        _write_layer_png(os.path.join(cfg.output_dir, name, "mask.png"), plane_u8=masks[i])
         print(f"Extracted (swatch): {name} | nz={int(np.count_nonzero(masks[i]))}")
     print("Color extraction: done.")
 
 
 def color_extract_main(cfg) -> dict:
     """02_color_extract.py:66-175.  k-means mode is the only one reachable through config.json; the swatch branch
-    (:82-109) is honoured when the Config object carries extraction_mode == "swatch".  The fused GPU call of the
-    k-means mode also produces the stage-03 edge planes; they are cached for detect_all_edges() when both
-    stages run in one process, and recomputed from mask.png when stage 03 runs on its own."""
+    (:82-109) is honoured when the Config object carries extraction_mode == "swatch".  Only stage 02's own work is done
+    here (assignment + RECT open/close): the layers come off the GPU as packed bit rows and go straight into 1-bit PNGs."""
     os.makedirs(cfg.output_dir, exist_ok=True)
     path = os.path.join(cfg.output_dir, "resized.png")
     img = cv2.imread(path, cv2.IMREAD_COLOR)
@@ -154,28 +164,44 @@ def color_extract_main(cfg) -> dict:
         raise RuntimeError(f"Cannot read resized image: {path}")
     img = _ensure_bgr(img)
     names = list(cfg.color_names)
+    K_cfg = int(getattr(cfg, "cluster_k", len(names)))
+    K = max(2, min(len(names), K_cfg))
     if str(getattr(cfg, "extraction_mode", "kmeans")).lower() == "swatch":
         _swatch_extract(cfg, img, names)
         return {}
-    K = max(2, len(names))
-    centers = kmeans_lab_centers(img, K)
+    centers = kmeans_lab_centers(img, K, sample_limit=int(getattr(cfg, "kmeans_sample_limit", 200_000)),
+                                 attempts=int(getattr(cfg, "kmeans_attempts", 3)))
     order, lut = darkness_lut(centers)
     centers_sorted = centers[order]
-    ec = EdgeConfig.from_cfg(cfg)
-    r = get_engine().host_color_edge(img, centers, lut.astype(np.uint8), ec, want_labels=False)
+    open_iters = int(getattr(cfg, "extract_open_iters", 1))
+    close_iters = int(getattr(cfg, "extract_close_iters", 1))
+    h, w = img.shape[:2]
+    eng = get_engine()
+    if open_iters == 1 and close_iters == 1:
+        r = eng.host_color_edge_packed(img, centers, lut.astype(np.uint8), None, msb_first=True)
+        bits, planes, counts = r["mask_bits"], None, r["counts"]
+    else:                                              # other iteration counts: the unfused operators (any count, 02:151-154)
+        import torch
+        d_lab = eng.assign_lab(torch.from_numpy(np.ascontiguousarray(img)).cuda(), centers, lut.astype(np.uint8))
+        planes = eng.layer_masks(d_lab, K, open_iters, close_iters).cpu().numpy()
+        lab_h = d_lab.cpu().numpy()
+        bits = None
+        counts = np.array([[int((lab_h == k).sum()), int(np.count_nonzero(planes[k])), 0] for k in range(K)], np.int64)
     names_sorted = sorted(names, key=_darkness_rank)
-    mapping = list(zip(names_sorted, range(len(names_sorted))))
+    mapping = list(zip(names_sorted, range(K)))
     palette = {}
     for name, _k in mapping:
         os.makedirs(os.path.join(cfg.output_dir, name), exist_ok=True)
-    with _io_pool(cfg, len(mapping)) as pool:                      # K PNG encodes in parallel (cv2 releases the GIL)
-        list(pool.map(lambda nk: cv2.imwrite(os.path.join(cfg.output_dir, nk[0], "mask.png"), r["masks"][nk[1]]), mapping))
+    with _io_pool(cfg, len(mapping)) as pool:                      # K PNG encodes in parallel (zlib / cv2 release the GIL)
+        list(pool.map(lambda nk: _write_layer_png(os.path.join(cfg.output_dir, nk[0], "mask.png"),
+                                                  plane_u8=None if planes is None else planes[nk[1]],
+                                                  bits=None if bits is None else bits[nk[1]], w=w), mapping))
     for name, k in mapping:
         lab = centers_sorted[k]
         palette[name] = {
             "mode": "kmeans", "cluster_index": int(k), "cluster_lab": [int(lab[0]), int(lab[1]), int(lab[2])],
-            "approx_bgr": list(_lab_to_bgr(np.uint8(lab))), "pixels": int(r["counts"][k, 0]),
-            "mask_nonzero": int(r["counts"][k, 1]),
+            "approx_bgr": list(_lab_to_bgr(lab.astype(np.uint8))), "pixels": int(counts[k, 0]),
+            "mask_nonzero": int(counts[k, 1]),
         }
         print(f"Extracted (kmeans): {name} | cluster={k} | L*={lab[0]:.1f} | "
               f"pixels={palette[name]['pixels']} | nz={palette[name]['mask_nonzero']}")
@@ -184,8 +210,6 @@ def color_extract_main(cfg) -> dict:
         json.dump(palette, fh, ensure_ascii=False, indent=2)
     print(f"Palette saved: {pal_path}")
     print("Color extraction: done.")
-    _CACHE[os.path.abspath(cfg.output_dir)] = {"names": dict(mapping), "edges": r["edges"], "masks": r["masks"],
-                                               "ec": ec}
     return palette
 
 
@@ -211,7 +235,7 @@ def process_color(color_name: str, cfg):
     mask = _read_mask(color_name, cfg)
     edges = get_engine().host_edges(mask[None], EdgeConfig.from_cfg(cfg))[0]
     out_path = os.path.join(cfg.output_dir, color_name, "edges.png")
-    cv2.imwrite(out_path, edges)
+    _write_layer_png(out_path, plane_u8=edges)
     print(f"Edges extracted: {color_name} | nz={int(np.count_nonzero(edges))}")
     return color_name, out_path
 
@@ -241,7 +265,7 @@ def detect_all_edges(cfg) -> list:
         edges = [get_engine().host_edges(m[None], EdgeConfig.from_cfg(cfg))[0] for m in masks]
     paths = [os.path.join(cfg.output_dir, n, "edges.png") for n in names]
     with _io_pool(cfg, len(names)) as pool:
-        list(pool.map(lambda pe: cv2.imwrite(pe[0], pe[1]), zip(paths, edges)))
+        list(pool.map(lambda pe: _write_layer_png(pe[0], plane_u8=pe[1]), zip(paths, edges)))
     for n, e, out_path in zip(names, edges, paths):
         print(f"Edges extracted: {n} | nz={int(np.count_nonzero(e))}")
         results.append((n, out_path))

@@ -344,12 +344,12 @@ def test_full_size_config2(eng):
     assert torch.equal(eng.edges(m2, omni_b200.EdgeConfig()), edges)
 
 
-@pytest.mark.parametrize("shape", [(8192, 8192, 16, 1, 64), (1080, 1920, 8, 0, 32), (2000, 2000, 4, 2, 32)],
-                         ids=["config3_8192_k16", "config4_1080p_k8", "default_2000_k4"])
+@pytest.mark.parametrize("shape", [(4096, 4096, 16, 0, 32), (1080, 1920, 8, 0, 32), (2000, 2000, 4, 2, 32)],
+                         ids=["config5_4096_k16", "config4_1080p_k8", "default_2000_k4"])
 def test_full_size_families_agree(eng, shape):
-    """BASELINE configs 3 and 4 (and the default max_dimension size) at FULL size: the two fast kernel families behind
-    the ABI -- sparse tile runs + RGB cells (default) and dense edges + Lab cells -- must give identical bytes; the oracle
-    pins one layer (its CPU chain needs ~1 s per 64 Mpx layer)."""
+    """BASELINE configs 4, 5 (and the default max_dimension size) at FULL size: the three fast kernel families behind the ABI --
+    label-domain pipeline (default), first generation (RGB cells + sparse tile runs), dense edges + Lab cells -- must give
+    identical bytes; the oracle pins one layer here (configs[2], every layer: tests/test_gpu_packed.py)."""
     import omni_b200
     cm, rp = _cm(), _rp()
     h, w, K, seed, cell = shape
@@ -362,11 +362,12 @@ def test_full_size_families_agree(eng, shape):
     try:
         eng.set_fast_path(1)
         l1, m1, e1 = eng.color_edge(d, ctr, lut, ec, want_labels=True)
-        eng.set_fast_path(2)
-        l2, m2, e2 = eng.color_edge(d, ctr, lut, ec, want_labels=True)
+        for mode in (3, 2):
+            eng.set_fast_path(mode)
+            l2, m2, e2 = eng.color_edge(d, ctr, lut, ec, want_labels=True)
+            assert torch.equal(l1, l2) and torch.equal(m1, m2) and torch.equal(e1, e2), mode
     finally:
         eng.set_fast_path(1)
-    assert torch.equal(l1, l2) and torch.equal(m1, m2) and torch.equal(e1, e2)
     # size-independent property: the labels partition the image
     assert int(torch.bincount(l1.flatten().int(), minlength=K).sum()) == h * w
     k = K // 2
