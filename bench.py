@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """bench.py -- megapixels/sec of the stage 01-03 hot path (resize + colour layers + edges) on B200.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload config2|config3|config4]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload config5|config2|config3|config4]
 
 One "step" = one pass of the hot path over one image per GPU: 01 resize_if_needed (a no-op for the
 named config, exactly as in the reference: max_dimension = image size), 02 nearest-centre assignment
@@ -9,10 +9,15 @@ in 8-bit Lab -> K layer masks (+RECT-3 open/close), 03 per-layer ELLIPSE-3 open/
 -> Canny.  K-means centres are an INPUT of the path (computed once on the host before timing, the way
 02_color_extract.py:39-49 does) for both arms.
 
-  value      device-resident: image already in HBM, masks+edges left in HBM; CUDA events per step on
-             the launching stream, L2 flushed (untimed) between steps; max over ranks.
-  e2e        the same through the host-buffer C-ABI call (omni_host_color_edge): pinned host image in,
-             masks + edges back in pinned host memory, every step.
+  workload   default = the shape north_star quotes its target on (BASELINE configs[4] image: 4096x4096, 16 colours, Canny
+             50/150, blur 3); configs[1] and configs[2] are measured in the same run as extra records (N = 1), configs[3]
+             (512 x 1080p frames sharded over the ranks, strong scaling) as the `configs3` record at every N.
+  value      device-resident: image already in HBM, masks+edges (u8 planes) left in HBM; CUDA events per step on
+             the launching stream, L2 flushed (untimed) between steps; max over ranks.  Single-image workloads rebuild the
+             candidate-centre tables every step (a new image has new k-means centres).
+  e2e        the same through the host-buffer C-ABI call with pinned host buffers, every step: omni_host_color_edge_packed
+             (image in, the K masks and K edge planes out as 1 bit per pixel -- what the drop-in stage scripts write into
+             1-bit PNGs); `e2e_u8` is the byte-plane call omni_host_color_edge.
   roofline   dominant kernel of the step, CUDA-event timed inside the timed region (omni_profile_*).
   cpu_baseline / --impl reference
              the reference's own CPU implementation of the path (oracle/refport.py: the cv2/NumPy call
@@ -38,7 +43,6 @@ for _p in (ROOT, os.path.join(ROOT, "omnirevolve-image-processor_b200")):
 import numpy as np  # noqa: E402
 
 WORKLOADS = {
-    # BASELINE.json configs[1]: the configuration the metric is quoted on
     "config2": dict(h=4096, w=4096, K=8, seed=0, cell=32, low=50, high=150, ksize=3,
                     name="configs[1]: single 4096x4096 RGB image, 8 colours, Canny 50/150, blur 3, max_dimension=4096"),
     "config3": dict(h=8192, w=8192, K=16, seed=1, cell=64, low=50, high=150, ksize=3,
@@ -193,15 +197,231 @@ KERNEL_BYTES = {
     "canny_nms": lambda N, K: N * 2 * K,
     "hyst_pass": lambda N, K: N * 2 * K,
     "hyst_final": lambda N, K: N * 2 * K,
-    "assign_bits": lambda N, K: N * 3,               # image read; one-hot bit-planes stay in L2
+    "assign_bits": lambda N, K: N * 3,               # image read; label bit-slices stay in L2
+    "label_open": lambda N, K: 0,                    # bit-planes only
     "morph_bits": lambda N, K: N * K,                # mask byte planes written
     "edges3_bits": lambda N, K: N * K,               # bit-planes in; edge byte planes (strong set) written
     "hysteresis_bits": lambda N, K: 0,               # bit-planes only + a few promoted pixels
     "build_cells": lambda N, K: 0,
+    "build_rgbcells": lambda N, K: 0,
 }
 # stage grouping for the report: colour = image -> K masks, edge = K masks -> K edges (masks are not re-read)
-STAGES = {"color": ("build_cells", "build_rgbcells", "assign_bits", "morph_bits", "assign", "onehot"),
+STAGES = {"color": ("build_cells", "build_rgbcells", "assign_bits", "label_open", "morph_bits", "assign", "onehot"),
           "edge": ("edge_runs", "edges3_bits", "hysteresis_bits", "morph", "blur", "canny_nms", "hyst_pass", "hyst_final")}
+
+
+def measure_fused(torch, eng, wl, img, centers, lut, steps, warmup, flush, barrier, cache_tables):
+    """Device-resident fused call on one image (or one frame batch): CUDA events per step, L2 flushed (untimed) between steps,
+    then a second pass of the same steps with per-kernel events."""
+    import omni_b200
+    h, w, K = wl["h"], wl["w"], wl["K"]
+    B = int(wl.get("batch", 1))
+    ec = omni_b200.EdgeConfig(low=wl["low"], high=wl["high"], ksize=wl["ksize"])
+    d_img = torch.from_numpy(img).cuda()
+    d_masks = torch.empty(((B, K, h, w) if B > 1 else (K, h, w)), dtype=torch.uint8, device="cuda")
+    d_edges = torch.empty_like(d_masks)
+    eng.set_table_cache(cache_tables)
+
+    def step():
+        # 01: resize_if_needed is a no-op here (max_dimension == image size), as in the reference
+        if B > 1:
+            eng.color_edge_batch(d_img, centers, lut, ec, masks=d_masks, edges=d_edges)
+        else:
+            eng.color_edge(d_img, centers, lut, ec, masks=d_masks, edges=d_edges)
+
+    for _ in range(max(warmup, 3)):
+        step()
+    barrier()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    n0 = eng.launch_count()
+    barrier()
+    t0 = time.perf_counter()
+    for a, b in ev:
+        flush.fill_(1)                       # L2 flush, outside the event-timed span
+        a.record()
+        step()
+        b.record()
+    barrier()
+    wall = time.perf_counter() - t0
+    launches = eng.launch_count() - n0
+    eng.profile(True)
+    pev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for a, b in pev:
+        flush.fill_(1)
+        a.record()
+        step()
+        b.record()
+    torch.cuda.synchronize()
+    prof = eng.profile_summary()
+    eng.profile(False)
+    eng.set_table_cache(True)
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    return {"step_ms": step_ms, "total_ms": sum(step_ms), "launches": launches, "prof": prof,
+            "prof_step_ms": sum(a.elapsed_time(b) for a, b in pev) / steps, "wall": wall, "passes": eng.last_hysteresis_passes(),
+            "d_edges": d_edges, "ec": ec}
+
+
+def roofline_record(prof, prof_step_ms, ms_per_step, steps, N, K, workload, peak, peak_src):
+    dom = max(prof.items(), key=lambda kv: kv[1][1]) if prof else None
+    if dom is None:
+        return None
+    name, (n_l, ms) = dom
+    per_launch_ms = ms / n_l
+    bytes_fn = KERNEL_BYTES.get(name)
+    alg = bytes_fn(N * steps / n_l, K) if bytes_fn else None        # pixels per launch of this kernel
+    ach = alg / (per_launch_ms / 1e3) / 1e9 if alg is not None else None
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get(workload, {}).get(name)
+        except Exception:
+            traffic = None
+    step_bytes = N * (3 + 2 * K)
+    return {"bound": "hbm", "kernel": name, "achieved": ach, "peak": peak, "unit": "GB/s",
+            "frac": (ach / peak) if ach is not None else None, "traffic": traffic, "peak_source": peak_src,
+            "algorithmic_bytes_per_launch": alg, "launches_per_step": n_l / steps,
+            "ms_per_launch": per_launch_ms, "share_of_step": ms / (prof_step_ms * steps),
+            "timing": "CUDA events around every kernel launch, second pass of the same K steps (%.4f ms/step with the "
+                      "events vs %.4f without)" % (prof_step_ms, ms_per_step),
+            "step": {"algorithmic_bytes": step_bytes, "achieved": step_bytes / (ms_per_step / 1e3) / 1e9,
+                     "frac": step_bytes / (ms_per_step / 1e3) / 1e9 / peak},
+            "kernels_ms_per_step": {k: v[1] / steps for k, v in prof.items()},
+            "kernels_frac_of_peak": {k: (KERNEL_BYTES[k](N * steps / v[0], K) / (v[1] / v[0] / 1e3) / 1e9 / peak)
+                                     for k, v in prof.items() if k in KERNEL_BYTES and KERNEL_BYTES[k](N, K)},
+            "stages_ms_per_step": {sname: sum(v[1] for k, v in prof.items() if k in members) / steps
+                                   for sname, members in STAGES.items()},
+            # what the dominant kernel itself moved through DRAM (ncu capture), over its live duration
+            "achieved_from_traffic": (traffic / (per_launch_ms / 1e3) / 1e9) if traffic else None,
+            "note": "edges3_bits walks only the live tile runs; the zeros of the dead tiles (the rest of its K*N algorithmic bytes) "
+                    "are bulk copies (TMA engine) issued by assign_bits inside the timed step -- `step` is the figure that "
+                    "accounts for everything"}
+
+
+def configs3_record(torch, dist, eng, rank, world, flush, barrier, n_frames, peak):
+    """BASELINE configs[3]: a batch of 1920x1080 frames, 8 colours, ONE centre set, sharded over the ranks in contiguous blocks
+    (omni_b200/batch.py), strong scaling: every rank handles ceil(B / G) frames, no data-path collective.
+    kernel: frames resident in HBM, u8 planes left in HBM (groups of 4 frames per omni_color_edge_batch call).
+    e2e   : pinned host frames -> omni_host_color_edge_packed (H2D / kernels / D2H of consecutive groups overlapped) -> packed masks and
+            edges in pinned host memory + per-frame counts, gathered to rank 0 in frame order."""
+    import omni_b200
+    from omni_b200 import batch as ob
+    from omni_b200.synth import synth
+    from omni_b200 import stages
+    h, w, K = 1080, 1920, 8
+    distinct = 16                                       # distinct synthetic frames, repeated to fill the batch
+    base = [synth(h, w, 1000 + i, 32) for i in range(distinct)]
+    centers = stages.kmeans_lab_centers(base[0], K)
+    _o, lut = stages.darkness_lut(centers)
+    lut = lut.astype(np.uint8)
+    ec = omni_b200.EdgeConfig()
+    mine = ob.shard_range(n_frames, world, rank)
+    n_mine = len(mine)
+    rb = (w + 7) // 8
+    h_frames = omni_b200.pinned_empty((max(1, n_mine), h, w, 3))
+    for j, f in enumerate(mine):
+        h_frames[j] = base[f % distinct]
+    h_mb = omni_b200.pinned_empty((max(1, n_mine) * K, h, rb))
+    h_eb = omni_b200.pinned_empty((max(1, n_mine) * K, h, rb))
+    # ---- kernel only ----
+    G = 32 // K
+    d_grp = torch.from_numpy(np.stack([base[i % distinct] for i in range(G)])).cuda()
+    d_m = torch.empty((G, K, h, w), dtype=torch.uint8, device="cuda")
+    d_e = torch.empty_like(d_m)
+    for _ in range(3):
+        eng.color_edge_batch(d_grp, centers, lut, ec, masks=d_m, edges=d_e)
+    n_calls = (n_mine + G - 1) // G
+    barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(n_calls):
+        eng.color_edge_batch(d_grp, centers, lut, ec, masks=d_m, edges=d_e)
+    b.record()
+    barrier()
+    k_ms = a.elapsed_time(b) if n_calls else 0.0
+    # ---- e2e ----
+    if n_mine:
+        eng.host_color_edge_packed(h_frames[:min(n_mine, 2 * G)], centers, lut, ec, mask_bits=h_mb[:min(n_mine, 2 * G) * K],
+                                   edge_bits=h_eb[:min(n_mine, 2 * G) * K], want_counts=False)
+    barrier()
+    t0 = time.perf_counter()
+    counts, _r = ob.process_shard_packed(eng, h_frames, mine, centers, lut, ec, mask_bits=h_mb[:n_mine * K] if n_mine else None,
+                                         edge_bits=h_eb[:n_mine * K] if n_mine else None)
+    torch.cuda.synchronize()
+    e_s = time.perf_counter() - t0
+    barrier()
+    allc = ob.gather_counts(counts, n_frames, K, dist if world > 1 else None)
+    t = torch.tensor([k_ms, e_s * 1e3], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    k_ms, e_ms = float(t[0].item()), float(t[1].item())
+    if rank != 0:
+        return None
+    mp = n_frames * h * w / 1e6
+    ok = bool(allc is not None and (allc[:, :, 0].sum(axis=1) == h * w).all())      # every frame's labels partition it
+    return {"workload": "configs[3]: %d frames 1920x1080 (%d distinct synthetic frames repeated), 8 colours, one centre set, contiguous "
+                        "frame shards over %d rank(s), no collective" % (n_frames, distinct, world),
+            "scaling": "strong", "frames": n_frames, "frames_per_rank": -(-n_frames // world),
+            "kernel": {"value": mp / (k_ms / 1e3), "unit": UNIT, "ms_total": k_ms,
+                       "frac_of_hbm_peak": n_frames * h * w * (3 + 2 * K) / (k_ms / 1e3) / 1e9 / peak / world,
+                       "what": "omni_color_edge_batch, 4 frames per call, frames resident in HBM, u8 planes out (max over ranks)"},
+            "e2e": {"value": mp / (e_ms / 1e3), "unit": UNIT, "ms_total": e_ms,
+                    "h2d_bytes": int(n_frames * h * w * 3), "d2h_bytes": int(2 * n_frames * K * h * rb),
+                    "host_gbs_per_rank": (n_mine * h * w * 3 + 2 * n_mine * K * h * rb) / (e_ms / 1e3) / 1e9,
+                    "what": "omni_host_color_edge_packed on each rank's shard: pinned frames in, packed masks + edges + counts out (max over ranks)"},
+            "counts_gathered_in_frame_order": ok}
+
+
+def stage_wall_record():
+    """What a user of pipeline.py sees: the three stage scripts as subprocesses (interpreter start, CUDA context, PNG decode /
+    encode included), ours (omnirevolve-image-processor_b200/image_processor/) beside the reference's as-shipped structure
+    replayed on the CPU (oracle/refstages.py), on the same input and config."""
+    import subprocess
+    import tempfile
+    import cv2
+    from omni_b200.synth import synth
+    out = {}
+    for tag, (hh, ww_, K) in {"1024x1024 K=4 (configs[0])": (1024, 1024, 4), "4096x4096 K=8 (configs[1])": (4096, 4096, 8)}.items():
+        with tempfile.TemporaryDirectory() as td:
+            src = os.path.join(td, "input.png")
+            cv2.imwrite(src, synth(hh, ww_, 0, 32))
+            names = ["layer_dark", "layer_mid", "layer_skin", "layer_light"] if K == 4 else [f"layer_{i:02d}" for i in range(K)]
+            rng = np.random.default_rng(7)
+            cfg = {"input_image": src, "max_dimension": max(hh, ww_), "color_names": names,
+                   "colors": [[int(v) for v in rng.integers(0, 256, 3)] for _ in range(K)]}
+            rec = {}
+            for arm, scripts in (("ours", [os.path.join(ROOT, "omnirevolve-image-processor_b200", "image_processor", s)
+                                           for s in ("01_resize.py", "02_color_extract.py", "03_edge_detect.py")]),
+                                 ("reference_port", [[os.path.join(ROOT, "oracle", "refstages.py"), s] for s in ("01", "02", "03")])):
+                od = os.path.join(td, arm)
+                os.makedirs(od)
+                c = dict(cfg, output_dir=od)
+                cp = os.path.join(od, "config.json")
+                json.dump(c, open(cp, "w"))
+                env = dict(os.environ, CONFIG_PATH=cp, PYTHONUNBUFFERED="1")
+                ts = []
+                for sc in scripts:
+                    cmd = [sys.executable] + (sc if isinstance(sc, list) else [sc])
+                    t0 = time.perf_counter()
+                    r = subprocess.run(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+                    ts.append(time.perf_counter() - t0)
+                    if r.returncode != 0:
+                        ts[-1] = None
+                        break
+                rec[arm] = {"stage_s": ts, "total_s": (sum(ts) if None not in ts else None)}
+            same = None
+            try:
+                same = all(np.array_equal(cv2.imread(os.path.join(td, "ours", n, f), 0), cv2.imread(os.path.join(td, "reference_port", n, f), 0))
+                           for n in names for f in ("mask.png", "edges.png"))
+            except Exception:
+                pass
+            rec["identical_masks_and_edges"] = same
+            rec["MP/s"] = {a: (hh * ww_ / 1e6 / rec[a]["total_s"]) if rec[a]["total_s"] else None for a in ("ours", "reference_port")}
+            out[tag] = rec
+    out["what"] = ("stages 01-03 as one subprocess each with CONFIG_PATH (pipeline.py:88-111): interpreter + imports + CUDA context "
+                   "+ PNG decode/encode included; reference_port = oracle/refstages.py (the reference's stage structure replayed "
+                   "with its cv2/NumPy arithmetic; the reference tree is not on this box)")
+    return out
 
 
 def run_ours(args, wl):
@@ -227,6 +447,7 @@ def run_ours(args, wl):
         torch.cuda.synchronize()
 
     eng = omni_b200.Engine(local)
+    peak, peak_src = peaks()
     h, w, K = wl["h"], wl["w"], wl["K"]
     B = int(wl.get("batch", 1))                                # frames per step per GPU (1: a single image)
     N = h * w * B
@@ -234,92 +455,83 @@ def run_ours(args, wl):
     centers = stages.kmeans_lab_centers(img, K)               # host k-means, an input of the path
     _order, lut = stages.darkness_lut(centers)
     lut = lut.astype(np.uint8)
-    ec = omni_b200.EdgeConfig(low=wl["low"], high=wl["high"], ksize=wl["ksize"])
-
-    h_img = omni_b200.pinned_empty((h, w, 3))
-    h_img[:] = img
-    h_masks = omni_b200.pinned_empty((K, h, w))
-    h_edges = omni_b200.pinned_empty((K, h, w))
-    d_img = torch.from_numpy(img).cuda()
-    if B > 1:
-        frames = np.stack([img] + [synth(h, w, wl["seed"] + rank + 1000 * b, wl["cell"]) for b in range(1, B)])
-        d_img = torch.from_numpy(frames).cuda()
-    d_masks = torch.empty(((B, K, h, w) if B > 1 else (K, h, w)), dtype=torch.uint8, device="cuda")
-    d_edges = torch.empty_like(d_masks)
+    frames = img if B == 1 else np.stack([img] + [synth(h, w, wl["seed"] + rank + 1000 * b, wl["cell"]) for b in range(1, B)])
     flush = torch.empty(384 << 20, dtype=torch.uint8, device="cuda")      # > 126 MB L2
-
-    def step():
-        # 01: resize_if_needed is a no-op here (max_dimension == image size), as in the reference
-        if B > 1:
-            eng.color_edge_batch(d_img, centers, lut, ec, masks=d_masks, edges=d_edges)
-        else:
-            eng.color_edge(d_img, centers, lut, ec, masks=d_masks, edges=d_edges)
-
-    for _ in range(max(args.warmup, 3)):
-        step()
-    barrier()
 
     sampler = ClockSampler(physical_gpu_index(local))
     sampler.start()
     time.sleep(0.05)
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    n_launch0 = eng.launch_count()
-    barrier()
-    t_wall0 = time.perf_counter()
-    for a, b in ev:
-        flush.fill_(1)                       # L2 flush, outside the event-timed span
-        a.record()
-        step()
-        b.record()
-    barrier()
-    t_wall = time.perf_counter() - t_wall0
-    launches = eng.launch_count() - n_launch0
-    # per-kernel CUDA events cost ~20 us per step, so they run in a second pass of the same K steps (same inputs,
-    # same L2 flush) right after the timed region instead of inside it
-    eng.profile(True)
-    pev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    for a, b in pev:
-        flush.fill_(1)
-        a.record()
-        step()
-        b.record()
-    torch.cuda.synchronize()
-    prof = eng.profile_summary()
-    eng.profile(False)
-    prof_step_ms = sum(a.elapsed_time(b) for a, b in pev) / args.steps
+    m = measure_fused(torch, eng, wl, frames, centers, lut, args.steps, args.warmup, flush, barrier, cache_tables=(B > 1))
     clocks = sampler.result()
-    step_ms = [a.elapsed_time(b) for a, b in ev]
-    total_ms = sum(step_ms)
-    t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
+    t = torch.tensor([m["total_ms"]], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms_max = float(t.item())
-    ms_per_step = total_ms_max / args.steps
+    ms_per_step = float(t.item()) / args.steps
     value = world * N / 1e6 / (ms_per_step / 1e3)
+    ec = m["ec"]
 
     # ---- e2e: host buffers through the C ABI, H2D + kernels + D2H every step ----
-    def e2e_step():
-        for _b in range(B):                  # the host-buffer call is per frame
-            eng.host_color_edge(h_img, centers, lut, ec, want_labels=False, masks=h_masks, edges=h_edges, want_counts=False)
+    h_img = omni_b200.pinned_empty((B, h, w, 3))
+    h_img[:] = frames if B > 1 else frames[None]
+    rb = (w + 7) // 8
+    h_mb = omni_b200.pinned_empty((B * K, h, rb))
+    h_eb = omni_b200.pinned_empty((B * K, h, rb))
 
-    for _ in range(2):
-        e2e_step()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        e2e_step()
-    barrier()
-    e2e_s = time.perf_counter() - t0
-    t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_s = float(t.item())
+    def e2e_step():
+        eng.host_color_edge_packed(h_img, centers, lut, ec, mask_bits=h_mb, edge_bits=h_eb, want_counts=False)
+
+    def time_e2e(fn, steps):
+        for _ in range(2):
+            fn()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            fn()
+        barrier()
+        s = time.perf_counter() - t0
+        tt = torch.tensor([s], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return float(tt.item())
+
+    e2e_s = time_e2e(e2e_step, args.steps)
     e2e_val = world * N * args.steps / 1e6 / e2e_s
+    # the u8-plane host call (what round 1 reported as e2e): 2 K bytes per pixel leave the GPU instead of 2 K bits
+    h_masks = omni_b200.pinned_empty((K, h, w))
+    h_edges = omni_b200.pinned_empty((K, h, w))
+
+    def e2e_u8_step():
+        for b in range(B):
+            eng.host_color_edge(h_img[b], centers, lut, ec, want_labels=False, masks=h_masks, edges=h_edges, want_counts=False)
+
+    u8_steps = max(3, args.steps // 4)
+    e2e_u8_s = time_e2e(e2e_u8_step, u8_steps)
+    e2e_u8_val = world * N * u8_steps / 1e6 / e2e_u8_s
+    del h_masks, h_edges
+
+    extra = {}
+    if rank == 0 and world == 1:
+        # ---- the other single-image configs of BASELINE.json, same measurement, fewer steps ----
+        for name in ("config2", "config3"):
+            if name == args.workload:
+                continue
+            w2 = WORKLOADS[name]
+            img2 = synth(w2["h"], w2["w"], w2["seed"], w2["cell"])
+            c2 = stages.kmeans_lab_centers(img2, w2["K"])
+            _o2, lut2 = stages.darkness_lut(c2)
+            st2 = max(5, args.steps // 2)
+            m2 = measure_fused(torch, eng, w2, img2, c2, lut2.astype(np.uint8), st2, 3, flush, barrier, cache_tables=False)
+            ms2 = m2["total_ms"] / st2
+            N2 = w2["h"] * w2["w"]
+            extra[name] = {"workload": w2["name"], "ms_per_step": ms2, "value": N2 / 1e6 / (ms2 / 1e3), "unit": UNIT,
+                           "roofline": roofline_record(m2["prof"], m2["prof_step_ms"], ms2, st2, N2, w2["K"], name, peak, peak_src),
+                           "step_ms": {"min": min(m2["step_ms"]), "median": statistics.median(m2["step_ms"]), "max": max(m2["step_ms"])}}
+            del m2, img2
+            torch.cuda.empty_cache()
 
     # ---- stage 01 on its own (not part of the step: the named config needs no resize) ----
     resize_extra = None
     if rank == 0 and world == 1:
-        peak0, _src0 = peaks()
         resize_extra = {}
         for tag, (sh, sw, dh, dw) in {"2:1 exact 8192x8192->4096x4096": (8192, 8192, 4096, 4096),
                                       "fractional 4096x4096->2000x2000 (default max_dimension)": (4096, 4096, 2000, 2000)}.items():
@@ -336,15 +548,14 @@ def run_ours(args, wl):
                 tms.append(a.elapsed_time(b))
             ms = statistics.median(tms)
             nbytes = 3 * (sh * sw + dh * dw)
-            resize_extra[tag] = {"ms": ms, "GB/s": nbytes / ms / 1e6, "frac_of_peak": nbytes / ms / 1e6 / peak0,
+            resize_extra[tag] = {"ms": ms, "GB/s": nbytes / ms / 1e6, "frac_of_peak": nbytes / ms / 1e6 / peak,
                                  "MP/s_src": sh * sw / ms / 1e3}
             del src, dst
 
     # ---- stage 04 thinning of the K edge planes the step just produced (not part of the step) ----
     thin_extra = None
     if rank == 0 and world == 1:
-        peak0, _src0 = peaks()
-        d_planes = d_edges.reshape(-1, h, w)                 # [B*K, H, W]: every layer of every frame is a plane
+        d_planes = m["d_edges"].reshape(-1, h, w)                 # [B*K, H, W]: every layer of every frame is a plane
         d_skel = torch.empty_like(d_planes)
         _o, removed, iters = eng.thin_zhangsuen(d_planes, out=d_skel, with_log=True)
         tms = []
@@ -356,67 +567,44 @@ def run_ours(args, wl):
             tms.append(a.elapsed_time(b))
         ms = statistics.median(tms)
         thin_extra = {"ms": ms, "iterations_max": int(iters.max()), "removed_px": int(removed.sum()),
-                      "algorithmic_bytes": 2 * K * N, "GB/s": 2 * K * N / ms / 1e6, "frac_of_peak": 2 * K * N / ms / 1e6 / peak0,
+                      "algorithmic_bytes": 2 * K * N, "GB/s": 2 * K * N / ms / 1e6, "frac_of_peak": 2 * K * N / ms / 1e6 / peak,
                       "layer_MP/s": K * N / ms / 1e3,
                       "what": "omni_thin_zhangsuen on the K edge planes (bytes in -> bit-planes -> cooperative Zhang-Suen -> bytes out)"}
         del d_skel
+    del m["d_edges"]
+    torch.cuda.empty_cache()
+
+    # ---- BASELINE configs[3]: the 512-frame batch, sharded over the ranks (every N, strong scaling) ----
+    c3 = configs3_record(torch, dist, eng, rank, world, flush, barrier, args.frames, peak)
 
     if rank == 0:
-        peak, peak_src = peaks()
-        dom = max(prof.items(), key=lambda kv: kv[1][1]) if prof else None
-        roof = None
-        if dom is not None:
-            name, (n_l, ms) = dom
-            per_launch_ms = ms / n_l
-            bytes_fn = KERNEL_BYTES.get(name)
-            alg = bytes_fn(N * args.steps / n_l, K) if bytes_fn else None        # pixels per launch of this kernel
-            ach = alg / (per_launch_ms / 1e3) / 1e9 if alg is not None else None
-            traffic = None
-            tp = os.path.join(ROOT, "profiles", "traffic.json")
-            if os.path.exists(tp):
-                try:
-                    traffic = json.load(open(tp)).get(args.workload, {}).get(name)
-                except Exception:
-                    traffic = None
-            roof = {"bound": "hbm", "kernel": name, "achieved": ach, "peak": peak, "unit": "GB/s",
-                    "frac": (ach / peak) if ach is not None else None, "traffic": traffic, "peak_source": peak_src,
-                    "algorithmic_bytes_per_launch": alg, "launches_per_step": n_l / args.steps,
-                    "ms_per_launch": per_launch_ms, "share_of_step": ms / (prof_step_ms * args.steps),
-                    "timing": "CUDA events around every kernel launch, second pass of the same K steps (%.4f ms/step with the "
-                              "events vs %.4f without)" % (prof_step_ms, ms_per_step),
-                    "step": {"algorithmic_bytes": N * (3 + 2 * K),
-                             "achieved": N * (3 + 2 * K) / (ms_per_step / 1e3) / 1e9,
-                             "frac": N * (3 + 2 * K) / (ms_per_step / 1e3) / 1e9 / peak},
-                    "kernels_ms_per_step": {k: v[1] / args.steps for k, v in prof.items()},
-                    "kernels_frac_of_peak": {k: (KERNEL_BYTES[k](N * args.steps / v[0], K) / (v[1] / v[0] / 1e3) / 1e9 / peak)
-                                             for k, v in prof.items() if k in KERNEL_BYTES and KERNEL_BYTES[k](N, K)},
-                    "stages_ms_per_step": {sname: sum(v[1] for k, v in prof.items() if k in members) / args.steps
-                                           for sname, members in STAGES.items()},
-                    # what the dominant kernel itself moved through DRAM (ncu capture), over its live duration
-                    "achieved_from_traffic": (traffic / (per_launch_ms / 1e3) / 1e9) if traffic else None,
-                    "note": "edges3_bits walks only the live tile runs; the zeros of the dead tiles (the rest of its K*N algorithmic "
-                            "bytes) are a cudaMemsetAsync on a side stream that overlaps assign_bits inside the timed step -- "
-                            "`step` is the figure that accounts for everything"}
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8", "data": "synthetic",
             "config": {"workload": wl["name"], "h": h, "w": w, "K": K, "low": wl["low"], "high": wl["high"], "ksize": wl["ksize"],
-                       "frames_per_step_per_gpu": B, "sharding": "by frame, no collective",
+                       "frames_per_step_per_gpu": B,
+                       "sharding": "one image per rank (replicas: a single image does not shard, SURVEY 8e); the sharded batch is `configs3`",
                        "l2": "flushed between steps (384 MB write, untimed); working set %d MB per step" % (N * (3 + 2 * K) // 1000000),
-                       "hysteresis_passes": eng.last_hysteresis_passes(), "fast_path": True},
-            "gpu_launches": launches, "clocks": clocks,
-            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(h_img.nbytes) * B,
-                    "d2h_bytes_per_step": int(h_masks.nbytes + h_edges.nbytes) * B, "ms_per_step": e2e_s / args.steps * 1e3,
-                    "api": "omni_host_color_edge (pinned host image in, masks+edges out to pinned host memory)"},
-            "roofline": roof,
-            "step_ms": {"min": min(step_ms), "median": statistics.median(step_ms), "max": max(step_ms)},
-            "wall_s_timed_region": t_wall,
+                       "tables": "candidate-centre tables rebuilt every step (new centres per image)" if B == 1 else "cached (one centre set)",
+                       "hysteresis_passes": m["passes"], "fast_path": True},
+            "gpu_launches": m["launches"], "clocks": clocks,
+            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(h_img.nbytes),
+                    "d2h_bytes_per_step": int(h_mb.nbytes + h_eb.nbytes), "ms_per_step": e2e_s / args.steps * 1e3,
+                    "api": "omni_host_color_edge_packed (pinned host image in; K masks + K edge planes out to pinned host memory as 1 bit per "
+                           "pixel, the row format of the 1-bit PNGs the drop-in stage scripts write)"},
+            "e2e_u8": {"value": e2e_u8_val, "unit": UNIT, "h2d_bytes_per_step": int(h_img.nbytes), "d2h_bytes_per_step": int(2 * B * K * h * w),
+                       "ms_per_step": e2e_u8_s / u8_steps * 1e3, "api": "omni_host_color_edge (u8 planes out)"},
+            "roofline": roofline_record(m["prof"], m["prof_step_ms"], ms_per_step, args.steps, N, K, args.workload, peak, peak_src),
+            "step_ms": {"min": min(m["step_ms"]), "median": statistics.median(m["step_ms"]), "max": max(m["step_ms"])},
+            "wall_s_timed_region": m["wall"],
+            "configs1": extra.get("config2"), "configs2": extra.get("config3"), "configs3": c3,
             "resize_kernel": resize_extra,
             "thinning_kernel": thin_extra,
         }
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline_leg(wl, img, centers)
+            out["stage_wall"] = stage_wall_record()
         print(json.dumps(out))
     if world > 1:
         dist.barrier()
@@ -430,7 +618,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
-    ap.add_argument("--workload", choices=sorted(WORKLOADS), default="config2")
+    ap.add_argument("--workload", choices=sorted(WORKLOADS), default="config5")
+    ap.add_argument("--frames", type=int, default=512, help="frames of the configs[3] batch record")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]

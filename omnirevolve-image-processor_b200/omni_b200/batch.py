@@ -1,8 +1,9 @@
 """Frame batches over several GPUs: the path shards by frame with NO data-path collective.
 
-One process per GPU (torchrun).  Each rank takes a contiguous block of ceil(B/G) frames, runs the fused
-colour+edge call per frame on its own device, keeps its masks/edges in its own (pinned) host buffers, and only
-the per-frame counts (the numbers the reference logs: pixels, mask_nonzero, edge nz) are gathered to rank 0.
+One process per GPU (torchrun).  Each rank takes a contiguous block of ceil(B/G) frames, runs them through the pipelined
+host call on its own device (groups of 32 / K frames per device pass), keeps its packed masks/edges in its own (pinned)
+host buffers, and only the per-frame counts (the numbers the reference logs: pixels, mask_nonzero, edge nz) are gathered
+to rank 0 in frame order.  bench.py's `configs3` record and tests/test_gpu_packed.py run exactly this.
 torch.distributed is plumbing here: gloo on CPU boxes (tests), nccl on GPU boxes.
 """
 from __future__ import annotations
@@ -46,34 +47,12 @@ def gather_counts(local: dict, n_frames: int, K: int, dist=None) -> np.ndarray |
     return out
 
 
-class FrameBatcher:
-    """Runs omni_host_color_edge over this rank's frames with fixed centres (one Engine, pinned result buffers)."""
-
-    def __init__(self, engine, centers, lut, edge_cfg, h: int, w: int):
-        from .ops import pinned_empty
-        self.eng, self.centers, self.lut, self.ec = engine, np.asarray(centers, np.float32), lut, edge_cfg
-        K = self.centers.shape[0]
-        self.masks = pinned_empty((K, h, w))
-        self.edges = pinned_empty((K, h, w))
-
-    def __call__(self, frame: np.ndarray) -> np.ndarray:
-        r = self.eng.host_color_edge(frame, self.centers, self.lut, self.ec, want_labels=False,
-                                     masks=self.masks, edges=self.edges, want_counts=True)
-        return r["counts"]
-
-
-def frame_groups(n_frames: int, K: int, max_planes: int = 32) -> list:
-    """Split a rank's frames into groups whose n * K layers fit the plane dimension of one omni_color_edge_batch pass."""
-    per = max(1, max_planes // max(1, K))
-    return [range(lo, min(n_frames, lo + per)) for lo in range(0, n_frames, per)]
-
-
-class DeviceFrameBatcher:
-    """Device-resident frames of one rank through omni_color_edge_batch, a group of frames per call (their n * K layers are
-    the plane dimension of one morphology / edge / hysteresis launch).  Returns (masks, edges) tensors [n,K,H,W]."""
-
-    def __init__(self, engine, centers, lut, edge_cfg):
-        self.eng, self.centers, self.lut, self.ec = engine, np.asarray(centers, np.float32), lut, edge_cfg
-
-    def __call__(self, frames, masks=None, edges=None):
-        return self.eng.color_edge_batch(frames, self.centers, self.lut, self.ec, masks=masks, edges=edges)
+def process_shard_packed(engine, frames, frame_ids, centers, lut, edge_cfg, mask_bits=None, edge_bits=None):
+    """This rank's frames [n,H,W,3] (host, ideally pinned) through omni_host_color_edge_packed: the masks and edge planes of frame
+    j land in mask_bits / edge_bits [j*K:(j+1)*K] (1 bit per pixel); returns ({frame_id: counts[K,3]}, result dict) for gather_counts."""
+    ids = [int(i) for i in frame_ids]
+    if not ids:
+        return {}, None
+    K = np.asarray(centers).reshape(-1, 3).shape[0]
+    r = engine.host_color_edge_packed(frames[:len(ids)], centers, lut, edge_cfg, mask_bits=mask_bits, edge_bits=edge_bits)
+    return {f: r["counts"][j * K:(j + 1) * K] for j, f in enumerate(ids)}, r

@@ -22,11 +22,6 @@ def test_shard_range_partitions(n, world):
     assert seen == list(range(n))                 # contiguous, ordered, no overlap, complete
 
 
-def test_frame_groups():
-    assert [list(g) for g in batch.frame_groups(10, 8)] == [[0, 1, 2, 3], [4, 5, 6, 7], [8, 9]]
-    assert [list(g) for g in batch.frame_groups(3, 16)] == [[0, 1], [2]]
-    assert [list(g) for g in batch.frame_groups(2, 32)] == [[0], [1]]
-    assert batch.frame_groups(0, 8) == []
 
 
 def test_gather_single_process():
