@@ -194,6 +194,9 @@ int omni_count_nonzero(omni_ctx *ctx, const uint8_t *d_planes, int K, int h, int
 int omni_edges_composite(omni_ctx *ctx, const uint8_t *d_edges, int K, int h, int w, size_t e_plane_stride, size_t epitch,
                          const uint8_t *h_colors_bgr, uint8_t *d_canvas, size_t cpitch, void *stream);
 
+int omni_host_edges_composite(omni_ctx *ctx, const uint8_t *h_edges, int K, int h, int w, size_t e_plane_stride, size_t epitch,
+                              const uint8_t *h_colors_bgr, uint8_t *h_canvas, size_t cpitch);
+
 /* ---- stage 04 (first step): 04_find_contours.py:35-99  thinning_zhangsuen(bin_0_255, layer) ---- */
 /* K independent planes; a pixel > 0 is foreground (`(roi > 0)`, 04:43).  Zhang-Suen thinning with the reference's
  * neighbour naming, both sub-steps per iteration, until an iteration deletes nothing or max_iter (the reference

@@ -770,6 +770,24 @@ extern "C" int omni_edges_composite(omni_ctx *ctx, const uint8_t *d_edges, int K
     return OMNI_OK;
 }
 
+// host planes in, host canvas out (what 03_edge_detect.py:60-111 does with the edges.png files it has just read)
+extern "C" int omni_host_edges_composite(omni_ctx *ctx, const uint8_t *h_edges, int K, int h, int w, size_t e_plane_stride, size_t epitch,
+                                         const uint8_t *h_colors_bgr, uint8_t *h_canvas, size_t cpitch)
+{
+    OMNI_TRY(set_device(ctx));
+    OMNI_REQUIRE(h_edges && h_canvas && h_colors_bgr && K >= 1 && K <= OMNI_MAX_K && h > 0 && w > 0 && epitch >= (size_t)w &&
+                 cpitch >= (size_t)w * 3, "omni_host_edges_composite: bad arguments");
+    const size_t ep = pad16((size_t)w), eplane = ep * h, cp = pad16((size_t)w * 3);
+    OMNI_TRY(omni_ws_reserve(ctx, 3, eplane * K + cp * h));
+    u8 *de = (u8 *)ctx->ws[3], *dc = de + eplane * K;
+    for (int k = 0; k < K; k++)
+        OMNI_CUDA(cudaMemcpy2DAsync(de + k * eplane, ep, h_edges + k * e_plane_stride, epitch, (size_t)w, h, cudaMemcpyHostToDevice, ctx->stream));
+    OMNI_TRY(omni_edges_composite(ctx, de, K, h, w, eplane, ep, h_colors_bgr, dc, cp, ctx->stream));
+    OMNI_CUDA(cudaMemcpy2DAsync(h_canvas, cpitch, dc, cp, (size_t)w * 3, h, cudaMemcpyDeviceToHost, ctx->stream));
+    OMNI_CUDA(cudaStreamSynchronize(ctx->stream));
+    return OMNI_OK;
+}
+
 // ---- host-buffer entry points -------------------------------------------------------------------------------
 // Staging layout in workspace slot 3: [image | labels | masks | edges], rows padded to 16 bytes.
 

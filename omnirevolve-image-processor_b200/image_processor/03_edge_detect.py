@@ -13,6 +13,6 @@ detect_all_edges = stages.detect_all_edges
 save_edges_composite = stages.save_edges_composite
 
 if __name__ == "__main__":
-    config = load_config()
-    detect_all_edges(config)
-    save_edges_composite(config)
+    # detect_all_edges + save_edges_composite (03:112-115); when this tree's stage 02 has just run on the same masks and edge
+    # keys, its parked planes are published instead of recomputed (omni_b200/stages.py, "hand-off 02 -> 03")
+    stages.edge_detect_main(load_config())

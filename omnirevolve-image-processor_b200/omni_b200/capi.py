@@ -23,7 +23,7 @@ EXPORTS = [
     "omni_edges", "omni_host_edges", "omni_color_edge", "omni_host_color_edge", "omni_count_nonzero",
     "omni_edges_composite", "omni_last_hysteresis_passes", "omni_launch_count", "omni_profile_enable",
     "omni_profile_summary", "omni_thin_zhangsuen", "omni_host_thin_zhangsuen", "omni_swatch_masks", "omni_color_edge_batch", "omni_skeleton_degree",
-    "omni_set_table_cache", "omni_color_edge_packed", "omni_host_color_edge_packed",
+    "omni_set_table_cache", "omni_host_edges_composite", "omni_color_edge_packed", "omni_host_color_edge_packed",
 ]
 
 
@@ -76,6 +76,7 @@ def lib():
         "omni_host_color_edge": ([vp, u8p, i, i, sz, f32p, i, hu8, epp, u8p, sz, u8p, sz, sz, u8p, sz, sz, i64p], i),
         "omni_count_nonzero": ([vp, u8p, i, i, i, sz, sz, i64p, vp], i),
         "omni_edges_composite": ([vp, u8p, i, i, i, sz, sz, hu8, u8p, sz, vp], i),
+        "omni_host_edges_composite": ([vp, u8p, i, i, i, sz, sz, hu8, u8p, sz], i),
         "omni_last_hysteresis_passes": ([vp], i),
         "omni_launch_count": ([vp], C.c_longlong),
         "omni_profile_enable": ([vp, i], i),

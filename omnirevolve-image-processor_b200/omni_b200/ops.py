@@ -411,6 +411,18 @@ class Engine:
                                            C.byref(p), out.ctypes.data, out.strides[0], out.strides[1]))
         return out
 
+    def host_edges_composite(self, edges: np.ndarray, colors_bgr) -> np.ndarray:
+        """03_edge_detect.py:93-106 on host planes [K,H,W] -> host canvas [H,W,3] (no torch needed)."""
+        edges = np.ascontiguousarray(edges, dtype=np.uint8)
+        K, h, w = edges.shape
+        col = np.ascontiguousarray(colors_bgr, dtype=np.uint8).reshape(-1, 3)[:K]
+        if col.shape[0] < K:
+            raise IndexError("list index out of range")        # what cfg.colors[i] raises in 03:90
+        out = np.empty((h, w, 3), np.uint8)
+        capi.check(self._L.omni_host_edges_composite(self._h, edges.ctypes.data, K, h, w, edges.strides[0], edges.strides[1],
+                                                     _u8p(col), out.ctypes.data, out.strides[0]))
+        return out
+
     def host_color_edge(self, img_bgr: np.ndarray, centers, lut, ec: EdgeConfig, want_labels: bool = True,
                         masks: np.ndarray | None = None, edges: np.ndarray | None = None, want_counts: bool = True):
         """Host image -> dict(labels, masks, edges, counts) as host arrays (pass pinned arrays from

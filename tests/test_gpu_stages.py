@@ -58,6 +58,52 @@ def test_stage_scripts_match_reference_files(case, tmp_path):
         assert f"Edges extracted: {n} | nz={int(np.count_nonzero(z['edges'][i]))}" in log
     comp = cv2.imread(str(out / "edges_composite.png"), cv2.IMREAD_COLOR)
     assert np.array_equal(comp, z["composite"])
+    # stage 03 again, now on its own (`--start-step 3`): nothing parked by stage 02 is left, it recomputes from mask.png
+    assert not (out / ".omni_b200_handoff.json").exists()
+    for n in names:
+        os.remove(out / n / "edges.png")
+    os.remove(out / "edges_composite.png")
+    log2 = run_stage("03_edge_detect.py", str(cfg_path))
+    for i, n in enumerate(names):
+        e = cv2.imread(str(out / n / "edges.png"), cv2.IMREAD_GRAYSCALE)
+        assert np.array_equal(e, z["edges"][i]), n
+        assert f"Edges extracted: {n} | nz={int(np.count_nonzero(z['edges'][i]))}" in log2
+    assert np.array_equal(cv2.imread(str(out / "edges_composite.png"), cv2.IMREAD_COLOR), z["composite"])
+
+
+def test_handoff_is_dropped_when_masks_or_keys_change(tmp_path):
+    """The planes stage 02 parks for stage 03 are used only for unchanged masks and edge keys: a hand-edited mask.png or a changed
+    threshold makes stage 03 recompute from the files (what the reference would do)."""
+    z, meta = load_pipe_case(PIPE_CASES[0])
+    cfg = dict(meta["config"])
+    names = meta["names"]
+    out = tmp_path / "out"
+    out.mkdir()
+    cv2.imwrite(str(out / "resized.png"), z["resized"])
+    cfg.update(input_image=str(tmp_path / "unused.png"), output_dir=str(out))
+    cfg_path = out / "config.json"
+    cfg_path.write_text(json.dumps(cfg))
+    run_stage("02_color_extract.py", str(cfg_path))
+    assert (out / ".omni_b200_handoff.json").exists()
+    # (a) changed edge key
+    cfg2 = dict(cfg, edge_low_threshold=100, edge_high_threshold=200)
+    cfg_path.write_text(json.dumps(cfg2))
+    run_stage("03_edge_detect.py", str(cfg_path))
+    from oracle import refport as rp
+    for i, n in enumerate(names):
+        want = rp.edge_layer(z["masks"][i], 100, 200, cfg["edge_kernel_size"], cfg["edge_morph_kernel"], cfg["edge_morph_open_iters"],
+                             cfg["edge_morph_close_iters"])
+        assert np.array_equal(cv2.imread(str(out / n / "edges.png"), cv2.IMREAD_GRAYSCALE), want), n
+    # (b) hand-edited mask
+    cfg_path.write_text(json.dumps(cfg))
+    run_stage("02_color_extract.py", str(cfg_path))
+    m = z["masks"][0].copy()
+    m[10:40, 10:60] = 255
+    cv2.imwrite(str(out / names[0] / "mask.png"), m)
+    run_stage("03_edge_detect.py", str(cfg_path))
+    want = rp.edge_layer(m, cfg["edge_low_threshold"], cfg["edge_high_threshold"], cfg["edge_kernel_size"], cfg["edge_morph_kernel"],
+                         cfg["edge_morph_open_iters"], cfg["edge_morph_close_iters"])
+    assert np.array_equal(cv2.imread(str(out / names[0] / "edges.png"), cv2.IMREAD_GRAYSCALE), want)
 
 
 def test_stage_error_behaviour(tmp_path):
