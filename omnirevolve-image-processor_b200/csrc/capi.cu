@@ -71,6 +71,7 @@ extern "C" int omni_ctx_destroy(omni_ctx *c)
     for (auto &kv : c->resize_tabs) if (kv.second.d_blob) cudaFree(kv.second.d_blob);
     if (c->d_flags) cudaFree(c->d_flags);
     if (c->d_rgb_boxes) cudaFree(c->d_rgb_boxes);
+    if (c->d_rgb_boxes3) cudaFree(c->d_rgb_boxes3);
     if (c->d_counts) cudaFree(c->d_counts);
     if (c->h_flags) cudaFreeHost(c->h_flags);
     if (c->h_counts) cudaFreeHost(c->h_counts);
@@ -535,7 +536,7 @@ extern "C" int omni_color_edge(omni_ctx *ctx, const uint8_t *d_bgr, int h, int w
     AssignParams P;
     OMNI_TRY(fill_assign(&P, h_centers, nullptr, K, h_lut));
     cudaStream_t st = (cudaStream_t)stream;
-    if (ctx->fast && fast_edges_supported(prm)) {
+    if (ctx->fast && fast_fused_supported(prm)) {
         int rc = fast_color_edge(ctx, d_bgr, h, w, pitch, P, prm, bp, low, high, d_labels, lpitch,
                                  d_masks, m_plane_stride, mpitch, d_edges, e_plane_stride, epitch, st);
         if (rc != OMNI_ERR_UNSUPPORTED) return rc;
@@ -577,7 +578,7 @@ extern "C" int omni_color_edge_batch(omni_ctx *ctx, const uint8_t *d_bgr, int n_
         const uint8_t *src = d_bgr + (size_t)f0 * frame_stride;
         uint8_t *dm = d_masks + (size_t)f0 * K * m_plane_stride, *de = d_edges + (size_t)f0 * K * e_plane_stride;
         int rc = OMNI_ERR_UNSUPPORTED;
-        if (ctx->fast && fast_edges_supported(prm) && nf > 1)
+        if (ctx->fast && fast_fused_supported(prm) && nf > 1)
             rc = fast_color_edge_batch(ctx, src, nf, frame_stride, h, w, pitch, P, prm, low, high, dm, m_plane_stride, mpitch,
                                        de, e_plane_stride, epitch, st);
         if (rc == OMNI_ERR_UNSUPPORTED) {                  // outside the fast path (or a single frame): frame by frame

@@ -65,10 +65,13 @@ struct E3Args {
     u32 *sbits, *cbits; u8 *edges; size_t estride, epitch; int aligned16;
     int *wl_count; u32 *worklist; int wl_cap;         // words with weak candidates, for the hysteresis kernel
     const int *run_counts; int *run_next; const u32 *run_items; unsigned run_off[ET_MAXT];   // sparse: run lists
+    const u8 *blur; size_t bstride, bpitch;           // BYTES: the blurred planes (edge_kernel_size 5 / 7, fk_blur_bits), rows 4-byte aligned
 };
 
-template <bool SPARSE>
-__global__ void __launch_bounds__(E3V_WARPS * 32) fk_edges3_simd(const __grid_constant__ E3Args A)
+// BYTES = false: blur 3 from the bit-plane m2 (steps 1-3 below).  BYTES = true: the blurred image comes as u8 planes (any blur
+// size; Sobel's BORDER_REPLICATE = clamped coordinates), steps 1-3 are a 40-byte row load.
+template <bool SPARSE, bool BYTES>
+__global__ void __launch_bounds__(E3V_WARPS * 32, 6) fk_edges3_simd(const __grid_constant__ E3Args A)
 {
     __shared__ E3WarpSmem sm[E3V_WARPS];
     __shared__ u32 s_lut6[64];
@@ -127,6 +130,27 @@ __global__ void __launch_bounds__(E3V_WARPS * 32) fk_edges3_simd(const __grid_co
             if (c + 1 < ww) pf_r = __ldg(row + c + 1);
         }
     };
+    u32 pb[BYTES ? 10 : 1];                              // BYTES: the 40 blurred pixels of the next row (window e <-> pixel 32c - 4 + e)
+    auto load_brow = [&](const int t1) {
+        if (!BYTES) return;
+#pragma unroll
+        for (int q = 0; q < (BYTES ? 10 : 1); q++) pb[q] = 0u;
+        if (!active) return;
+        const u8 *row = A.blur + (size_t)k * A.bstride + (size_t)min(max(t1, 0), h - 1) * A.bpitch;
+        if (32 * c - 4 >= 0 && 32 * c + 36 <= w) {
+            const u32 *p = reinterpret_cast<const u32 *>(row + 32 * c - 4);
+#pragma unroll
+            for (int q = 0; q < (BYTES ? 10 : 1); q++) pb[q] = __ldg(p + q);
+        } else {
+#pragma unroll
+            for (int q = 0; q < (BYTES ? 10 : 1); q++) {
+                u32 v = 0u;
+#pragma unroll
+                for (int i = 0; i < 4; i++) v |= (u32)row[min(max(32 * c - 4 + 4 * q + i, 0), w - 1)] << (8 * i);
+                pb[q] = v;
+            }
+        }
+    };
     auto step = [&](const int tt, u32 (&hA)[10], u32 (&hB)[10], u32 (&hC)[10], u32 (&UA)[20], u32 (&UB)[20], u32 (&UC)[20]) {
         const int t = y0 + tt;
         // ---- (0) candidate list of row t-3 (its candidate mask is known since the previous step): compacted over the warp.
@@ -153,6 +177,16 @@ __global__ void __launch_bounds__(E3V_WARPS * 32) fk_edges3_simd(const __grid_co
                 if ((mk >> e) & 1u) S.list[pos++] = (u16)(tag | e);
             S.cw[lane] = 0u; S.sw[lane] = 0u;
         }
+        if (BYTES) {
+            // ---- (1-3) blurred row t-1 (prefetched one step ahead): bytes -> half2 -----------------------------------------
+#pragma unroll
+            for (int q = 0; q < 10; q++) {
+                const u32 bq = pb[BYTES ? q : 0];
+                UC[2 * q] = as_u32(__hsub2(as_h2(__byte_perm(bq, 0x64646464u, 0x4140)), k1024));
+                UC[2 * q + 1] = as_u32(__hsub2(as_h2(__byte_perm(bq, 0x64646464u, 0x4342)), k1024));
+            }
+            load_brow(t);
+        } else {
         // ---- (1) bit row t (prefetched one step ahead), 40-pixel window: index e <-> pixel 32c - 4 + e ---------------
         u32 lo = (pf_l >> 28) | (pf_o << 4), hi = (pf_o >> 28) | (pf_r << 4);
         if (is_lb) {                                   // pixels -1, -2 := pixels 1, 0
@@ -187,6 +221,7 @@ __global__ void __launch_bounds__(E3V_WARPS * 32) fk_edges3_simd(const __grid_co
                 UC[2 * q] = as_u32(__hsub2(as_h2(__byte_perm(B[q], 0x64646464u, 0x4140)), k1024));
                 UC[2 * q + 1] = as_u32(__hsub2(as_h2(__byte_perm(B[q], 0x64646464u, 0x4342)), k1024));
             }
+        }
         }
         // ---- (4) row r = t-2: Sobel, magnitude, candidate mask; rows into shared memory ----------------------------
         const int r = t - 2, rr = tt - 2;                                   // absolute / relative
@@ -308,7 +343,8 @@ __global__ void __launch_bounds__(E3V_WARPS * 32) fk_edges3_simd(const __grid_co
 #pragma unroll
     for (int j = 0; j < 20; j++) UA[j] = UB[j] = UC[j] = 0u;
     const int tt_end = nrows + 2;
-    load_row(y0 - 3);
+    if (BYTES) load_brow(y0 - 4);
+    else load_row(y0 - 3);
 #ifndef E3_ROTATE_THREE
     // one instance of the step (a third of the code: the three rotated copies do not fit the instruction caches); the rolling
     // rows move by register copies instead
@@ -518,7 +554,7 @@ static void e3_dense_grid(int h, int ww, int K, int sm_count, int *tr_out, int *
 
 cudaError_t launch_edges3_simd(const u32 *m2, int ws, size_t plane, int h, int w, int K, int low, int high, int sm_count,
                                u32 *sbits, u32 *cbits, u8 *edges, size_t estride, size_t epitch, int aligned16, int *wl_count, u32 *worklist, int wl_cap,
-                               cudaStream_t st)
+                               cudaStream_t st, const u8 *blur, size_t bstride, size_t bpitch)
 {
     E3Args A{};
     A.m2 = m2; A.ws = ws; A.plane = plane; A.h = h; A.w = w; A.low = low; A.high = high;
@@ -526,7 +562,11 @@ cudaError_t launch_edges3_simd(const u32 *m2, int ws, size_t plane, int h, int w
     A.wl_count = wl_count; A.worklist = worklist; A.wl_cap = wl_cap;
     dim3 grid;
     e3_dense_grid(h, (w + 31) >> 5, K, sm_count, &A.tr, &A.wcols, &grid);
-    fk_edges3_simd<false><<<grid, E3V_WARPS * 32, 0, st>>>(A);
+    if (blur) {
+        A.blur = blur; A.bstride = bstride; A.bpitch = bpitch;
+        fk_edges3_simd<false, true><<<grid, E3V_WARPS * 32, 0, st>>>(A);
+    } else
+        fk_edges3_simd<false, false><<<grid, E3V_WARPS * 32, 0, st>>>(A);
     return cudaGetLastError();
 }
 
@@ -559,7 +599,8 @@ cudaError_t launch_edge_runs(const u32 *m2, int ws, size_t plane, int h, int w, 
 
 cudaError_t launch_edges3_sparse(const u32 *m2, int ws, size_t plane, int h, int w, int K, int low, int high, int grid_blocks,
                                  u32 *sbits, u32 *cbits, u8 *edges, size_t estride, size_t epitch, int aligned16, int *wl_count,
-                                 u32 *worklist, int wl_cap, const int *run_counts, int *run_next, const u32 *run_items, cudaStream_t st)
+                                 u32 *worklist, int wl_cap, const int *run_counts, int *run_next, const u32 *run_items, cudaStream_t st,
+                                 const u8 *blur, size_t bstride, size_t bpitch)
 {
     E3Args A{};
     A.m2 = m2; A.ws = ws; A.plane = plane; A.h = h; A.w = w; A.low = low; A.high = high;
@@ -567,16 +608,149 @@ cudaError_t launch_edges3_sparse(const u32 *m2, int ws, size_t plane, int h, int
     A.wl_count = wl_count; A.worklist = worklist; A.wl_cap = wl_cap;
     A.run_counts = run_counts; A.run_next = run_next; A.run_items = run_items;
     edges3_run_words(h, w, K, A.run_off);
-    fk_edges3_simd<true><<<grid_blocks, E3V_WARPS * 32, 0, st>>>(A);
+    if (blur) {
+        A.blur = blur; A.bstride = bstride; A.bpitch = bpitch;
+        fk_edges3_simd<true, true><<<grid_blocks, E3V_WARPS * 32, 0, st>>>(A);
+    } else
+        fk_edges3_simd<true, false><<<grid_blocks, E3V_WARPS * 32, 0, st>>>(A);
     return cudaGetLastError();
 }
 
 int edges3_sparse_blocks_per_sm()
 {
     int per_sm = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fk_edges3_simd<true>, E3V_WARPS * 32, 0) != cudaSuccess || per_sm < 1) {
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fk_edges3_simd<true, false>, E3V_WARPS * 32, 0) != cudaSuccess || per_sm < 1) {
         cudaGetLastError();
         per_sm = 1;
     }
     return per_sm;
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// cv2.GaussianBlur(mask, (k, k), 0) for k = 5, 7 on a {0,255} mask given as a bit-plane (03_edge_detect.py:33):
+//   out = (255 * sum_y w_y sum_x w_x b(y, x) + 32768) >> 16,  BORDER_REFLECT_101,  w = 8.8 fixed point weights with sum 256
+//   k = 5: w = 16 * (1,4,6,4,1)        -> S5 = sum of the small weights in [0,256],   out = (255 S5 + 128) >> 8 = S5 - (S5 > 128)
+//   k = 7: w = 4 * (2,7,14,18,14,7,2)  -> S7 in [0,4096],                             out = (255 S7 + 2048) >> 12
+// A thread produces 4 adjacent pixels: per source row one table lookup (4 + k - 1 window bits -> the 4 horizontal sums as bytes),
+// the vertical sum in two 16-bit lanes per word.  Output: u8 planes (rows 4-byte aligned) for the BYTES variant of the edge kernel.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int e3_reflect101(int p, int len)
+{
+    if (len == 1) return 0;
+    while (p < 0 || p >= len) p = p < 0 ? -p : 2 * (len - 1) - p;
+    return p;
+}
+
+#define BB_ROWS 64                        // output rows per strip (+ KS - 1 rows of ramp)
+
+template <int KS>
+__host__ __device__ constexpr u32 blur_w(int i)               // the small integer weights: 16 * (1,4,6,4,1) / 4 * (2,7,14,18,14,7,2) = cv2's
+{
+    return KS == 5 ? (i == 0 || i == 4 ? 1u : i == 2 ? 6u : 4u) : (i == 0 || i == 6 ? 2u : i == 1 || i == 5 ? 7u : i == 3 ? 18u : 14u);
+}
+
+// A lane owns 16 adjacent pixels (4 groups of 4) and walks down a strip of rows; a warp covers 512 adjacent pixels.  Per source row:
+// three word loads -> a 32-bit window (pixels 16q - 8 .. 16q + 23), per group one table lookup (4 + KS - 1 window bits -> the 4
+// horizontal sums as bytes) and the vertical filter in transposed form (KS - 1 running sums in two 16-bit lanes per word, one
+// multiply-add each per row: FMA pipe).  REFLECT_101: rows by index, columns by patching the window of the lanes at the borders.
+template <int KS>
+__global__ void __launch_bounds__(128) fk_blur_bits(const u32 *__restrict__ m2, int ws, size_t plane, int K, int h, int w,
+                                                    u8 *__restrict__ out, size_t ostride, size_t opitch, int wcols)
+{
+    constexpr int R = KS / 2, NB = 4 + 2 * R;
+    __shared__ u32 s_lut[1 << NB];
+    for (int i = threadIdx.x; i < (1 << NB); i += blockDim.x) {
+        u32 v = 0u;
+        for (int px = 0; px < 4; px++) {
+            u32 sum = 0u;
+#pragma unroll
+            for (int d = 0; d < KS; d++) sum += blur_w<KS>(d) * (((u32)i >> (px + d)) & 1u);
+            v |= sum << (8 * px);
+        }
+        s_lut[i] = v;
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int wx = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (wx >= wcols) return;
+    const int q = wx * 32 + lane;                              // 16-pixel column
+    const int k = blockIdx.z;
+    const int y0 = blockIdx.y * BB_ROWS, y1 = min(h, y0 + BB_ROWS);
+    const int x16 = 16 * q;
+    if (x16 >= w) return;
+    const int ww = (w + 31) >> 5, wi = q >> 1;
+    const bool edge = x16 - R < 0 || x16 + 16 + R > w;         // the window leaves the image: mirrored columns
+    const bool tiny = w <= 2 * R || h <= R;                    // reflections may repeat: bit-by-bit path
+    const u32 *pl = m2 + (size_t)k * plane;
+    u8 *op = out + (size_t)k * ostride + x16;
+    u32 ae[4][KS - 1], ao[4][KS - 1];                          // running sums, even / odd pixels of each group
+#pragma unroll
+    for (int g = 0; g < 4; g++)
+#pragma unroll
+        for (int i = 0; i < KS - 1; i++) ae[g][i] = ao[g][i] = 0u;
+    for (int t = y0 - R; t < y1 + R; t++) {
+        const int tr = tiny ? e3_reflect101(t, h) : (t < 0 ? -t : t >= h ? 2 * (h - 1) - t : t);
+        const u32 *row = pl + (size_t)tr * ws;
+        u32 win;                                               // bit i = pixel 16q - 8 + i
+        if (!(edge && tiny)) {
+            const u32 o = __ldg(row + wi);
+            if (q & 1) win = (o >> 8) | ((wi + 1 < ww ? __ldg(row + wi + 1) : 0u) << 24);
+            else win = ((wi > 0 ? __ldg(row + wi - 1) : 0u) >> 24) | (o << 8);
+            if (edge) {                                        // pixel -j := pixel j, pixel w-1+j := pixel w-1-j  (j = 1..R)
+                if (x16 == 0) {
+#pragma unroll
+                    for (int j = 1; j <= R; j++) win = (win & ~(1u << (8 - j))) | (((win >> (8 + j)) & 1u) << (8 - j));
+                }
+                const int il = w - 1 - x16 + 8;                // window bit of pixel w-1 (>= 8: this lane holds image pixels)
+                if (x16 + 16 + R > w) {
+#pragma unroll
+                    for (int j = 1; j <= R; j++)
+                        if (il + j < 32) win = (win & ~(1u << (il + j))) | (((win >> (il - j)) & 1u) << (il + j));
+                }
+            }
+        } else {
+            win = 0u;
+            for (int i = 8 - R; i < 24 + R; i++) {
+                const int x = e3_reflect101(x16 - 8 + i, w);
+                win |= ((__ldg(row + (x >> 5)) >> (x & 31)) & 1u) << i;
+            }
+        }
+        u32 ob[4];
+#pragma unroll
+        for (int g = 0; g < 4; g++) {
+            const u32 hs = s_lut[(win >> (8 + 4 * g - R)) & ((1u << NB) - 1u)];
+            const u32 he = hs & 0x00FF00FFu, ho = (hs >> 8) & 0x00FF00FFu;
+            // transposed FIR: a[i] holds the partial sum that still lacks its last KS - 1 - i rows
+            const u32 se = ae[g][KS - 2] + blur_w<KS>(KS - 1) * he, so = ao[g][KS - 2] + blur_w<KS>(KS - 1) * ho;
+#pragma unroll
+            for (int i = KS - 2; i >= 1; i--) {
+                ae[g][i] = ae[g][i - 1] + blur_w<KS>(i) * he;
+                ao[g][i] = ao[g][i - 1] + blur_w<KS>(i) * ho;
+            }
+            ae[g][0] = blur_w<KS>(0) * he; ao[g][0] = blur_w<KS>(0) * ho;
+            const u32 S0 = se & 0xFFFFu, S2 = se >> 16, S1 = so & 0xFFFFu, S3 = so >> 16;
+            u32 b0, b1, b2, b3;
+            if (KS == 5) {
+                b0 = S0 - (S0 > 128u ? 1u : 0u); b1 = S1 - (S1 > 128u ? 1u : 0u); b2 = S2 - (S2 > 128u ? 1u : 0u); b3 = S3 - (S3 > 128u ? 1u : 0u);
+            } else {
+                b0 = (255u * S0 + 2048u) >> 12; b1 = (255u * S1 + 2048u) >> 12; b2 = (255u * S2 + 2048u) >> 12; b3 = (255u * S3 + 2048u) >> 12;
+            }
+            ob[g] = b0 | (b1 << 8) | (b2 << 16) | (b3 << 24);
+        }
+        const int y = t - R;
+        if (y >= y0 && y < y1) *reinterpret_cast<uint4 *>(op + (size_t)y * opitch) = make_uint4(ob[0], ob[1], ob[2], ob[3]);
+    }
+}
+
+cudaError_t launch_blur_bits(int ksize, const u32 *m2, int ws, size_t plane, int K, int h, int w, u8 *out, size_t ostride, size_t opitch,
+                             int blocks, cudaStream_t st)
+{
+    (void)blocks;
+    const int cols16 = (w + 15) / 16, wcols = (cols16 + 31) / 32;
+    dim3 grid((wcols + 3) / 4, (h + BB_ROWS - 1) / BB_ROWS, K);
+    if (ksize == 5) fk_blur_bits<5><<<grid, 128, 0, st>>>(m2, ws, plane, K, h, w, out, ostride, opitch, wcols);
+    else if (ksize == 7) fk_blur_bits<7><<<grid, 128, 0, st>>>(m2, ws, plane, K, h, w, out, ostride, opitch, wcols);
+    else return cudaErrorInvalidValue;
+    return cudaGetLastError();
 }

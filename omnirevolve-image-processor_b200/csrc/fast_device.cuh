@@ -138,6 +138,8 @@ struct MorphRuns {
     u32 *sbits, *cbits; u8 *edges; size_t estride, epitch; int aligned16;
     int *run_counts; u32 *run_items; E3RunOff off; int maxt;
     int zero_fill;                    // 1: the kernel writes the zeros of the dead tiles; 0: the planes were cleared beforehand
+    int grow;                         // a tile is dead when the tile grown by `grow` pixels is uniform: 2 for blur 3 (5x5 neighbourhoods),
+                                      // 3 for blur 5, 4 for blur 7 (radius of blur + Sobel); 0 is read as 2
 };
 
 

@@ -766,7 +766,8 @@ __global__ void __launch_bounds__(128, MORPH_MINB) fk_morph(const u32 *__restric
                                                 const __grid_constant__ MorphRuns R)
 {
     constexpr int N = code_len(CODE);
-    constexpr int EXT = RUNS ? 2 : 0;
+    const int GROW = RUNS ? (R.grow ? R.grow : 2) : 0;   // 2..4, see MorphRuns
+    const int EXT = GROW;
     constexpr int TILES = TR / ET_R;
     __shared__ uint2 s_lut8[256];
     __shared__ u32 s_item[RUNS ? 4 : 1][RUNS ? TILES : 1][32];
@@ -828,14 +829,14 @@ __global__ void __launch_bounds__(128, MORPH_MINB) fk_morph(const u32 *__restric
             }
         }
         if (RUNS) {
-            if (r >= y0 - 2 && r < y1 + 2 && (!ROWFIX || (r >= 0 && r < h))) {
-                // window bits 14..49 = pixels 32c-2 .. 32c+33; fin is already 0 outside the image
-                const u32 m_lo = 0xFFFFC000u & colvalid.lo, m_hi = 0x0003FFFFu & colvalid.hi;
+            if (r >= y0 - GROW && r < y1 + GROW && (!ROWFIX || (r >= 0 && r < h))) {
+                // window bits 16-GROW .. 47+GROW = pixels 32c-GROW .. 32c+31+GROW; fin is already 0 outside the image
+                const u32 m_lo = (0xFFFFFFFFu << (16 - GROW)) & colvalid.lo, m_hi = (0xFFFFFFFFu >> (16 - GROW)) & colvalid.hi;
                 const bool h1 = ((fin.lo & m_lo) | (fin.hi & m_hi)) != 0u, h0 = ((~fin.lo & m_lo) | (~fin.hi & m_hi)) != 0u;
                 const int rr = r - y0, sub = rr & 7;
                 u32 m = 1u << ((rr >> 3) + 1);                          // tile rr / 8 (floor), biased by one
-                if (sub < 2) m |= m >> 1;                                // also the 2-row halo of the tile above
-                if (sub >= 6) m |= m << 1;                               // ... of the tile below
+                if (sub < GROW) m |= m >> 1;                             // also the halo rows of the tile above
+                if (sub >= 8 - GROW) m |= m << 1;                        // ... of the tile below
                 m = (m >> 1) & ((1u << TILES) - 1u);
                 if (h1) live1 |= m;
                 if (h0) live0 |= m;
@@ -1324,8 +1325,10 @@ int morph03_kind(const omni_edge_params *p)
 
 bool fast_edges_supported(const omni_edge_params *prm)
 {
-    return morph03_kind(prm) >= 0 && prm->ksize == 3;
+    return morph03_kind(prm) >= 0 && (prm->ksize == 3 || prm->ksize == 5 || prm->ksize == 7);
 }
+
+bool fast_fused_supported(const omni_edge_params *prm) { return morph03_kind(prm) >= 0 && prm->ksize == 3; }
 
 bool fast_morph03_supported(const omni_edge_params *prm) { return morph03_kind(prm) >= 0; }
 
@@ -1428,7 +1431,8 @@ int edge_pass_begin(omni_ctx *ctx, const BitGeom &g, int K, u32 *sbits, u32 *cbi
 // bit-planes M2 -> edge byte planes.  sbits doubles as the working set E of the hysteresis.  edge_pass_begin has run;
 // runs_done: the morphology kernel has already produced the run lists and zero-filled the dead tiles.
 static int edges_from_bits(omni_ctx *ctx, const u32 *m2, u32 *sbits, u32 *cbits, const BitGeom &g, int K, int low, int high,
-                           u8 *d_edges, size_t e_plane, size_t epitch, cudaStream_t st, bool sparse, bool runs_done)
+                           u8 *d_edges, size_t e_plane, size_t epitch, cudaStream_t st, bool sparse, bool runs_done,
+                           const u8 *blur = nullptr /* edge_kernel_size 5 / 7: the blurred planes */, size_t bstride = 0, size_t bpitch = 0)
 {
     int al = ((uintptr_t)d_edges % 16 == 0) && (e_plane % 16 == 0) && (epitch % 16 == 0);
     if (ctx->edge_join) {                               // the side stream has cleared the output planes
@@ -1442,11 +1446,11 @@ static int edges_from_bits(omni_ctx *ctx, const u32 *m2, u32 *sbits, u32 *cbits,
         OMNI_LAUNCH(ctx, st, "edges3_bits", launch_edges3_sparse(m2, g.ws, g.plane, g.h, g.w, K, low, high, persist_blocks(ctx, ctx->e3s_per_sm),
                                                                  sbits, cbits, d_edges, e_plane, epitch, al, ctx->d_flags + 4,
                                                                  (u32 *)ctx->ws[5] + HYST_WL_OFFSET, HY_WL_CAP, ctx->d_flags + 16,
-                                                                 ctx->d_flags + 20, (const u32 *)ctx->ws[6], st));
+                                                                 ctx->d_flags + 20, (const u32 *)ctx->ws[6], st, blur, bstride, bpitch));
     } else {
         OMNI_LAUNCH(ctx, st, "edges3_bits", launch_edges3_simd(m2, g.ws, g.plane, g.h, g.w, K, low, high, ctx->sm_count, sbits, cbits,
                                                                d_edges, e_plane, epitch, al, ctx->d_flags + 4,
-                                                               (u32 *)ctx->ws[5] + HYST_WL_OFFSET, HY_WL_CAP, st));
+                                                               (u32 *)ctx->ws[5] + HYST_WL_OFFSET, HY_WL_CAP, st, blur, bstride, bpitch));
     }
     return run_hysteresis(ctx, sbits, cbits, g, K, d_edges, e_plane, epitch, st);
 }
@@ -1474,12 +1478,27 @@ int fast_edges(omni_ctx *ctx, const u8 *d_masks, int K, int h, int w, size_t m_p
     const u32 *m2 = bpp[0];
     MorphRuns R{};
     bool sparse = false;
+    const int ks = prm->ksize;
     FK_TRY(edge_pass_begin(ctx, g, K, bpp[2], bpp[3], d_edges, e_plane, epitch, st, &R, &sparse, false));
+    // a tile is dead when the tile grown by the radius of blur + Sobel is uniform; only the morphology kernel classifies with a
+    // growth other than 2, so blur 5 / 7 without stage-03 morphology takes the dense edge kernel
+    R.grow = ks == 3 ? 2 : ks == 5 ? 3 : 4;
+    if (ks != 3 && kind <= 0) sparse = false;
     if (kind > 0) {
         OMNI_LAUNCH(ctx, st, "morph_bits", launch_morph(false, kind, bpp[0], bpp[1], g, K, nullptr, 0, 0, st, 0, -1, sparse ? &R : nullptr));
         m2 = bpp[1];
     }
-    return edges_from_bits(ctx, m2, bpp[2], bpp[3], g, K, low, high, d_edges, e_plane, epitch, st, sparse, sparse && kind > 0);
+    const u8 *blur = nullptr;
+    size_t bp_pitch = 0, bp_plane = 0;
+    if (ks != 3) {                                       // GaussianBlur 5 / 7 of the bit-planes -> u8 planes (workspace slot 0)
+        bp_pitch = ((size_t)w + 15) & ~(size_t)15; bp_plane = bp_pitch * h;
+        FK_TRY(omni_ws_reserve(ctx, 0, bp_plane * K));
+        OMNI_LAUNCH(ctx, st, "blur_bits", launch_blur_bits(ks, m2, g.ws, g.plane, K, h, w, (u8 *)ctx->ws[0], bp_plane, bp_pitch,
+                                                           persist_blocks(ctx, 16), st));
+        blur = (const u8 *)ctx->ws[0];
+    }
+    return edges_from_bits(ctx, m2, bpp[2], bpp[3], g, K, low, high, d_edges, e_plane, epitch, st, sparse, sparse && kind > 0, blur, bp_plane,
+                           bp_pitch);
 }
 
 int fast_color_edge(omni_ctx *ctx, const u8 *d_bgr, int h, int w, size_t pitch, const AssignParams &P,
@@ -1578,7 +1597,7 @@ int fast_host_color_edge(omni_ctx *ctx, const u8 *h_bgr, int h, int w, size_t pi
                          u8 *d_img, size_t ip, u8 *d_labels, size_t lp, u8 *d_masks, size_t mplane, size_t mp,
                          u8 *d_edges, size_t eplane, size_t ep, bool want_labels)
 {
-    if (low < 0 || !fast_edges_supported(prm)) return OMNI_ERR_UNSUPPORTED;
+    if (low < 0 || !fast_fused_supported(prm)) return OMNI_ERR_UNSUPPORTED;
     FK_TRY(pipe_init(ctx));
     OMNI_CUDA(fast_tables());
     const int K = P.K;

@@ -47,10 +47,15 @@ cudaError_t launch_edge_runs(const u32 *m2, int ws, size_t plane, int h, int w, 
                              size_t estride, size_t epitch, int aligned16, int *run_counts, u32 *run_items, int resident_warps, cudaStream_t st);
 cudaError_t launch_edges3_sparse(const u32 *m2, int ws, size_t plane, int h, int w, int K, int low, int high, int grid_blocks,
                                  u32 *sbits, u32 *cbits, u8 *edges, size_t estride, size_t epitch, int aligned16, int *wl_count,
-                                 u32 *worklist, int wl_cap, const int *run_counts, int *run_next, const u32 *run_items, cudaStream_t st);
+                                 u32 *worklist, int wl_cap, const int *run_counts, int *run_next, const u32 *run_items, cudaStream_t st,
+                                 const u8 *blur = nullptr, size_t bstride = 0, size_t bpitch = 0);
 cudaError_t launch_edges3_simd(const u32 *m2, int ws, size_t plane, int h, int w, int K, int low, int high, int sm_count,
                                u32 *sbits, u32 *cbits, u8 *edges, size_t estride, size_t epitch, int aligned16, int *wl_count, u32 *worklist, int wl_cap,
-                               cudaStream_t st);
+                               cudaStream_t st, const u8 *blur = nullptr, size_t bstride = 0, size_t bpitch = 0);
+// GaussianBlur 5 / 7 of bit-plane masks -> u8 planes (rows 4-byte aligned, opitch >= 4 * ceil(w / 4)); edges3.cu
+cudaError_t launch_blur_bits(int ksize, const u32 *m2, int ws, size_t plane, int K, int h, int w, u8 *out, size_t ostride, size_t opitch,
+                             int blocks, cudaStream_t st);
+bool fast_fused_supported(const omni_edge_params *prm);   // the fused colour+edge kernels: edge_kernel_size 3 only
 
 // host-buffer fused call with H2D / kernels / D2H overlapped over row bands; OMNI_ERR_UNSUPPORTED when the parameters
 // are outside the fast path.  On success all work is ordered before later work on ctx->stream.

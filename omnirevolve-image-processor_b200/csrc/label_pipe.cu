@@ -34,7 +34,18 @@
 // cell i lives in byte (i & 0x1FFFF), high nibble when i >= 2^17; K == 16 has a separate "several candidates" bit per cell.
 // The pruning rule is fk_build_rgbcells' (fast_kernels.cu): exact Lab box of the cell, dmin <= min dmax + 2.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) fk_build_rgbcells3(const __grid_constant__ AssignParams P, const u8 *__restrict__ boxes,
+// the Lab boxes of fk_rgb_boxes (B slowest) re-ordered to this index layout, once per context: the table build then reads them
+// with consecutive threads on consecutive cells
+__global__ void __launch_bounds__(256) fk_permute_boxes3(const u8 *__restrict__ boxes, u8 *__restrict__ boxes3)
+{
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= RC_COUNT) return;
+    const int ci = ((idx & 63) << 12) | (((idx >> 6) & 63) << 6) | (idx >> 12);
+#pragma unroll
+    for (int d = 0; d < 6; d++) boxes3[6 * idx + d] = boxes[6 * ci + d];
+}
+
+__global__ void __launch_bounds__(256) fk_build_rgbcells3(const __grid_constant__ AssignParams P, const u8 *__restrict__ boxes3,
                                                           u8 *__restrict__ nb, u32 *__restrict__ mb)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;                // < 2^17
@@ -44,10 +55,9 @@ __global__ void __launch_bounds__(256) fk_build_rgbcells3(const __grid_constant_
 #pragma unroll
     for (int hs = 0; hs < 2; hs++) {
         const int idx = i + (hs << 17);
-        const int ci = ((idx & 63) << 12) | (((idx >> 6) & 63) << 6) | (idx >> 12);     // box index: B slowest (fk_rgb_boxes)
         float lo[3], hi[3];
 #pragma unroll
-        for (int d = 0; d < 3; d++) { lo[d] = (float)boxes[6 * ci + d]; hi[d] = (float)boxes[6 * ci + 3 + d]; }
+        for (int d = 0; d < 3; d++) { lo[d] = (float)boxes3[6 * idx + d]; hi[d] = (float)boxes3[6 * idx + 3 + d]; }
         float U = 3.0e38f;
         bool sane = true;
         for (int k = 0; k < K; k++) {
@@ -594,9 +604,15 @@ static int label_tables(omni_ctx *ctx, const AssignParams &P, u32 **cells, u8 **
     memcpy(ctx->cells3_lut, P.lut, P.K);
     ctx->cells3_K = P.K; ctx->cells3_stream = (void *)st; ctx->cells3_valid = 1; ctx->cells3_ws = ctx->ws[5];
     OMNI_LAUNCH(ctx, st, "build_cells", launch_build_cells(P, *cells, st));
-    SP_TRY(fast_rgb_boxes(ctx, st));
+    if (!ctx->d_rgb_boxes3) {                          // centre-independent: once per context
+        SP_TRY(fast_rgb_boxes(ctx, st));
+        OMNI_CUDA(cudaMalloc(&ctx->d_rgb_boxes3, (size_t)RC_COUNT * 6));
+        KScope ks(ctx, "rgb_boxes", st);
+        fk_permute_boxes3<<<RC_COUNT / 256, 256, 0, st>>>(ctx->d_rgb_boxes, ctx->d_rgb_boxes3);
+        OMNI_CUDA(cudaGetLastError());
+    }
     KScope ks(ctx, "build_rgbcells", st);
-    fk_build_rgbcells3<<<(1 << 17) / 256, 256, 0, st>>>(P, ctx->d_rgb_boxes, *rtab, (u32 *)(*rtab + RC_NIB_BYTES));
+    fk_build_rgbcells3<<<(1 << 17) / 256, 256, 0, st>>>(P, ctx->d_rgb_boxes3, *rtab, (u32 *)(*rtab + RC_NIB_BYTES));
     OMNI_CUDA(cudaGetLastError());
     return OMNI_OK;
 }

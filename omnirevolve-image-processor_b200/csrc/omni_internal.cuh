@@ -100,6 +100,7 @@ struct omni_ctx {
     void *cells3_stream = nullptr, *cells3_ws = nullptr;
     float cells3_c[OMNI_MAX_K * 3];
     u8 cells3_lut[OMNI_MAX_K] = {};
+    u8 *d_rgb_boxes3 = nullptr;                // d_rgb_boxes in the cell order of fk_assign_slices
     int table_cache = 1;                       // 0: rebuild the candidate tables on every call (omni_set_table_cache)
     int occ_assign_sl = 0;
     // streams / events / pinned counts of omni_host_color_edge_packed (two staging slots)
