@@ -8,16 +8,15 @@ tail -4 gpurun_out/pytest_gpu.log
 timeout 300 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; tail -1 gpurun_out/smoke.log
 timeout 900 python bench.py > gpurun_out/bench_default.json 2> gpurun_out/bench_default.err; tail -c 400 gpurun_out/bench_default.json
 timeout 900 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_reference_arm.json 2> gpurun_out/bench_reference_arm.err; tail -c 300 gpurun_out/bench_reference_arm.json
-timeout 300 python bench.py --no-cpu-baseline --workload config3 --steps 10 --warmup 3 > gpurun_out/bench_config3.json 2> gpurun_out/bench_config3.err
 timeout 300 python bench.py --no-cpu-baseline --workload config4 --steps 20 --warmup 5 > gpurun_out/bench_config4.json 2> gpurun_out/bench_config4.err
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_bench.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_launches.log 2>&1
-timeout 600 ncu --set full --import-source on --clock-control none -k regex:"fk_assign|fk_morph|fk_edges3|fk_hyst|fk_build" --launch-skip 6 --launch-count 6 -o gpurun_out/prof_final_step -f python tools/profile_once.py > gpurun_out/ncu_full_step.log 2>&1
+timeout 600 ncu --set full --import-source on --clock-control none -k regex:"fk_assign|fk_morph|fk_edges3|fk_hyst|fk_build|fk_label" --launch-skip 14 --launch-count 7 -o gpurun_out/prof_final_step -f python tools/profile_once.py config5 > gpurun_out/ncu_full_step.log 2>&1
 tail -2 gpurun_out/ncu_full_step.log
 timeout 600 ncu --set full --import-source on --clock-control none -k regex:"fk_thin|fk_bytes_to_bits|fk_expand_bits" --launch-skip 3 --launch-count 3 -o gpurun_out/prof_final_thin -f python tools/profile_thin.py > gpurun_out/ncu_full_thin.log 2>&1
 timeout 600 ncu --set full --import-source on --clock-control none -k regex:"fk_resize" --launch-skip 2 --launch-count 1 -o gpurun_out/prof_final_resize -f python tools/profile_resize.py > gpurun_out/ncu_full_resize.log 2>&1
 python - <<'PY'
 import json
-for f in ("bench_default","bench_reference_arm","bench_config3","bench_config4"):
+for f in ("bench_default","bench_reference_arm","bench_config4"):
     try:
         d=json.loads(open(f"gpurun_out/{f}.json").read().strip().splitlines()[-1])
         print(f, d.get("value"), d.get("ms_per_step"), (d.get("roofline") or {}).get("kernels_ms_per_step"), (d.get("e2e") or {}).get("ms_per_step"), (d.get("cpu_baseline") or {}).get("value"))
