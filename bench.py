@@ -204,9 +204,10 @@ KERNEL_BYTES = {
     "hysteresis_bits": lambda N, K: 0,               # bit-planes only + a few promoted pixels
     "build_cells": lambda N, K: 0,
     "build_rgbcells": lambda N, K: 0,
+    "build_tables": lambda N, K: 0,
 }
 # stage grouping for the report: colour = image -> K masks, edge = K masks -> K edges (masks are not re-read)
-STAGES = {"color": ("build_cells", "build_rgbcells", "assign_bits", "label_open", "morph_bits", "assign", "onehot"),
+STAGES = {"color": ("build_cells", "build_rgbcells", "build_tables", "assign_bits", "label_open", "morph_bits", "assign", "onehot"),
           "edge": ("edge_runs", "edges3_bits", "hysteresis_bits", "morph", "blur", "canny_nms", "hyst_pass", "hyst_final")}
 
 

@@ -34,10 +34,11 @@
 
 // Per-warp shared memory.  Every lane stores ITS OWN window of a row (no cross-lane exchange is needed to
 // build the rows); the compacted candidate list lets any lane process any lane's candidates.
-struct __align__(16) E3WarpSmem {
+struct __align__(128) E3WarpSmem {
     u16 m[3][32 * E3V_LSTRIDE];           // ring of magnitude rows (fp16 bit patterns); lane region index i <-> window pixel e = i + 2
-    u16 dx[2][1024];                      // dx, dy of the lanes' own pixels, two rows alternating (fp16 bit patterns):
-    u16 dy[2][1024];                      // index = 32 * lane + pixel
+    u16 dx[2][1024];                      // dx, dy of the lanes' own pixels, two rows alternating (fp16 bit patterns): index =
+    u16 dy[2][1024];                      // 32 * lane + pixel, the 16-byte chunk of the pixel XOR-swizzled with bits 1, 2 of the lane
+                                          // (E3_DXY_SWZ): a quarter warp's 16-byte stores then cover all 32 banks
     u16 list[1024];                       // candidates of one row: (owner lane << 5) | pixel
     u32 cw[32], sw[32];                   // result words of the row being resolved
 };
@@ -97,6 +98,11 @@ __global__ void __launch_bounds__(E3V_WARPS * 32, 6) fk_edges3_simd(const __grid
     const int high_bits = (int)__half_as_ushort(__float2half_rn((float)highc));
     const __half2 k1024 = __floats2half2_rn(1024.f, 1024.f), k2 = __floats2half2_rn(2.f, 2.f);
     const int lreg = lane * E3V_LSTRIDE;                 // this lane's region (u16 units)
+#ifndef E3_NO_DXY_SWZ
+    const int dxy_off = 64 * lane, dxy_swz = (lane << 3) & 0x30;     // dx / dy rows: byte offset of the lane's region, chunk swizzle
+#else
+    const int dxy_off = 64 * lane, dxy_swz = 0;
+#endif
 
     // rows [y0, y1) of word column c of plane k (this lane's item); `nrows` is the warp-uniform row count of the item
     // (y1 <= y0 + nrows); lanes without an item run along with `active` false.
@@ -261,11 +267,11 @@ __global__ void __launch_bounds__(E3V_WARPS * 32, 6) fk_edges3_simd(const __grid
 #pragma unroll
                 for (int jj = 0; jj < 4; jj++) mv[jj] = make_uint4(mb[4 * jj], mb[4 * jj + 1], mb[4 * jj + 2], mb[4 * jj + 3]);
                 *reinterpret_cast<uint2 *>(mreg + 32) = make_uint2(mb[16], mb[17]);
-                uint4 *dxv = reinterpret_cast<uint4 *>(S.dx[rr & 1] + 32 * lane), *dyv = reinterpret_cast<uint4 *>(S.dy[rr & 1] + 32 * lane);
+                u8 *dxv = reinterpret_cast<u8 *>(S.dx[rr & 1]) + dxy_off, *dyv = reinterpret_cast<u8 *>(S.dy[rr & 1]) + dxy_off;
 #pragma unroll
                 for (int jj = 0; jj < 4; jj++) {
-                    dxv[jj] = make_uint4(dxb[1 + 4 * jj], dxb[2 + 4 * jj], dxb[3 + 4 * jj], dxb[4 + 4 * jj]);
-                    dyv[jj] = make_uint4(dyb[1 + 4 * jj], dyb[2 + 4 * jj], dyb[3 + 4 * jj], dyb[4 + 4 * jj]);
+                    *reinterpret_cast<uint4 *>(dxv + ((16 * jj) ^ dxy_swz)) = make_uint4(dxb[1 + 4 * jj], dxb[2 + 4 * jj], dxb[3 + 4 * jj], dxb[4 + 4 * jj]);
+                    *reinterpret_cast<uint4 *>(dyv + ((16 * jj) ^ dxy_swz)) = make_uint4(dyb[1 + 4 * jj], dyb[2 + 4 * jj], dyb[3 + 4 * jj], dyb[4 + 4 * jj]);
                 }
                 // the magnitude is 0 outside the image (only the pixels next to image pixels matter)
                 if (is_lb) mreg[1] = 0;                                   // pixel -1 (window e = 3)
@@ -293,7 +299,12 @@ __global__ void __launch_bounds__(E3V_WARPS * 32, 6) fk_edges3_simd(const __grid
                 const int m0 = pc[0];
                 // cv2.Canny's direction test  |dy| * 2^15 < |dx| * TG22  /  > |dx| * (TG22 + 2^16), TG22 = 13573, in float32:
                 // |dx|, |dy| <= 1020 are integers, so |dx| * 13573 < 2^24 and (|dy| - 2|dx|) * 2^15 are exact
-                const u32 dxb = dxr[item], dyb = dyr[item];
+#ifndef E3_NO_DXY_SWZ
+                const int si = item ^ ((item >> 3) & 0x18);                 // the writer's chunk swizzle (owner lane bits 1, 2)
+#else
+                const int si = item;
+#endif
+                const u32 dxb = dxr[si], dyb = dyr[si];
                 const float ax = fabsf(__half2float(__ushort_as_half((u16)dxb))), ay = fabsf(__half2float(__ushort_as_half((u16)dyb)));
                 const float tg = __fmul_rn(ax, 13573.f);
                 const bool hz = __fmul_rn(ay, 32768.f) < tg, vt = __fmul_rn(__fsub_rn(ay, __fadd_rn(ax, ax)), 32768.f) > tg;
@@ -332,7 +343,7 @@ __global__ void __launch_bounds__(E3V_WARPS * 32, 6) fk_edges3_simd(const __grid
             }
             // edge bytes for E = S; the hysteresis kernel patches the (rare) promoted weak pixels afterwards
             // (arithmetic bit->byte expansion: a 2 KB table would cost the 6th resident CTA per SM)
-            if (edges) store_word_bytes(edges + (size_t)k * estride + (size_t)rn * epitch, 32 * c, w, sw, aligned16 != 0);     // NULL: bit-planes only
+            if (edges) store_word_bytes(edges + (size_t)k * estride + (size_t)rn * epitch, 32 * c, w, sw, aligned16);     // NULL: bit-planes only
         }
         cand_prev = cand;
     };
@@ -489,7 +500,7 @@ __global__ void __launch_bounds__(ER_WARPS * 32) fk_edge_runs(const u32 *__restr
                 for (int y = j * ET_R; y < y1; y++) {
                     const size_t o = (size_t)k * plane + (size_t)y * ws + c;
                     cbits[o] = 0u; sbits[o] = 0u;
-                    if (edges) store_word_bytes(edges + (size_t)k * estride + (size_t)y * epitch, 32 * c, w, 0u, aligned16 != 0);
+                    if (edges) store_word_bytes(edges + (size_t)k * estride + (size_t)y * epitch, 32 * c, w, 0u, aligned16);
                 }
             }
         }

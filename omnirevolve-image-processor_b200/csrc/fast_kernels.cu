@@ -736,7 +736,7 @@ __global__ void __launch_bounds__(256) fk_expand_bits(const u32 *__restrict__ bi
     for (long long u = (long long)blockIdx.x * blockDim.x + threadIdx.x; u < total; u += (long long)gridDim.x * blockDim.x) {
         const int y = (int)(u / ww), c = (int)(u - (long long)y * ww);
         u32 word = bits[(size_t)k * plane + (size_t)y * ws + c];
-        store_word_bytes(out + (size_t)k * ostride + (size_t)y * opitch, c * 32, w, word, aligned16 != 0);
+        store_word_bytes(out + (size_t)k * ostride + (size_t)y * opitch, c * 32, w, word, aligned16);
     }
 }
 
@@ -818,7 +818,7 @@ __global__ void __launch_bounds__(128, MORPH_MINB) fk_morph(const u32 *__restric
             const int r = t - TAP;
             if (r >= y0 && r < y1 && active) {
                 u32 word = (tap.lo >> 16) | (tap.hi << 16);
-                store_word_bytes_lut(masks + (size_t)k * mstride + (size_t)r * mpitch, 32 * c, w, word, aligned16 != 0, s_lut8);
+                store_word_bytes_lut(masks + (size_t)k * mstride + (size_t)r * mpitch, 32 * c, w, word, aligned16, s_lut8);
             }
         }
         const int r = t - N;
@@ -874,7 +874,7 @@ __global__ void __launch_bounds__(128, MORPH_MINB) fk_morph(const u32 *__restric
                     for (int y = ty0; y < ty1; y++) {
                         const size_t o = (size_t)k * plane + (size_t)y * ws + c;
                         R.cbits[o] = 0u; R.sbits[o] = 0u;
-                        if (R.edges) store_word_bytes(R.edges + (size_t)k * R.estride + (size_t)y * R.epitch, 32 * c, w, 0u, R.aligned16 != 0);
+                        if (R.edges) store_word_bytes(R.edges + (size_t)k * R.estride + (size_t)y * R.epitch, 32 * c, w, 0u, R.aligned16);
                     }
                 }
             }
@@ -915,7 +915,7 @@ static cudaError_t launch_morph(bool with02, int morph03, const u32 *in_bits, u3
     if (warps_at(MORPH_TR_BIG) >= MORPH_BIG_MIN_WARPS && (y_lo % MORPH_TR_BIG) == 0) tr = MORPH_TR_BIG;
     else if (warps_at(MORPH_TR_MID) >= MORPH_MID_MIN_WARPS && (y_lo % MORPH_TR_MID) == 0) tr = MORPH_TR_MID;
     dim3 b(128), grid((g.ww + 127) / 128, (y_hi - y_lo + tr - 1) / tr, K);
-    int al = masks && ((uintptr_t)masks % 16 == 0) && (mstride % 16 == 0) && (mpitch % 16 == 0);
+    int al = plane_align(masks, mstride, mpitch);
     MorphRuns R{};
     if (runs) R = *runs;
 #define LM2(CODE, TAP, RUNS, TR) fk_morph<CODE, TAP, RUNS, TR><<<grid, b, 0, st>>>(in_bits, out_bits, g.ws, g.plane, g.h, g.w, masks, mstride, mpitch, al, y_lo, y_hi, R)
@@ -1303,7 +1303,7 @@ int fast_layer_masks(omni_ctx *ctx, const u8 *d_labels, int h, int w, size_t lpi
         fk_labels_to_bits<<<persist_blocks(ctx, 8), 256, 0, st>>>(d_labels, h, w, lpitch, K, bp[0], g.ws, g.plane);
         OMNI_CUDA(cudaGetLastError());
     }
-    int al = ((uintptr_t)d_masks % 16 == 0) && (plane_stride % 16 == 0) && (mpitch % 16 == 0);
+    int al = plane_align(d_masks, plane_stride, mpitch);
     if (open_iters == 1 && close_iters == 1) {
         OMNI_LAUNCH(ctx, st, "morph_bits", launch_morph(true, 0, bp[0], nullptr, g, K, d_masks, plane_stride, mpitch, st));
     } else {
@@ -1354,7 +1354,7 @@ int fast_morph03_bytes(omni_ctx *ctx, const u8 *d_masks, int K, int h, int w, si
         OMNI_LAUNCH(ctx, st, "morph_bits", launch_morph(false, kind, bpp[0], bpp[1], g, K, nullptr, 0, 0, st));
         m2 = bpp[1];
     }
-    int al = ((uintptr_t)d_out % 16 == 0) && (o_plane % 16 == 0) && (opitch % 16 == 0);
+    int al = plane_align(d_out, o_plane, opitch);
     KScope ks(ctx, "expand_bits", st);
     fk_expand_bits<<<dim3(persist_blocks(ctx, 4), K), 256, 0, st>>>(m2, g.ws, g.plane, h, w, d_out, o_plane, opitch, al);
     OMNI_CUDA(cudaGetLastError());
@@ -1396,7 +1396,7 @@ int edge_pass_begin(omni_ctx *ctx, const BitGeom &g, int K, u32 *sbits, u32 *cbi
     if (ctx->e3s_per_sm == 0) ctx->e3s_per_sm = edges3_sparse_blocks_per_sm();
     FK_TRY(omni_ws_reserve(ctx, 6, edges3_run_words(g.h, g.w, K, R->off.v) * sizeof(u32)));
     R->sbits = sbits; R->cbits = cbits; R->edges = d_edges; R->estride = e_plane; R->epitch = epitch;
-    R->aligned16 = ((uintptr_t)d_edges % 16 == 0) && (e_plane % 16 == 0) && (epitch % 16 == 0);
+    R->aligned16 = plane_align(d_edges, e_plane, epitch);
     R->run_counts = ctx->d_flags + 16; R->run_items = (u32 *)ctx->ws[6];
     R->maxt = edges3_pick_maxt(g.h, g.w, K, 2 * persist_blocks(ctx, ctx->e3s_per_sm));
     R->zero_fill = side_fill ? 0 : 1;
@@ -1434,7 +1434,7 @@ static int edges_from_bits(omni_ctx *ctx, const u32 *m2, u32 *sbits, u32 *cbits,
                            u8 *d_edges, size_t e_plane, size_t epitch, cudaStream_t st, bool sparse, bool runs_done,
                            const u8 *blur = nullptr /* edge_kernel_size 5 / 7: the blurred planes */, size_t bstride = 0, size_t bpitch = 0)
 {
-    int al = ((uintptr_t)d_edges % 16 == 0) && (e_plane % 16 == 0) && (epitch % 16 == 0);
+    int al = plane_align(d_edges, e_plane, epitch);
     if (ctx->edge_join) {                               // the side stream has cleared the output planes
         OMNI_CUDA(cudaStreamWaitEvent(st, ctx->edge_join, 0));
         ctx->edge_join = nullptr;
@@ -1842,7 +1842,7 @@ int fast_thin(omni_ctx *ctx, const u8 *d_in, int K, int h, int w, size_t in_plan
     BitGeom g = make_geom(h, w);
     u32 *bpp[2];
     FK_TRY(bit_planes(ctx, g, K, 2, bpp));
-    int al = ((uintptr_t)d_out % 16 == 0) && (out_plane % 16 == 0) && (out_pitch % 16 == 0);
+    int al = plane_align(d_out, out_plane, out_pitch);
     if (max_iter < 0) max_iter = 0;
     const size_t n_rem = (size_t)K * (max_iter > 0 ? max_iter : 1);
     if (ctx->thin_blocks == 0) {

@@ -34,62 +34,85 @@
 // cell i lives in byte (i & 0x1FFFF), high nibble when i >= 2^17; K == 16 has a separate "several candidates" bit per cell.
 // The pruning rule is fk_build_rgbcells' (fast_kernels.cu): exact Lab box of the cell, dmin <= min dmax + 2.
 // ------------------------------------------------------------------------------------------------
-// the Lab boxes of fk_rgb_boxes (B slowest) re-ordered to this index layout, once per context: the table build then reads them
-// with consecutive threads on consecutive cells
-__global__ void __launch_bounds__(256) fk_permute_boxes3(const u8 *__restrict__ boxes, u8 *__restrict__ boxes3)
+// the Lab boxes of fk_rgb_boxes (B slowest) re-ordered to this index layout, 8 bytes per cell (min L, a, b, max L, a, b, 0, 0), once
+// per context: the table build then reads them with consecutive threads on consecutive cells, one 8-byte load per cell
+__global__ void __launch_bounds__(256) fk_permute_boxes3(const u8 *__restrict__ boxes, uint2 *__restrict__ boxes3)
 {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= RC_COUNT) return;
     const int ci = ((idx & 63) << 12) | (((idx >> 6) & 63) << 6) | (idx >> 12);
-#pragma unroll
-    for (int d = 0; d < 6; d++) boxes3[6 * idx + d] = boxes[6 * ci + d];
+    const u8 *q = boxes + 6 * ci;
+    boxes3[idx] = make_uint2((u32)q[0] | ((u32)q[1] << 8) | ((u32)q[2] << 16) | ((u32)q[3] << 24), (u32)q[4] | ((u32)q[5] << 8));
 }
 
-__global__ void __launch_bounds__(256) fk_build_rgbcells3(const __grid_constant__ AssignParams P, const u8 *__restrict__ boxes3,
-                                                          u8 *__restrict__ nb, u32 *__restrict__ mb)
+// candidate set of a box [lo, hi]^3 (fk_build_cells' rule): centres k with dmin_k <= min_j dmax_j + 2
+__device__ __forceinline__ u32 lp_candidates(const AssignParams &P, const float (&lo)[3], const float (&hi)[3], bool &sane)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;                // < 2^17
     const int K = P.K;
+    float U = 3.0e38f;
+    sane = true;
+    for (int k = 0; k < K; k++) {
+        float dmax = 0.f;
+#pragma unroll
+        for (int d = 0; d < 3; d++) {
+            const float c = P.c[3 * k + d];
+            sane = sane && (fabsf(c) < 1.0e4f);                 // also false for NaN
+            const float m = fmaxf(fabsf(lo[d] - c), fabsf(hi[d] - c));
+            dmax += m * m;
+        }
+        U = fminf(U, dmax);
+    }
+    u32 mask = 0u;
+    for (int k = 0; k < K; k++) {
+        float dmin = 0.f;
+#pragma unroll
+        for (int d = 0; d < 3; d++) {
+            const float c = P.c[3 * k + d];
+            const float n = fminf(fmaxf(c, lo[d]), hi[d]);
+            dmin += (n - c) * (n - c);
+        }
+        if (dmin <= U + 2.0f) mask |= 1u << k;
+    }
+    return mask;
+}
+
+// Both candidate tables of a centre set in ONE launch: blocks [0, 512) the RGB-cell tables (a thread = the cells c and c + 2^17 that
+// share a label byte), blocks [512, 640) the Lab-cell table of fk_build_cells (bit sets; same rule, same arithmetic).
+#define LP_RGB_BLOCKS ((1 << 17) / 256)
+#define LP_TAB_BLOCKS (LP_RGB_BLOCKS + CELL_COUNT / 256)
+__global__ void __launch_bounds__(256) fk_build_tables3(const __grid_constant__ AssignParams P, const uint2 *__restrict__ boxes3,
+                                                        u8 *__restrict__ nb, u32 *__restrict__ mb, u32 *__restrict__ cells)
+{
+    const int K = P.K;
+    if (blockIdx.x >= LP_RGB_BLOCKS) {
+        const int ci = (blockIdx.x - LP_RGB_BLOCKS) * 256 + threadIdx.x;
+        const float lo[3] = {(float)((ci >> (2 * 5)) << CELL_SHIFT), (float)(((ci >> 5) & 31) << CELL_SHIFT), (float)((ci & 31) << CELL_SHIFT)};
+        const float span = (float)((1 << CELL_SHIFT) - 1);
+        const float hi[3] = {lo[0] + span, lo[1] + span, lo[2] + span};
+        bool sane;
+        u32 mask = lp_candidates(P, lo, hi, sane);
+        if (!sane || mask == 0u) mask = K >= 32 ? 0xffffffffu : ((1u << K) - 1u);
+        cells[ci] = mask;
+        return;
+    }
+    const u32 cell = blockIdx.x * 256 + threadIdx.x;                    // < 2^17
     u32 byte = 0u;
     bool multi[2];
 #pragma unroll
     for (int hs = 0; hs < 2; hs++) {
-        const int idx = i + (hs << 17);
-        float lo[3], hi[3];
-#pragma unroll
-        for (int d = 0; d < 3; d++) { lo[d] = (float)boxes3[6 * idx + d]; hi[d] = (float)boxes3[6 * idx + 3 + d]; }
-        float U = 3.0e38f;
-        bool sane = true;
-        for (int k = 0; k < K; k++) {
-            float dmax = 0.f;
-#pragma unroll
-            for (int d = 0; d < 3; d++) {
-                float c = P.c[3 * k + d];
-                sane = sane && (fabsf(c) < 1.0e4f);                 // also false for NaN
-                float m = fmaxf(fabsf(lo[d] - c), fabsf(hi[d] - c));
-                dmax += m * m;
-            }
-            U = fminf(U, dmax);
-        }
-        u32 mask = 0u;
-        for (int k = 0; k < K; k++) {
-            float dmin = 0.f;
-#pragma unroll
-            for (int d = 0; d < 3; d++) {
-                float c = P.c[3 * k + d];
-                float n = fminf(fmaxf(c, lo[d]), hi[d]);
-                dmin += (n - c) * (n - c);
-            }
-            if (dmin <= U + 2.0f) mask |= 1u << k;
-        }
+        const uint2 bx = __ldg(boxes3 + cell + ((u32)hs << 17));
+        const float lo[3] = {(float)(bx.x & 255u), (float)((bx.x >> 8) & 255u), (float)((bx.x >> 16) & 255u)};
+        const float hi[3] = {(float)(bx.x >> 24), (float)(bx.y & 255u), (float)((bx.y >> 8) & 255u)};
+        bool sane;
+        const u32 mask = lp_candidates(P, lo, hi, sane);
         const bool single = sane && mask != 0u && (mask & (mask - 1u)) == 0u;
         multi[hs] = !single;
         const u32 nib = single ? (u32)(P.lut[__ffs(mask) - 1] & 15u) : (K < 16 ? 15u : 0u);
         byte |= nib << (4 * hs);
     }
-    nb[i] = (u8)byte;
+    nb[cell] = (u8)byte;
     const u32 b0 = __ballot_sync(0xffffffffu, multi[0]), b1 = __ballot_sync(0xffffffffu, multi[1]);
-    if ((threadIdx.x & 31) == 0) { mb[i >> 5] = b0; mb[(i + (1 << 17)) >> 5] = b1; }
+    if ((threadIdx.x & 31) == 0) { mb[cell >> 5] = b0; mb[(cell >> 5) + (1u << 12)] = b1; }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -509,7 +532,7 @@ __global__ void __launch_bounds__(128, ML_MINB) fk_morph_lab(const uint4 *__rest
             {
                 const int r = t - TAP;
                 if (r >= y0 && r < y1 && owned) {
-                    if (masks) store_word_bytes_lut(mrow, 32 * c, w, tap, aligned16 != 0, s_lut8);
+                    if (masks) store_word_bytes_lut(mrow, 32 * c, w, tap, aligned16, s_lut8);
                     if (tap_bits) *trow = tap & colvalid;
                 }
                 mrow += mpitch; trow += ws;
@@ -559,7 +582,7 @@ __global__ void __launch_bounds__(128, ML_MINB) fk_morph_lab(const uint4 *__rest
                 for (int y = ty0; y < ty1; y++) {
                     const size_t o = (size_t)p * plane + (size_t)y * ws + c;
                     R.cbits[o] = 0u; R.sbits[o] = 0u;
-                    if (R.edges) store_word_bytes(R.edges + (size_t)p * R.estride + (size_t)y * R.epitch, 32 * c, w, 0u, R.aligned16 != 0);
+                    if (R.edges) store_word_bytes(R.edges + (size_t)p * R.estride + (size_t)y * R.epitch, 32 * c, w, 0u, R.aligned16);
                 }
             }
         }
@@ -603,16 +626,15 @@ static int label_tables(omni_ctx *ctx, const AssignParams &P, u32 **cells, u8 **
     memcpy(ctx->cells3_c, P.c, sizeof(float) * 3 * P.K);
     memcpy(ctx->cells3_lut, P.lut, P.K);
     ctx->cells3_K = P.K; ctx->cells3_stream = (void *)st; ctx->cells3_valid = 1; ctx->cells3_ws = ctx->ws[5];
-    OMNI_LAUNCH(ctx, st, "build_cells", launch_build_cells(P, *cells, st));
     if (!ctx->d_rgb_boxes3) {                          // centre-independent: once per context
         SP_TRY(fast_rgb_boxes(ctx, st));
-        OMNI_CUDA(cudaMalloc(&ctx->d_rgb_boxes3, (size_t)RC_COUNT * 6));
+        OMNI_CUDA(cudaMalloc(&ctx->d_rgb_boxes3, (size_t)RC_COUNT * sizeof(uint2)));
         KScope ks(ctx, "rgb_boxes", st);
-        fk_permute_boxes3<<<RC_COUNT / 256, 256, 0, st>>>(ctx->d_rgb_boxes, ctx->d_rgb_boxes3);
+        fk_permute_boxes3<<<RC_COUNT / 256, 256, 0, st>>>(ctx->d_rgb_boxes, (uint2 *)ctx->d_rgb_boxes3);
         OMNI_CUDA(cudaGetLastError());
     }
-    KScope ks(ctx, "build_rgbcells", st);
-    fk_build_rgbcells3<<<(1 << 17) / 256, 256, 0, st>>>(P, ctx->d_rgb_boxes3, *rtab, (u32 *)(*rtab + RC_NIB_BYTES));
+    KScope ks(ctx, "build_tables", st);
+    fk_build_tables3<<<LP_TAB_BLOCKS, 256, 0, st>>>(P, (const uint2 *)ctx->d_rgb_boxes3, *rtab, (u32 *)(*rtab + RC_NIB_BYTES), *cells);
     OMNI_CUDA(cudaGetLastError());
     return OMNI_OK;
 }
@@ -626,7 +648,7 @@ static cudaError_t launch_morph_lab(int kind /* -1: masks only */, const uint4 *
                                     u8 *masks, size_t mstride, size_t mpitch, u32 *tap_bits, const MorphRuns &R, cudaStream_t st)
 {
     const int wcols = (g.ww + LP_COLS - 1) / LP_COLS;
-    const int al = masks && ((uintptr_t)masks % 16 == 0) && (mstride % 16 == 0) && (mpitch % 16 == 0);
+    const int al = plane_align(masks, mstride, mpitch);
     // taller strips (less halo work) once there are plenty of warps
     const long long warps64 = (long long)wcols * ((g.h + 63) / 64) * KT;
 #ifdef ML_TR
@@ -730,7 +752,7 @@ static int label_pipeline(omni_ctx *ctx, const u8 *d_bgr, int nf, size_t frame_s
         OMNI_CUDA(cudaStreamWaitEvent(st, ctx->edge_join, 0));
         ctx->edge_join = nullptr;
     }
-    const int al16 = d_edges && ((uintptr_t)d_edges % 16 == 0) && (e_plane % 16 == 0) && (epitch % 16 == 0);
+    const int al16 = plane_align(d_edges, e_plane, epitch);
     OMNI_LAUNCH(ctx, st, "edges3_bits", launch_edges3_sparse(M2, g.ws, g.plane, h, w, KT, low, high, persist_blocks(ctx, ctx->e3s_per_sm),
                                                              sbits, cbits, d_edges, e_plane, epitch, al16, ctx->d_flags + 4,
                                                              (u32 *)ctx->ws[5] + HYST_WL_OFFSET, HY_WL_CAP, ctx->d_flags + 16,

@@ -155,6 +155,13 @@ cudaError_t g_pack_bytes(const u8 *src, size_t s_plane, size_t spitch, int K, in
 cudaError_t g_copy2d_planes(const u8 *src, size_t s_plane, size_t spitch, u8 *dst, size_t d_plane, size_t dpitch,
                             int K, int h, int w, cudaStream_t st);
 
+// alignment class of a set of byte planes for the 32-pixel stores: 2 = base, plane stride and pitch are multiples of 32, 1 = of 16
+static inline int plane_align(const void *base, size_t plane, size_t pitch)
+{
+    const size_t v = (size_t)(uintptr_t)base | plane | pitch;
+    return base == nullptr ? 0 : (v % 32 == 0) ? 2 : (v % 16 == 0) ? 1 : 0;
+}
+
 #ifdef __CUDACC__
 // bits i of a 32-bit word whose pixel (start_px + i) lies in [0, w)
 __device__ __forceinline__ u32 range_mask(int start_px, int w)
@@ -171,17 +178,32 @@ __device__ __forceinline__ u32 expand4(u32 nib)
     return ((nib * 0x00204081u) & 0x01010101u) * 255u;
 }
 
-// store 32 pixels (bits of `word`) as 0/255 bytes at dst (pixel x0 = first), only pixels < w
-__device__ __forceinline__ void store_word_bytes(u8 *row, int x0, int w, u32 word, bool aligned16)
+// one 32-byte store (sm_100: STG.256): a lane writes a whole sector, a warp of adjacent lanes one contiguous run
+__device__ __forceinline__ void st_global_256(void *p, const uint4 a, const uint4 b)
 {
-    if (x0 + 32 <= w && aligned16) {
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y),
+                 "r"(b.z), "r"(b.w) : "memory");
+}
+__device__ __forceinline__ void store_32bytes(u8 *dst, const uint4 a, const uint4 b, int align)
+{
+#ifndef OMNI_NO_ST256
+    if (align == 2) { st_global_256(dst, a, b); return; }
+#endif
+    uint4 *p = reinterpret_cast<uint4 *>(dst);
+    p[0] = a; p[1] = b;
+}
+
+// store 32 pixels (bits of `word`) as 0/255 bytes at dst (pixel x0 = first), only pixels < w.
+// align (host: plane_align()): 0 = byte stores, 1 = rows / planes 16-byte aligned, 2 = 32-byte aligned
+__device__ __forceinline__ void store_word_bytes(u8 *row, int x0, int w, u32 word, int align)
+{
+    if (x0 + 32 <= w && align) {
         uint4 a, b;
         a.x = expand4(word & 15u);         a.y = expand4((word >> 4) & 15u);
         a.z = expand4((word >> 8) & 15u);  a.w = expand4((word >> 12) & 15u);
         b.x = expand4((word >> 16) & 15u); b.y = expand4((word >> 20) & 15u);
         b.z = expand4((word >> 24) & 15u); b.w = expand4(word >> 28);
-        uint4 *p = reinterpret_cast<uint4 *>(row + x0);
-        p[0] = a; p[1] = b;
+        store_32bytes(row + x0, a, b, align);
     } else {
         int n = min(32, w - x0);
         for (int i = 0; i < n; i++) row[x0 + i] = (word >> i) & 1u ? 255 : 0;
@@ -193,13 +215,11 @@ __device__ __forceinline__ void expand_lut_init(uint2 *lut8, int tid, int nthrea
 {
     for (int b = tid; b < 256; b += nthreads) lut8[b] = make_uint2(expand4(b & 15u), expand4((u32)b >> 4));
 }
-__device__ __forceinline__ void store_word_bytes_lut(u8 *row, int x0, int w, u32 word, bool aligned16, const uint2 *lut8)
+__device__ __forceinline__ void store_word_bytes_lut(u8 *row, int x0, int w, u32 word, int align, const uint2 *lut8)
 {
-    if (x0 + 32 <= w && aligned16) {
+    if (x0 + 32 <= w && align) {
         const uint2 a = lut8[word & 255u], b = lut8[(word >> 8) & 255u], c = lut8[(word >> 16) & 255u], d = lut8[word >> 24];
-        uint4 *p = reinterpret_cast<uint4 *>(row + x0);
-        p[0] = make_uint4(a.x, a.y, b.x, b.y);
-        p[1] = make_uint4(c.x, c.y, d.x, d.y);
+        store_32bytes(row + x0, make_uint4(a.x, a.y, b.x, b.y), make_uint4(c.x, c.y, d.x, d.y), align);
     } else {
         int n = min(32, w - x0);
         for (int i = 0; i < n; i++) row[x0 + i] = (word >> i) & 1u ? 255 : 0;

@@ -123,11 +123,14 @@ def test_stage_error_behaviour(tmp_path):
 
 def test_assign_labels_dropin():
     sys.path.insert(0, SCRIPTS)
-    import process_colors_gpu
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("dropin_process_colors", os.path.join(SCRIPTS, "process_colors.py"))
+    pc = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(pc)
     from helpers import GOLDEN
     z = np.load(f"{GOLDEN}/functions.npz")
     for K in (2, 4, 8, 16):
-        assert np.array_equal(process_colors_gpu.assign_labels(z["al_img"], z[f"al_pal{K}"]), z[f"al_lab{K}"])
+        assert np.array_equal(pc.assign_labels(z["al_img"], z[f"al_pal{K}"]), z[f"al_lab{K}"])
 
 
 def test_stage04_shim_swaps_only_the_thinning(tmp_path):
