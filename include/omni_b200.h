@@ -72,6 +72,17 @@ int omni_set_fast_path(omni_ctx *ctx, int enable);
  * (default, enable != 0: frames of a video share one centre set).  enable == 0 rebuilds them on every
  * call -- what a stream of single images with their own k-means centres pays. */
 int omni_set_table_cache(omni_ctx *ctx, int enable);
+/* Workspaces.  The ctx owns its device scratch and grows it on demand (cudaFree + cudaMalloc inside the call that needs more).
+ * omni_workspace_bytes: device bytes the fused device-resident calls (omni_color_edge, omni_color_edge_batch,
+ * omni_color_edge_packed) allocate for n_frames frames of h x w pixels with K colours and edge_kernel_size ksize (0 for bad
+ * arguments).  omni_ctx_reserve: allocates them now, builds the centre-independent tables and waits for that -- afterwards calls
+ * of this geometry (or a smaller one) on this ctx only enqueue work: no allocation, no implicit synchronisation. */
+size_t omni_workspace_bytes(int h, int w, int K, int ksize, int n_frames);
+int omni_ctx_reserve(omni_ctx *ctx, int h, int w, int K, int ksize, int n_frames);
+/* omni_edges / omni_host_edges check on the device that the masks are strictly {0,255} (hand-edited mask.png files need not be)
+ * and wait for the answer before they choose the kernels.  enable = 1: the caller vouches for {0,255} masks (e.g. planes written
+ * by omni_layer_masks): the check is skipped and omni_edges only enqueues; other mask values then give undefined edges. */
+int omni_set_assume_binary_masks(omni_ctx *ctx, int enable);
 int omni_ctx_create(int device, omni_ctx **out);
 int omni_ctx_destroy(omni_ctx *ctx);
 /* Pinned host memory for the omni_host_* entry points (pageable memory works, but is slower). */

@@ -2,6 +2,7 @@
 #include <stdlib.h>
 #include "omni_internal.cuh"
 #include "fast_kernels.cuh"
+#include "fast_device.cuh"
 
 #include <math.h>
 #include <stdarg.h>
@@ -96,6 +97,13 @@ extern "C" int omni_set_fast_path(omni_ctx *ctx, int enable)
         ctx->edge_sparse = ctx->assign_rgbcell = (enable == 2) ? 0 : 1;
         ctx->pipeline = (enable == 1) ? 1 : 0;
     }
+    return OMNI_OK;
+}
+
+extern "C" int omni_set_assume_binary_masks(omni_ctx *ctx, int enable)
+{
+    OMNI_REQUIRE(ctx != nullptr, "omni_set_assume_binary_masks: ctx is NULL");
+    ctx->assume_binary = enable ? 1 : 0;
     return OMNI_OK;
 }
 
@@ -295,6 +303,40 @@ static int set_device(omni_ctx *ctx)
 }
 #define OMNI_TRY(expr) do { int rc__ = (expr); if (rc__ != OMNI_OK) return rc__; } while (0)
 
+// slots the fused device-resident calls use for this geometry, before the growth slack of omni_ws_reserve
+static void fused_ws_plan(int h, int w, int K, int ksize, int nf, size_t out[OMNI_WS_SLOTS])
+{
+    for (int i = 0; i < OMNI_WS_SLOTS; i++) out[i] = 0;
+    label_ws_bytes(h, w, K, nf, out);
+    dense_ws_bytes(h, w, K, nf, ksize, out);
+}
+
+extern "C" size_t omni_workspace_bytes(int h, int w, int K, int ksize, int n_frames)
+{
+    if (h <= 0 || w <= 0 || K < 1 || K > OMNI_MAX_K || n_frames < 1 || n_frames * K > OMNI_MAX_K) return 0;
+    size_t plan[OMNI_WS_SLOTS], total = 0;
+    fused_ws_plan(h, w, K, ksize, n_frames, plan);
+    for (int i = 0; i < OMNI_WS_SLOTS; i++) total += plan[i] + plan[i] / 8;
+    return total;
+}
+
+extern "C" int omni_ctx_reserve(omni_ctx *ctx, int h, int w, int K, int ksize, int n_frames)
+{
+    OMNI_TRY(set_device(ctx));
+    OMNI_REQUIRE(h > 0 && w > 0 && K >= 1 && K <= OMNI_MAX_K && n_frames >= 1 && n_frames * K <= OMNI_MAX_K,
+                 "omni_ctx_reserve: bad geometry (%d x %d, K=%d, %d frames)", w, h, K, n_frames);
+    size_t plan[OMNI_WS_SLOTS];
+    fused_ws_plan(h, w, K, ksize, n_frames, plan);
+    for (int i = 0; i < OMNI_WS_SLOTS; i++)
+        if (plan[i]) OMNI_TRY(omni_ws_reserve(ctx, i, plan[i]));
+    // one-time objects of the fused path: constant tables, the centre-independent RGB-cell boxes
+    OMNI_CUDA(fast_tables());
+    OMNI_TRY(fast_rgb_boxes(ctx, ctx->stream));
+    OMNI_CUDA(cudaStreamSynchronize(ctx->stream));
+    return OMNI_OK;
+}
+
+
 // ---- stage 01 ----------------------------------------------------------------------------------------
 extern "C" int omni_resize_area_u8c3(omni_ctx *ctx, const uint8_t *d_src, int sh, int sw, size_t spitch,
                                      uint8_t *d_dst, int dh, int dw, size_t dpitch, void *stream)
@@ -317,7 +359,14 @@ extern "C" int omni_resize_area_u8c3(omni_ctx *ctx, const uint8_t *d_src, int sh
         const ResizeTab *t = omni_get_resize_tab(ctx, sh, sw, dh, dw, st);
         if (!t) { omni_set_error("omni_resize_area_u8c3: cannot build resize tables"); return OMNI_ERR_NOMEM; }
         bool done = false;
-        if (ctx->fast) {
+        if (ctx->fast == 1 && ctx->pipeline == 1) {    // default family: TMA-staged separable kernel
+            KScope ks(ctx, "resize_frac_tma", st);
+            cudaError_t e = tma_resize_frac(d_src, sh, sw, spitch, d_dst, dh, dw, dpitch, &t->dev, st);
+            if (e == cudaSuccess) done = true;
+            else if (e != cudaErrorNotSupported) OMNI_CUDA(e);
+            else ctx->launches--;                      // nothing was launched
+        }
+        if (!done && ctx->fast) {
             KScope ks(ctx, "resize_frac_v", st);
             cudaError_t e = fast_resize_frac(d_src, sh, sw, spitch, d_dst, dh, dw, dpitch, &t->dev, st);
             if (e == cudaSuccess) done = true;

@@ -1183,6 +1183,21 @@ static int bit_planes(omni_ctx *ctx, const BitGeom &g, int K, int n, u32 **out /
     return OMNI_OK;
 }
 
+// workspace of the dense generation of the fused call (bit_planes: four plane sets in slot 4; blurred byte planes of
+// edge_kernel_size 5 / 7 in slot 0; tables in slot 5; run lists in slot 6; a label plane in slot 2 when the caller passes none)
+void dense_ws_bytes(int h, int w, int K, int nf, int ksize, size_t out[OMNI_WS_SLOTS])
+{
+    const BitGeom g = make_geom(h, w);
+    const int KT = nf * K;
+    size_t one = (g.plane * (size_t)KT * sizeof(u32) + 255) & ~(size_t)255;
+    unsigned off[ET_MAXT];
+    out[4] = std::max(out[4], one * 4);
+    out[5] = std::max(out[5], WS5_BYTES);
+    out[6] = std::max(out[6], edges3_run_words(h, w, KT, off) * sizeof(u32));
+    out[2] = std::max(out[2], (((size_t)w + 15) & ~(size_t)15) * h);
+    if (ksize != 3) out[0] = std::max(out[0], (((size_t)w + 15) & ~(size_t)15) * h * KT);
+}
+
 // the RGB-cell tables hold output labels in 4 bits (15 = "several candidates" when K <= 15): every label must be < K
 bool lut_below_k(const AssignParams &P)
 {
@@ -1345,9 +1360,11 @@ int fast_morph03_bytes(omni_ctx *ctx, const u8 *d_masks, int K, int h, int w, si
                                                                          ctx->d_flags + 8);
         OMNI_CUDA(cudaGetLastError());
     }
-    OMNI_CUDA(cudaMemcpyAsync(ctx->h_flags + 8, ctx->d_flags + 8, sizeof(int), cudaMemcpyDeviceToHost, st));
-    OMNI_CUDA(cudaStreamSynchronize(st));
-    if (ctx->h_flags[8]) return OMNI_ERR_UNSUPPORTED;     // not a {0,255} mask
+    if (!ctx->assume_binary) {                            // (omni_set_assume_binary_masks: the caller vouches, nothing to wait for)
+        OMNI_CUDA(cudaMemcpyAsync(ctx->h_flags + 8, ctx->d_flags + 8, sizeof(int), cudaMemcpyDeviceToHost, st));
+        OMNI_CUDA(cudaStreamSynchronize(st));
+        if (ctx->h_flags[8]) return OMNI_ERR_UNSUPPORTED;     // not a {0,255} mask
+    }
     const int kind = morph03_kind(prm);
     const u32 *m2 = bpp[0];
     if (kind > 0) {
@@ -1471,9 +1488,11 @@ int fast_edges(omni_ctx *ctx, const u8 *d_masks, int K, int h, int w, size_t m_p
                                                                          ctx->d_flags + 8);
         OMNI_CUDA(cudaGetLastError());
     }
-    OMNI_CUDA(cudaMemcpyAsync(ctx->h_flags + 8, ctx->d_flags + 8, sizeof(int), cudaMemcpyDeviceToHost, st));
-    OMNI_CUDA(cudaStreamSynchronize(st));
-    if (ctx->h_flags[8]) return OMNI_ERR_UNSUPPORTED;     // not a {0,255} mask
+    if (!ctx->assume_binary) {                            // (omni_set_assume_binary_masks: the caller vouches, nothing to wait for)
+        OMNI_CUDA(cudaMemcpyAsync(ctx->h_flags + 8, ctx->d_flags + 8, sizeof(int), cudaMemcpyDeviceToHost, st));
+        OMNI_CUDA(cudaStreamSynchronize(st));
+        if (ctx->h_flags[8]) return OMNI_ERR_UNSUPPORTED;     // not a {0,255} mask
+    }
     int kind = morph03_kind(prm);
     const u32 *m2 = bpp[0];
     MorphRuns R{};

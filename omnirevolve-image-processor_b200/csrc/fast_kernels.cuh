@@ -11,6 +11,11 @@ cudaError_t fast_resize_2x(const u8 *src, size_t spitch, u8 *dst, int dh, int dw
 cudaError_t fast_resize_frac(const u8 *src, int sh, int sw, size_t spitch, u8 *dst, int dh, int dw, size_t dpitch, const ResizeTabDev *tab,
                              cudaStream_t st);
 
+// the same with the source rectangle staged by one TMA bulk-tensor copy and the separable two-pass form (resize_tma.cu);
+// cudaErrorNotSupported when the geometry is outside it (rows not 16-byte aligned / not a whole number of words, large ratios)
+cudaError_t tma_resize_frac(const u8 *src, int sh, int sw, size_t spitch, u8 *dst, int dh, int dw, size_t dpitch, const ResizeTabDev *tab,
+                            cudaStream_t st);
+
 cudaError_t fast_assign(omni_ctx *ctx, const u8 *px, int h, int w, size_t pitch, const AssignParams &P, int mode_lab,
                         u8 *labels, size_t lpitch, cudaStream_t st);
 

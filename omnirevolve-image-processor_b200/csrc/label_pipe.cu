@@ -696,7 +696,7 @@ static int label_pipeline(omni_ctx *ctx, const u8 *d_bgr, int nf, size_t frame_s
     auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
     const size_t o_sl = 0, o_od = al(o_sl + pbytes * 4 * nf), o_m2 = al(o_od + pbytes * nf), o_s = al(o_m2 + pbytes * KT),
                  o_c = o_s + al(pbytes * KT), o_mb = al(o_c + pbytes * KT), bits_total = al(o_mb + (want_mask_bits ? pbytes * KT : 0));
-    SP_TRY(omni_ws_reserve(ctx, 4, bits_total));
+    SP_TRY(omni_ws_reserve(ctx, 4, bits_total));           // (label_ws_bytes() below states the same sizes for omni_workspace_bytes)
     u8 *b4 = (u8 *)ctx->ws[4];
     u32 *slices = (u32 *)(b4 + o_sl), *od = (u32 *)(b4 + o_od), *M2 = (u32 *)(b4 + o_m2), *sbits = (u32 *)(b4 + o_s), *cbits = (u32 *)(b4 + o_c);
     u32 *mbits = want_mask_bits ? (u32 *)(b4 + o_mb) : nullptr;
@@ -758,6 +758,21 @@ static int label_pipeline(omni_ctx *ctx, const u8 *d_bgr, int nf, size_t frame_s
                                                              (u32 *)ctx->ws[5] + HYST_WL_OFFSET, HY_WL_CAP, ctx->d_flags + 16,
                                                              ctx->d_flags + 20, (const u32 *)ctx->ws[6], st));
     return run_hysteresis(ctx, sbits, cbits, g, KT, d_edges, e_plane, epitch, st);
+}
+
+// workspace of the label pipeline for n_frames frames of h x w with K colours each (slots 4, 5, 6): omni_workspace_bytes / omni_ctx_reserve
+void label_ws_bytes(int h, int w, int K, int nf, size_t out[OMNI_WS_SLOTS])
+{
+    const BitGeom g = make_geom(h, w);
+    const int KT = nf * K;
+    const size_t pbytes = g.plane * sizeof(u32);
+    auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    const size_t o_od = al(pbytes * 4 * nf), o_m2 = al(o_od + pbytes * nf), o_s = al(o_m2 + pbytes * KT), o_c = o_s + al(pbytes * KT),
+                 o_mb = al(o_c + pbytes * KT);
+    unsigned off[ET_MAXT];
+    out[4] = std::max(out[4], al(o_mb + pbytes * KT));
+    out[5] = std::max(out[5], WS5_BYTES + WS5_LABEL_BYTES);
+    out[6] = std::max(out[6], edges3_run_words(h, w, KT, off) * sizeof(u32));
 }
 
 int sparse_color_edge(omni_ctx *ctx, const u8 *d_bgr, int nf, size_t frame_stride, int h, int w, size_t pitch, const AssignParams &P,

@@ -84,6 +84,7 @@ struct omni_ctx {
     int e3s_per_sm = 0;              // resident CTAs per SM of the sparse edge kernel (0 = not queried yet)
     int assign_rgbcell = 1;          // 0: Lab-cell assignment kernel (the previous generation; set_fast_path mode 2)
     int edge_sparse = 1;             // 0: dense edge kernel (A/B runs, OMNI_B200_EDGE_DENSE=1)
+    int assume_binary = 0;           // omni_set_assume_binary_masks: omni_edges does not wait for the "masks are {0,255}" check
     // side streams + events of the pipelined host-buffer call (fast_host_color_edge)
     int pipe_ready = 0;
     cudaStream_t s_in = nullptr, s_out = nullptr;

@@ -111,6 +111,15 @@ class Engine:
         2: dense generation with the dense edge kernel; 3: dense generation as shipped in round 1."""
         capi.check(self._L.omni_set_fast_path(self._h, int(enable)))
 
+    def reserve(self, h: int, w: int, K: int, ksize: int = 3, n_frames: int = 1) -> int:
+        """Allocate the workspaces of the fused calls for this geometry now (omni_ctx_reserve); returns their size in bytes."""
+        capi.check(self._L.omni_ctx_reserve(self._h, h, w, K, ksize, n_frames))
+        return int(self._L.omni_workspace_bytes(h, w, K, ksize, n_frames))
+
+    def assume_binary_masks(self, enable: bool):
+        """True: `edges` skips the device-side {0,255} check and its wait (the caller vouches for the masks)."""
+        capi.check(self._L.omni_set_assume_binary_masks(self._h, 1 if enable else 0))
+
     def set_table_cache(self, enable: bool):
         """False: rebuild the candidate-centre tables on every call (single images with their own centres)."""
         capi.check(self._L.omni_set_table_cache(self._h, 1 if enable else 0))

@@ -185,3 +185,52 @@ def test_hysteresis_pass_count_survives_thinning(eng):
     _s, removed, iters = eng.thin_zhangsuen(e, with_log=True)
     assert int(iters.max()) >= 2                         # thinning ran several iterations ...
     assert eng.last_hysteresis_passes() == p0 >= 1       # ... and did not overwrite the pass count
+
+
+def test_reserved_ctx_does_not_allocate_in_the_call():
+    """omni_workspace_bytes / omni_ctx_reserve: after the reservation a fused call of that geometry (device-resident, byte planes or
+    packed, blur 3 or 5) leaves the free device memory where it was -- no cudaMalloc inside the timed call."""
+    import omni_b200
+    e = omni_b200.Engine(0)
+    try:
+        h, w, K = 1100, 1700, 8
+        img = synth(h, w, 3)
+        ctr, lut = _centres(img, K)
+        d = dev(img)
+        masks = torch.empty((K, h, w), dtype=torch.uint8, device="cuda")
+        edges = torch.empty_like(masks)
+        torch.cuda.synchronize()
+        free0 = torch.cuda.mem_get_info()[0]
+        need = e.reserve(h, w, K, ksize=5)
+        torch.cuda.synchronize()
+        free1 = torch.cuda.mem_get_info()[0]
+        assert need > 0 and free0 - free1 >= need * 0.9          # the driver rounds allocations up, never down
+        for ec in (omni_b200.EdgeConfig(), omni_b200.EdgeConfig(ksize=5)):
+            e.color_edge(d, ctr, lut, ec, masks=masks, edges=edges)
+            e.color_edge_packed(d[None], ctr, lut, omni_b200.EdgeConfig())
+        torch.cuda.synchronize()
+        # torch's caching allocator may have grown for the packed outputs; the library's own slots must not have
+        free2 = torch.cuda.mem_get_info()[0]
+        assert free1 - free2 <= 64 << 20, (free1, free2)
+        e.color_edge(d, ctr, lut, omni_b200.EdgeConfig(), masks=masks, edges=edges)
+        torch.cuda.synchronize()
+        assert torch.cuda.mem_get_info()[0] == free2
+    finally:
+        e.close()
+
+
+def test_assume_binary_masks_skips_only_the_check(eng):
+    import omni_b200
+    from oracle import cmodel as cm
+    masks = np.stack([blob_mask(300, 500, s, p=0.4) for s in range(3)])
+    want = np.stack([cm.edge_chain(m, 3, 1, 1, 3, 50, 150) for m in masks])
+    ec = omni_b200.EdgeConfig()
+    eng.assume_binary_masks(True)
+    try:
+        assert np.array_equal(host(eng.edges(dev(masks), ec)), want)
+        ec5 = omni_b200.EdgeConfig(ksize=5)
+        want5 = np.stack([cm.edge_chain(m, 3, 1, 1, 5, 50, 150) for m in masks])
+        assert np.array_equal(host(eng.edges(dev(masks), ec5)), want5)
+    finally:
+        eng.assume_binary_masks(False)
+    assert np.array_equal(host(eng.edges(dev(masks), ec)), want)

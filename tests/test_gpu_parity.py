@@ -74,6 +74,26 @@ def test_resize_golden(eng_mode):
         assert np.abs(got.astype(np.int16) - dst.astype(np.int16)).max() <= (0 if "to1" in tag else 1), tag
 
 
+@pytest.mark.parametrize("hs,ws,nh,nw", [(4096, 4096, 2000, 2000), (3000, 4000, 1500, 2000), (2160, 3840, 1125, 2000), (1201, 1604, 1000, 1335),
+                                         (777, 1028, 300, 397), (64, 132, 9, 17), (5000, 2000, 2000, 800)])
+def test_resize_tma_equals_staged_and_oracle(eng, hs, ws, nh, nw):
+    """The TMA-staged separable kernel (default) against the register-tap kernel of round 1 (mode 3) and the C oracle:
+    identical bytes (same float32 operation order)."""
+    cm = _cm()
+    src = synth(hs, ws, hs + 3 * ws, cell=24)
+    d = dev(src)
+    eng.set_fast_path(1)
+    n0 = eng.launch_count()
+    a = host(eng.resize_area(d, nw, nh))
+    assert eng.launch_count() == n0 + 1
+    eng.set_fast_path(3)
+    b = host(eng.resize_area(d, nw, nh))
+    eng.set_fast_path(1)
+    assert np.array_equal(a, b)
+    if hs * ws <= 4000 * 3000:
+        assert np.array_equal(a, cm.resize_area(src, nw, nh))
+
+
 def test_resize_strided_views(eng):
     """pitch != 3*w on both sides (a crop of a larger tensor)."""
     cm = _cm()
