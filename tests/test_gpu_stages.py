@@ -133,9 +133,10 @@ def test_assign_labels_dropin():
         assert np.array_equal(pc.assign_labels(z["al_img"], z[f"al_pal{K}"]), z[f"al_lab{K}"])
 
 
-def test_stage04_shim_swaps_only_the_thinning(tmp_path):
+def test_stage04_shim_swaps_thinning_and_tracing(tmp_path):
     """The stage-04 shim loads `04_find_contours_ref.py` (the reference's renamed file -- here a stand-in with the same
-    surface), replaces `thinning_zhangsuen` by the GPU mirror and runs the original `vectorize_all`."""
+    surface), replaces `thinning_zhangsuen` and `trace_centerlines` by the GPU-backed mirrors and runs the original
+    `vectorize_all`."""
     import shutil
     import subprocess
     import sys
@@ -154,11 +155,13 @@ def test_stage04_shim_swaps_only_the_thinning(tmp_path):
         "def thinning_zhangsuen(img, layer):\n"
         "    raise RuntimeError('the CPU thinning must have been replaced')\n"
         "def trace_centerlines(skel, layer):\n"
-        "    return [skel]\n"
+        "    raise RuntimeError('the per-component tracing must have been replaced')\n"
         "def vectorize_layer(name, cfg):\n"
+        "    import pickle\n"
         "    e = cv2.imread(os.path.join(cfg.output_dir, name, 'edges.png'), cv2.IMREAD_GRAYSCALE)\n"
         "    sk = thinning_zhangsuen(e, layer=name)\n"
-        "    np.save(os.path.join(cfg.output_dir, name, 'skel.npy'), trace_centerlines(sk, name)[0]); return name, []\n"
+        "    np.save(os.path.join(cfg.output_dir, name, 'skel.npy'), sk)\n"
+        "    pickle.dump(trace_centerlines(sk, layer=name), open(os.path.join(cfg.output_dir, name, 'paths.pkl'), 'wb')); return name, []\n"
         "def vectorize_all(cfg):\n"
         "    return dict(vectorize_layer(n, cfg) for n in cfg.color_names)\n")
     out = tmp_path / "out"
@@ -173,5 +176,17 @@ def test_stage04_shim_swaps_only_the_thinning(tmp_path):
                        stderr=subprocess.STDOUT, text=True, timeout=300)
     assert r.returncode == 0, r.stdout[-2000:]
     assert "[layer_a] Thinning ROI" in r.stdout and "Thinning done" in r.stdout
+    import contextlib
+    import io
+    import pickle
+    from omni_b200 import contours
     for n in want:
         assert np.array_equal(np.load(out / n / "skel.npy"), want[n]), n
+        S = (want[n] > 0).astype(np.uint8)
+        k = np.ones((3, 3), np.uint8); k[1, 1] = 0
+        deg = cv2.filter2D(S, cv2.CV_8U, k, borderType=cv2.BORDER_CONSTANT)
+        with contextlib.redirect_stdout(io.StringIO()):
+            ref_paths = contours.trace_centerlines(want[n], n, maps=(deg, (S == 1) & (deg == 1), (S == 1) & (deg >= 3)))
+        got = pickle.load(open(out / n / "paths.pkl", "rb"))
+        assert len(got) == len(ref_paths) > 0 and all(np.array_equal(a, b) for a, b in zip(got, ref_paths)), n
+        assert f"[{n}] Trace done: {len(got)} polylines" in r.stdout
