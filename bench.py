@@ -553,6 +553,27 @@ def run_ours(args, wl):
                                  "MP/s_src": sh * sw / ms / 1e3}
             del src, dst
 
+    # ---- process_colors.py:69-77 assign_labels (RGB palette, int16 wrap) on its own: 4096 x 4096, 16 colours ----
+    i16_extra = None
+    if rank == 0 and world == 1:
+        pal = np.random.default_rng(1234).integers(0, 256, (16, 3)).astype(np.uint8)       # the fixed palette of config 2
+        src = torch.from_numpy(synth(4096, 4096, 0, 32)[:, :, ::-1].copy()).cuda()
+        lab = torch.empty((4096, 4096), dtype=torch.uint8, device="cuda")
+        for _ in range(3):
+            eng.assign_rgb_i16wrap(src, pal, out=lab)
+        tms = []
+        for _ in range(5):
+            flush.fill_(4)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); eng.assign_rgb_i16wrap(src, pal, out=lab); b.record()
+            torch.cuda.synchronize()
+            tms.append(a.elapsed_time(b))
+        ms = statistics.median(tms)
+        nb = 4096 * 4096 * 4
+        i16_extra = {"ms": ms, "GB/s": nb / ms / 1e6, "frac_of_peak": nb / ms / 1e6 / peak, "MP/s": 4096 * 4096 / ms / 1e3,
+                     "what": "omni_assign_rgb_i16wrap, 4096x4096 RGB, 16 palette colours -> u8 labels (3 + 1 bytes per pixel)"}
+        del src, lab
+
     # ---- stage 04 thinning of the K edge planes the step just produced (not part of the step) ----
     thin_extra = None
     if rank == 0 and world == 1:
@@ -602,6 +623,7 @@ def run_ours(args, wl):
             "configs1": extra.get("config2"), "configs2": extra.get("config3"), "configs3": c3,
             "resize_kernel": resize_extra,
             "thinning_kernel": thin_extra,
+            "assign_i16wrap_kernel": i16_extra,
         }
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline_leg(wl, img, centers)

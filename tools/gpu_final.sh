@@ -10,7 +10,7 @@ timeout 900 python bench.py > gpurun_out/bench_default.json 2> gpurun_out/bench_
 timeout 900 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_reference_arm.json 2> gpurun_out/bench_reference_arm.err; tail -c 300 gpurun_out/bench_reference_arm.json
 timeout 300 python bench.py --no-cpu-baseline --workload config4 --steps 20 --warmup 5 > gpurun_out/bench_config4.json 2> gpurun_out/bench_config4.err
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_bench.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_launches.log 2>&1
-timeout 600 ncu --set full --import-source on --clock-control none -k regex:"fk_assign|fk_morph|fk_edges3|fk_hyst|fk_build|fk_label" --launch-skip 14 --launch-count 7 -o gpurun_out/prof_final_step -f python tools/profile_once.py config5 > gpurun_out/ncu_full_step.log 2>&1
+timeout 600 ncu --set full --import-source on --clock-control none -k regex:"fk_assign_slices|fk_morph_lab|fk_edges3|fk_hyst|fk_build_tables3|fk_label_open" --launch-skip 12 --launch-count 6 -o gpurun_out/prof_final_step -f python tools/profile_once.py config5 > gpurun_out/ncu_full_step.log 2>&1
 tail -2 gpurun_out/ncu_full_step.log
 timeout 600 ncu --set full --import-source on --clock-control none -k regex:"fk_thin|fk_bytes_to_bits|fk_expand_bits" --launch-skip 3 --launch-count 3 -o gpurun_out/prof_final_thin -f python tools/profile_thin.py > gpurun_out/ncu_full_thin.log 2>&1
 timeout 600 ncu --set full --import-source on --clock-control none -k regex:"fk_resize" --launch-skip 2 --launch-count 1 -o gpurun_out/prof_final_resize -f python tools/profile_resize.py > gpurun_out/ncu_full_resize.log 2>&1

@@ -12,6 +12,7 @@ from omni_b200 import stages                   # noqa: E402
 cfg = {"config5": (4096, 4096, 16, 0, 32), "config2": (4096, 4096, 8, 0, 32), "config3": (8192, 8192, 16, 1, 64), "config4": (1080, 1920, 8, 0, 32)}[sys.argv[1] if len(sys.argv) > 1 else "config2"]
 h, w, K, seed, cell = cfg
 eng = omni_b200.Engine(0)
+eng.set_table_cache(False)              # a single image brings its own centres: the tables are rebuilt in every call
 img = synth(h, w, seed, cell)
 ctr = stages.kmeans_lab_centers(img, K)
 _o, lut = stages.darkness_lut(ctr)
