@@ -132,6 +132,16 @@ int omni_swatch_masks(omni_ctx *ctx, const uint8_t *d_bgr, int h, int w, size_t 
                       const int32_t *h_colors, int K, int tol,
                       uint8_t *d_masks, size_t plane_stride, size_t mpitch, int32_t *h_choice, void *stream);
 
+/* OPT-IN replacement for the cv2.kmeans call of 02_color_extract.py:39-50 (0.26-0.29 s of host time per image): k-means++
+ * seeding (3 trials per centre), Lloyd iterations until no centre moves by more than eps or max_iter, best of `attempts` by
+ * compactness -- on the 8-bit Lab values of the pixels h_sample_idx[0 .. n_samples) (host array; pass the reference's own
+ * `default_rng(42).choice(h*w, 200000, replace=False)`; NULL = every pixel, h*w <= 2^24).  cv2.kmeans draws from OpenCV's global
+ * RNG, so its centres cannot be reproduced bit for bit; this call is deterministic for a given seed (integer accumulation) and
+ * returns centres whose compactness (sum of squared distances of the samples to their centre, *h_compactness if not NULL) is
+ * within 2 % of cv2.kmeans' on the same sample (tests/test_gpu_kmeans.py).  Synchronises the stream (centres go to the host). */
+int omni_kmeans_lab(omni_ctx *ctx, const uint8_t *d_bgr, int h, int w, size_t pitch, const int32_t *h_sample_idx, int n_samples,
+                    int K, int attempts, int max_iter, double eps, uint64_t seed, float *h_centers, double *h_compactness, void *stream);
+
 /* ---- stage 03: 03_edge_detect.py:23-34 per layer ------------------------------------------- */
 /* K independent planes: ELLIPSE(morph_k) open/close -> GaussianBlur(ksize, sigma 0) -> Canny(low,
  * high) (aperture 3, L1, 8-connected hysteresis).  Output {0,255}.  In and out may not alias.

@@ -466,6 +466,25 @@ extern "C" int omni_layer_masks(omni_ctx *ctx, const uint8_t *d_labels, int h, i
     return generic_layer_masks(ctx, d_labels, h, w, lpitch, K, open_iters, close_iters, d_masks, plane_stride, mpitch, st);
 }
 
+// opt-in: the Lab centres of 02_color_extract.py:39-50 on the device (see kmeans.cu for the contract)
+extern "C" int omni_kmeans_lab(omni_ctx *ctx, const uint8_t *d_bgr, int h, int w, size_t pitch, const int32_t *h_sample_idx, int n_samples,
+                               int K, int attempts, int max_iter, double eps, uint64_t seed, float *h_centers, double *h_compactness,
+                               void *stream)
+{
+    OMNI_TRY(set_device(ctx));
+    OMNI_REQUIRE(d_bgr && h_centers, "omni_kmeans_lab: NULL pointer");
+    OMNI_REQUIRE(h > 0 && w > 0 && pitch >= (size_t)w * 3 && (long long)h * w < (1ll << 31), "omni_kmeans_lab: bad geometry");
+    OMNI_REQUIRE(K >= 1 && K <= OMNI_MAX_K, "omni_kmeans_lab: K=%d outside [1,%d]", K, OMNI_MAX_K);
+    OMNI_REQUIRE(attempts >= 1 && attempts <= 64 && max_iter >= 1 && max_iter <= 1000 && eps >= 0.0, "omni_kmeans_lab: bad criteria");
+    const int n = h_sample_idx ? n_samples : h * w;
+    OMNI_REQUIRE(n >= K && n <= (1 << 24), "omni_kmeans_lab: %d samples (need K <= n <= 2^24: integer accumulators)", n);
+    if (h_sample_idx)
+        for (int i = 0; i < n; i++)
+            OMNI_REQUIRE(h_sample_idx[i] >= 0 && h_sample_idx[i] < h * w, "omni_kmeans_lab: sample index %d out of range", h_sample_idx[i]);
+    return kmeans_lab(ctx, d_bgr, h, w, pitch, h_sample_idx, n, K, attempts, max_iter, (float)eps, (unsigned long long)seed, h_centers,
+                      h_compactness, (cudaStream_t)stream);
+}
+
 // ---- stage 03 ----------------------------------------------------------------------------------------
 static int check_edge_params(const omni_edge_params *p, BlurParams *bp, int *low, int *high)
 {

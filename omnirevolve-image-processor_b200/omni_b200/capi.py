@@ -24,7 +24,7 @@ EXPORTS = [
     "omni_edges_composite", "omni_last_hysteresis_passes", "omni_launch_count", "omni_profile_enable",
     "omni_profile_summary", "omni_thin_zhangsuen", "omni_host_thin_zhangsuen", "omni_swatch_masks", "omni_color_edge_batch", "omni_skeleton_degree",
     "omni_set_table_cache", "omni_host_edges_composite", "omni_color_edge_packed", "omni_host_color_edge_packed",
-    "omni_workspace_bytes", "omni_ctx_reserve", "omni_set_assume_binary_masks",
+    "omni_workspace_bytes", "omni_ctx_reserve", "omni_set_assume_binary_masks", "omni_kmeans_lab",
 ]
 
 
@@ -64,6 +64,7 @@ def lib():
         "omni_set_assume_binary_masks": ([vp, i], i),
         "omni_workspace_bytes": ([i, i, i, i, i], sz),
         "omni_ctx_reserve": ([vp, i, i, i, i, i], i),
+        "omni_kmeans_lab": ([vp, u8p, i, i, sz, i32p, i, i, i, i, C.c_double, C.c_uint64, f32p, C.POINTER(C.c_double), vp], i),
         "omni_ctx_create": ([i, C.POINTER(vp)], i),
         "omni_ctx_destroy": ([vp], i),
         "omni_host_alloc": ([sz, C.POINTER(vp)], i),

@@ -111,6 +111,22 @@ class Engine:
         2: dense generation with the dense edge kernel; 3: dense generation as shipped in round 1."""
         capi.check(self._L.omni_set_fast_path(self._h, int(enable)))
 
+    def kmeans_lab(self, bgr: torch.Tensor, K: int, sample_idx=None, attempts: int = 3, max_iter: int = 40, eps: float = 0.5,
+                   seed: int = 0):
+        """Opt-in device k-means of the Lab centres (omni_kmeans_lab): (centers f32 [K,3], compactness).  sample_idx: the pixel
+        indices to cluster (the reference's seeded 200k subsample), None = every pixel."""
+        _check_img(bgr, 3)
+        ctr = np.empty((K, 3), np.float32)
+        comp = C.c_double(0.0)
+        if sample_idx is None:
+            idx_p, n = None, 0
+        else:
+            idx = np.ascontiguousarray(sample_idx, dtype=np.int32)
+            idx_p, n = idx.ctypes.data_as(C.POINTER(C.c_int32)), idx.size
+        capi.check(self._L.omni_kmeans_lab(self._h, bgr.data_ptr(), bgr.shape[0], bgr.shape[1], bgr.stride(0), idx_p, n, K, attempts,
+                                           max_iter, float(eps), int(seed), _f32p(ctr), C.byref(comp), self._stream()))
+        return ctr, float(comp.value)
+
     def reserve(self, h: int, w: int, K: int, ksize: int = 3, n_frames: int = 1) -> int:
         """Allocate the workspaces of the fused calls for this geometry now (omni_ctx_reserve); returns their size in bytes."""
         capi.check(self._L.omni_ctx_reserve(self._h, h, w, K, ksize, n_frames))

@@ -89,8 +89,14 @@ def kmeans_lab_centers(img_bgr: np.ndarray, k: int, sample_limit: int = 200_000,
     h, w = img_bgr.shape[:2]
     n = h * w
     flat = img_bgr.reshape(-1, 3)
-    if n > sample_limit:
-        pick = np.random.default_rng(42).choice(n, size=sample_limit, replace=False)
+    pick = np.random.default_rng(42).choice(n, size=sample_limit, replace=False) if n > sample_limit else None
+    if os.environ.get("OMNI_B200_KMEANS", "").lower() == "gpu":
+        # opt-in: the same subsample, clustered on the device -- cv2.kmeans' own centres cannot be reproduced
+        # (global RNG); the contract is their quality (include/omni_b200.h omni_kmeans_lab, tests/test_gpu_kmeans.py)
+        import torch
+        centers, _comp = get_engine().kmeans_lab(torch.from_numpy(np.ascontiguousarray(img_bgr)).cuda(), k, pick, attempts=attempts)
+        return centers
+    if pick is not None:
         flat = flat[pick]
     lab = cv2.cvtColor(np.ascontiguousarray(flat).reshape(-1, 1, 3), cv2.COLOR_BGR2LAB)
     sample = lab.reshape(-1, 3).astype(np.float32)
