@@ -478,12 +478,20 @@ __global__ void __launch_bounds__(128, ML_MINB) fk_morph_lab(const uint4 *__rest
     // warp unit = (plane, strip, group of 30 word columns), columns fastest: every warp of every CTA has work
     const long long unit = (long long)blockIdx.x * 4 + wid;
     if (unit >= n_units) return;                              // whole warps only: the list flush below is warp-wide
+#if ML_ORDER == 3
+    // planes fastest: the 4 warps of a CTA are 4 planes of ONE (strip, column group) -- they load the same label slices / Od words
+    // at about the same time, so three of the four find them in L1
+    const int p = (int)(unit % n_planes);
+    const long long u2 = unit / n_planes;
+    const int wx = (int)(u2 % wcols), strip = (int)(u2 / wcols);
+#else
     const int wx = (int)(unit % wcols);
     const long long u2 = unit / wcols;
 #if ML_ORDER == 1
     const int p = (int)(u2 % n_planes), strip = (int)(u2 / n_planes);       // the planes of a strip run together: they share its label rows
 #else
     const int strip = (int)(u2 % strips), p = (int)(u2 / strips);
+#endif
 #endif
     const int ww = (w + 31) >> 5;
     const int c = wx * LP_COLS - 1 + lane;
