@@ -410,6 +410,15 @@ def stage_wall_record():
                         ts[-1] = None
                         break
                 rec[arm] = {"stage_s": ts, "total_s": (sum(ts) if None not in ts else None)}
+            # the same three stages in ONE process (front_half.py: in-memory hand-off, one interpreter start, one CUDA context)
+            od = os.path.join(td, "ours_one_process")
+            os.makedirs(od)
+            cp = os.path.join(od, "config.json")
+            json.dump(dict(cfg, output_dir=od), open(cp, "w"))
+            t0 = time.perf_counter()
+            r = subprocess.run([sys.executable, os.path.join(ROOT, "omnirevolve-image-processor_b200", "image_processor", "front_half.py")],
+                               env=dict(os.environ, CONFIG_PATH=cp, PYTHONUNBUFFERED="1"), stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+            rec["ours_one_process"] = {"total_s": (time.perf_counter() - t0) if r.returncode == 0 else None}
             same = None
             try:
                 same = all(np.array_equal(cv2.imread(os.path.join(td, "ours", n, f), 0), cv2.imread(os.path.join(td, "reference_port", n, f), 0))
@@ -417,7 +426,7 @@ def stage_wall_record():
             except Exception:
                 pass
             rec["identical_masks_and_edges"] = same
-            rec["MP/s"] = {a: (hh * ww_ / 1e6 / rec[a]["total_s"]) if rec[a]["total_s"] else None for a in ("ours", "reference_port")}
+            rec["MP/s"] = {a: (hh * ww_ / 1e6 / rec[a]["total_s"]) if rec[a]["total_s"] else None for a in ("ours", "ours_one_process", "reference_port")}
             out[tag] = rec
     out["what"] = ("stages 01-03 as one subprocess each with CONFIG_PATH (pipeline.py:88-111): interpreter + imports + CUDA context "
                    "+ PNG decode/encode included; reference_port = oracle/refstages.py (the reference's stage structure replayed "
@@ -588,7 +597,22 @@ def run_ours(args, wl):
             torch.cuda.synchronize()
             tms.append(a.elapsed_time(b))
         ms = statistics.median(tms)
-        thin_extra = {"ms": ms, "iterations_max": int(iters.max()), "removed_px": int(removed.sum()),
+        # the same from / to packed planes (1 bit per pixel): the device-side stage 03 -> 04 hand-off without byte planes
+        packed_ms = None
+        if B == 1:
+            _mbits, ebits = eng.color_edge_packed(torch.from_numpy(frames).cuda()[None], centers, lut, ec)
+            sk_bits = torch.empty_like(ebits)
+            eng.thin_zhangsuen_packed(ebits, w, out=sk_bits)
+            tp = []
+            for _ in range(5):
+                flush.fill_(3)
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(); eng.thin_zhangsuen_packed(ebits, w, out=sk_bits); b.record()
+                torch.cuda.synchronize()
+                tp.append(a.elapsed_time(b))
+            packed_ms = statistics.median(tp)
+            del _mbits, ebits, sk_bits
+        thin_extra = {"ms": ms, "packed_ms": packed_ms, "iterations_max": int(iters.max()), "removed_px": int(removed.sum()),
                       "algorithmic_bytes": 2 * K * N, "GB/s": 2 * K * N / ms / 1e6, "frac_of_peak": 2 * K * N / ms / 1e6 / peak,
                       "layer_MP/s": K * N / ms / 1e3,
                       "what": "omni_thin_zhangsuen on the K edge planes (bytes in -> bit-planes -> cooperative Zhang-Suen -> bytes out)"}

@@ -232,6 +232,11 @@ int omni_thin_zhangsuen(omni_ctx *ctx, const uint8_t *d_in, int K, int h, int w,
 int omni_host_thin_zhangsuen(omni_ctx *ctx, const uint8_t *h_in, int K, int h, int w, size_t in_plane_stride, size_t in_pitch,
                              int max_iter, uint8_t *h_out, size_t out_plane_stride, size_t out_pitch,
                              int32_t *h_removed, int32_t *h_iters);
+/* The same on planes of 1 bit per pixel, in and out (pitches in bytes, bit_order as for omni_color_edge_packed): the stage 03 -> 04
+ * hand-off on the device without byte planes (the edge planes of omni_color_edge_packed go straight in).  In and out may alias. */
+int omni_thin_zhangsuen_packed(omni_ctx *ctx, const uint8_t *d_bits_in, int K, int h, int w, size_t in_plane_stride, size_t in_pitch,
+                               int bit_order, int max_iter, uint8_t *d_bits_out, size_t out_plane_stride, size_t out_pitch,
+                               int32_t *h_removed, int32_t *h_iters, void *stream);
 
 /* 04_find_contours.py:121-125 for all components at once: d_deg = cv2.filter2D(S, CV_8U, ones(3,3) minus the centre,
  * borderType=BORDER_CONSTANT) with S = (skeleton > 0), i.e. the number of set 8-neighbours of every pixel; d_nodes: 1 on

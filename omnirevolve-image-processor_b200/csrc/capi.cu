@@ -955,6 +955,20 @@ extern "C" int omni_thin_zhangsuen(omni_ctx *ctx, const uint8_t *d_in, int K, in
                      (cudaStream_t)stream);
 }
 
+// the same on planes of 1 bit per pixel (the packed edge planes of omni_color_edge_packed): no byte planes on the way
+extern "C" int omni_thin_zhangsuen_packed(omni_ctx *ctx, const uint8_t *d_bits_in, int K, int h, int w, size_t in_plane_stride, size_t in_pitch,
+                                          int bit_order, int max_iter, uint8_t *d_bits_out, size_t out_plane_stride, size_t out_pitch,
+                                          int32_t *h_removed, int32_t *h_iters, void *stream)
+{
+    OMNI_TRY(set_device(ctx));
+    OMNI_REQUIRE(d_bits_in && d_bits_out && K >= 1 && K <= OMNI_MAX_K && h > 0 && w > 0, "omni_thin_zhangsuen_packed: bad arguments");
+    OMNI_REQUIRE(in_pitch >= (size_t)(w + 7) / 8 && out_pitch >= (size_t)(w + 7) / 8, "omni_thin_zhangsuen_packed: pitch smaller than a row");
+    OMNI_REQUIRE(bit_order == OMNI_BITS_LSB_FIRST || bit_order == OMNI_BITS_MSB_FIRST, "omni_thin_zhangsuen_packed: bad bit order");
+    OMNI_REQUIRE(max_iter >= 0 && max_iter <= 100000, "omni_thin_zhangsuen_packed: max_iter %d out of range", max_iter);
+    return fast_thin(ctx, d_bits_in, K, h, w, in_plane_stride, in_pitch, max_iter, d_bits_out, out_plane_stride, out_pitch, h_removed, h_iters,
+                     (cudaStream_t)stream, bit_order == OMNI_BITS_MSB_FIRST ? 2 : 1);
+}
+
 extern "C" int omni_host_thin_zhangsuen(omni_ctx *ctx, const uint8_t *h_in, int K, int h, int w, size_t in_plane_stride, size_t in_pitch,
                                         int max_iter, uint8_t *h_out, size_t out_plane_stride, size_t out_pitch,
                                         int32_t *h_removed, int32_t *h_iters)

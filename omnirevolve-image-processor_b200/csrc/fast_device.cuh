@@ -182,6 +182,11 @@ int morph03_kind(const omni_edge_params *p);
 #define RA_SMEM (RA_OFF_WARP + RA_WARPS * RA_WARP_BYTES)
 
 void label_ws_bytes(int h, int w, int K, int nf, size_t out[OMNI_WS_SLOTS]);     // label_pipe.cu
+// caller-layout packed planes (row pitch in bytes, LSB- / MSB-first) <-> internal bit-planes (label_pipe.cu)
+cudaError_t launch_unpack_planes(const u8 *src, size_t splane, size_t spitch, int msb_first, int K, int h, int w, u32 *dst, int ws,
+                                 size_t plane, int blocks, cudaStream_t st);
+cudaError_t launch_pack_planes(const u32 *src, int ws, size_t plane, int K, int h, int w, u8 *dst, size_t dplane, size_t dpitch, int msb_first,
+                               int blocks, cudaStream_t st);
 void dense_ws_bytes(int h, int w, int K, int nf, int ksize, size_t out[OMNI_WS_SLOTS]);   // fast_kernels.cu
 
 // opt-in device k-means of the Lab centres (kmeans.cu)

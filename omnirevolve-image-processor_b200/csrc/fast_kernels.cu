@@ -1855,8 +1855,9 @@ __global__ void __launch_bounds__(256) fk_thin(u32 *__restrict__ A, u32 *__restr
 
 // planes of u8 (> 0 = foreground) -> skeleton planes {0,255}; h_removed (K * max_iter ints, may be NULL) and h_iters (K ints,
 // may be NULL: iterations the reference would have run on that plane) are filled after a stream synchronisation.
+// packed: 0 = byte planes in and out; 1 / 2 = planes of 1 bit per pixel in the caller's layout (LSB- / MSB-first), pitches in bytes
 int fast_thin(omni_ctx *ctx, const u8 *d_in, int K, int h, int w, size_t in_plane, size_t in_pitch, int max_iter,
-              u8 *d_out, size_t out_plane, size_t out_pitch, int32_t *h_removed, int32_t *h_iters, cudaStream_t st)
+              u8 *d_out, size_t out_plane, size_t out_pitch, int32_t *h_removed, int32_t *h_iters, cudaStream_t st, int packed)
 {
     BitGeom g = make_geom(h, w);
     u32 *bpp[2];
@@ -1890,7 +1891,10 @@ int fast_thin(omni_ctx *ctx, const u8 *d_in, int K, int h, int w, size_t in_plan
     // the thinning kernel has its own flag block (d_flags[32..39]): d_flags[0] keeps the pass count of the last hysteresis
     OMNI_CUDA(cudaMemsetAsync(ctx->d_flags + 32, 0, 8 * sizeof(int), st));
     OMNI_CUDA(cudaMemsetAsync(ctx->d_flags + 8, 0, sizeof(int), st));
-    {
+    if (packed) {
+        OMNI_LAUNCH(ctx, st, "unpack_planes", launch_unpack_planes(d_in, in_plane, in_pitch, packed == 2, K, h, w, bpp[0], g.ws, g.plane,
+                                                                   persist_blocks(ctx, 8), st));
+    } else {
         KScope ks(ctx, "bytes_to_bits", st);
         fk_bytes_to_bits<<<dim3(persist_blocks(ctx, 2), K), 256, 0, st>>>(d_in, in_plane, in_pitch, h, w, bpp[0], g.ws, g.plane, ctx->d_flags + 8);
         OMNI_CUDA(cudaGetLastError());
@@ -1905,7 +1909,10 @@ int fast_thin(omni_ctx *ctx, const u8 *d_in, int K, int h, int w, size_t in_plan
         void *args[] = {&bpp[0], &bpp[1], &ws, &plane, &h, &w, &K, &max_iter, &d_removed, &flags, &d_unit, &units, &unit_rows};
         OMNI_LAUNCH(ctx, st, "thin_zhangsuen", cudaLaunchCooperativeKernel((const void *)fk_thin, dim3(blocks), dim3(256), args, 0, st));
     }
-    {
+    if (packed) {
+        OMNI_LAUNCH(ctx, st, "pack_planes", launch_pack_planes(bpp[0], g.ws, g.plane, K, h, w, d_out, out_plane, out_pitch, packed == 2,
+                                                               persist_blocks(ctx, 8), st));
+    } else {
         KScope ks(ctx, "expand_bits", st);
         fk_expand_bits<<<dim3(persist_blocks(ctx, 4), K), 256, 0, st>>>(bpp[0], g.ws, g.plane, h, w, d_out, out_plane, out_pitch, al);
         OMNI_CUDA(cudaGetLastError());

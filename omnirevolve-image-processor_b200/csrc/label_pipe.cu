@@ -854,6 +854,20 @@ __global__ void __launch_bounds__(256) fk_unpack_planes(const u8 *__restrict__ s
     }
 }
 
+// launch wrappers for the other translation units (packed thinning)
+cudaError_t launch_unpack_planes(const u8 *src, size_t splane, size_t spitch, int msb_first, int K, int h, int w, u32 *dst, int ws,
+                                 size_t plane, int blocks, cudaStream_t st)
+{
+    fk_unpack_planes<<<blocks, 256, 0, st>>>(src, splane, spitch, msb_first, K, h, w, dst, ws, plane);
+    return cudaGetLastError();
+}
+cudaError_t launch_pack_planes(const u32 *src, int ws, size_t plane, int K, int h, int w, u8 *dst, size_t dplane, size_t dpitch, int msb_first,
+                               int blocks, cudaStream_t st)
+{
+    fk_pack_planes<<<blocks, 256, 0, st>>>(src, ws, plane, K, h, w, dst, dplane, dpitch, msb_first, nullptr);
+    return cudaGetLastError();
+}
+
 // pixels per label from the label bit-slices (one thread per word, K ballots)
 __global__ void __launch_bounds__(256) fk_count_labels_sl(const uint4 *__restrict__ slices, int ws, int h, int w, int K,
                                                           unsigned long long *__restrict__ counts)

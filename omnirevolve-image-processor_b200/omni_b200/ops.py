@@ -364,6 +364,20 @@ class Engine:
             removed.ctypes.data_as(i32p) if with_log else None, iters.ctypes.data_as(i32p) if with_log else None, self._stream()))
         return (out, removed[:, :max_iter], iters) if with_log else out
 
+    def thin_zhangsuen_packed(self, bits: torch.Tensor, w: int, max_iter: int = 120, msb_first: bool = True, out: torch.Tensor | None = None):
+        """Thinning of planes given as 1 bit per pixel ([K, H, ceil(W/8)] u8, the packed edge planes of color_edge_packed): the
+        skeletons in the same layout.  No byte planes are touched on the way (stage 03 -> 04 on the device)."""
+        _check_planes(bits)
+        K, h, rb = bits.shape
+        if rb < (w + 7) // 8:
+            raise ValueError("rows too short for w pixels")
+        if out is None:
+            out = torch.empty_like(bits)
+        capi.check(self._L.omni_thin_zhangsuen_packed(
+            self._h, bits.data_ptr(), K, h, w, bits.stride(0), bits.stride(1), capi.BITS_MSB_FIRST if msb_first else capi.BITS_LSB_FIRST,
+            int(max_iter), out.data_ptr(), out.stride(0), out.stride(1), None, None, self._stream()))
+        return out
+
     def skeleton_degree(self, skel: torch.Tensor):
         """04_find_contours.py:121-125 on K skeleton planes: (deg[K,H,W] = set 8-neighbours per pixel, nodes[K,H,W] with
         1 = endpoint, 2 = junction)."""

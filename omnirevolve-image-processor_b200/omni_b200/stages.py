@@ -159,13 +159,14 @@ def _swatch_extract(cfg, img, names) -> None:
     print("Color extraction: done.")
 
 
-def color_extract_main(cfg) -> dict:
+def color_extract_main(cfg, img=None) -> dict:
     """02_color_extract.py:66-175.  k-means mode is the only one reachable through config.json; the swatch branch
     (:82-109) is honoured when the Config object carries extraction_mode == "swatch".  Only stage 02's own work is done
     here (assignment + RECT open/close): the layers come off the GPU as packed bit rows and go straight into 1-bit PNGs."""
     os.makedirs(cfg.output_dir, exist_ok=True)
     path = os.path.join(cfg.output_dir, "resized.png")
-    img = cv2.imread(path, cv2.IMREAD_COLOR)
+    if img is None:                                    # (front_half_main hands the array over: the PNG is lossless, same pixels)
+        img = cv2.imread(path, cv2.IMREAD_COLOR)
     if img is None:
         raise RuntimeError(f"Cannot read resized image: {path}")
     img = _ensure_bgr(img)
@@ -321,6 +322,25 @@ def edge_detect_main(cfg) -> None:
         return
     detect_all_edges(cfg)
     save_edges_composite(cfg)
+
+
+def front_half_main(cfg) -> None:
+    """Stages 01 -> 02 -> 03 in ONE process (in-memory hand-off): the same files and log lines as the three stage
+    scripts run one after the other, but one interpreter start and one CUDA context, the resized image goes from stage 01 to
+    stage 02 as an array (resized.png is written in the background, not decoded again), and stage 03 publishes the edge planes the
+    fused stage-02 call has produced.  `python front_half.py` with CONFIG_PATH set, in place of steps 1-3 of pipeline.py."""
+    import threading
+    cfg.ensure_output_dirs()
+    img = resize_if_needed(cfg.input_image, cfg)
+    path = os.path.join(cfg.output_dir, "resized.png")
+    writer = threading.Thread(target=cv2.imwrite, args=(path, img))       # cv2 releases the GIL while it encodes
+    writer.start()
+    try:
+        color_extract_main(cfg, img=img)
+    finally:
+        writer.join()
+    print(f"Saved: {path}")
+    edge_detect_main(cfg)
 
 
 # ---- 03_edge_detect.py ---------------------------------------------------------------------------------

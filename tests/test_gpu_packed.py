@@ -234,3 +234,23 @@ def test_assume_binary_masks_skips_only_the_check(eng):
     finally:
         eng.assume_binary_masks(False)
     assert np.array_equal(host(eng.edges(dev(masks), ec)), want)
+
+
+@pytest.mark.parametrize("hw,K,msb", [((300, 517), 4, True), ((64, 40), 3, False), ((1080, 1920), 8, True)])
+def test_thinning_on_packed_planes_equals_byte_planes(eng, hw, K, msb):
+    """omni_thin_zhangsuen_packed: the packed edge planes of the fused call go straight into the thinning kernel."""
+    import omni_b200
+    h, w = hw
+    img = synth(h, w, 5)
+    ctr, lut = _centres(img, K)
+    d = dev(img)
+    _m, e_bits = eng.color_edge_packed(d[None], ctr, lut, omni_b200.EdgeConfig(), msb_first=msb)
+    _lab, _mb, eb = eng.color_edge(d, ctr, lut, omni_b200.EdgeConfig())
+    want = host(eng.thin_zhangsuen(eb))
+    got_bits = host(eng.thin_zhangsuen_packed(e_bits, w, msb_first=msb))
+    got = np.unpackbits(got_bits, axis=2, bitorder="big" if msb else "little")[:, :, :w] * 255
+    assert np.array_equal(got, want)
+    # in place
+    e2 = e_bits.clone()
+    eng.thin_zhangsuen_packed(e2, w, msb_first=msb, out=e2)
+    assert torch.equal(e2, torch.from_numpy(got_bits).cuda())

@@ -71,6 +71,35 @@ def test_stage_scripts_match_reference_files(case, tmp_path):
     assert np.array_equal(cv2.imread(str(out / "edges_composite.png"), cv2.IMREAD_COLOR), z["composite"])
 
 
+@pytest.mark.parametrize("case", PIPE_CASES)
+def test_front_half_one_process_matches_reference_files(case, tmp_path):
+    """front_half.py = stages 01-03 in one process (in-memory hand-off): the files of the unmodified reference's three stages."""
+    z, meta = load_pipe_case(case)
+    cfg = dict(meta["config"])
+    names = meta["names"]
+    src = tmp_path / "input.png"
+    cv2.imwrite(str(src), z["input"])
+    out = tmp_path / "out"
+    out.mkdir()
+    cfg.update(input_image=str(src), output_dir=str(out))
+    cfg_path = out / "config.json"
+    cfg_path.write_text(json.dumps(cfg))
+    log = run_stage("front_half.py", str(cfg_path))
+    resized = cv2.imread(str(out / "resized.png"), cv2.IMREAD_COLOR)
+    assert resized.shape == z["resized"].shape
+    assert np.abs(resized.astype(np.int16) - z["resized"].astype(np.int16)).max() <= 1
+    assert "Color extraction: done." in log and "Edges composite saved:" in log and "Saved:" in log
+    if np.array_equal(resized, z["resized"]):          # (a fractional resize may differ by 1 LSB: the later stages then see another image)
+        assert json.load(open(out / "palette_by_name.json")) == meta["palette_by_name"]
+        for i, n in enumerate(names):
+            assert np.array_equal(cv2.imread(str(out / n / "mask.png"), cv2.IMREAD_GRAYSCALE), z["masks"][i]), n
+            assert np.array_equal(cv2.imread(str(out / n / "edges.png"), cv2.IMREAD_GRAYSCALE), z["edges"][i]), n
+            assert f"Edges extracted: {n} | nz={int(np.count_nonzero(z['edges'][i]))}" in log
+        assert np.array_equal(cv2.imread(str(out / "edges_composite.png"), cv2.IMREAD_COLOR), z["composite"])
+    else:
+        pytest.fail("resized.png differs from the reference's: expected identical bytes on the golden cases")
+
+
 def test_handoff_is_dropped_when_masks_or_keys_change(tmp_path):
     """The planes stage 02 parks for stage 03 are used only for unchanged masks and edge keys: a hand-edited mask.png or a changed
     threshold makes stage 03 recompute from the files (what the reference would do)."""
