@@ -419,6 +419,21 @@ def stage_wall_record():
             r = subprocess.run([sys.executable, os.path.join(ROOT, "omnirevolve-image-processor_b200", "image_processor", "front_half.py")],
                                env=dict(os.environ, CONFIG_PATH=cp, PYTHONUNBUFFERED="1"), stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
             rec["ours_one_process"] = {"total_s": (time.perf_counter() - t0) if r.returncode == 0 else None}
+            if hh * ww_ <= 1024 * 1024:
+                # stage 04 on these edge planes (152 s in the reference at this size): GPU thinning + the tracing
+                # mirror with GPU degree maps, layer by layer as vectorize_all does (04:207-232), log lines discarded
+                import contextlib
+                import io
+                from omni_b200 import contours
+                t0 = time.perf_counter()
+                n_paths = 0
+                with contextlib.redirect_stdout(io.StringIO()):
+                    for n in names:
+                        e = cv2.imread(os.path.join(td, "ours", n, "edges.png"), cv2.IMREAD_GRAYSCALE)
+                        sk = contours.thinning_zhangsuen(e, layer=n)
+                        n_paths += len([p_ for p_ in contours.trace_centerlines(sk, layer=n) if len(p_) >= 5])
+                rec["stage04_ours_s"] = time.perf_counter() - t0
+                rec["stage04_polylines"] = n_paths
             same = None
             try:
                 same = all(np.array_equal(cv2.imread(os.path.join(td, "ours", n, f), 0), cv2.imread(os.path.join(td, "reference_port", n, f), 0))
