@@ -72,6 +72,14 @@ int omni_set_fast_path(omni_ctx *ctx, int enable);
  * (default, enable != 0: frames of a video share one centre set).  enable == 0 rebuilds them on every
  * call -- what a stream of single images with their own k-means centres pays. */
 int omni_set_table_cache(omni_ctx *ctx, int enable);
+/* omni_host_color_edge_packed with ONE frame of at least 1024 rows / 2 MP pipelines the image in row bands: the upload of band
+ * b+1, the kernels of band b and the download of band b-1 overlap (a band is computed with 16 halo rows; the chain reaches 11).
+ * mode 2 (default): a band's edge rows leave with the band, from the hysteresis of the rows seen so far; after the last band the
+ * final planes are compared with what was sent and the bands that changed (a weak chain promoted from a later band) are sent again
+ * -- omni_last_band_resends() says how many (-1: the last call was not banded).  mode 1: the edge planes leave after the last band.
+ * mode 0: no bands (copy in, compute, copy out).  The bytes in the host buffers are the same in every mode. */
+int omni_set_host_bands(omni_ctx *ctx, int mode);
+int omni_last_band_resends(omni_ctx *ctx);
 /* Workspaces.  The ctx owns its device scratch and grows it on demand (cudaFree + cudaMalloc inside the call that needs more).
  * omni_workspace_bytes: device bytes the fused device-resident calls (omni_color_edge, omni_color_edge_batch,
  * omni_color_edge_packed) allocate for n_frames frames of h x w pixels with K colours and edge_kernel_size ksize (0 for bad

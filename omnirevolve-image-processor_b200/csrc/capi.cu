@@ -85,6 +85,7 @@ extern "C" int omni_ctx_destroy(omni_ctx *c)
         for (auto e : c->pk_ev) cudaEventDestroy(e);
     }
     if (c->pk_counts) cudaFreeHost(c->pk_counts);
+    if (c->bd_ready) for (auto e : c->bd_ev) cudaEventDestroy(e);
     delete c;
     return OMNI_OK;
 }
@@ -114,6 +115,16 @@ extern "C" int omni_set_table_cache(omni_ctx *ctx, int enable)
     if (!enable) ctx->cells_valid = ctx->cells3_valid = 0;
     return OMNI_OK;
 }
+
+extern "C" int omni_set_host_bands(omni_ctx *ctx, int mode)
+{
+    OMNI_REQUIRE(ctx != nullptr, "ctx is NULL");
+    OMNI_REQUIRE(mode >= 0 && mode <= 2, "omni_set_host_bands: mode must be 0, 1 or 2");
+    ctx->host_bands = mode;
+    return OMNI_OK;
+}
+
+extern "C" int omni_last_band_resends(omni_ctx *ctx) { return ctx ? ctx->last_band_resends : -1; }
 
 extern "C" int omni_host_alloc(size_t bytes, void **out)
 {
@@ -759,6 +770,17 @@ extern "C" int omni_host_color_edge_packed(omni_ctx *ctx, const uint8_t *h_bgr, 
         OMNI_CUDA(cudaStreamCreateWithFlags(&ctx->pk_out, cudaStreamNonBlocking));
         for (auto &e : ctx->pk_ev) OMNI_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         ctx->pk_ready = 1;
+    }
+    ctx->last_band_resends = -1;                            // -1: the last call was not banded
+    if (n_frames == 1) {                                    // one image: row bands overlap its own copies and kernels
+        BlurParams bp; int low = 0, high = 0;
+        if (prm) OMNI_TRY(check_edge_params(prm, &bp, &low, &high));
+        AssignParams P;
+        OMNI_TRY(fill_assign(&P, h_centers, nullptr, K, h_lut));
+        OMNI_REQUIRE(bit_order == OMNI_BITS_LSB_FIRST || bit_order == OMNI_BITS_MSB_FIRST, "bit_order must be OMNI_BITS_LSB_FIRST or OMNI_BITS_MSB_FIRST");
+        int rc = label_host_packed_banded(ctx, h_bgr, h, w, pitch, P, prm, low, high, h_mask_bits, mb_plane_stride, mb_pitch, h_edge_bits,
+                                          eb_plane_stride, eb_pitch, bit_order == OMNI_BITS_MSB_FIRST, h_counts);
+        if (rc != OMNI_ERR_UNSUPPORTED) return rc;
     }
     if (h_counts && ctx->pk_counts_cap < (size_t)n_groups) {        // pinned: one block of counts per group, read after the last copy
         if (ctx->pk_counts) OMNI_CUDA(cudaFreeHost(ctx->pk_counts));

@@ -1379,7 +1379,7 @@ int fast_morph03_bytes(omni_ctx *ctx, const u8 *d_masks, int K, int h, int w, si
 }
 
 int run_hysteresis(omni_ctx *ctx, u32 *ebits, const u32 *cbits, const BitGeom &g, int K, u8 *d_edges,
-                          size_t e_plane, size_t epitch, cudaStream_t st)
+                          size_t e_plane, size_t epitch, cudaStream_t st, int *flags_in, const u32 *worklist_in)
 {
     if (ctx->hyst_blocks == 0) {
         int per_sm = 0;
@@ -1389,13 +1389,15 @@ int run_hysteresis(omni_ctx *ctx, u32 *ebits, const u32 *cbits, const BitGeom &g
     }
     int ws = g.ws, h = g.h, w = g.w;
     size_t plane = g.plane;
-    int *flags = ctx->d_flags;
-    const u32 *worklist = (const u32 *)ctx->ws[5] + HYST_WL_OFFSET;
+    int *flags = flags_in ? flags_in : ctx->d_flags;
+    const u32 *worklist = worklist_in ? worklist_in : (const u32 *)ctx->ws[5] + HYST_WL_OFFSET;
     void *args[] = {&ebits, &cbits, &ws, &plane, &h, &w, &K, &flags, &worklist, &d_edges, &e_plane, &epitch};
     OMNI_LAUNCH(ctx, st, "hysteresis_bits", cudaLaunchCooperativeKernel((const void *)fk_hysteresis, dim3(ctx->hyst_blocks), dim3(HY_THREADS),
                                                                         args, 0, st));
-    ctx->last_hyst_passes = -1;           // lives in d_flags[0]; fetched lazily by omni_last_hysteresis_passes
-    ctx->last_hyst_stream = st;
+    if (!flags_in) {
+        ctx->last_hyst_passes = -1;       // lives in d_flags[0]; fetched lazily by omni_last_hysteresis_passes
+        ctx->last_hyst_stream = st;
+    }
     return OMNI_OK;
 }
 

@@ -88,3 +88,8 @@ int fast_color_edge_batch(omni_ctx *ctx, const u8 *d_bgr, int n, size_t frame_st
 int label_color_edge_packed(omni_ctx *ctx, const u8 *d_bgr, int nf, size_t frame_stride, int h, int w, size_t pitch, const AssignParams &P,
                             const omni_edge_params *prm, int low, int high, u8 *d_mask_bits, size_t mb_plane, size_t mb_pitch,
                             u8 *d_edge_bits, size_t eb_plane, size_t eb_pitch, int msb_first, unsigned long long *d_counts, cudaStream_t st);
+// one image in HOST memory, row bands pipelined (H2D of band b+1 | kernels of band b | D2H of band b-1); OMNI_ERR_UNSUPPORTED: not
+// applicable (small image, outside the label pipeline) -- the caller takes the frame-group path
+int label_host_packed_banded(omni_ctx *ctx, const u8 *h_bgr, int h, int w, size_t pitch, const AssignParams &P, const omni_edge_params *prm,
+                             int low, int high, u8 *h_mask_bits, size_t mb_plane, size_t mb_pitch, u8 *h_edge_bits, size_t eb_plane,
+                             size_t eb_pitch, int msb_first, int64_t *h_counts);

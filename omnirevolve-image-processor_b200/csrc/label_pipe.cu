@@ -628,7 +628,7 @@ static int label_tables(omni_ctx *ctx, const AssignParams &P, u32 **cells, u8 **
     SP_TRY(omni_ws_reserve(ctx, 5, WS5_BYTES + WS5_LABEL_BYTES));
     *cells = (u32 *)((u8 *)ctx->ws[5] + WS5_BYTES);
     *rtab = (u8 *)(*cells + CELL_COUNT);
-    if (ctx->table_cache && ctx->cells3_valid && ctx->cells3_ws == ctx->ws[5] && ctx->cells3_stream == (void *)st && ctx->cells3_K == P.K &&
+    if ((ctx->table_cache || ctx->tables_hold) && ctx->cells3_valid && ctx->cells3_ws == ctx->ws[5] && ctx->cells3_stream == (void *)st && ctx->cells3_K == P.K &&
         memcmp(ctx->cells3_c, P.c, sizeof(float) * 3 * P.K) == 0 && memcmp(ctx->cells3_lut, P.lut, P.K) == 0)
         return OMNI_OK;
     memcpy(ctx->cells3_c, P.c, sizeof(float) * 3 * P.K);
@@ -683,14 +683,14 @@ static cudaError_t launch_morph_lab(int kind /* -1: masks only */, const uint4 *
 
 // Internal bit-planes of the last label-pipeline call on a ctx (valid until the next call): bit i of word c of row y = pixel 32c + i,
 // rows g.ws words apart, planes g.plane words apart.
-struct LabelPlanes { u32 *slices, *mask_bits, *edge_bits; };
+struct LabelPlanes { u32 *slices, *mask_bits, *edge_bits, *cand_bits; };
 
 // prm == NULL: colour layers only (02_color_extract.py on its own: no stage-03 work).  d_masks / d_edges may be NULL (packed
 // outputs: the bit-planes in `out` are the result).
 static int label_pipeline(omni_ctx *ctx, const u8 *d_bgr, int nf, size_t frame_stride, int h, int w, size_t pitch, const AssignParams &P,
                           const omni_edge_params *prm, int low, int high, u8 *d_labels, size_t lpitch,
                           u8 *d_masks, size_t m_plane, size_t mpitch, u8 *d_edges, size_t e_plane, size_t epitch, bool want_mask_bits,
-                          cudaStream_t st, LabelPlanes *out)
+                          cudaStream_t st, LabelPlanes *out, bool skip_hysteresis = false /* bands: S and C are the result */)
 {
     const int K = P.K, KT = nf * K;
     const int kind = prm ? morph03_kind(prm) : -1;
@@ -708,7 +708,7 @@ static int label_pipeline(omni_ctx *ctx, const u8 *d_bgr, int nf, size_t frame_s
     u8 *b4 = (u8 *)ctx->ws[4];
     u32 *slices = (u32 *)(b4 + o_sl), *od = (u32 *)(b4 + o_od), *M2 = (u32 *)(b4 + o_m2), *sbits = (u32 *)(b4 + o_s), *cbits = (u32 *)(b4 + o_c);
     u32 *mbits = want_mask_bits ? (u32 *)(b4 + o_mb) : nullptr;
-    if (out) { out->slices = slices; out->mask_bits = mbits; out->edge_bits = prm ? sbits : nullptr; }
+    if (out) { out->slices = slices; out->mask_bits = mbits; out->edge_bits = prm ? sbits : nullptr; out->cand_bits = prm ? cbits : nullptr; }
     // the zeros of the dead edge tiles: byte planes -> they ride on the assignment kernel (ZeroJob; strided planes: side stream);
     // bit-planes only -> the morphology kernel clears the candidate / strong words of its dead tiles
     MorphRuns R{};
@@ -765,6 +765,7 @@ static int label_pipeline(omni_ctx *ctx, const u8 *d_bgr, int nf, size_t frame_s
                                                              sbits, cbits, d_edges, e_plane, epitch, al16, ctx->d_flags + 4,
                                                              (u32 *)ctx->ws[5] + HYST_WL_OFFSET, HY_WL_CAP, ctx->d_flags + 16,
                                                              ctx->d_flags + 20, (const u32 *)ctx->ws[6], st));
+    if (skip_hysteresis) return OMNI_OK;
     return run_hysteresis(ctx, sbits, cbits, g, KT, d_edges, e_plane, epitch, st);
 }
 
@@ -927,6 +928,268 @@ int label_color_edge_packed(omni_ctx *ctx, const u8 *d_bgr, int nf, size_t frame
             KScope ks(ctx, "count_labels", st);
             fk_count_labels_sl<<<blocks, 256, 0, st>>>((const uint4 *)L.slices + (size_t)f * g.plane, g.ws, h, w, K, d_counts + (size_t)f * K);
             OMNI_CUDA(cudaGetLastError());
+        }
+    return OMNI_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// One image in HOST memory, packed outputs, row bands pipelined over three streams:
+//     H2D of band b+1   |   kernels of band b   |   D2H of band b-1
+// (omni_host_color_edge_packed with one frame: without bands the 50 MB in, the kernels and the 67 MB out of a 4096^2, K=16 image run
+// one after the other.)
+//
+// A band is computed as an image of its own: rows [r0 - BD_HALO, r1 + BD_HALO) clipped to the image.  Label-domain open (2 rows),
+// RECT close (2), cross open / close (4), blur 3 (1), Sobel (1) and the NMS neighbours (1) reach 11 rows, so what the band image
+// gets wrong next to its artificial borders stays inside the halo; rows [r0, r1) of its mask bits and of its strong / candidate
+// planes S, C are exact and are merged into full-image planes.  The hysteresis is the one global step.  Mode 1 runs it once after
+// the last band and sends the edge planes then.  Mode 2 (default) runs it after every band on the prefix image [0, r1) -- a subset
+// of the final result, and on pipeline data almost always equal to it -- and sends the band's edge rows at once; every word that
+// holds a weak candidate is on the call's worklist (only such words can change), so after the last band one small kernel compares
+// the final planes with what was sent, repairs the device copy and reports the bands that changed; those rows are sent again.
+// ------------------------------------------------------------------------------------------------
+#define BD_MAX_BANDS 16
+#define BD_HALO 16
+#define BD_FLAGS 40                   // d_flags[40..44]: flag block of the banded hysteresis ([44] = worklist length), [48] = dirty bands
+
+__global__ void __launch_bounds__(256) fk_band_merge(const u32 *__restrict__ s_src, const u32 *__restrict__ c_src, size_t splane,
+                                                     u32 *__restrict__ s_dst, u32 *__restrict__ c_dst, size_t dplane, int ws, int ww, int rows, int K,
+                                                     int y0, int *wl_count, u32 *__restrict__ worklist, int wl_cap)
+{
+    const long long per = (long long)rows * ws, total = per * K;
+    for (long long u = (long long)blockIdx.x * blockDim.x + threadIdx.x; u < total; u += (long long)gridDim.x * blockDim.x) {
+        const int k = (int)(u / per);
+        const long long rem = u - (long long)k * per;
+        const int c = (int)(rem % ws);
+        u32 s = 0u, cd = 0u;
+        if (c < ww) { s = __ldg(s_src + (size_t)k * splane + rem); cd = __ldg(c_src + (size_t)k * splane + rem); }
+        const size_t o = (size_t)k * dplane + (size_t)y0 * ws + rem;
+        s_dst[o] = s;
+        c_dst[o] = cd;
+        if (cd & ~s) {
+            const int i = atomicAdd(wl_count, 1);
+            if (i < wl_cap) worklist[i] = (u32)o;
+        }
+    }
+}
+
+// final planes against the packed rows that were sent: repairs the device copy, dirty bit b = band b has to be sent again
+__global__ void __launch_bounds__(256) fk_band_verify(const u32 *__restrict__ ebits, int ws, size_t plane, int w, const int *wl_count,
+                                                      const u32 *__restrict__ worklist, int wl_cap, u8 *__restrict__ dst, size_t dplane, size_t dpitch,
+                                                      int msb_first, int band_rows, unsigned *dirty)
+{
+    const int n = *wl_count;
+    if (n > wl_cap) {                                    // list overflowed: the caller repacks and resends everything
+        if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(dirty, 0xffffffffu);
+        return;
+    }
+    const int rb = (w + 7) >> 3;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const u32 o = worklist[i];
+        const int k = (int)(o / plane);
+        const size_t rem = o - (size_t)k * plane;
+        const int y = (int)(rem / ws), c = (int)(rem - (size_t)y * ws);
+        const u32 word = __ldcg(ebits + o) & range_mask(32 * c, w);
+        const u32 v = msb_first ? __byte_perm(__brev(word), 0u, 0x0123) : word;
+        u8 *row = dst + (size_t)k * dplane + (size_t)y * dpitch + 4 * c;
+        bool diff = false;
+        for (int j = 0; j < 4 && 4 * c + j < rb; j++) {
+            const u8 b = (u8)(v >> (8 * j));
+            if (row[j] != b) { row[j] = b; diff = true; }
+        }
+        if (diff) atomicOr(dirty, 1u << (y / band_rows));
+    }
+}
+
+__global__ void __launch_bounds__(256) fk_count_bits(const u32 *__restrict__ src, int ws, size_t plane, int K, int h, int w,
+                                                     unsigned long long *__restrict__ counts)
+{
+    const int k = blockIdx.y, ww = (w + 31) >> 5;
+    const long long total = (long long)h * ww;
+    unsigned long long n = 0;
+    for (long long u = (long long)blockIdx.x * blockDim.x + threadIdx.x; u < total; u += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(u % ww), y = (int)(u / ww);
+        n += (unsigned)__popc(__ldg(src + (size_t)k * plane + (size_t)y * ws + c) & range_mask(32 * c, w));
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) n += __shfl_xor_sync(0xffffffffu, n, d);
+    if ((threadIdx.x & 31) == 0 && n) atomicAdd(counts + k, n);
+    (void)K;
+}
+
+// rows [y0, y0 + rows) of K packed planes, device -> host
+static cudaError_t d2h_rows(u8 *h_dst, size_t h_plane, size_t h_pitch, const u8 *d_src, size_t d_plane, size_t d_pitch, size_t rb, int y0, int rows,
+                            int K, cudaStream_t st)
+{
+    if (h_pitch == d_pitch && d_pitch == rb)             // gap-free rows: the band of all K planes in one strided copy ("row" = a plane's band)
+        return cudaMemcpy2DAsync(h_dst + (size_t)y0 * h_pitch, h_plane, d_src + (size_t)y0 * d_pitch, d_plane, (size_t)(rows - 1) * d_pitch + rb,
+                                 K, cudaMemcpyDeviceToHost, st);
+    for (int k = 0; k < K; k++) {
+        cudaError_t e = cudaMemcpy2DAsync(h_dst + (size_t)k * h_plane + (size_t)y0 * h_pitch, h_pitch, d_src + (size_t)k * d_plane + (size_t)y0 * d_pitch,
+                                          d_pitch, rb, rows, cudaMemcpyDeviceToHost, st);
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+}
+
+struct HoldTables {                                      // the candidate tables of the first band serve the whole call
+    omni_ctx *c;
+    explicit HoldTables(omni_ctx *ctx) : c(ctx) {}
+    ~HoldTables() { c->tables_hold = 0; }
+};
+
+int label_host_packed_banded(omni_ctx *ctx, const u8 *h_bgr, int h, int w, size_t pitch, const AssignParams &P, const omni_edge_params *prm,
+                             int low, int high, u8 *h_mb, size_t mb_plane, size_t mb_pitch, u8 *h_eb, size_t eb_plane, size_t eb_pitch,
+                             int msb_first, int64_t *h_counts)
+{
+    const int K = P.K, mode = ctx->host_bands;
+    if (mode == 0 || !ctx->fast || ctx->pipeline != 1 || h < 1024 || (long long)h * w < (2ll << 20)) return OMNI_ERR_UNSUPPORTED;
+    if (prm && (low < 0 || morph03_kind(prm) < 0 || prm->ksize != 3)) return OMNI_ERR_UNSUPPORTED;
+    if (K > RC_MAX_K || !lut_below_k(P)) return OMNI_ERR_UNSUPPORTED;
+    // ---- bands ----
+    int band_rows = ((h + 7) / 8 + 31) & ~31;                // 8 bands, rows a multiple of 32
+    if (band_rows < 256) band_rows = 256;
+    const int nb = (h + band_rows - 1) / band_rows;
+    if (nb < 2 || nb > BD_MAX_BANDS) return OMNI_ERR_UNSUPPORTED;
+    const int hs_max = std::min(h, band_rows + 2 * BD_HALO);
+    if (!edges3_sparse_ok(hs_max, w, K) || !edges3_sparse_ok(h, w, K)) return OMNI_ERR_UNSUPPORTED;
+    if (!ctx->bd_ready) {
+        for (auto &e : ctx->bd_ev) OMNI_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        ctx->bd_ready = 1;
+    }
+    cudaEvent_t *evH = ctx->bd_ev, *evB = ctx->bd_ev + BD_MAX_BANDS, evStart = ctx->bd_ev[2 * BD_MAX_BANDS], evEdges = ctx->bd_ev[2 * BD_MAX_BANDS + 1];
+    cudaStream_t sc = ctx->stream, si = ctx->pk_in, so = ctx->pk_out;
+    // ---- workspace: slot 3 = [image | packed masks | packed edges | S | C | worklist]; slots 4-6 sized for the tallest band image ----
+    const BitGeom g = make_geom(h, w);
+    const size_t rb = ((size_t)w + 7) / 8;
+    auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    const size_t ip = ((size_t)w * 3 + 15) & ~(size_t)15;
+    // device pitch = the host pitch when the host rows are gap-free (one strided copy per band); rows with gaps are copied row by row,
+    // so that no byte outside the caller's view is written
+    const size_t rb16 = (rb + 15) & ~(size_t)15;
+    const size_t dpm = (mb_pitch == rb && rb % 4 == 0) ? rb : rb16, dpe = (prm && eb_pitch == rb && rb % 4 == 0) ? rb : rb16;
+    const size_t pbytes = g.plane * sizeof(u32) * (size_t)K;
+    const size_t o_img = 0, o_mb = al(o_img + ip * h), o_eb = al(o_mb + dpm * h * K), o_s = al(o_eb + (prm ? dpe * h * K : 0)),
+                 o_c = al(o_s + (prm ? pbytes : 0)), o_wl = al(o_c + (prm ? pbytes : 0)), total = al(o_wl + HY_WL_CAP * sizeof(u32));
+    SP_TRY(omni_ws_reserve(ctx, 3, total));
+    {
+        size_t plan[OMNI_WS_SLOTS] = {};
+        label_ws_bytes(hs_max, w, K, 1, plan);
+        for (int i = 4; i <= 6; i++) SP_TRY(omni_ws_reserve(ctx, i, plan[i]));
+    }
+    u8 *base = (u8 *)ctx->ws[3], *d_img = base + o_img, *d_mb = base + o_mb, *d_eb = base + o_eb;
+    u32 *S = (u32 *)(base + o_s), *C = (u32 *)(base + o_c), *wl = (u32 *)(base + o_wl);
+    int *bflags = ctx->d_flags + BD_FLAGS;
+    unsigned *d_dirty = (unsigned *)(ctx->d_flags + BD_FLAGS + 8);
+    unsigned long long *dc = h_counts ? ctx->d_counts : nullptr;
+    const int blocks = persist_blocks(ctx, 8);
+    HoldTables hold(ctx);
+    // ---- start: side streams after earlier work of this ctx; all H2D bands queued at once ----
+    OMNI_CUDA(cudaMemsetAsync(ctx->d_flags + BD_FLAGS, 0, 16 * sizeof(int), sc));
+    if (dc) OMNI_CUDA(cudaMemsetAsync(dc, 0, 3 * OMNI_MAX_K * sizeof(unsigned long long), sc));
+    OMNI_CUDA(cudaEventRecord(evStart, sc));
+    OMNI_CUDA(cudaStreamWaitEvent(si, evStart, 0));
+    OMNI_CUDA(cudaStreamWaitEvent(so, evStart, 0));
+    for (int b = 0, y = 0; b < nb; b++) {                    // band b needs rows up to r1 + halo
+        const int ye = std::min(h, (b + 1 == nb) ? h : (b + 1) * band_rows + BD_HALO);
+        OMNI_CUDA(cudaMemcpy2DAsync(d_img + (size_t)y * ip, ip, h_bgr + (size_t)y * pitch, pitch, (size_t)w * 3, ye - y, cudaMemcpyHostToDevice, si));
+        OMNI_CUDA(cudaEventRecord(evH[b], si));
+        y = ye;
+    }
+    for (int b = 0; b < nb; b++) {
+        const int r0 = b * band_rows, r1 = std::min(h, r0 + band_rows), a = std::max(0, r0 - BD_HALO), e = std::min(h, r1 + BD_HALO), hs = e - a;
+        const BitGeom gs = make_geom(hs, w);
+        OMNI_CUDA(cudaStreamWaitEvent(sc, evH[b], 0));
+        LabelPlanes L{};
+        int rc = label_pipeline(ctx, d_img + (size_t)a * ip, 1, 0, hs, w, ip, P, prm, low, high, nullptr, 0, nullptr, 0, 0, nullptr, 0, 0, true, sc, &L, true);
+        if (rc != OMNI_OK) {                                 // UNSUPPORTED can only come from the first band (same width, K, parameters)
+            if (b > 0 && rc == OMNI_ERR_UNSUPPORTED) { omni_set_error("banded call: band %d outside the label pipeline", b); rc = OMNI_ERR_CUDA; }
+            cudaStreamSynchronize(si);
+            return rc;
+        }
+        ctx->tables_hold = 1;
+        const size_t roff = (size_t)(r0 - a) * gs.ws;
+        {
+            KScope ks(ctx, "pack_planes", sc);
+            fk_pack_planes<<<blocks, 256, 0, sc>>>(L.mask_bits + roff, gs.ws, gs.plane, K, r1 - r0, w, d_mb + (size_t)r0 * dpm, dpm * h, dpm, msb_first,
+                                                   dc ? dc + OMNI_MAX_K : nullptr);
+            OMNI_CUDA(cudaGetLastError());
+        }
+        if (dc) {
+            KScope ks(ctx, "count_labels", sc);
+            fk_count_labels_sl<<<blocks, 256, 0, sc>>>((const uint4 *)L.slices + roff, gs.ws, r1 - r0, w, K, dc);
+            OMNI_CUDA(cudaGetLastError());
+        }
+        if (prm) {
+            {
+                KScope ks(ctx, "band_merge", sc);
+                fk_band_merge<<<blocks, 256, 0, sc>>>(L.edge_bits + roff, L.cand_bits + roff, gs.plane, S, C, g.plane, g.ws, g.ww, r1 - r0, K, r0, bflags + 4,
+                                                      wl, HY_WL_CAP);
+                OMNI_CUDA(cudaGetLastError());
+            }
+            if (mode >= 2 || b + 1 == nb) {                  // hysteresis of the prefix image [0, r1); the last one is the final result
+                BitGeom gp = g;
+                gp.h = r1;
+                OMNI_CUDA(cudaMemsetAsync(bflags, 0, 4 * sizeof(int), sc));
+                SP_TRY(run_hysteresis(ctx, S, C, gp, K, nullptr, 0, 0, sc, bflags, wl));
+            }
+            if (mode >= 2) {
+                KScope ks(ctx, "pack_planes", sc);
+                fk_pack_planes<<<blocks, 256, 0, sc>>>(S + (size_t)r0 * g.ws, g.ws, g.plane, K, r1 - r0, w, d_eb + (size_t)r0 * dpe, dpe * h, dpe, msb_first, nullptr);
+                OMNI_CUDA(cudaGetLastError());
+            }
+        }
+        OMNI_CUDA(cudaEventRecord(evB[b], sc));
+        OMNI_CUDA(cudaStreamWaitEvent(so, evB[b], 0));
+        OMNI_CUDA(d2h_rows(h_mb, mb_plane, mb_pitch, d_mb, dpm * h, dpm, rb, r0, r1 - r0, K, so));
+        if (prm && mode >= 2) OMNI_CUDA(d2h_rows(h_eb, eb_plane, eb_pitch, d_eb, dpe * h, dpe, rb, r0, r1 - r0, K, so));
+    }
+    // ---- after the last band ----
+    if (prm) {
+        if (mode >= 2) {
+            KScope ks(ctx, "band_verify", sc);
+            fk_band_verify<<<32, 256, 0, sc>>>(S, g.ws, g.plane, w, bflags + 4, wl, HY_WL_CAP, d_eb, dpe * h, dpe, msb_first, band_rows, d_dirty);
+            OMNI_CUDA(cudaGetLastError());
+            OMNI_CUDA(cudaMemcpyAsync(ctx->h_flags + BD_FLAGS + 8, d_dirty, sizeof(unsigned), cudaMemcpyDeviceToHost, sc));
+        } else {
+            KScope ks(ctx, "pack_planes", sc);
+            fk_pack_planes<<<blocks, 256, 0, sc>>>(S, g.ws, g.plane, K, h, w, d_eb, dpe * h, dpe, msb_first, nullptr);
+            OMNI_CUDA(cudaGetLastError());
+            OMNI_CUDA(cudaEventRecord(evEdges, sc));
+            OMNI_CUDA(cudaStreamWaitEvent(so, evEdges, 0));
+            OMNI_CUDA(d2h_rows(h_eb, eb_plane, eb_pitch, d_eb, dpe * h, dpe, rb, 0, h, K, so));
+        }
+        if (dc) {
+            KScope ks(ctx, "count_bits", sc);
+            fk_count_bits<<<dim3(64, K), 256, 0, sc>>>(S, g.ws, g.plane, K, h, w, dc + 2 * OMNI_MAX_K);
+            OMNI_CUDA(cudaGetLastError());
+        }
+    }
+    if (dc) OMNI_CUDA(cudaMemcpyAsync(ctx->h_counts, dc, 3 * OMNI_MAX_K * sizeof(unsigned long long), cudaMemcpyDeviceToHost, sc));
+    OMNI_CUDA(cudaStreamSynchronize(sc));
+    ctx->last_band_resends = 0;
+    if (prm && mode >= 2) {
+        unsigned dirty = (unsigned)ctx->h_flags[BD_FLAGS + 8];
+        if (dirty == 0xffffffffu) {                          // worklist overflow: the device copy was not repaired -- repack, send everything
+            KScope ks(ctx, "pack_planes", sc);
+            fk_pack_planes<<<blocks, 256, 0, sc>>>(S, g.ws, g.plane, K, h, w, d_eb, dpe * h, dpe, msb_first, nullptr);
+            OMNI_CUDA(cudaGetLastError());
+            OMNI_CUDA(cudaStreamSynchronize(sc));
+            dirty = (1u << nb) - 1u;
+        }
+        dirty &= (1u << (nb - 1)) - 1u;                      // the last band was packed from the final planes
+        for (int b = 0; b < nb; b++)
+            if (dirty >> b & 1u) {
+                const int r0 = b * band_rows, r1 = std::min(h, r0 + band_rows);
+                OMNI_CUDA(d2h_rows(h_eb, eb_plane, eb_pitch, d_eb, dpe * h, dpe, rb, r0, r1 - r0, K, so));
+                ctx->last_band_resends++;
+            }
+    }
+    OMNI_CUDA(cudaStreamSynchronize(so));
+    if (h_counts)
+        for (int k = 0; k < K; k++) {
+            h_counts[3 * k] = (int64_t)ctx->h_counts[k];
+            h_counts[3 * k + 1] = (int64_t)ctx->h_counts[OMNI_MAX_K + k];
+            h_counts[3 * k + 2] = (int64_t)ctx->h_counts[2 * OMNI_MAX_K + k];
         }
     return OMNI_OK;
 }

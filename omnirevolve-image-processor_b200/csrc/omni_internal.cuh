@@ -103,11 +103,16 @@ struct omni_ctx {
     u8 cells3_lut[OMNI_MAX_K] = {};
     u8 *d_rgb_boxes3 = nullptr;                // d_rgb_boxes in the cell order of fk_assign_slices
     int table_cache = 1;                       // 0: rebuild the candidate tables on every call (omni_set_table_cache)
+    int tables_hold = 0;                       // inside one banded host call: the tables of its first band serve the other bands
     int occ_assign_sl = 0;
     // streams / events / pinned counts of omni_host_color_edge_packed (two staging slots)
     int pk_ready = 0;
     cudaStream_t pk_in = nullptr, pk_out = nullptr;
     cudaEvent_t pk_ev[7] = {};
+    cudaEvent_t bd_ev[2 * 16 + 2] = {};        // banded single-image call: H2D of a band done, outputs of a band ready, start, edges ready
+    int bd_ready = 0;
+    int host_bands = 2;                        // omni_set_host_bands: 0 = off, 1 = edge planes after the last band, 2 = edge rows with their band
+    int last_band_resends = 0;                 // bands of the last banded call whose edge rows were sent twice (mode 2)
     unsigned long long *pk_counts = nullptr;
     size_t pk_counts_cap = 0;                  // groups of 3 * OMNI_MAX_K counts
     int pipeline = 1;                          // fused colour+edge call: 1 = sparse generation (label_pipe.cu), 0 = dense generation

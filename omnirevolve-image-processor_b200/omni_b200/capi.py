@@ -25,7 +25,7 @@ EXPORTS = [
     "omni_profile_summary", "omni_thin_zhangsuen", "omni_host_thin_zhangsuen", "omni_swatch_masks", "omni_color_edge_batch", "omni_skeleton_degree",
     "omni_set_table_cache", "omni_host_edges_composite", "omni_color_edge_packed", "omni_host_color_edge_packed",
     "omni_workspace_bytes", "omni_ctx_reserve", "omni_set_assume_binary_masks", "omni_kmeans_lab",
-    "omni_thin_zhangsuen_packed",
+    "omni_thin_zhangsuen_packed", "omni_set_host_bands", "omni_last_band_resends",
 ]
 
 
@@ -62,6 +62,8 @@ def lib():
         "omni_device_count": ([], i),
         "omni_set_fast_path": ([vp, i], i),
         "omni_set_table_cache": ([vp, i], i),
+        "omni_set_host_bands": ([vp, i], i),
+        "omni_last_band_resends": ([vp], i),
         "omni_set_assume_binary_masks": ([vp, i], i),
         "omni_workspace_bytes": ([i, i, i, i, i], sz),
         "omni_ctx_reserve": ([vp, i, i, i, i, i], i),

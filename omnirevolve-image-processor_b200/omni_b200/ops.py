@@ -140,6 +140,15 @@ class Engine:
         """False: rebuild the candidate-centre tables on every call (single images with their own centres)."""
         capi.check(self._L.omni_set_table_cache(self._h, 1 if enable else 0))
 
+    def set_host_bands(self, mode: int):
+        """Row-band pipelining of `host_color_edge_packed` with one frame: 0 off, 1 edge planes after the last band, 2 (default)
+        edge rows with their band + resend of the bands a later band changed.  Same bytes in every mode."""
+        capi.check(self._L.omni_set_host_bands(self._h, int(mode)))
+
+    def last_band_resends(self) -> int:
+        """Bands of the last banded call whose edge rows went out twice (-1: the last call was not banded)."""
+        return int(self._L.omni_last_band_resends(self._h))
+
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 

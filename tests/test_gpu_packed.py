@@ -254,3 +254,98 @@ def test_thinning_on_packed_planes_equals_byte_planes(eng, hw, K, msb):
     e2 = e_bits.clone()
     eng.thin_zhangsuen_packed(e2, w, msb_first=msb, out=e2)
     assert torch.equal(e2, torch.from_numpy(got_bits).cuda())
+
+
+# ---- row-band pipelining of the single-image host call (omni_set_host_bands) ------------------------------------------------
+def _host_packed(eng, img, ctr, lut, ec, bands, msb=True, counts=True):
+    eng.set_host_bands(bands)
+    try:
+        r = eng.host_color_edge_packed(img, ctr, lut, ec, msb_first=msb, want_counts=counts)
+        return r, eng.last_band_resends()
+    finally:
+        eng.set_host_bands(2)
+
+
+@pytest.mark.parametrize("hw,K,msb", [((1100, 2048), 4, True), ((1500, 1999), 5, False), ((2051, 1025), 16, True), ((4096, 4096), 16, True)])
+def test_banded_host_call_equals_unbanded(eng, hw, K, msb):
+    """One image through omni_host_color_edge_packed: bands off / edge planes after the last band / edge rows with their band give
+    the same bytes and counts as the device-resident call (gap-free rows, odd widths, pitches that are no multiple of 16)."""
+    import omni_b200
+    h, w = hw
+    img = synth(h, w, K + 3, cell=32)
+    ctr, lut = _centres(img[: min(h, 1024)], K)
+    ec = omni_b200.EdgeConfig()
+    mb0, eb0, c0 = eng.color_edge_packed(dev(img), ctr, lut, ec, msb_first=msb, want_counts=True)
+    mb0, eb0 = host(mb0), host(eb0)
+    for bands in (0, 1, 2):
+        r, resends = _host_packed(eng, img, ctr, lut, ec, bands, msb)
+        assert (resends >= 0) == (bands > 0), (bands, resends)
+        assert np.array_equal(r["mask_bits"], mb0), bands
+        assert np.array_equal(r["edge_bits"], eb0), bands
+        assert np.array_equal(r["counts"], c0), bands
+    r, resends = _host_packed(eng, img, ctr, lut, None, 2, msb)           # colour layers only
+    assert resends == 0 and r["edge_bits"] is None and np.array_equal(r["mask_bits"], mb0)
+
+
+def test_banded_host_call_against_the_oracle(eng):
+    """The banded call against the CPU oracle directly (not only against the unbanded GPU path)."""
+    import omni_b200
+    rp = _rp()
+    h, w, K = 1300, 1700, 4
+    img = synth(h, w, 11, cell=48)
+    ctr, lut = _centres(img, K)
+    r, resends = _host_packed(eng, img, ctr, lut, omni_b200.EdgeConfig(), 2)
+    assert resends >= 0
+    _c, labels, masks = rp.color_extract(img, K, ctr)
+    for k in range(K):
+        assert np.array_equal(np.unpackbits(r["mask_bits"][k], axis=1)[:, :w] * 255, masks[k]), k
+        assert np.array_equal(np.unpackbits(r["edge_bits"][k], axis=1)[:, :w] * 255, rp.edge_layer(masks[k])), k
+    assert np.array_equal(r["counts"][:, 0], np.bincount(labels.ravel(), minlength=K)[:K])
+
+
+def test_banded_host_call_weak_chains_across_bands(eng):
+    """Thresholds that leave most straight edges weak and only corners strong: weak chains run across band borders, so a later band
+    promotes pixels of rows that have left already -- those bands must be sent again (and with more than 8192 weak words the
+    worklist overflows and everything is resent).  Bytes must equal the unbanded call whatever happened."""
+    import omni_b200
+    seen = []
+    for (h, w, K, cell) in ((1100, 2048, 3, 96), (4096, 4096, 8, 64)):
+        img = synth(h, w, 5, cell=cell)
+        ctr, lut = _centres(img[:1024], K)
+        for high in (400.0, 700.0, 800.0, 900.0, 1000.0):
+            ec = omni_b200.EdgeConfig(low=50.0, high=high)
+            r0, _ = _host_packed(eng, img, ctr, lut, ec, 0, counts=True)
+            for bands in (1, 2):
+                r, resends = _host_packed(eng, img, ctr, lut, ec, bands, counts=True)
+                assert np.array_equal(r["mask_bits"], r0["mask_bits"]), (h, high, bands)
+                assert np.array_equal(r["edge_bits"], r0["edge_bits"]), (h, high, bands)
+                assert np.array_equal(r["counts"], r0["counts"]), (h, high, bands)
+                if bands == 2:
+                    seen.append(resends)
+    print("band resends:", seen)
+    assert max(seen) > 0, seen          # the resend path was exercised
+
+
+def test_banded_host_call_leaves_row_gaps_alone(eng):
+    """Host planes whose rows are wider than ceil(w/8) (a view into a larger array): bytes outside the view stay untouched."""
+    import ctypes as C
+    import omni_b200
+    from omni_b200 import capi
+    h, w, K = 1200, 2000, 3
+    rb = (w + 7) // 8
+    img = synth(h, w, 2, cell=64)
+    ctr, lut = _centres(img, K)
+    ec = omni_b200.EdgeConfig()
+    want, _ = _host_packed(eng, img, ctr, lut, ec, 0)
+    for gap in (6, 22):
+        big_m = np.full((K, h, rb + gap), 0xA5, np.uint8)
+        big_e = np.full((K, h, rb + gap), 0x5A, np.uint8)
+        p = ec.to_c()
+        ctr32 = np.ascontiguousarray(ctr, np.float32)
+        capi.check(eng._L.omni_host_color_edge_packed(
+            eng._h, img.ctypes.data, 1, img.strides[0] * h, h, w, img.strides[0], ctr32.ctypes.data_as(C.POINTER(C.c_float)), K,
+            lut.ctypes.data_as(C.POINTER(C.c_uint8)), C.byref(p), big_m.ctypes.data, big_m.strides[0], big_m.strides[1],
+            big_e.ctypes.data, big_e.strides[0], big_e.strides[1], capi.BITS_MSB_FIRST, None))
+        assert eng.last_band_resends() >= 0
+        assert np.array_equal(big_m[:, :, :rb], want["mask_bits"]) and np.array_equal(big_e[:, :, :rb], want["edge_bits"])
+        assert (big_m[:, :, rb:] == 0xA5).all() and (big_e[:, :, rb:] == 0x5A).all()
