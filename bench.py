@@ -521,6 +521,12 @@ def run_ours(args, wl):
 
     e2e_s = time_e2e(e2e_step, args.steps)
     e2e_val = world * N * args.steps / 1e6 / e2e_s
+    band_resends = eng.last_band_resends()
+    # the same call without row bands (copy in, compute, copy out one after the other: what round 2 reported until r2_c)
+    eng.set_host_bands(0)
+    nb_steps = max(3, args.steps // 2)
+    e2e_nb_s = time_e2e(e2e_step, nb_steps)
+    eng.set_host_bands(2)
     # the u8-plane host call (what round 1 reported as e2e): 2 K bytes per pixel leave the GPU instead of 2 K bits
     h_masks = omni_b200.pinned_empty((K, h, w))
     h_edges = omni_b200.pinned_empty((K, h, w))
@@ -653,7 +659,11 @@ def run_ours(args, wl):
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(h_img.nbytes),
                     "d2h_bytes_per_step": int(h_mb.nbytes + h_eb.nbytes), "ms_per_step": e2e_s / args.steps * 1e3,
                     "api": "omni_host_color_edge_packed (pinned host image in; K masks + K edge planes out to pinned host memory as 1 bit per "
-                           "pixel, the row format of the 1-bit PNGs the drop-in stage scripts write)"},
+                           "pixel, the row format of the 1-bit PNGs the drop-in stage scripts write)",
+                    "row_bands": ("one image per call: upload of band b+1 | kernels of band b | download of band b-1 overlap; edge rows leave with "
+                                  "their band, bands changed by a later band are sent again (%d of the last call)" % band_resends)
+                                 if band_resends >= 0 else "not used (frame groups are pipelined instead)",
+                    "ms_per_step_without_bands": e2e_nb_s / nb_steps * 1e3},
             "e2e_u8": {"value": e2e_u8_val, "unit": UNIT, "h2d_bytes_per_step": int(h_img.nbytes), "d2h_bytes_per_step": int(2 * B * K * h * w),
                        "ms_per_step": e2e_u8_s / u8_steps * 1e3, "api": "omni_host_color_edge (u8 planes out)"},
             "roofline": roofline_record(m["prof"], m["prof_step_ms"], ms_per_step, args.steps, N, K, args.workload, peak, peak_src),

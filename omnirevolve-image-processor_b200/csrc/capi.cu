@@ -85,7 +85,8 @@ extern "C" int omni_ctx_destroy(omni_ctx *c)
         for (auto e : c->pk_ev) cudaEventDestroy(e);
     }
     if (c->pk_counts) cudaFreeHost(c->pk_counts);
-    if (c->bd_ready) for (auto e : c->bd_ev) cudaEventDestroy(e);
+    if (c->bd_ready) { for (auto e : c->bd_ev) cudaEventDestroy(e); cudaStreamDestroy(c->bd_tail); }
+    if (c->band_helper) omni_ctx_destroy(c->band_helper);
     delete c;
     return OMNI_OK;
 }

@@ -166,6 +166,7 @@ cudaError_t launch_build_cells(const AssignParams &P, u32 *cells, cudaStream_t s
 // flags / worklist: NULL = the ctx's own (d_flags[0..4], the list the edge kernel wrote); the banded host call passes its own
 int run_hysteresis(omni_ctx *ctx, u32 *ebits, const u32 *cbits, const BitGeom &g, int K, u8 *d_edges, size_t e_plane, size_t epitch,
                    cudaStream_t st, int *flags = nullptr, const u32 *worklist = nullptr);
+int run_hysteresis_wl(omni_ctx *ctx, u32 *ebits, const u32 *cbits, const BitGeom &g, int K, cudaStream_t st, const int *flags, const u32 *worklist);
 int edge_pass_begin(omni_ctx *ctx, const BitGeom &g, int K, u32 *sbits, u32 *cbits, u8 *d_edges, size_t e_plane, size_t epitch,
                     cudaStream_t st, MorphRuns *R, bool *sparse, bool side_fill, ZeroJob *zjob = nullptr);
 int morph03_kind(const omni_edge_params *p);

@@ -977,6 +977,65 @@ __device__ __forceinline__ void hy_patch_bytes(u8 *row, u32 promoted)
     }
 }
 
+// worklist mode of the hysteresis: every word that holds a weak candidate (C & ~S) is listed; on pipeline data that is a few hundred
+// words, so ONE CTA resolves them.  Returns the number of rounds.
+__device__ __forceinline__ int hy_worklist(u32 *__restrict__ ebits, const u32 *__restrict__ cbits, int ws, size_t plane, int h, int w, int n_weak,
+                                   const u32 *__restrict__ worklist, u8 *__restrict__ edges, size_t estride, size_t epitch)
+{
+    const int wwl = (w + 31) >> 5;
+    int rounds = 0;
+    for (;;) {
+        int changed = 0;
+        for (int i = threadIdx.x; i < n_weak; i += HY_THREADS) {
+            const u32 o = worklist[i];
+            const int k = (int)(o / plane), rem = (int)(o - (size_t)k * plane);
+            const int y = rem / ws, c = rem - y * ws;
+            u32 *E = ebits + (size_t)k * plane + (size_t)y * ws;
+            // every load of the item is issued at once (one L2 round trip instead of three dependent ones)
+            const u32 cv = __ldg(cbits + o);
+            u32 m3[3], l3[3], r3[3];
+#pragma unroll
+            for (int dy = -1; dy <= 1; dy++) {
+                const bool in = y + dy >= 0 && y + dy < h;
+                const u32 *Er = E + (ptrdiff_t)dy * ws;
+                m3[dy + 1] = in ? __ldcg(Er + c) : 0u;
+                l3[dy + 1] = (in && c > 0) ? __ldcg(Er + c - 1) : 0u;
+                r3[dy + 1] = (in && c + 1 < wwl) ? __ldcg(Er + c + 1) : 0u;
+            }
+            const u32 ev = m3[1];
+            if ((cv & ~ev) == 0u) continue;
+            u32 d = 0u;
+#pragma unroll
+            for (int q = 0; q < 3; q++) d |= m3[q] | (m3[q] << 1) | (m3[q] >> 1) | (l3[q] >> 31) | (r3[q] << 31);
+            u32 nv = ev | (cv & d);
+            for (;;) {
+                u32 t = nv | (cv & ((nv << 1) | (nv >> 1)));
+                if (t == nv) break;
+                nv = t;
+            }
+            if (nv != ev) {
+                E[c] = nv;
+                changed = 1;
+                hy_patch_bytes(edges ? edges + (size_t)k * estride + (size_t)y * epitch + 32 * c : nullptr, nv & ~ev);
+            }
+        }
+        rounds++;
+        __threadfence_block();
+        if (!__syncthreads_or(changed)) break;
+    }
+    return rounds;
+}
+
+// The same as a plain (non-cooperative) one-CTA launch: the banded host call resolves the prefix image after every band with it.  A list
+// that overflowed is left alone (any subset of the final result is good enough there; the last band runs fk_hysteresis).
+__global__ void __launch_bounds__(HY_THREADS) fk_hysteresis_wl(u32 *__restrict__ ebits, const u32 *__restrict__ cbits, int ws, size_t plane, int h,
+                                                               int w, const int *flags, const u32 *__restrict__ worklist)
+{
+    const int n_weak = flags[4];
+    if (n_weak > HY_WL_CAP) return;
+    hy_worklist(ebits, cbits, ws, plane, h, w, n_weak, worklist, nullptr, 0, 0);
+}
+
 __global__ void __launch_bounds__(HY_THREADS) fk_hysteresis(u32 *__restrict__ ebits, const u32 *__restrict__ cbits, int ws, size_t plane, int h,
                                                      int w, int K, int *flags /* [0]=rounds, [1..3]=rotating "changed" flags, [4]=worklist count */,
                                                      const u32 *__restrict__ worklist,
@@ -988,47 +1047,7 @@ __global__ void __launch_bounds__(HY_THREADS) fk_hysteresis(u32 *__restrict__ eb
     const int n_weak = flags[4];
     if (n_weak <= HY_WL_CAP) {
         if (blockIdx.x != 0) return;
-        const int wwl = (w + 31) >> 5;
-        int rounds = 0;
-        for (;;) {
-            int changed = 0;
-            for (int i = threadIdx.x; i < n_weak; i += HY_THREADS) {
-                const u32 o = worklist[i];
-                const int k = (int)(o / plane), rem = (int)(o - (size_t)k * plane);
-                const int y = rem / ws, c = rem - y * ws;
-                u32 *E = ebits + (size_t)k * plane + (size_t)y * ws;
-                // every load of the item is issued at once (one L2 round trip instead of three dependent ones)
-                const u32 cv = __ldg(cbits + o);
-                u32 m3[3], l3[3], r3[3];
-#pragma unroll
-                for (int dy = -1; dy <= 1; dy++) {
-                    const bool in = y + dy >= 0 && y + dy < h;
-                    const u32 *Er = E + (ptrdiff_t)dy * ws;
-                    m3[dy + 1] = in ? __ldcg(Er + c) : 0u;
-                    l3[dy + 1] = (in && c > 0) ? __ldcg(Er + c - 1) : 0u;
-                    r3[dy + 1] = (in && c + 1 < wwl) ? __ldcg(Er + c + 1) : 0u;
-                }
-                const u32 ev = m3[1];
-                if ((cv & ~ev) == 0u) continue;
-                u32 d = 0u;
-#pragma unroll
-                for (int q = 0; q < 3; q++) d |= m3[q] | (m3[q] << 1) | (m3[q] >> 1) | (l3[q] >> 31) | (r3[q] << 31);
-                u32 nv = ev | (cv & d);
-                for (;;) {
-                    u32 t = nv | (cv & ((nv << 1) | (nv >> 1)));
-                    if (t == nv) break;
-                    nv = t;
-                }
-                if (nv != ev) {
-                    E[c] = nv;
-                    changed = 1;
-                    hy_patch_bytes(edges ? edges + (size_t)k * estride + (size_t)y * epitch + 32 * c : nullptr, nv & ~ev);
-                }
-            }
-            rounds++;
-            __threadfence_block();
-            if (!__syncthreads_or(changed)) break;
-        }
+        const int rounds = hy_worklist(ebits, cbits, ws, plane, h, w, n_weak, worklist, edges, estride, epitch);
         if (threadIdx.x == 0) flags[0] = rounds;
         return;
     }
@@ -1398,6 +1417,15 @@ int run_hysteresis(omni_ctx *ctx, u32 *ebits, const u32 *cbits, const BitGeom &g
         ctx->last_hyst_passes = -1;       // lives in d_flags[0]; fetched lazily by omni_last_hysteresis_passes
         ctx->last_hyst_stream = st;
     }
+    return OMNI_OK;
+}
+
+int run_hysteresis_wl(omni_ctx *ctx, u32 *ebits, const u32 *cbits, const BitGeom &g, int K, cudaStream_t st, const int *flags, const u32 *worklist)
+{
+    (void)K;
+    KScope ks(ctx, "hysteresis_wl", st);
+    fk_hysteresis_wl<<<1, HY_THREADS, 0, st>>>(ebits, cbits, g.ws, g.plane, g.h, g.w, flags, worklist);
+    OMNI_CUDA(cudaGetLastError());
     return OMNI_OK;
 }
 

@@ -23,6 +23,9 @@
 #include "fast_device.cuh"
 
 #include <algorithm>
+#include <vector>
+#include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #define LP_ZBUF 8192                      // zeroed shared-memory block behind the tables of fk_assign_slices (bulk-store source)
@@ -972,10 +975,12 @@ __global__ void __launch_bounds__(256) fk_band_merge(const u32 *__restrict__ s_s
     }
 }
 
+struct BandRows { int n; int y[BD_MAX_BANDS + 1]; };     // band b = rows [y[b], y[b+1])
+
 // final planes against the packed rows that were sent: repairs the device copy, dirty bit b = band b has to be sent again
 __global__ void __launch_bounds__(256) fk_band_verify(const u32 *__restrict__ ebits, int ws, size_t plane, int w, const int *wl_count,
                                                       const u32 *__restrict__ worklist, int wl_cap, u8 *__restrict__ dst, size_t dplane, size_t dpitch,
-                                                      int msb_first, int band_rows, unsigned *dirty)
+                                                      int msb_first, const BandRows B, unsigned *dirty)
 {
     const int n = *wl_count;
     if (n > wl_cap) {                                    // list overflowed: the caller repacks and resends everything
@@ -996,7 +1001,11 @@ __global__ void __launch_bounds__(256) fk_band_verify(const u32 *__restrict__ eb
             const u8 b = (u8)(v >> (8 * j));
             if (row[j] != b) { row[j] = b; diff = true; }
         }
-        if (diff) atomicOr(dirty, 1u << (y / band_rows));
+        if (diff) {
+            int b = 0;
+            while (b + 1 < B.n && y >= B.y[b + 1]) b++;
+            atomicOr(dirty, 1u << b);
+        }
     }
 }
 
@@ -1045,19 +1054,45 @@ int label_host_packed_banded(omni_ctx *ctx, const u8 *h_bgr, int h, int w, size_
     if (mode == 0 || !ctx->fast || ctx->pipeline != 1 || h < 1024 || (long long)h * w < (2ll << 20)) return OMNI_ERR_UNSUPPORTED;
     if (prm && (low < 0 || morph03_kind(prm) < 0 || prm->ksize != 3)) return OMNI_ERR_UNSUPPORTED;
     if (K > RC_MAX_K || !lut_below_k(P)) return OMNI_ERR_UNSUPPORTED;
-    // ---- bands ----
-    int band_rows = ((h + 7) / 8 + 31) & ~31;                // 8 bands, rows a multiple of 32
-    if (band_rows < 256) band_rows = 256;
-    const int nb = (h + band_rows - 1) / band_rows;
+    // ---- bands: a tall image starts with short bands (128, 256, 512 rows) so that the first results leave for the host while most
+    // of the image is still arriving; the rest is split evenly (rows a multiple of 32) ----
+    BandRows B{};
+    {
+        int y = 0;
+        if (h >= 2048)
+            for (int lead : {128, 256, 512}) { B.y[++B.n] = (y += lead); }
+        const int left = h - y;
+        int n_even = std::max(1, std::min(BD_MAX_BANDS - B.n - 1, 5));
+        while (n_even > 1 && left / n_even < 256) n_even--;
+        const int per = ((left + n_even - 1) / n_even + 31) & ~31;
+        while (y < h) { y = std::min(h, y + per); B.y[++B.n] = y; }
+    }
+    const int nb = B.n;
     if (nb < 2 || nb > BD_MAX_BANDS) return OMNI_ERR_UNSUPPORTED;
-    const int hs_max = std::min(h, band_rows + 2 * BD_HALO);
+    int tallest = 0;
+    for (int b = 0; b < nb; b++) tallest = std::max(tallest, B.y[b + 1] - B.y[b]);
+    const int hs_max = std::min(h, tallest + 2 * BD_HALO);
     if (!edges3_sparse_ok(hs_max, w, K) || !edges3_sparse_ok(h, w, K)) return OMNI_ERR_UNSUPPORTED;
     if (!ctx->bd_ready) {
         for (auto &e : ctx->bd_ev) OMNI_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        OMNI_CUDA(cudaStreamCreateWithFlags(&ctx->bd_tail, cudaStreamNonBlocking));
         ctx->bd_ready = 1;
     }
-    cudaEvent_t *evH = ctx->bd_ev, *evB = ctx->bd_ev + BD_MAX_BANDS, evStart = ctx->bd_ev[2 * BD_MAX_BANDS], evEdges = ctx->bd_ev[2 * BD_MAX_BANDS + 1];
-    cudaStream_t sc = ctx->stream, si = ctx->pk_in, so = ctx->pk_out;
+    cudaEvent_t *evH = ctx->bd_ev, *evF = ctx->bd_ev + BD_MAX_BANDS, *evB = ctx->bd_ev + 2 * BD_MAX_BANDS, evStart = ctx->bd_ev[3 * BD_MAX_BANDS],
+                evEdges = ctx->bd_ev[3 * BD_MAX_BANDS + 1];
+    // streams: copies in (si) and out (so); the band images (assignment .. edge kernel) alternate between this ctx and a helper ctx
+    // with workspaces of its own, so that two of them are in flight (their kernels are short and latency-bound); what follows a band
+    // image -- packing, the merge into the full planes, the hysteresis -- runs in band order on the tail stream tt
+    omni_ctx *hx = nullptr;
+    if (ctx->band_overlap && !ctx->prof_on) {
+        if (!ctx->band_helper) {
+            SP_TRY(omni_ctx_create(ctx->device, &ctx->band_helper));
+            ctx->band_helper->edge_sparse = ctx->edge_sparse;
+            ctx->band_helper->assign_rgbcell = ctx->assign_rgbcell;
+        }
+        hx = ctx->band_helper;
+    }
+    cudaStream_t sc = ctx->stream, si = ctx->pk_in, so = ctx->pk_out, tt = ctx->bd_tail;
     // ---- workspace: slot 3 = [image | packed masks | packed edges | S | C | worklist]; slots 4-6 sized for the tallest band image ----
     const BitGeom g = make_geom(h, w);
     const size_t rb = ((size_t)w + 7) / 8;
@@ -1074,7 +1109,10 @@ int label_host_packed_banded(omni_ctx *ctx, const u8 *h_bgr, int h, int w, size_
     {
         size_t plan[OMNI_WS_SLOTS] = {};
         label_ws_bytes(hs_max, w, K, 1, plan);
-        for (int i = 4; i <= 6; i++) SP_TRY(omni_ws_reserve(ctx, i, plan[i]));
+        for (int i = 4; i <= 6; i++) {
+            SP_TRY(omni_ws_reserve(ctx, i, plan[i]));
+            if (hx) SP_TRY(omni_ws_reserve(hx, i, plan[i]));
+        }
     }
     u8 *base = (u8 *)ctx->ws[3], *d_img = base + o_img, *d_mb = base + o_mb, *d_eb = base + o_eb;
     u32 *S = (u32 *)(base + o_s), *C = (u32 *)(base + o_c), *wl = (u32 *)(base + o_wl);
@@ -1082,109 +1120,147 @@ int label_host_packed_banded(omni_ctx *ctx, const u8 *h_bgr, int h, int w, size_
     unsigned *d_dirty = (unsigned *)(ctx->d_flags + BD_FLAGS + 8);
     unsigned long long *dc = h_counts ? ctx->d_counts : nullptr;
     const int blocks = persist_blocks(ctx, 8);
-    HoldTables hold(ctx);
+    HoldTables hold(ctx), hold_h(hx ? hx : ctx);
+    const int lag = hx ? 2 : 1;                              // the band image before this one on the same ctx
+    // OMNI_B200_BAND_TRACE=1: timeline of the call on stderr (timing events: H2D done, kernels done, D2H done per band)
+    static const bool trace = getenv("OMNI_B200_BAND_TRACE") != nullptr;
+    std::vector<cudaEvent_t> tev;
+    std::vector<int> tkind;                                  // 0 start, 1 H2D done, 2 kernels done, 3 D2H done (each in band order)
+    auto tmark = [&](cudaStream_t s, int kind = 0) { if (trace) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, s); tev.push_back(e); tkind.push_back(kind); } };
     // ---- start: side streams after earlier work of this ctx; all H2D bands queued at once ----
     OMNI_CUDA(cudaMemsetAsync(ctx->d_flags + BD_FLAGS, 0, 16 * sizeof(int), sc));
     if (dc) OMNI_CUDA(cudaMemsetAsync(dc, 0, 3 * OMNI_MAX_K * sizeof(unsigned long long), sc));
+    tmark(sc);
     OMNI_CUDA(cudaEventRecord(evStart, sc));
     OMNI_CUDA(cudaStreamWaitEvent(si, evStart, 0));
     OMNI_CUDA(cudaStreamWaitEvent(so, evStart, 0));
-    for (int b = 0, y = 0; b < nb; b++) {                    // band b needs rows up to r1 + halo
-        const int ye = std::min(h, (b + 1 == nb) ? h : (b + 1) * band_rows + BD_HALO);
-        OMNI_CUDA(cudaMemcpy2DAsync(d_img + (size_t)y * ip, ip, h_bgr + (size_t)y * pitch, pitch, (size_t)w * 3, ye - y, cudaMemcpyHostToDevice, si));
+    OMNI_CUDA(cudaStreamWaitEvent(tt, evStart, 0));
+    if (hx) OMNI_CUDA(cudaStreamWaitEvent(hx->stream, evStart, 0));
+    // the uploads are queued two bands ahead of the kernels (not all at once: the first band's kernels should not wait behind 2 nb
+    // copy calls on the host); band b needs rows up to r1 + halo
+    int h2d_next = 0, h2d_y = 0;
+    auto queue_h2d = [&]() -> int {
+        const int b = h2d_next++;
+        const int ye = std::min(h, (b + 1 == nb) ? h : B.y[b + 1] + BD_HALO);
+        OMNI_CUDA(cudaMemcpy2DAsync(d_img + (size_t)h2d_y * ip, ip, h_bgr + (size_t)h2d_y * pitch, pitch, (size_t)w * 3, ye - h2d_y, cudaMemcpyHostToDevice, si));
         OMNI_CUDA(cudaEventRecord(evH[b], si));
-        y = ye;
-    }
+        tmark(si, 1);
+        h2d_y = ye;
+        return OMNI_OK;
+    };
+    SP_TRY(queue_h2d());
+    SP_TRY(queue_h2d());
     for (int b = 0; b < nb; b++) {
-        const int r0 = b * band_rows, r1 = std::min(h, r0 + band_rows), a = std::max(0, r0 - BD_HALO), e = std::min(h, r1 + BD_HALO), hs = e - a;
+        const int r0 = B.y[b], r1 = B.y[b + 1], a = std::max(0, r0 - BD_HALO), e = std::min(h, r1 + BD_HALO), hs = e - a;
         const BitGeom gs = make_geom(hs, w);
-        OMNI_CUDA(cudaStreamWaitEvent(sc, evH[b], 0));
+        if (h2d_next < nb) SP_TRY(queue_h2d());
+        omni_ctx *cx = (hx && (b & 1)) ? hx : ctx;
+        cudaStream_t sf = cx->stream;
+        OMNI_CUDA(cudaStreamWaitEvent(sf, evH[b], 0));
+        if (b >= lag) OMNI_CUDA(cudaStreamWaitEvent(sf, evB[b - lag], 0));      // the tail of that band has read cx's bit-planes
         LabelPlanes L{};
-        int rc = label_pipeline(ctx, d_img + (size_t)a * ip, 1, 0, hs, w, ip, P, prm, low, high, nullptr, 0, nullptr, 0, 0, nullptr, 0, 0, true, sc, &L, true);
+        int rc = label_pipeline(cx, d_img + (size_t)a * ip, 1, 0, hs, w, ip, P, prm, low, high, nullptr, 0, nullptr, 0, 0, nullptr, 0, 0, true, sf, &L, true);
         if (rc != OMNI_OK) {                                 // UNSUPPORTED can only come from the first band (same width, K, parameters)
             if (b > 0 && rc == OMNI_ERR_UNSUPPORTED) { omni_set_error("banded call: band %d outside the label pipeline", b); rc = OMNI_ERR_CUDA; }
-            cudaStreamSynchronize(si);
+            cudaDeviceSynchronize();
             return rc;
         }
-        ctx->tables_hold = 1;
+        cx->tables_hold = 1;
+        OMNI_CUDA(cudaEventRecord(evF[b], sf));
+        OMNI_CUDA(cudaStreamWaitEvent(tt, evF[b], 0));
         const size_t roff = (size_t)(r0 - a) * gs.ws;
         {
-            KScope ks(ctx, "pack_planes", sc);
-            fk_pack_planes<<<blocks, 256, 0, sc>>>(L.mask_bits + roff, gs.ws, gs.plane, K, r1 - r0, w, d_mb + (size_t)r0 * dpm, dpm * h, dpm, msb_first,
+            KScope ks(ctx, "pack_planes", tt);
+            fk_pack_planes<<<blocks, 256, 0, tt>>>(L.mask_bits + roff, gs.ws, gs.plane, K, r1 - r0, w, d_mb + (size_t)r0 * dpm, dpm * h, dpm, msb_first,
                                                    dc ? dc + OMNI_MAX_K : nullptr);
             OMNI_CUDA(cudaGetLastError());
         }
         if (dc) {
-            KScope ks(ctx, "count_labels", sc);
-            fk_count_labels_sl<<<blocks, 256, 0, sc>>>((const uint4 *)L.slices + roff, gs.ws, r1 - r0, w, K, dc);
+            KScope ks(ctx, "count_labels", tt);
+            fk_count_labels_sl<<<blocks, 256, 0, tt>>>((const uint4 *)L.slices + roff, gs.ws, r1 - r0, w, K, dc);
             OMNI_CUDA(cudaGetLastError());
         }
         if (prm) {
             {
-                KScope ks(ctx, "band_merge", sc);
-                fk_band_merge<<<blocks, 256, 0, sc>>>(L.edge_bits + roff, L.cand_bits + roff, gs.plane, S, C, g.plane, g.ws, g.ww, r1 - r0, K, r0, bflags + 4,
+                KScope ks(ctx, "band_merge", tt);
+                fk_band_merge<<<blocks, 256, 0, tt>>>(L.edge_bits + roff, L.cand_bits + roff, gs.plane, S, C, g.plane, g.ws, g.ww, r1 - r0, K, r0, bflags + 4,
                                                       wl, HY_WL_CAP);
                 OMNI_CUDA(cudaGetLastError());
             }
-            if (mode >= 2 || b + 1 == nb) {                  // hysteresis of the prefix image [0, r1); the last one is the final result
-                BitGeom gp = g;
-                gp.h = r1;
-                OMNI_CUDA(cudaMemsetAsync(bflags, 0, 4 * sizeof(int), sc));
-                SP_TRY(run_hysteresis(ctx, S, C, gp, K, nullptr, 0, 0, sc, bflags, wl));
+            BitGeom gp = g;                                  // hysteresis of the prefix image [0, r1); the last one is the final result
+            gp.h = r1;
+            if (b + 1 == nb) {
+                OMNI_CUDA(cudaMemsetAsync(bflags, 0, 4 * sizeof(int), tt));
+                SP_TRY(run_hysteresis(ctx, S, C, gp, K, nullptr, 0, 0, tt, bflags, wl));
+            } else if (mode >= 2) {
+                SP_TRY(run_hysteresis_wl(ctx, S, C, gp, K, tt, bflags, wl));
             }
             if (mode >= 2) {
-                KScope ks(ctx, "pack_planes", sc);
-                fk_pack_planes<<<blocks, 256, 0, sc>>>(S + (size_t)r0 * g.ws, g.ws, g.plane, K, r1 - r0, w, d_eb + (size_t)r0 * dpe, dpe * h, dpe, msb_first, nullptr);
+                KScope ks(ctx, "pack_planes", tt);
+                fk_pack_planes<<<blocks, 256, 0, tt>>>(S + (size_t)r0 * g.ws, g.ws, g.plane, K, r1 - r0, w, d_eb + (size_t)r0 * dpe, dpe * h, dpe, msb_first, nullptr);
                 OMNI_CUDA(cudaGetLastError());
             }
         }
-        OMNI_CUDA(cudaEventRecord(evB[b], sc));
+        OMNI_CUDA(cudaEventRecord(evB[b], tt));
+        tmark(tt, 2);
         OMNI_CUDA(cudaStreamWaitEvent(so, evB[b], 0));
         OMNI_CUDA(d2h_rows(h_mb, mb_plane, mb_pitch, d_mb, dpm * h, dpm, rb, r0, r1 - r0, K, so));
         if (prm && mode >= 2) OMNI_CUDA(d2h_rows(h_eb, eb_plane, eb_pitch, d_eb, dpe * h, dpe, rb, r0, r1 - r0, K, so));
+        tmark(so, 3);
     }
     // ---- after the last band ----
     if (prm) {
         if (mode >= 2) {
-            KScope ks(ctx, "band_verify", sc);
-            fk_band_verify<<<32, 256, 0, sc>>>(S, g.ws, g.plane, w, bflags + 4, wl, HY_WL_CAP, d_eb, dpe * h, dpe, msb_first, band_rows, d_dirty);
+            KScope ks(ctx, "band_verify", tt);
+            fk_band_verify<<<32, 256, 0, tt>>>(S, g.ws, g.plane, w, bflags + 4, wl, HY_WL_CAP, d_eb, dpe * h, dpe, msb_first, B, d_dirty);
             OMNI_CUDA(cudaGetLastError());
-            OMNI_CUDA(cudaMemcpyAsync(ctx->h_flags + BD_FLAGS + 8, d_dirty, sizeof(unsigned), cudaMemcpyDeviceToHost, sc));
+            OMNI_CUDA(cudaMemcpyAsync(ctx->h_flags + BD_FLAGS + 8, d_dirty, sizeof(unsigned), cudaMemcpyDeviceToHost, tt));
         } else {
-            KScope ks(ctx, "pack_planes", sc);
-            fk_pack_planes<<<blocks, 256, 0, sc>>>(S, g.ws, g.plane, K, h, w, d_eb, dpe * h, dpe, msb_first, nullptr);
+            KScope ks(ctx, "pack_planes", tt);
+            fk_pack_planes<<<blocks, 256, 0, tt>>>(S, g.ws, g.plane, K, h, w, d_eb, dpe * h, dpe, msb_first, nullptr);
             OMNI_CUDA(cudaGetLastError());
-            OMNI_CUDA(cudaEventRecord(evEdges, sc));
+            OMNI_CUDA(cudaEventRecord(evEdges, tt));
             OMNI_CUDA(cudaStreamWaitEvent(so, evEdges, 0));
             OMNI_CUDA(d2h_rows(h_eb, eb_plane, eb_pitch, d_eb, dpe * h, dpe, rb, 0, h, K, so));
         }
         if (dc) {
-            KScope ks(ctx, "count_bits", sc);
-            fk_count_bits<<<dim3(64, K), 256, 0, sc>>>(S, g.ws, g.plane, K, h, w, dc + 2 * OMNI_MAX_K);
+            KScope ks(ctx, "count_bits", tt);
+            fk_count_bits<<<dim3(64, K), 256, 0, tt>>>(S, g.ws, g.plane, K, h, w, dc + 2 * OMNI_MAX_K);
             OMNI_CUDA(cudaGetLastError());
         }
     }
-    if (dc) OMNI_CUDA(cudaMemcpyAsync(ctx->h_counts, dc, 3 * OMNI_MAX_K * sizeof(unsigned long long), cudaMemcpyDeviceToHost, sc));
-    OMNI_CUDA(cudaStreamSynchronize(sc));
+    if (dc) OMNI_CUDA(cudaMemcpyAsync(ctx->h_counts, dc, 3 * OMNI_MAX_K * sizeof(unsigned long long), cudaMemcpyDeviceToHost, tt));
+    OMNI_CUDA(cudaStreamSynchronize(tt));
+    if (hx) { ctx->launches += hx->launches; hx->launches = 0; }
     ctx->last_band_resends = 0;
     if (prm && mode >= 2) {
         unsigned dirty = (unsigned)ctx->h_flags[BD_FLAGS + 8];
         if (dirty == 0xffffffffu) {                          // worklist overflow: the device copy was not repaired -- repack, send everything
-            KScope ks(ctx, "pack_planes", sc);
-            fk_pack_planes<<<blocks, 256, 0, sc>>>(S, g.ws, g.plane, K, h, w, d_eb, dpe * h, dpe, msb_first, nullptr);
+            KScope ks(ctx, "pack_planes", tt);
+            fk_pack_planes<<<blocks, 256, 0, tt>>>(S, g.ws, g.plane, K, h, w, d_eb, dpe * h, dpe, msb_first, nullptr);
             OMNI_CUDA(cudaGetLastError());
-            OMNI_CUDA(cudaStreamSynchronize(sc));
+            OMNI_CUDA(cudaStreamSynchronize(tt));
             dirty = (1u << nb) - 1u;
         }
         dirty &= (1u << (nb - 1)) - 1u;                      // the last band was packed from the final planes
         for (int b = 0; b < nb; b++)
             if (dirty >> b & 1u) {
-                const int r0 = b * band_rows, r1 = std::min(h, r0 + band_rows);
+                const int r0 = B.y[b], r1 = B.y[b + 1];
                 OMNI_CUDA(d2h_rows(h_eb, eb_plane, eb_pitch, d_eb, dpe * h, dpe, rb, r0, r1 - r0, K, so));
                 ctx->last_band_resends++;
             }
     }
     OMNI_CUDA(cudaStreamSynchronize(so));
+    if (trace) {
+        float t[4][BD_MAX_BANDS] = {};
+        int n[4] = {};
+        for (size_t i = 1; i < tev.size(); i++) cudaEventElapsedTime(&t[tkind[i]][n[tkind[i]]++], tev[0], tev[i]);
+        fprintf(stderr, "[bands] %d bands, rows:", nb);
+        for (int b = 0; b < nb; b++) fprintf(stderr, " %d", B.y[b + 1] - B.y[b]);
+        fprintf(stderr, "\n[bands] band: H2D done | kernels done | D2H done (ms after the start)\n");
+        for (int b = 0; b < nb; b++) fprintf(stderr, "[bands] %2d: %7.3f | %7.3f | %7.3f\n", b, t[1][b], t[2][b], t[3][b]);
+        for (auto e : tev) cudaEventDestroy(e);
+    }
     if (h_counts)
         for (int k = 0; k < K; k++) {
             h_counts[3 * k] = (int64_t)ctx->h_counts[k];

@@ -109,8 +109,11 @@ struct omni_ctx {
     int pk_ready = 0;
     cudaStream_t pk_in = nullptr, pk_out = nullptr;
     cudaEvent_t pk_ev[7] = {};
-    cudaEvent_t bd_ev[2 * 16 + 2] = {};        // banded single-image call: H2D of a band done, outputs of a band ready, start, edges ready
+    cudaEvent_t bd_ev[3 * 16 + 2] = {};        // banded single-image call: H2D of a band done, band image done, outputs of a band ready, start, edges ready
     int bd_ready = 0;
+    cudaStream_t bd_tail = nullptr;            // packing / merge / hysteresis of the bands, in band order
+    omni_ctx *band_helper = nullptr;           // second set of workspaces + stream: two band images in flight
+    int band_overlap = 1;
     int host_bands = 2;                        // omni_set_host_bands: 0 = off, 1 = edge planes after the last band, 2 = edge rows with their band
     int last_band_resends = 0;                 // bands of the last banded call whose edge rows were sent twice (mode 2)
     unsigned long long *pk_counts = nullptr;

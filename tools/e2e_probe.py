@@ -10,6 +10,7 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "omnirevolve-image-processor_b200"))
 sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, ROOT)
 import omni_b200  # noqa: E402
 from helpers import synth  # noqa: E402
 from oracle import refport as rp  # noqa: E402  (centres only)
@@ -49,6 +50,12 @@ for mode in (0, 1, 2):
     ref = ref or cur
     print(f"bands={mode}: median {med:.3f} ms  min {mn:.3f} ms  -> {h * w / med / 1e3:.0f} MP/s  resends={eng.last_band_resends()}  same_bytes={same}")
 eng.set_host_bands(2)
+eng.profile(True)
+eng.host_color_edge_packed(h_img, ctr, lut, ec, mask_bits=h_mb, edge_bits=h_eb, want_counts=False)
+torch.cuda.synchronize()
+ps = eng.profile_summary()
+eng.profile(False)
+print("kernels of one banded call (launches, total ms):", {k: (n, round(ms, 4)) for k, (n, ms) in ps.items()}, "sum", round(sum(ms for _n, ms in ps.values()), 4))
 
 # raw copies of the same sizes
 d_in = torch.empty(h * w * 3, dtype=torch.uint8, device="cuda")
