@@ -632,6 +632,73 @@ __global__ void __launch_bounds__(256) fk_assign_bits(const u8 *__restrict__ px,
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// process_colors.assign_labels (process_colors.py:69-77) for K <= 16: argmin_k of  sum_c (i16)((v_c - p_kc)^2)  -- the products wrap to
+// int16, the sum is wide.  |d| <= 255, so the wrapped square is d^2 - 65536 [ |d| >= 182 ], and
+//     dist_k = sum_c v_c^2  +  sum_c p_kc^2  -  2 sum_c v_c p_kc  -  65536 n_k,      n_k = channels of centre k with |v_c - p_kc| >= 182.
+// The first term is the same for every k; the dot product is one DP4A on the packed bytes; n_k comes from three table words per pixel
+// (2-bit fields per k, one table per channel in shared memory: the fields add without carries, n_k <= 3).  key_k = 16 dist_k + k keeps
+// np.argmin's first minimum under a plain integer min.  A lane takes 4 adjacent pixels (three 4-byte loads, one 4-byte label store).
+// ------------------------------------------------------------------------------------------------
+template <int KMAX>                                         // palette colours rounded up to 4, 8 or 16
+__global__ void __launch_bounds__(256) fk_assign_i16wrap(const u8 *__restrict__ px, int h, int w, size_t pitch, const __grid_constant__ AssignParams P,
+                                                         u8 *__restrict__ labels, size_t lpitch)
+{
+    __shared__ u32 s_wrap[3][256];
+    __shared__ u8 s_lut[16];
+    const int K = P.K;
+    for (int i = threadIdx.x; i < 768; i += 256) {
+        const int c = i >> 8, v = i & 255;
+        u32 word = 0u;
+        for (int k = 0; k < K; k++) {
+            const int d = v - (int)P.pal[3 * k + c];
+            word |= (u32)(d >= 182 || d <= -182) << (2 * k);
+        }
+        s_wrap[c][v] = word;
+    }
+    if (threadIdx.x < 16) s_lut[threadIdx.x] = P.lut[threadIdx.x];
+    u32 pk[KMAX];
+    int ck[KMAX];
+#pragma unroll
+    for (int k = 0; k < KMAX; k++) {
+        const int p0 = P.pal[3 * k], p1 = P.pal[3 * k + 1], p2 = P.pal[3 * k + 2];
+        pk[k] = k < K ? ((u32)p0 | ((u32)p1 << 8) | ((u32)p2 << 16)) : 0u;
+        ck[k] = k < K ? 16 * (p0 * p0 + p1 * p1 + p2 * p2) + k : 0x7ffffff0;          // k >= K never wins
+    }
+    __syncthreads();
+    auto label_of = [&](const u32 v) -> u32 {                // v = c0 | c1 << 8 | c2 << 16 (| anything << 24: pk has a zero there)
+        const u32 cnt = s_wrap[0][v & 255u] + s_wrap[1][(v >> 8) & 255u] + s_wrap[2][(v >> 16) & 255u];
+        int best = 0x7fffffff;
+#pragma unroll
+        for (int k = 0; k < KMAX; k++) {
+            const int dot = (int)__dp4a(v, pk[k], 0u);
+            const int n = (int)((cnt >> (2 * k)) & 3u);
+            best = min(best, ck[k] - 32 * dot - (n << 20));
+        }
+        return (u32)s_lut[best & 15];
+    };
+    const int groups = (w + 3) >> 2;                          // 4 pixels per lane
+    const bool fast_rows = (((uintptr_t)px | pitch) & 3) == 0;
+    const bool fast_out = (((uintptr_t)labels | lpitch) & 3) == 0;
+    const long long total = (long long)h * groups;
+    for (long long u = (long long)blockIdx.x * blockDim.x + threadIdx.x; u < total; u += (long long)gridDim.x * blockDim.x) {
+        const int y = (int)(u / groups), g = (int)(u - (long long)y * groups);
+        const u8 *row = px + (size_t)y * pitch + (size_t)g * 12;
+        u8 *lrow = labels + (size_t)y * lpitch + (size_t)g * 4;
+        if (fast_rows && g * 4 + 4 <= w) {
+            const u32 a = __ldg(reinterpret_cast<const u32 *>(row)), b = __ldg(reinterpret_cast<const u32 *>(row) + 1),
+                      c = __ldg(reinterpret_cast<const u32 *>(row) + 2);
+            const u32 l0 = label_of(a), l1 = label_of(__byte_perm(a, b, 0x4543)), l2 = label_of(__byte_perm(b, c, 0x4432)),
+                      l3 = label_of(c >> 8);
+            if (fast_out) *reinterpret_cast<u32 *>(lrow) = l0 | (l1 << 8) | (l2 << 16) | (l3 << 24);
+            else { lrow[0] = (u8)l0; lrow[1] = (u8)l1; lrow[2] = (u8)l2; lrow[3] = (u8)l3; }
+        } else {
+            for (int i = 0; i < 4 && g * 4 + i < w; i++)
+                lrow[i] = (u8)label_of((u32)row[3 * i] | ((u32)row[3 * i + 1] << 8) | ((u32)row[3 * i + 2] << 16));
+        }
+    }
+}
+
 const u16 *fast_lab_table()
 {
     void *p = nullptr;
@@ -1314,7 +1381,12 @@ cudaError_t fast_assign(omni_ctx *ctx, const u8 *px, int h, int w, size_t pitch,
     if (e != cudaSuccess) return e;
     if (mode_lab) {
         if (launch_assign_lab(ctx, px, h, w, pitch, P, labels, lpitch, nullptr, 0, 0, st, false) != OMNI_OK) return cudaErrorUnknown;
-    } else {
+    } else if (P.K <= 16) {
+        const int grid = resident_grid(ctx, fk_assign_i16wrap<16>, 256, &ctx->occ_assign_i16);
+        if (P.K <= 4) fk_assign_i16wrap<4><<<grid, 256, 0, st>>>(px, h, w, pitch, P, labels, lpitch);
+        else if (P.K <= 8) fk_assign_i16wrap<8><<<grid, 256, 0, st>>>(px, h, w, pitch, P, labels, lpitch);
+        else fk_assign_i16wrap<16><<<grid, 256, 0, st>>>(px, h, w, pitch, P, labels, lpitch);
+    } else {                                                 // more than 16 palette colours: the plain K loop
         int grid = resident_grid(ctx, fk_assign_bits<0>, 256, &ctx->occ_assign_pal);
         fk_assign_bits<0><<<grid, 256, 0, st>>>(px, h, w, pitch, P, nullptr, labels, lpitch, nullptr, 0, 0);
     }

@@ -90,7 +90,7 @@ struct omni_ctx {
     cudaStream_t s_in = nullptr, s_out = nullptr;
     cudaEvent_t pipe_ev[24] = {};          // 8 H2D bands, 8 morph bands, 4 pipeline joins, 2 zero-fill fork/join
     cudaEvent_t edge_join = nullptr;        // pending join of the zero-fill side stream (edge_pass_begin -> edges_from_bits)
-    int occ_assign_lab = 0, occ_assign_pal = 0, occ_assign_rgb = 0;   // resident CTAs per SM of the persistent assignment kernels
+    int occ_assign_lab = 0, occ_assign_pal = 0, occ_assign_rgb = 0, occ_assign_i16 = 0;   // resident CTAs per SM of the persistent assignment kernels
     // centres the candidate-cell table in ws[5] was built for (fast colour assignment)
     int cells_valid = 0, cells_K = 0;
     void *cells_stream = nullptr;
