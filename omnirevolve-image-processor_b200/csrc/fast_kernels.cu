@@ -756,30 +756,41 @@ __global__ void __launch_bounds__(256) fk_labels_to_bits(const u8 *__restrict__ 
 // A warp packs 512 pixels per step: every lane reads 16 bytes with one load, turns them into 16 bits (high bit of
 // "byte != 0" per byte, gathered with shifts), lane pairs are joined into words by a shuffle.  All ws words of a row
 // are written (the padding words as zeros).
-__device__ __forceinline__ u32 nz4(u32 v, u32 &bad)            // 4 bytes -> 4 bits "byte != 0"
+// CHECK = true (stage 03: masks must be {0,255}, anything else raises `bad` and the caller takes the generic kernels, so the bits only
+// matter for clean masks): bit = low bit of the byte.  CHECK = false (thinning: foreground = byte > 0): bit = "byte != 0".
+template <bool CHECK>
+__device__ __forceinline__ u32 nz4(u32 v, u32 &bad)            // 4 bytes -> 4 bits; the partial products of the gather land on distinct bits
 {
-    const u32 t = ((((v & 0x7f7f7f7fu) + 0x7f7f7f7fu) | v) & 0x80808080u) >> 7;      // 0x01 per non-zero byte
-    bad |= v ^ (t * 255u);                                                           // a non-zero byte that is not 0xFF
-    return (t | (t >> 7) | (t >> 14) | (t >> 21)) & 15u;
+    if (CHECK) {
+        const u32 t = v & 0x01010101u;
+        bad |= v ^ (t * 255u);
+        return (t * 0x01020408u) >> 24;
+    }
+    const u32 t7 = (((v & 0x7f7f7f7fu) + 0x7f7f7f7fu) | v) & 0x80808080u;      // 0x80 per non-zero byte
+    return (t7 * 0x00204081u) >> 28;
 }
 
+template <bool CHECK>
 __global__ void __launch_bounds__(256) fk_bytes_to_bits(const u8 *__restrict__ planes, size_t pstride, size_t pitch, int h, int w,
                                                         u32 *__restrict__ bits, int ws, size_t plane, int *d_bad)
 {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int k = blockIdx.y;
     const int chunks = (ws + 15) >> 4;                         // 16 words = 512 pixels per warp step
-    const long long total = (long long)h * chunks;
     const bool vec_ok = (((uintptr_t)(planes + (size_t)k * pstride) | pitch) & 15) == 0;
     u32 bad = 0u;
-    for (long long u = (long long)blockIdx.x * 8 + warp; u < total; u += (long long)gridDim.x * 8) {
-        const int y = (int)(u / chunks), ch = (int)(u - (long long)y * chunks);
+    // (row, chunk) of this warp's step and the constant stride between its steps: no division inside the loop
+    const int stride = (int)gridDim.x * 8, dy = stride / chunks, dch = stride - dy * chunks;
+    const int u0 = (int)blockIdx.x * 8 + warp;
+    int y = u0 / chunks, ch = u0 - y * chunks;
+    for (; y < h; y += dy, ch += dch) {
+        if (ch >= chunks) { ch -= chunks; if (++y >= h) break; }
         const int x = ch * 512 + 16 * lane;
         const u8 *row = planes + (size_t)k * pstride + (size_t)y * pitch;
         u32 m16 = 0u;
         if (vec_ok && x + 16 <= w) {
             const uint4 v = __ldg(reinterpret_cast<const uint4 *>(row + x));
-            m16 = nz4(v.x, bad) | (nz4(v.y, bad) << 4) | (nz4(v.z, bad) << 8) | (nz4(v.w, bad) << 12);
+            m16 = nz4<CHECK>(v.x, bad) | (nz4<CHECK>(v.y, bad) << 4) | (nz4<CHECK>(v.z, bad) << 8) | (nz4<CHECK>(v.w, bad) << 12);
         } else {
             for (int i = 0; i < 16 && x + i < w; i++) {
                 const u32 v = row[x + i];
@@ -791,7 +802,7 @@ __global__ void __launch_bounds__(256) fk_bytes_to_bits(const u8 *__restrict__ p
         const int c = ch * 16 + (lane >> 1);
         if (!(lane & 1) && c < ws) bits[(size_t)k * plane + (size_t)y * ws + c] = m16 | (other << 16);
     }
-    if (__any_sync(0xffffffffu, bad != 0u) && lane == 0) atomicOr(d_bad, 1);
+    if (CHECK && __any_sync(0xffffffffu, bad != 0u) && lane == 0) atomicOr(d_bad, 1);
 }
 
 // bit-planes -> 0/255 byte planes
@@ -1447,8 +1458,8 @@ int fast_morph03_bytes(omni_ctx *ctx, const u8 *d_masks, int K, int h, int w, si
     OMNI_CUDA(cudaMemsetAsync(ctx->d_flags + 8, 0, sizeof(int), st));
     {
         KScope ks(ctx, "bytes_to_bits", st);
-        fk_bytes_to_bits<<<dim3(persist_blocks(ctx, 2), K), 256, 0, st>>>(d_masks, m_plane, mpitch, h, w, bpp[0], g.ws, g.plane,
-                                                                         ctx->d_flags + 8);
+        fk_bytes_to_bits<true><<<dim3(persist_blocks(ctx, 2), K), 256, 0, st>>>(d_masks, m_plane, mpitch, h, w, bpp[0], g.ws, g.plane,
+                                                                               ctx->d_flags + 8);
         OMNI_CUDA(cudaGetLastError());
     }
     if (!ctx->assume_binary) {                            // (omni_set_assume_binary_masks: the caller vouches, nothing to wait for)
@@ -1586,8 +1597,8 @@ int fast_edges(omni_ctx *ctx, const u8 *d_masks, int K, int h, int w, size_t m_p
     OMNI_CUDA(cudaMemsetAsync(ctx->d_flags + 8, 0, sizeof(int), st));
     {
         KScope ks(ctx, "bytes_to_bits", st);
-        fk_bytes_to_bits<<<dim3(persist_blocks(ctx, 2), K), 256, 0, st>>>(d_masks, m_plane, mpitch, h, w, bpp[0], g.ws, g.plane,
-                                                                         ctx->d_flags + 8);
+        fk_bytes_to_bits<true><<<dim3(persist_blocks(ctx, 2), K), 256, 0, st>>>(d_masks, m_plane, mpitch, h, w, bpp[0], g.ws, g.plane,
+                                                                               ctx->d_flags + 8);
         OMNI_CUDA(cudaGetLastError());
     }
     if (!ctx->assume_binary) {                            // (omni_set_assume_binary_masks: the caller vouches, nothing to wait for)
@@ -1998,7 +2009,7 @@ int fast_thin(omni_ctx *ctx, const u8 *d_in, int K, int h, int w, size_t in_plan
                                                                    persist_blocks(ctx, 8), st));
     } else {
         KScope ks(ctx, "bytes_to_bits", st);
-        fk_bytes_to_bits<<<dim3(persist_blocks(ctx, 2), K), 256, 0, st>>>(d_in, in_plane, in_pitch, h, w, bpp[0], g.ws, g.plane, ctx->d_flags + 8);
+        fk_bytes_to_bits<false><<<dim3(persist_blocks(ctx, 2), K), 256, 0, st>>>(d_in, in_plane, in_pitch, h, w, bpp[0], g.ws, g.plane, ctx->d_flags + 8);
         OMNI_CUDA(cudaGetLastError());
     }
     if (max_iter > 0) {

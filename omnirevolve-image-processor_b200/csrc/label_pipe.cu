@@ -803,41 +803,39 @@ __global__ void __launch_bounds__(256) fk_pack_planes(const u32 *__restrict__ sr
                                                       u8 *__restrict__ dst, size_t dplane, size_t dpitch, int msb_first,
                                                       unsigned long long *__restrict__ counts)
 {
+    // grid = (row groups, planes): a warp walks rows of one plane, its lanes the words of the row (no divisions)
     const int ww = (w + 31) >> 5, rb = (w + 7) >> 3;
-    const long long total = (long long)K * h * ww;
-    const int lane = threadIdx.x & 31;
-    for (long long base = ((long long)blockIdx.x * blockDim.x + threadIdx.x) - lane; base < total; base += (long long)gridDim.x * blockDim.x) {
-        const long long u = base + lane;
-        u32 word = 0u;
-        int k = 0;
-        if (u < total) {
-            const int c = (int)(u % ww);
-            const long long r2 = u / ww;
-            const int y = (int)(r2 % h);
-            k = (int)(r2 / h);
-            word = src[(size_t)k * plane + (size_t)y * ws + c] & range_mask(32 * c, w);
+    const int lane = threadIdx.x & 31, k = blockIdx.y;
+    const int warps = (int)gridDim.x * (int)(blockDim.x >> 5);
+    if (k >= K) return;
+    const u32 *sp = src + (size_t)k * plane;
+    u8 *dp = dst + (size_t)k * dplane;
+    const bool aligned = (((uintptr_t)dp | dpitch) & 3) == 0;
+    unsigned n = 0;
+    for (int y = (int)blockIdx.x * (int)(blockDim.x >> 5) + (int)(threadIdx.x >> 5); y < h; y += warps) {
+        const u32 *srow = sp + (size_t)y * ws;
+        u8 *row = dp + (size_t)y * dpitch;
+        for (int c = lane; c < ww; c += 32) {
+            const u32 word = srow[c] & range_mask(32 * c, w);
             const u32 o = msb_first ? __byte_perm(__brev(word), 0u, 0x0123) : word;
-            u8 *row = dst + (size_t)k * dplane + (size_t)y * dpitch + 4 * c;
-            if (4 * c + 4 <= rb && (((uintptr_t)row) & 3) == 0) *reinterpret_cast<u32 *>(row) = o;
+            if (aligned && 4 * c + 4 <= rb) *reinterpret_cast<u32 *>(row + 4 * c) = o;
             else
-                for (int i = 0; 4 * c + i < rb && i < 4; i++) row[i] = (u8)(o >> (8 * i));
-        }
-        if (counts) {
-            const int n = __popc(word);
-            if ((long long)h * ww < 32) {                        // tiny planes: a warp may touch many of them
-                if (n) atomicAdd(counts + k, (unsigned long long)n);
-            } else {                                             // a warp straddles at most two planes: one atomic per plane
-                const int k0 = __shfl_sync(0xffffffffu, k, 0);
-                int a = (k == k0) ? n : 0, b = (k == k0) ? 0 : n;
-#pragma unroll
-                for (int d = 16; d > 0; d >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, d); b += __shfl_xor_sync(0xffffffffu, b, d); }
-                if (lane == 0) {
-                    if (a) atomicAdd(counts + k0, (unsigned long long)a);
-                    if (b) atomicAdd(counts + k0 + 1, (unsigned long long)b);
-                }
-            }
+                for (int i = 0; 4 * c + i < rb && i < 4; i++) row[4 * c + i] = (u8)(o >> (8 * i));
+            n += (unsigned)__popc(word);
         }
     }
+    if (counts) {
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) n += __shfl_xor_sync(0xffffffffu, n, d);
+        if (lane == 0 && n) atomicAdd(counts + k, (unsigned long long)n);
+    }
+}
+
+// grid of fk_pack_planes / fk_unpack_planes: enough warps for the rows of a plane, about `blocks` CTAs in all
+static inline dim3 pack_grid(int blocks, int K, int h)
+{
+    const int per_plane = std::max(1, std::min((h + 7) / 8, (blocks + K - 1) / K));
+    return dim3((unsigned)per_plane, (unsigned)K);
 }
 
 // caller layout (pitch, bit order) -> internal bit-planes (padding words zero)
@@ -868,7 +866,7 @@ cudaError_t launch_unpack_planes(const u8 *src, size_t splane, size_t spitch, in
 cudaError_t launch_pack_planes(const u32 *src, int ws, size_t plane, int K, int h, int w, u8 *dst, size_t dplane, size_t dpitch, int msb_first,
                                int blocks, cudaStream_t st)
 {
-    fk_pack_planes<<<blocks, 256, 0, st>>>(src, ws, plane, K, h, w, dst, dplane, dpitch, msb_first, nullptr);
+    fk_pack_planes<<<pack_grid(blocks, K, h), 256, 0, st>>>(src, ws, plane, K, h, w, dst, dplane, dpitch, msb_first, nullptr);
     return cudaGetLastError();
 }
 
@@ -916,13 +914,13 @@ int label_color_edge_packed(omni_ctx *ctx, const u8 *d_bgr, int nf, size_t frame
     const int blocks = persist_blocks(ctx, 8);
     {
         KScope ks(ctx, "pack_planes", st);
-        fk_pack_planes<<<blocks, 256, 0, st>>>(L.mask_bits, g.ws, g.plane, KT, h, w, d_mask_bits, mb_plane, mb_pitch, msb_first,
+        fk_pack_planes<<<pack_grid(blocks, KT, h), 256, 0, st>>>(L.mask_bits, g.ws, g.plane, KT, h, w, d_mask_bits, mb_plane, mb_pitch, msb_first,
                                                d_counts ? d_counts + OMNI_MAX_K : nullptr);
         OMNI_CUDA(cudaGetLastError());
     }
     if (prm) {
         KScope ks(ctx, "pack_planes", st);
-        fk_pack_planes<<<blocks, 256, 0, st>>>(L.edge_bits, g.ws, g.plane, KT, h, w, d_edge_bits, eb_plane, eb_pitch, msb_first,
+        fk_pack_planes<<<pack_grid(blocks, KT, h), 256, 0, st>>>(L.edge_bits, g.ws, g.plane, KT, h, w, d_edge_bits, eb_plane, eb_pitch, msb_first,
                                                d_counts ? d_counts + 2 * OMNI_MAX_K : nullptr);
         OMNI_CUDA(cudaGetLastError());
     }
@@ -1171,7 +1169,7 @@ int label_host_packed_banded(omni_ctx *ctx, const u8 *h_bgr, int h, int w, size_
         const size_t roff = (size_t)(r0 - a) * gs.ws;
         {
             KScope ks(ctx, "pack_planes", tt);
-            fk_pack_planes<<<blocks, 256, 0, tt>>>(L.mask_bits + roff, gs.ws, gs.plane, K, r1 - r0, w, d_mb + (size_t)r0 * dpm, dpm * h, dpm, msb_first,
+            fk_pack_planes<<<pack_grid(blocks, K, r1 - r0), 256, 0, tt>>>(L.mask_bits + roff, gs.ws, gs.plane, K, r1 - r0, w, d_mb + (size_t)r0 * dpm, dpm * h, dpm, msb_first,
                                                    dc ? dc + OMNI_MAX_K : nullptr);
             OMNI_CUDA(cudaGetLastError());
         }
@@ -1197,7 +1195,7 @@ int label_host_packed_banded(omni_ctx *ctx, const u8 *h_bgr, int h, int w, size_
             }
             if (mode >= 2) {
                 KScope ks(ctx, "pack_planes", tt);
-                fk_pack_planes<<<blocks, 256, 0, tt>>>(S + (size_t)r0 * g.ws, g.ws, g.plane, K, r1 - r0, w, d_eb + (size_t)r0 * dpe, dpe * h, dpe, msb_first, nullptr);
+                fk_pack_planes<<<pack_grid(blocks, K, r1 - r0), 256, 0, tt>>>(S + (size_t)r0 * g.ws, g.ws, g.plane, K, r1 - r0, w, d_eb + (size_t)r0 * dpe, dpe * h, dpe, msb_first, nullptr);
                 OMNI_CUDA(cudaGetLastError());
             }
         }
@@ -1217,7 +1215,7 @@ int label_host_packed_banded(omni_ctx *ctx, const u8 *h_bgr, int h, int w, size_
             OMNI_CUDA(cudaMemcpyAsync(ctx->h_flags + BD_FLAGS + 8, d_dirty, sizeof(unsigned), cudaMemcpyDeviceToHost, tt));
         } else {
             KScope ks(ctx, "pack_planes", tt);
-            fk_pack_planes<<<blocks, 256, 0, tt>>>(S, g.ws, g.plane, K, h, w, d_eb, dpe * h, dpe, msb_first, nullptr);
+            fk_pack_planes<<<pack_grid(blocks, K, h), 256, 0, tt>>>(S, g.ws, g.plane, K, h, w, d_eb, dpe * h, dpe, msb_first, nullptr);
             OMNI_CUDA(cudaGetLastError());
             OMNI_CUDA(cudaEventRecord(evEdges, tt));
             OMNI_CUDA(cudaStreamWaitEvent(so, evEdges, 0));
@@ -1237,7 +1235,7 @@ int label_host_packed_banded(omni_ctx *ctx, const u8 *h_bgr, int h, int w, size_
         unsigned dirty = (unsigned)ctx->h_flags[BD_FLAGS + 8];
         if (dirty == 0xffffffffu) {                          // worklist overflow: the device copy was not repaired -- repack, send everything
             KScope ks(ctx, "pack_planes", tt);
-            fk_pack_planes<<<blocks, 256, 0, tt>>>(S, g.ws, g.plane, K, h, w, d_eb, dpe * h, dpe, msb_first, nullptr);
+            fk_pack_planes<<<pack_grid(blocks, K, h), 256, 0, tt>>>(S, g.ws, g.plane, K, h, w, d_eb, dpe * h, dpe, msb_first, nullptr);
             OMNI_CUDA(cudaGetLastError());
             OMNI_CUDA(cudaStreamSynchronize(tt));
             dirty = (1u << nb) - 1u;
