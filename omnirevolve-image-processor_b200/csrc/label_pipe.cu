@@ -1044,9 +1044,24 @@ struct HoldTables {                                      // the candidate tables
     ~HoldTables() { c->tables_hold = 0; }
 };
 
+static int banded_body(omni_ctx *ctx, const u8 *h_bgr, int h, int w, size_t pitch, const AssignParams &P, const omni_edge_params *prm,
+                       int low, int high, u8 *h_mb, size_t mb_plane, size_t mb_pitch, u8 *h_eb, size_t eb_plane, size_t eb_pitch,
+                       int msb_first, int64_t *h_counts);
+
 int label_host_packed_banded(omni_ctx *ctx, const u8 *h_bgr, int h, int w, size_t pitch, const AssignParams &P, const omni_edge_params *prm,
                              int low, int high, u8 *h_mb, size_t mb_plane, size_t mb_pitch, u8 *h_eb, size_t eb_plane, size_t eb_pitch,
                              int msb_first, int64_t *h_counts)
+{
+    const int rc = banded_body(ctx, h_bgr, h, w, pitch, P, prm, low, high, h_mb, mb_plane, mb_pitch, h_eb, eb_plane, eb_pitch, msb_first, h_counts);
+    // a failure in the middle leaves copies queued that read and write the caller's buffers: let them finish before the caller
+    // gets the error and may free the buffers (UNSUPPORTED is decided before anything is queued)
+    if (rc != OMNI_OK && rc != OMNI_ERR_UNSUPPORTED) cudaDeviceSynchronize();
+    return rc;
+}
+
+static int banded_body(omni_ctx *ctx, const u8 *h_bgr, int h, int w, size_t pitch, const AssignParams &P, const omni_edge_params *prm,
+                       int low, int high, u8 *h_mb, size_t mb_plane, size_t mb_pitch, u8 *h_eb, size_t eb_plane, size_t eb_pitch,
+                       int msb_first, int64_t *h_counts)
 {
     const int K = P.K, mode = ctx->host_bands;
     if (mode == 0 || !ctx->fast || ctx->pipeline != 1 || h < 1024 || (long long)h * w < (2ll << 20)) return OMNI_ERR_UNSUPPORTED;
