@@ -349,3 +349,26 @@ def test_banded_host_call_leaves_row_gaps_alone(eng):
         assert eng.last_band_resends() >= 0
         assert np.array_equal(big_m[:, :, :rb], want["mask_bits"]) and np.array_equal(big_e[:, :, :rb], want["edge_bits"])
         assert (big_m[:, :, rb:] == 0xA5).all() and (big_e[:, :, rb:] == 0x5A).all()
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_banded_host_call_randomised(eng, seed):
+    """Random geometry (odd widths, heights that leave a short last band), K, thresholds, morphology switches, bit order: the
+    banded call (both modes) against the unbanded one, bytes and counts."""
+    import omni_b200
+    rng = np.random.default_rng(1000 + seed)
+    h = int(rng.integers(1024, 2600))
+    w = int(rng.integers(2 * 1024 * 1024 // h + 1, 2600))
+    K = int(rng.integers(2, 17))
+    img = synth(h, w, seed, cell=int(rng.choice([16, 32, 64, 128])))
+    ctr, lut = _centres(img[:768, :768], K)
+    low, high = sorted(float(v) for v in rng.integers(0, 900, 2))
+    ec = omni_b200.EdgeConfig(low=low, high=high, open_iters=int(rng.integers(0, 2)), close_iters=int(rng.integers(0, 2)))
+    msb = bool(rng.integers(0, 2))
+    r0, _ = _host_packed(eng, img, ctr, lut, ec, 0, msb)
+    for bands in (2, 1):
+        r, resends = _host_packed(eng, img, ctr, lut, ec, bands, msb)
+        assert resends >= 0, (h, w, K)
+        assert np.array_equal(r["mask_bits"], r0["mask_bits"]), (h, w, K, bands)
+        assert np.array_equal(r["edge_bits"], r0["edge_bits"]), (h, w, K, bands, low, high, resends)
+        assert np.array_equal(r["counts"], r0["counts"]), (h, w, K, bands)
