@@ -1104,6 +1104,7 @@ static int banded_body(omni_ctx *ctx, const u8 *h_bgr, int h, int w, size_t pitc
             ctx->band_helper->assign_rgbcell = ctx->assign_rgbcell;
         }
         hx = ctx->band_helper;
+        hx->table_cache = ctx->table_cache;                  // "rebuild the tables on every call" holds for the helper's copy too
     }
     cudaStream_t sc = ctx->stream, si = ctx->pk_in, so = ctx->pk_out, tt = ctx->bd_tail;
     // ---- workspace: slot 3 = [image | packed masks | packed edges | S | C | worklist]; slots 4-6 sized for the tallest band image ----
