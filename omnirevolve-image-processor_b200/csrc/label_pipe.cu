@@ -660,18 +660,38 @@ static cudaError_t launch_morph_lab(int kind /* -1: masks only */, const uint4 *
 {
     const int wcols = (g.ww + LP_COLS - 1) / LP_COLS;
     const int al = plane_align(masks, mstride, mpitch);
-    // taller strips (less halo work) once there are plenty of warps
-    const long long warps64 = (long long)wcols * ((g.h + 63) / 64) * KT;
+    // Strip height.  A warp walks its strip row by row (+ ~20 rows of halo and pipeline), and the kernel is latency-bound: its time is
+    // about  waves x (rows + 20),  waves = ceil(strip-warps / resident warps).  Short strips for small grids (one wave: the shortest
+    // walk wins), tall ones once there are several waves, and 56 rows where that lands the grid on a whole number of waves
+    // (4096^2: 2960 resident warps = the 5 x 74 x 8 strip-warps of K = 8, half those of K = 16).
 #ifdef ML_TR
     const int tr = ML_TR;
 #else
-    const int tr = warps64 >= 4096 ? 64 : 32;
+    static int resident = 0;
+    if (resident == 0) {
+        int per_sm = 0, dev = 0, sms = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fk_morph_lab<CODE_L_OC, 2, 64, true>, 128, 0) != cudaSuccess || per_sm < 1) per_sm = 4;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms < 1) sms = 148;
+        cudaGetLastError();
+        resident = per_sm * 4 * sms;
+    }
+    int tr = 32;
+    long long best = -1;
+    for (int cand : {32, 56, 64}) {
+        const long long units = (long long)wcols * ((g.h + cand - 1) / cand) * KT;
+        const long long cost = ((units + resident - 1) / resident) * (cand + 20);
+        if (best < 0 || cost <= best) { best = cost; tr = cand; }
+    }
 #endif
     const int strips = (g.h + tr - 1) / tr;
     const long long n_units = (long long)wcols * strips * KT;
     dim3 b(128), grid((unsigned)((n_units + 3) / 4));
 #define LL2(CODE, TRV, RUNS) fk_morph_lab<CODE, 2, TRV, RUNS><<<grid, b, 0, st>>>(slices, od, m2, g.ws, g.plane, g.h, g.w, K, masks, mstride, mpitch, al, tap_bits, wcols, strips, KT, n_units, R)
-#define LL(CODE, RUNS) do { if (tr == 64) LL2(CODE, 64, RUNS); else LL2(CODE, 32, RUNS); } while (0)
+#ifdef ML_TR
+#define LL(CODE, RUNS) LL2(CODE, ML_TR, RUNS)
+#else
+#define LL(CODE, RUNS) do { if (tr == 64) LL2(CODE, 64, RUNS); else if (tr == 56) LL2(CODE, 56, RUNS); else LL2(CODE, 32, RUNS); } while (0)
+#endif
     switch (kind) {
     case -1: LL(CODE_L_N, false); break;
     case 0: LL(CODE_L_N, true); break;
