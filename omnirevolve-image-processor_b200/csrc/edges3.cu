@@ -588,8 +588,10 @@ int edges3_pick_maxt(int h, int w, int K, int resident_warps)
 {
     const double live = 0.35 * (double)K * ((h + ET_R - 1) / ET_R) * ((w + 31) / 32);
     const double avg[ET_MAXT] = {1.0, 1.6, 2.0, 2.4};
+    // at least ~1.5 warp items per resident warp: with fewer the persistent warps end far apart (4096^2, K=8: runs of <= 3 tiles
+    // instead of 4 take the kernel from 127 to 122 us; K=16 has enough items either way)
     int maxt = ET_MAXT;
-    while (maxt > 1 && live / avg[maxt - 1] / 32.0 < (double)resident_warps) maxt--;
+    while (maxt > 1 && live / avg[maxt - 1] / 32.0 < 1.5 * (double)resident_warps) maxt--;
     return maxt;
 }
 
