@@ -92,11 +92,12 @@ class ClockSampler(threading.Thread):
                 for bit, name in self.REASONS.items():
                     if r & bit:
                         self.reasons.add(name)
-                try:
-                    self.power.append(nv.nvmlDeviceGetPowerUsage(h) / 1000.0)
-                except Exception:
-                    pass
-                time.sleep(0.004)
+                if len(self.samples) % 4 == 1:                 # (every NVML query is a round trip to the GPU's management unit)
+                    try:
+                        self.power.append(nv.nvmlDeviceGetPowerUsage(h) / 1000.0)
+                    except Exception:
+                        pass
+                time.sleep(0.010)
         except Exception as exc:                       # noqa: BLE001
             self.err = repr(exc)
 
